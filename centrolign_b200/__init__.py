@@ -10,3 +10,6 @@ from .batch import (AlignmentParameters, CpuChecker, GraphSide, WindowBatch, bat
 
 __all__ = ["AlignmentParameters", "CpuChecker", "GraphSide", "WindowBatch", "batch_from_graph_pairs",
            "graph_from_edges", "synth_windows"]
+from .popoa import ClbError, DeviceBatch, po_poa, po_poa_batch  # noqa: E402,F401
+
+__all__ += ["ClbError", "DeviceBatch", "po_poa", "po_poa_batch"]

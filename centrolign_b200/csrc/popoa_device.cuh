@@ -1,0 +1,71 @@
+// popoa_device.cuh -- data layout shared by the host flattening code and the sm_100a kernels.
+//
+// Matrix coordinates.  A window's DP matrix has rows 0..n1 and columns 0..n2.  Row / column 0
+// is the reference's "boundary" row / column (the extra final row / column of its table,
+// include/centrolign/alignment.hpp:788-790, moved to the front); row i >= 1 is the graph-1 node
+// with topological rank i-1, column j >= 1 likewise for graph 2.  Every predecessor therefore
+// has a smaller index, sources carry the extra predecessor 0 appended LAST in their list
+// (alignment.hpp:1078-1084), and (n1+1)*(n2+1) is the cell count of the GCUPS metric.
+#pragma once
+#include <stdint.h>
+
+namespace clb {
+
+constexpr int kMinInf = INT32_MIN / 2;  // cell_t::mininf, alignment.hpp:740
+constexpr int kStrip = 32;              // columns per strip = lanes per warp
+constexpr int kRowBlock = 64;           // rows per traceback tile
+constexpr int kNear = 3;                // predecessors at most this far back are served from the shared-memory ring
+constexpr int kRingRows = 8;            // fill-kernel ring depth (>= 2*kNear+2)
+
+// per-node info word
+constexpr uint32_t kInfoLabelMask = 0xffu;
+constexpr uint32_t kInfoRegular = 1u << 8;  // exactly one predecessor and it is index-1
+constexpr uint32_t kInfoPersist = 1u << 9;  // row / column is kept in the window workspace
+
+// One side (graph 1 = rows, graph 2 = columns) of all windows, concatenated on the device.
+struct SideArrays {
+    const uint32_t* info;   // per window n+1 entries (index 0 = boundary): label | flags
+    const int32_t* slot;    // per window n+1 entries: workspace slot of a persisted row/column, else -1
+    const uint32_t* depth;  // per window n+1 entries: fewest nodes on a path from a source (0 = unreachable)
+    const uint32_t* poff;   // per window n+2 entries: predecessor list offsets (window-relative)
+    const uint32_t* pidx;   // predecessor matrix indices, previous() order, 0 appended last for sources
+    const uint32_t* sinks;  // sink matrix indices, caller order
+};
+
+struct WindowMeta {
+    uint32_t n1, n2;
+    uint32_t nsnk1, nsnk2;
+    uint32_t nrslot, ncslot;  // persisted rows / columns
+    int64_t node1, node2;     // base of info/slot/depth entries
+    int64_t poff1, poff2;     // base of poff entries
+    int64_t pidx1, pidx2;     // base of pidx entries
+    int64_t snk1, snk2;       // base of sinks entries
+    int64_t out;              // first (id1,id2) pair slot of this window in the output
+};
+
+struct Params {
+    int match, mismatch;  // mismatch stored positive
+    int oe[3];            // open + extend
+    int e[3];
+};
+
+struct LaunchArgs {
+    SideArrays s1, s2;
+    const WindowMeta* meta;
+    const int32_t* order;   // window ids, largest first
+    int32_t n_windows;
+    int32_t* queue;         // atomic work counter
+    char* workspace;        // gridDim.x slots
+    int64_t slot_bytes;
+    int64_t* score;         // [n_windows]
+    int32_t* aln;           // pairs, written backwards from the end of each window's region
+    uint32_t* aln_len;      // [n_windows]
+    Params prm;
+};
+
+inline int64_t workspace_bytes(uint32_t n1, uint32_t n2, uint32_t nrslot, uint32_t ncslot) {
+    // rowbuf + colbuf + boundary row + boundary column, 16 bytes per entry
+    return 16 * ((int64_t)nrslot * (n2 + 1) + (int64_t)ncslot * (n1 + 1) + (n2 + 1) + (n1 + 1));
+}
+
+}  // namespace clb

@@ -1,0 +1,508 @@
+// popoa_host.cu -- host side of the C ABI (include/centrolign_b200.h).
+//
+// "Flattening": every window's two graphs arrive in the caller's node order, exactly as the
+// reference's po_poa receives them (include/centrolign/alignment.hpp:78-85).  Here each graph
+// is renumbered by a Kahn topological order (the reference does the same inside po_poa,
+// alignment.hpp:806-807 / topological_order.hpp:11-60; DP values do not depend on which
+// topological order is used), predecessor lists are rewritten in previous() order with the
+// boundary index 0 appended last for sources (alignment.hpp:1069-1084), and the rows / columns
+// the kernels must keep ("persisted") are chosen.  Flattening is multi-threaded over windows.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "centrolign_b200.h"
+#include "popoa_device.cuh"
+
+namespace clb {
+cudaError_t launch_popoa(int num_pw, const LaunchArgs& args, int grid, cudaStream_t stream);
+int popoa_smem_bytes();
+double int32_probe(int use_dpx, int sm_count);
+}  // namespace clb
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return fail(_e == cudaErrorMemoryAllocation ? CLB_ENOMEM : CLB_ECUDA,                   \
+                        std::string(#expr) + ": " + cudaGetErrorString(_e));                        \
+    } while (0)
+
+template <class T>
+struct Pinned {  // pinned host + device twin
+    T* h = nullptr;
+    T* d = nullptr;
+    size_t n = 0;
+    int alloc_host(size_t count) {
+        n = count;
+        if (cudaHostAlloc((void**)&h, std::max<size_t>(1, count) * sizeof(T), cudaHostAllocDefault) != cudaSuccess) {
+            h = nullptr;
+            return CLB_ENOMEM;
+        }
+        return CLB_OK;
+    }
+    int alloc_dev() {
+        if (cudaMalloc((void**)&d, std::max<size_t>(1, n) * sizeof(T)) != cudaSuccess) {
+            d = nullptr;
+            return CLB_ENOMEM;
+        }
+        return CLB_OK;
+    }
+    size_t bytes() const { return n * sizeof(T); }
+    void release() {
+        if (h) cudaFreeHost(h);
+        if (d) cudaFree(d);
+        h = d = nullptr;
+    }
+};
+
+struct SideStage {
+    Pinned<uint32_t> info, depth, poff, pidx, sinks;
+    Pinned<int32_t> slot;
+    std::vector<uint32_t> orig;  // matrix index -> caller node id (host only)
+    void release() {
+        info.release(); depth.release(); poff.release(); pidx.release(); sinks.release(); slot.release();
+    }
+};
+
+}  // namespace
+
+struct clb_batch {
+    int device = 0;
+    int32_t nw = 0;
+    clb_params params{};
+    SideStage s[2];
+    Pinned<clb::WindowMeta> meta;
+    Pinned<int32_t> order;
+    Pinned<int64_t> score;
+    Pinned<int32_t> aln;
+    Pinned<uint32_t> aln_len;
+    int32_t* d_queue = nullptr;
+    char* d_workspace = nullptr;
+    int64_t slot_bytes = 0;
+    int grid = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool uploaded = false, ran = false;
+    clb_batch_stats stats{};
+    std::vector<int64_t> out_off;  // pair offset per window in the device output
+};
+
+namespace {
+
+struct FlattenScratch {
+    std::vector<uint32_t> succ_off, succ, indeg, stack, tpos;
+    std::vector<uint8_t> is_src;
+};
+
+// Flatten one side of one window.  Returns CLB_OK / CLB_EINVAL / CLB_ECYCLE.
+int flatten_side(const clb_graph_batch& g, int64_t w, int side, SideStage& st, clb::WindowMeta& m, FlattenScratch& sc,
+                 int64_t& int_ops_deg /* sum of in-degrees incl. boundary edges */) {
+    const int64_t n0 = g.node_off[w];
+    const uint32_t n = (uint32_t)(g.node_off[w + 1] - n0);
+    const uint32_t* po = g.pred_off + n0 + w;
+    const uint32_t* pr = g.pred + g.edge_off[w];
+    const uint32_t E = (uint32_t)(g.edge_off[w + 1] - g.edge_off[w]);
+    const uint32_t nsrc = (uint32_t)(g.src_off[w + 1] - g.src_off[w]);
+    const uint32_t nsnk = (uint32_t)(g.snk_off[w + 1] - g.snk_off[w]);
+    const uint32_t* src = g.src + g.src_off[w];
+    const uint32_t* snk = g.snk + g.snk_off[w];
+    if (po[0] != 0 || po[n] != E) return CLB_EINVAL;
+    for (uint32_t v = 0; v < n; ++v)
+        if (po[v + 1] < po[v]) return CLB_EINVAL;
+    for (uint32_t k = 0; k < E; ++k)
+        if (pr[k] >= n) return CLB_EINVAL;
+    for (uint32_t k = 0; k < nsrc; ++k)
+        if (src[k] >= n) return CLB_EINVAL;
+    for (uint32_t k = 0; k < nsnk; ++k)
+        if (snk[k] >= n) return CLB_EINVAL;
+
+    // successor lists + Kahn order with a LIFO stack (keeps chains contiguous)
+    sc.succ_off.assign(n + 2, 0);
+    sc.succ.resize(E + 1);
+    sc.indeg.resize(n + 1);
+    sc.stack.clear();
+    sc.tpos.assign(n + 1, 0);
+    sc.is_src.assign(n + 1, 0);
+    for (uint32_t k = 0; k < E; ++k) sc.succ_off[pr[k] + 2]++;
+    for (uint32_t v = 0; v < n; ++v) sc.succ_off[v + 2] += sc.succ_off[v + 1];
+    for (uint32_t v = 0; v < n; ++v)
+        for (uint32_t k = po[v]; k < po[v + 1]; ++k) sc.succ[sc.succ_off[pr[k] + 1]++] = v;
+    // succ_off[v] .. succ_off[v+1] now delimit v's successors
+    const int64_t nb = (side == 0 ? m.node1 : m.node2);
+    const int64_t pb = (side == 0 ? m.poff1 : m.poff2);
+    const int64_t xb = (side == 0 ? m.pidx1 : m.pidx2);
+    const int64_t kb = (side == 0 ? m.snk1 : m.snk2);
+    uint32_t* info = st.info.h + nb;
+    int32_t* slot = st.slot.h + nb;
+    uint32_t* depth = st.depth.h + nb;
+    uint32_t* poff = st.poff.h + pb;
+    uint32_t* pidx = st.pidx.h + xb;
+    uint32_t* orig = st.orig.data() + nb;
+    for (uint32_t v = 0; v < n; ++v) {
+        sc.indeg[v] = po[v + 1] - po[v];
+        if (sc.indeg[v] == 0) sc.stack.push_back(v);
+    }
+    uint32_t cnt = 0;
+    while (!sc.stack.empty()) {
+        const uint32_t v = sc.stack.back();
+        sc.stack.pop_back();
+        sc.tpos[v] = ++cnt;
+        orig[cnt] = v;
+        for (uint32_t k = sc.succ_off[v]; k < sc.succ_off[v + 1]; ++k)
+            if (--sc.indeg[sc.succ[k]] == 0) sc.stack.push_back(sc.succ[k]);
+    }
+    if (cnt != n) return CLB_ECYCLE;
+    for (uint32_t k = 0; k < nsrc; ++k) sc.is_src[src[k]] = 1;
+
+    const uint32_t block = side == 0 ? (uint32_t)clb::kRowBlock : (uint32_t)clb::kStrip;
+    info[0] = clb::kInfoPersist;
+    depth[0] = 0;
+    orig[0] = 0xffffffffu;
+    poff[0] = 0;
+    poff[1] = 0;  // the boundary index has no predecessors
+    for (uint32_t i = 1; i <= n; ++i) info[i] = 0;
+    uint32_t fill = 0;
+    for (uint32_t i = 1; i <= n; ++i) {
+        const uint32_t v = orig[i];
+        uint32_t dmin = 0;
+        const uint32_t first = fill;
+        for (uint32_t k = po[v]; k < po[v + 1]; ++k) {
+            const uint32_t p = sc.tpos[pr[k]];
+            pidx[fill++] = p;
+            if (depth[p] && (dmin == 0 || depth[p] + 1 < dmin)) dmin = depth[p] + 1;
+            if (i - p > (uint32_t)clb::kNear || (i - 1) / block != (p - 1) / block) info[p] |= clb::kInfoPersist;
+        }
+        if (sc.is_src[v]) {
+            pidx[fill++] = 0;
+            dmin = 1;
+        }
+        depth[i] = dmin;
+        poff[i + 1] = fill;
+        uint32_t word = (uint32_t)g.label[n0 + v];
+        if (fill - first == 1 && pidx[first] == i - 1) word |= clb::kInfoRegular;
+        info[i] |= word;
+        int_ops_deg += fill - first;
+    }
+    uint32_t* sinks = st.sinks.h + kb;
+    for (uint32_t k = 0; k < nsnk; ++k) {
+        sinks[k] = sc.tpos[snk[k]];
+        if (side == 0) info[sinks[k]] |= clb::kInfoPersist;  // M at (sink1, sink2) is read from the persisted row
+    }
+    uint32_t nslot = 0;
+    for (uint32_t i = 0; i <= n; ++i) slot[i] = (info[i] & clb::kInfoPersist) ? (int32_t)nslot++ : -1;
+    if (side == 0) { m.n1 = n; m.nsnk1 = nsnk; m.nrslot = nslot; }
+    else { m.n2 = n; m.nsnk2 = nsnk; m.ncslot = nslot; }
+    return CLB_OK;
+}
+
+int check_side(const clb_graph_batch* g) {
+    if (!g || !g->node_off || !g->edge_off || !g->pred_off || !g->src_off || !g->snk_off) return CLB_EINVAL;
+    return CLB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* clb_last_error(void) { return g_err.c_str(); }
+
+int clb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+void clb_batch_destroy(clb_batch* b) {
+    if (!b) return;
+    cudaSetDevice(b->device);
+    for (auto& s : b->s) s.release();
+    b->meta.release(); b->order.release(); b->score.release(); b->aln.release(); b->aln_len.release();
+    if (b->d_queue) cudaFree(b->d_queue);
+    if (b->d_workspace) cudaFree(b->d_workspace);
+    if (b->ev0) cudaEventDestroy(b->ev0);
+    if (b->ev1) cudaEventDestroy(b->ev1);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+}
+
+int clb_batch_create(int device, int32_t n_windows, const clb_graph_batch* g1, const clb_graph_batch* g2,
+                     const clb_params* params, clb_batch** out) {
+    if (!out) return fail(CLB_EINVAL, "out is null");
+    *out = nullptr;
+    if (n_windows < 0 || !params || params->num_pw < 1 || params->num_pw > CLB_MAX_PW)
+        return fail(CLB_EINVAL, "bad n_windows or num_pw (must be 1..3)");
+    if (n_windows > 0 && (check_side(g1) || check_side(g2))) return fail(CLB_EINVAL, "null graph arrays");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(CLB_ECUDA, "no CUDA device: the gap-fill path has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(CLB_EINVAL, "device out of range");
+    CUDA_TRY(cudaSetDevice(device));
+
+    clb_batch* b = new clb_batch();
+    b->device = device;
+    b->nw = n_windows;
+    b->params = *params;
+    const int64_t nw = n_windows;
+    const clb_graph_batch* gs[2] = {g1, g2};
+    int rc = b->meta.alloc_host(nw) | b->order.alloc_host(nw) | b->score.alloc_host(nw) | b->aln_len.alloc_host(nw);
+    int64_t tot_pairs = 0;
+    b->out_off.assign(nw + 1, 0);
+    for (int sd = 0; sd < 2 && rc == CLB_OK; ++sd) {
+        const int64_t N = nw ? gs[sd]->node_off[nw] : 0, E = nw ? gs[sd]->edge_off[nw] : 0;
+        const int64_t S = nw ? gs[sd]->src_off[nw] : 0, K = nw ? gs[sd]->snk_off[nw] : 0;
+        if (N < 0 || E < 0 || S < 0 || K < 0) rc = CLB_EINVAL;
+        SideStage& st = b->s[sd];
+        rc |= st.info.alloc_host(N + nw) | st.slot.alloc_host(N + nw) | st.depth.alloc_host(N + nw) |
+              st.poff.alloc_host(N + 2 * nw) | st.pidx.alloc_host(E + S) | st.sinks.alloc_host(K);
+        st.orig.resize(N + nw);
+    }
+    if (rc != CLB_OK) {
+        clb_batch_destroy(b);
+        return fail(rc == CLB_EINVAL ? CLB_EINVAL : CLB_ENOMEM, "staging allocation failed");
+    }
+    for (int64_t w = 0; w < nw; ++w) {
+        clb::WindowMeta& m = b->meta.h[w];
+        memset(&m, 0, sizeof(m));
+        m.node1 = g1->node_off[w] + w; m.node2 = g2->node_off[w] + w;
+        m.poff1 = g1->node_off[w] + 2 * w; m.poff2 = g2->node_off[w] + 2 * w;
+        m.pidx1 = g1->edge_off[w] + g1->src_off[w]; m.pidx2 = g2->edge_off[w] + g2->src_off[w];
+        m.snk1 = g1->snk_off[w]; m.snk2 = g2->snk_off[w];
+        const int64_t n1 = g1->node_off[w + 1] - g1->node_off[w], n2 = g2->node_off[w + 1] - g2->node_off[w];
+        if (n1 < 0 || n2 < 0 || n1 > 0x3fffffff || n2 > 0x3fffffff) {
+            clb_batch_destroy(b);
+            return fail(CLB_EINVAL, "window size out of range");
+        }
+        m.out = tot_pairs;
+        b->out_off[w] = tot_pairs;
+        tot_pairs += n1 + n2;
+    }
+    b->out_off[nw] = tot_pairs;
+
+    // multi-threaded flatten
+    std::atomic<int64_t> next(0);
+    std::atomic<int> status(CLB_OK);
+    std::atomic<int64_t> bad_window(-1);
+    std::vector<int64_t> ops_part;
+    unsigned nthreads = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    if (nw < 64) nthreads = 1;
+    ops_part.assign(nthreads, 0);
+    std::vector<double> cells_part(nthreads, 0.0);
+    auto worker = [&](unsigned tix) {
+        FlattenScratch sc;
+        for (;;) {
+            const int64_t w0 = next.fetch_add(16);
+            if (w0 >= nw || status.load() != CLB_OK) break;
+            for (int64_t w = w0; w < std::min<int64_t>(nw, w0 + 16); ++w) {
+                clb::WindowMeta& m = b->meta.h[w];
+                int64_t deg1 = 0, deg2 = 0;
+                int r = flatten_side(*g1, w, 0, b->s[0], m, sc, deg1);
+                if (r == CLB_OK) r = flatten_side(*g2, w, 1, b->s[1], m, sc, deg2);
+                if (r != CLB_OK) {
+                    status.store(r);
+                    bad_window.store(w);
+                    return;
+                }
+                // per cell a*b + 1 + 4P(a+b) + 2P add/max; summed over the window this factorises:
+                //   sum_ij a_i*b_j = deg1*deg2,  sum_ij (a_i+b_j) = deg1*n2 + deg2*n1   (interior cells only)
+                const int64_t P = b->params.num_pw;
+                ops_part[tix] += deg1 * deg2 + (int64_t)m.n1 * m.n2 * (1 + 2 * P) + 4 * P * (deg1 * (int64_t)m.n2 + deg2 * (int64_t)m.n1);
+                cells_part[tix] += ((double)m.n1 + 1.0) * ((double)m.n2 + 1.0);
+            }
+        }
+    };
+    if (nthreads == 1) {
+        worker(0);
+    } else {
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < nthreads; ++t) pool.emplace_back(worker, t);
+        for (auto& t : pool) t.join();
+    }
+    if (status.load() != CLB_OK) {
+        const int r = status.load();
+        const int64_t bw = bad_window.load();
+        clb_batch_destroy(b);
+        return fail(r, std::string(r == CLB_ECYCLE ? "cyclic graph" : "malformed graph") + " in window " + std::to_string(bw));
+    }
+    b->stats.cells = 0;
+    b->stats.int_ops = 0;
+    for (unsigned t = 0; t < nthreads; ++t) { b->stats.cells += cells_part[t]; b->stats.int_ops += ops_part[t]; }
+
+    // work order: largest matrix first (longest-processing-time-first for the persistent CTAs)
+    std::vector<int32_t> ord(nw);
+    for (int64_t w = 0; w < nw; ++w) ord[w] = (int32_t)w;
+    std::stable_sort(ord.begin(), ord.end(), [&](int32_t a, int32_t c) {
+        const clb::WindowMeta &ma = b->meta.h[a], &mc = b->meta.h[c];
+        return ((int64_t)ma.n1 + 1) * ((int64_t)ma.n2 + 1) > ((int64_t)mc.n1 + 1) * ((int64_t)mc.n2 + 1);
+    });
+    if (nw) memcpy(b->order.h, ord.data(), nw * sizeof(int32_t));
+    b->slot_bytes = 16;
+    for (int64_t w = 0; w < nw; ++w) {
+        const clb::WindowMeta& m = b->meta.h[w];
+        b->slot_bytes = std::max(b->slot_bytes, clb::workspace_bytes(m.n1, m.n2, m.nrslot, m.ncslot));
+    }
+    b->slot_bytes = (b->slot_bytes + 255) & ~int64_t(255);
+    if (b->aln.alloc_host(2 * tot_pairs) != CLB_OK) {
+        clb_batch_destroy(b);
+        return fail(CLB_ENOMEM, "pinned output allocation failed");
+    }
+    *out = b;
+    return CLB_OK;
+}
+
+int clb_batch_upload(clb_batch* b) {
+    if (!b) return fail(CLB_EINVAL, "null batch");
+    if (b->uploaded) return fail(CLB_ESTATE, "batch already uploaded");
+    CUDA_TRY(cudaSetDevice(b->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, b->device));
+    if (prop.major < 10) return fail(CLB_ECUDA, "device is not sm_100-class; this library ships sm_100a code only");
+    CUDA_TRY(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&b->ev0));
+    CUDA_TRY(cudaEventCreate(&b->ev1));
+    int64_t h2d = 0;
+#define UP(P_)                                                                                               \
+    do {                                                                                                     \
+        if ((P_).alloc_dev() != CLB_OK) return fail(CLB_ENOMEM, "device allocation failed (" #P_ ")");       \
+        if ((P_).n) CUDA_TRY(cudaMemcpyAsync((P_).d, (P_).h, (P_).bytes(), cudaMemcpyHostToDevice, b->stream)); \
+        h2d += (int64_t)(P_).bytes();                                                                        \
+    } while (0)
+    for (auto& s : b->s) {
+        UP(s.info); UP(s.slot); UP(s.depth); UP(s.poff); UP(s.pidx); UP(s.sinks);
+    }
+    UP(b->meta);
+    UP(b->order);
+#undef UP
+    if (b->score.alloc_dev() || b->aln.alloc_dev() || b->aln_len.alloc_dev())
+        return fail(CLB_ENOMEM, "device allocation failed (outputs)");
+    CUDA_TRY(cudaMalloc((void**)&b->d_queue, sizeof(int32_t)));
+    // one workspace slot per persistent CTA; shrink the grid if memory is short
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    int grid = std::max(1, std::min<int>(b->nw, prop.multiProcessorCount));
+    const int64_t budget = (int64_t)(free_b * 0.92);
+    if (b->slot_bytes > budget) return fail(CLB_ENOMEM, "a single window's workspace exceeds device memory");
+    grid = (int)std::min<int64_t>(grid, budget / b->slot_bytes);
+    b->grid = std::max(1, grid);
+    CUDA_TRY(cudaMalloc((void**)&b->d_workspace, (size_t)b->grid * b->slot_bytes));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    b->stats.h2d_bytes = h2d;
+    b->stats.workspace_bytes = (int64_t)b->grid * b->slot_bytes;
+    b->uploaded = true;
+    return CLB_OK;
+}
+
+int clb_batch_run(clb_batch* b) {
+    if (!b) return fail(CLB_EINVAL, "null batch");
+    if (!b->uploaded) return fail(CLB_ESTATE, "upload the batch before running it");
+    CUDA_TRY(cudaSetDevice(b->device));
+    b->stats.kernel_launches = 0;
+    CUDA_TRY(cudaEventRecord(b->ev0, b->stream));
+    if (b->nw > 0) {
+        CUDA_TRY(cudaMemsetAsync(b->d_queue, 0, sizeof(int32_t), b->stream));
+        clb::LaunchArgs a;
+        for (int sd = 0; sd < 2; ++sd) {
+            clb::SideArrays& sa = sd == 0 ? a.s1 : a.s2;
+            sa.info = b->s[sd].info.d; sa.slot = b->s[sd].slot.d; sa.depth = b->s[sd].depth.d;
+            sa.poff = b->s[sd].poff.d; sa.pidx = b->s[sd].pidx.d; sa.sinks = b->s[sd].sinks.d;
+        }
+        a.meta = b->meta.d; a.order = b->order.d; a.n_windows = b->nw; a.queue = b->d_queue;
+        a.workspace = b->d_workspace; a.slot_bytes = b->slot_bytes;
+        a.score = b->score.d; a.aln = b->aln.d; a.aln_len = b->aln_len.d;
+        a.prm.match = (int)b->params.match;
+        a.prm.mismatch = (int)b->params.mismatch;
+        for (int k = 0; k < 3; ++k) {
+            a.prm.oe[k] = k < b->params.num_pw ? (int)(b->params.gap_open[k] + b->params.gap_extend[k]) : 0;
+            a.prm.e[k] = k < b->params.num_pw ? (int)b->params.gap_extend[k] : 0;
+        }
+        CUDA_TRY(clb::launch_popoa(b->params.num_pw, a, b->grid, b->stream));
+        b->stats.kernel_launches = 1;
+    }
+    CUDA_TRY(cudaEventRecord(b->ev1, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
+    b->stats.kernel_ms = ms;
+    b->stats.fill_ms = 0.0;
+    b->ran = true;
+    return CLB_OK;
+}
+
+int clb_batch_download(clb_batch* b, int64_t* score_out, const int64_t* aln_off, int32_t* aln_pairs, uint32_t* aln_len) {
+    if (!b) return fail(CLB_EINVAL, "null batch");
+    if (!b->ran) return fail(CLB_ESTATE, "run the batch before downloading results");
+    if (b->nw > 0 && (!score_out || !aln_off || !aln_pairs || !aln_len)) return fail(CLB_EINVAL, "null output arrays");
+    CUDA_TRY(cudaSetDevice(b->device));
+    const int64_t nw = b->nw;
+    for (int64_t w = 0; w < nw; ++w)
+        if (aln_off[w + 1] - aln_off[w] < b->out_off[w + 1] - b->out_off[w])
+            return fail(CLB_EINVAL, "alignment capacity of window " + std::to_string(w) + " is below n1+n2");
+    if (nw) {
+        CUDA_TRY(cudaMemcpyAsync(b->score.h, b->score.d, b->score.bytes(), cudaMemcpyDeviceToHost, b->stream));
+        CUDA_TRY(cudaMemcpyAsync(b->aln_len.h, b->aln_len.d, b->aln_len.bytes(), cudaMemcpyDeviceToHost, b->stream));
+        if (b->aln.n) CUDA_TRY(cudaMemcpyAsync(b->aln.h, b->aln.d, b->aln.bytes(), cudaMemcpyDeviceToHost, b->stream));
+        CUDA_TRY(cudaStreamSynchronize(b->stream));
+    }
+    b->stats.d2h_bytes = (int64_t)(b->score.bytes() + b->aln_len.bytes() + b->aln.bytes());
+    // translate topological ranks back to the caller's node ids; pairs were written backwards
+    // from the end of each window's region, so they are already in forward order
+    for (int64_t w = 0; w < nw; ++w) {
+        const clb::WindowMeta& m = b->meta.h[w];
+        const uint32_t len = b->aln_len.h[w];
+        const int64_t cap = b->out_off[w + 1] - b->out_off[w];
+        const int32_t* src = b->aln.h + 2 * (b->out_off[w] + cap - len);
+        int32_t* dst = aln_pairs + 2 * aln_off[w];
+        const uint32_t* o1 = b->s[0].orig.data() + m.node1;
+        const uint32_t* o2 = b->s[1].orig.data() + m.node2;
+        for (uint32_t k = 0; k < len; ++k) {
+            const int32_t a = src[2 * k], c = src[2 * k + 1];
+            dst[2 * k] = a < 0 ? CLB_GAP : (int32_t)o1[a + 1];
+            dst[2 * k + 1] = c < 0 ? CLB_GAP : (int32_t)o2[c + 1];
+        }
+        aln_len[w] = len;
+        score_out[w] = b->score.h[w];
+    }
+    return CLB_OK;
+}
+
+int clb_batch_get_stats(const clb_batch* b, clb_batch_stats* out) {
+    if (!b || !out) return fail(CLB_EINVAL, "null argument");
+    *out = b->stats;
+    return CLB_OK;
+}
+
+int clb_popoa_batch(int device, int32_t n_windows, const clb_graph_batch* g1, const clb_graph_batch* g2,
+                    const clb_params* params, int64_t* score_out, const int64_t* aln_off, int32_t* aln_pairs,
+                    uint32_t* aln_len) {
+    clb_batch* b = nullptr;
+    int rc = clb_batch_create(device, n_windows, g1, g2, params, &b);
+    if (rc == CLB_OK) rc = clb_batch_upload(b);
+    if (rc == CLB_OK) rc = clb_batch_run(b);
+    if (rc == CLB_OK) rc = clb_batch_download(b, score_out, aln_off, aln_pairs, aln_len);
+    clb_batch_destroy(b);
+    return rc;
+}
+
+double clb_int32_peak_tops(int device, int use_dpx) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return -1.0;
+    if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1.0;
+    return clb::int32_probe(use_dpx, prop.multiProcessorCount);
+}
+
+}  // extern "C"

@@ -1,0 +1,544 @@
+// popoa_kernels.cu -- hand-written sm_100a kernels for the piecewise-affine PO-to-PO graph DP.
+//
+// What is computed (pull form of the reference's push loop, include/centrolign/alignment.hpp:898-938):
+//   s(i,j)   = +match if label1(i)==label2(j) else -mismatch
+//   I_k(i,j) = max_{p in pred1(i)} max( M(p,j) - (o_k+e_k), I_k(p,j) - e_k )
+//   D_k(i,j) = max_{q in pred2(j)} max( M(i,q) - (o_k+e_k), D_k(i,q) - e_k )
+//   M(i,j)   = max( max_{p,q} M(p,q) + s(i,j), I_0..I_{P-1}, D_0..D_{P-1} )
+// Integer max distributes over "+const", so for a node with several predecessors the kernel
+// first folds the predecessor rows (columns) into ONE effective row (column) by an
+// element-wise max and then applies the single-predecessor update: identical values, and the
+// common case (one predecessor = previous index) never leaves registers.
+//
+// Execution model.  One CTA per window (persistent CTAs pull windows, largest first, from an
+// atomic queue).  The matrix is cut into strips of 32 columns; a warp sweeps a strip top to
+// bottom as a skewed wavefront (lane t is on row r-t), neighbours exchange M / D_k / diagonal
+// through warp shuffles, and the warps of the CTA pipeline over consecutive strips, the hand-off
+// being the last column of a strip, published through the window workspace with a
+// fence + progress word in shared memory.  DPX instructions (__viaddmax_s32, __vimax3_s32) carry
+// the three-piece affine recurrences.  No tensor cores: this is integer max-plus, not a GEMM.
+//
+// Traceback does not store the matrix.  The fill keeps only "persisted" rows {M,I_k} and
+// columns {M,D_k}: every 64th row / 32nd column plus any row / column that has a far successor.
+// The traceback warp re-computes the 64x32 tile the path is in (same strip routine, all cells
+// kept in shared memory) and applies the reference's own tests (alignment.hpp:1036-1138) to
+// the real cell values, so tie-breaking is the reference's by construction.
+#include <cuda_runtime.h>
+#include <limits.h>
+
+#include "popoa_device.cuh"
+
+namespace clb {
+
+constexpr int kWarps = 16;
+constexpr int kThreads = kWarps * 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+// window view, resolved once per window into shared memory
+struct Win {
+    int n1, n2;
+    int nsnk1, nsnk2;
+    const uint32_t *info1, *info2;
+    const int32_t *slot1, *slot2;
+    const uint32_t *depth1, *depth2;
+    const uint32_t *poff1, *poff2;
+    const uint32_t *pidx1, *pidx2;
+    const uint32_t *snk1, *snk2;
+    int4 *rowbuf, *colbuf, *brow, *bcol;
+    int64_t out;
+};
+
+__device__ __forceinline__ int imax(int a, int b) { return a > b ? a : b; }
+
+__device__ __forceinline__ void max4(int& m, int (&v)[3], const int4 a) {
+    m = imax(m, a.x);
+    v[0] = imax(v[0], a.y);
+    v[1] = imax(v[1], a.z);
+    v[2] = imax(v[2], a.w);
+}
+
+// ------------------------------------------------------------------------------------------
+// One strip (32 columns starting at C0) over rows R0..R1 as a skewed warp wavefront.
+//   TILE=false : DP fill. Ring of H rows in shared memory serves near predecessors; persisted
+//                rows / columns go to the window workspace; the last lane publishes progress.
+//   TILE=true  : traceback tile. H = kRowBlock, every cell of the tile stays in shared memory.
+// ------------------------------------------------------------------------------------------
+template <int P, int H, bool TILE>
+__device__ __forceinline__ void process_strip(const Win& Wsh, const Params& prm, const int C0, const int R0,
+                                              const int R1, int4* __restrict__ ringA, int4* __restrict__ ringB,
+                                              volatile unsigned long long* progress, const int cs, const int lane) {
+    const int n1 = Wsh.n1, n2 = Wsh.n2;
+    const uint32_t* __restrict__ info1 = Wsh.info1;
+    const int32_t* __restrict__ slot1 = Wsh.slot1;
+    const uint32_t* __restrict__ poff1 = Wsh.poff1;
+    const uint32_t* __restrict__ pidx1 = Wsh.pidx1;
+    const int32_t* __restrict__ slot2 = Wsh.slot2;
+    const uint32_t* __restrict__ pidx2 = Wsh.pidx2;
+    int4* rowbuf = Wsh.rowbuf;
+    int4* colbuf = Wsh.colbuf;
+    const int64_t rstride = (int64_t)n2 + 1, cstride = (int64_t)n1 + 1;
+
+    const int j = C0 + lane;
+    const bool jvalid = j <= n2;
+    const uint32_t cinfo = jvalid ? Wsh.info2[j] : 0u;
+    const int clabel = (int)(cinfo & kInfoLabelMask);
+    const bool creg = (cinfo & kInfoRegular) != 0;
+    const int cslot = (cinfo & kInfoPersist) ? slot2[j] : -1;
+    const uint32_t cp0 = jvalid ? Wsh.poff2[j] : 0u, cp1 = jvalid ? Wsh.poff2[j + 1] : 0u;
+    const int4* leftcol = nullptr;  // persisted column C0-1 (lane 0 only)
+    if (lane == 0) {
+        const int ls = slot2[C0 - 1];
+        if (ls >= 0) leftcol = colbuf + (int64_t)ls * cstride;
+    }
+    int4* mycol = cslot >= 0 ? colbuf + (int64_t)cslot * cstride : nullptr;
+
+    int upM = kMinInf, upI[3] = {kMinInf, kMinInf, kMinInf};
+    if (jvalid) {
+        const int s0 = slot1[R0 - 1];
+        if (s0 >= 0) {
+            const int4 a = rowbuf[(int64_t)s0 * rstride + j];
+            upM = a.x; upI[0] = a.y; upI[1] = a.z; upI[2] = a.w;
+        }
+    }
+    int outM = kMinInf, outD[3] = {kMinInf, kMinInf, kMinInf}, outEff = kMinInf;
+    int avail = (TILE || cs == 0) ? INT_MAX : 0;
+    const int nsteps = (R1 - R0 + 1) + 31;
+
+    for (int s = 0; s < nsteps; ++s) {
+        const int r = R0 + s - lane;
+        const bool active = jvalid && r >= R0 && r <= R1;
+        if (!TILE) {
+            const int need = min(R0 + s, R1);
+            if (avail < need) {
+                do {
+                    const unsigned long long v = progress[(cs - 1) & 63];
+                    avail = ((int)(v >> 32) == cs) ? (int)(v & 0xffffffffu) : 0;
+                } while (avail < need);
+                __threadfence_block();
+            }
+        }
+        int lM = __shfl_up_sync(kFull, outM, 1);
+        int lD[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) lD[k] = (k < P) ? __shfl_up_sync(kFull, outD[k], 1) : kMinInf;
+        int lEff = __shfl_up_sync(kFull, outEff, 1);
+
+        if (active) {
+            const uint32_t rinfo = info1[r];
+            const int rlabel = (int)(rinfo & kInfoLabelMask);
+            const bool rreg = (rinfo & kInfoRegular) != 0;
+            uint32_t rp0 = 0, rp1 = 0;
+            if (!rreg) { rp0 = poff1[r]; rp1 = poff1[r + 1]; }
+
+            // ---- effective predecessor row (same column) ----
+            int eM, eI[3];
+            if (rreg) {
+                eM = upM; eI[0] = upI[0]; eI[1] = upI[1]; eI[2] = upI[2];
+            } else {
+                eM = kMinInf; eI[0] = eI[1] = eI[2] = kMinInf;
+                for (uint32_t a = rp0; a < rp1; ++a) {
+                    const int p = (int)pidx1[a];
+                    const bool pin = TILE ? (p >= R0) : (p >= 1 && r - p <= kNear);
+                    const int4 v = pin ? ringA[(p & (H - 1)) * 32 + lane] : rowbuf[(int64_t)slot1[p] * rstride + j];
+                    max4(eM, eI, v);
+                }
+            }
+            // ---- effective predecessor column (same row) and diagonal ----
+            if (creg) {
+                if (lane == 0) {
+                    const int4 b = leftcol[r];
+                    lM = b.x; lD[0] = b.y; lD[1] = b.z; lD[2] = b.w;
+                    if (rreg) {
+                        lEff = leftcol[r - 1].x;
+                    } else {
+                        lEff = kMinInf;
+                        for (uint32_t a = rp0; a < rp1; ++a) lEff = imax(lEff, leftcol[pidx1[a]].x);
+                    }
+                }
+            } else {
+                lM = kMinInf; lD[0] = lD[1] = lD[2] = kMinInf; lEff = kMinInf;
+                for (uint32_t b = cp0; b < cp1; ++b) {
+                    const int q = (int)pidx2[b];
+                    const bool qin = (q >= C0) && (TILE || j - q <= kNear);
+                    const int4* colp = nullptr;
+                    int4 v;
+                    if (qin) {
+                        v = ringB[(r & (H - 1)) * 32 + (q - C0)];
+                    } else {
+                        colp = colbuf + (int64_t)slot2[q] * cstride;
+                        v = colp[r];
+                    }
+                    max4(lM, lD, v);
+                    // diagonal: max over predecessor rows p of M(p,q)
+                    const uint32_t a0 = rreg ? 0u : rp0, a1 = rreg ? 1u : rp1;
+                    for (uint32_t a = a0; a < a1; ++a) {
+                        const int p = rreg ? r - 1 : (int)pidx1[a];
+                        int m;
+                        if (!qin) {
+                            m = colp[p].x;
+                        } else {
+                            const bool pin = TILE ? (p >= R0) : (p >= 1 && r - p <= kNear);
+                            m = pin ? ringA[(p & (H - 1)) * 32 + (q - C0)].x : rowbuf[(int64_t)slot1[p] * rstride + q].x;
+                        }
+                        lEff = imax(lEff, m);
+                    }
+                }
+            }
+            // ---- the cell ----
+            const int sub = (rlabel == clabel) ? prm.match : -prm.mismatch;
+            int I[3] = {kMinInf, kMinInf, kMinInf}, D[3] = {kMinInf, kMinInf, kMinInf};
+            int M = __viaddmax_s32(lEff, sub, kMinInf);
+#pragma unroll
+            for (int k = 0; k < P; ++k) {
+                I[k] = __viaddmax_s32(eI[k], -prm.e[k], eM - prm.oe[k]);
+                D[k] = __viaddmax_s32(lD[k], -prm.e[k], lM - prm.oe[k]);
+                M = __vimax3_s32(M, I[k], D[k]);
+            }
+            const int4 cellA = make_int4(M, I[0], I[1], I[2]);
+            const int4 cellB = make_int4(M, D[0], D[1], D[2]);
+            ringA[(r & (H - 1)) * 32 + lane] = cellA;
+            ringB[(r & (H - 1)) * 32 + lane] = cellB;
+            if (!TILE) {
+                if (rinfo & kInfoPersist) rowbuf[(int64_t)slot1[r] * rstride + j] = cellA;
+                if (mycol) mycol[r] = cellB;
+            }
+            upM = M; upI[0] = I[0]; upI[1] = I[1]; upI[2] = I[2];
+            outM = M; outD[0] = D[0]; outD[1] = D[1]; outD[2] = D[2];
+            outEff = eM;
+        }
+        __syncwarp();
+        if (!TILE && lane == 31 && active && ((r & 3) == 0 || r == R1)) {
+            __threadfence_block();
+            progress[cs & 63] = ((unsigned long long)(cs + 1) << 32) | (unsigned)r;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Boundary row / column (alignment.hpp:814-894).  In the boundary column only the lead
+// insertion is extended, so I_k(i,0) = -(o_k + e_k * depth(i)) with depth = fewest nodes on a
+// path from a source; the host supplies depth, which makes this pass embarrassingly parallel.
+// ------------------------------------------------------------------------------------------
+template <int P>
+__device__ __forceinline__ int4 boundary_cell(uint32_t depth, const Params& prm) {
+    int v[3] = {kMinInf, kMinInf, kMinInf};
+    int m = kMinInf;
+    if (depth) {
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+            v[k] = imax(kMinInf, (int)(0u - (uint32_t)prm.oe[k] - (uint32_t)prm.e[k] * (depth - 1)));
+            m = imax(m, v[k]);
+        }
+    }
+    return make_int4(m, v[0], v[1], v[2]);
+}
+
+template <int P>
+__device__ void boundary_phase(const Win& W, const Params& prm, int tid, int nthreads) {
+    const int64_t rstride = (int64_t)W.n2 + 1, cstride = (int64_t)W.n1 + 1;
+    const int4 corner = make_int4(0, kMinInf, kMinInf, kMinInf);  // M(0,0)=0 seeds the sources (alignment.hpp:814-829)
+    for (int j = tid; j <= W.n2; j += nthreads) {
+        const int4 b = j == 0 ? corner : boundary_cell<P>(W.depth2[j], prm);
+        W.brow[j] = b;
+        W.rowbuf[j] = make_int4(b.x, kMinInf, kMinInf, kMinInf);  // row slot 0 = boundary row seen as a predecessor row
+        if (W.info2[j] & kInfoPersist) W.colbuf[(int64_t)W.slot2[j] * cstride] = b;
+    }
+    for (int i = tid; i <= W.n1; i += nthreads) {
+        const int4 b = i == 0 ? corner : boundary_cell<P>(W.depth1[i], prm);
+        W.bcol[i] = b;
+        W.colbuf[i] = make_int4(b.x, kMinInf, kMinInf, kMinInf);  // column slot 0
+        if (W.info1[i] & kInfoPersist) W.rowbuf[(int64_t)W.slot1[i] * rstride] = b;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Traceback (warp 0).  Mirrors alignment.hpp:979-1138 on recomputed cell values.
+// ------------------------------------------------------------------------------------------
+struct TileView {
+    int R0, R1, C0;  // tile rows R0..R1, columns C0..C0+31; R0 = 0 means "no tile"
+};
+
+template <int P>
+struct Walker {
+    const Win& W;
+    const Params& prm;
+    const int4* tileA;
+    const int4* tileB;
+    TileView tv;
+    int64_t rstride, cstride;
+
+    __device__ bool in_tile(int i, int j) const {
+        return tv.R0 > 0 && i >= tv.R0 && i <= tv.R1 && j >= tv.C0 && j < tv.C0 + kStrip && j <= W.n2;
+    }
+    // M(i,j); the corner reads as -inf in every traceback test (it is never a match)
+    __device__ int cM(int i, int j) const {
+        if (i == 0) return j == 0 ? kMinInf : W.brow[j].x;
+        if (j == 0) return W.bcol[i].x;
+        if (in_tile(i, j)) return tileA[(i & (kRowBlock - 1)) * 32 + (j - tv.C0)].x;
+        const int s = W.slot1[i];
+        if (s >= 0) return W.rowbuf[(int64_t)s * rstride + j].x;
+        return W.colbuf[(int64_t)W.slot2[j] * cstride + i].x;
+    }
+    __device__ int cI(int i, int j, int k) const {
+        if (i == 0) return kMinInf;
+        int4 v;
+        if (j == 0) v = W.bcol[i];
+        else if (in_tile(i, j)) v = tileA[(i & (kRowBlock - 1)) * 32 + (j - tv.C0)];
+        else v = W.rowbuf[(int64_t)W.slot1[i] * rstride + j];
+        return k == 0 ? v.y : (k == 1 ? v.z : v.w);
+    }
+    __device__ int cD(int i, int j, int k) const {
+        if (j == 0) return kMinInf;
+        int4 v;
+        if (i == 0) v = W.brow[j];
+        else if (in_tile(i, j)) v = tileB[(i & (kRowBlock - 1)) * 32 + (j - tv.C0)];
+        else v = W.colbuf[(int64_t)W.slot2[j] * cstride + i];
+        return k == 0 ? v.y : (k == 1 ? v.z : v.w);
+    }
+};
+
+template <int P>
+__device__ void traceback(const Win& W, const Params& prm, int4* tileA, int4* tileB, int lane, int64_t* score_out,
+                          int32_t* aln, uint32_t* len_out) {
+    const int n1 = W.n1, n2 = W.n2;
+    const int64_t rstride = (int64_t)n2 + 1;
+    // ---- best sink pair: first maximum in caller order, strict '>' (alignment.hpp:979-1008) ----
+    long long npairs;
+    if (n1 != 0 && n2 != 0) npairs = (long long)W.nsnk1 * W.nsnk2;
+    else if (n1 != 0) npairs = W.nsnk1;
+    else if (n2 != 0) npairs = W.nsnk2;
+    else npairs = 0;
+    int best = INT_MIN;
+    long long besti = LLONG_MAX;
+    for (long long x = lane; x < npairs; x += 32) {
+        int v;
+        if (n1 != 0 && n2 != 0) {
+            const int i = (int)W.snk1[x / W.nsnk2], j = (int)W.snk2[x % W.nsnk2];
+            v = W.rowbuf[(int64_t)W.slot1[i] * rstride + j].x;
+        } else if (n1 != 0) {
+            v = W.bcol[W.snk1[x]].x;
+        } else {
+            v = W.brow[W.snk2[x]].x;
+        }
+        if (v > best) { best = v; besti = x; }  // x ascending per lane: keeps the first maximum
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const int ob = __shfl_xor_sync(kFull, best, o);
+        const long long oi = __shfl_xor_sync(kFull, besti, o);
+        if (oi != LLONG_MAX && (besti == LLONG_MAX || ob > best || (ob == best && oi < besti))) { best = ob; besti = oi; }
+    }
+    int ci = -1, cj = -1;
+    if (besti != LLONG_MAX) {
+        if (n1 != 0 && n2 != 0) { ci = (int)W.snk1[besti / W.nsnk2]; cj = (int)W.snk2[besti % W.nsnk2]; }
+        else if (n1 != 0) { ci = (int)W.snk1[besti]; cj = 0; }
+        else { ci = 0; cj = (int)W.snk2[besti]; }
+    }
+    if (lane == 0) *score_out = (ci >= 0) ? (long long)best : 0;
+
+    Walker<P> wk{W, prm, tileA, tileB, TileView{0, 0, 0}, rstride, (int64_t)n1 + 1};
+    const int cap = n1 + n2;
+    int len = 0, comp = 0;
+    while (ci >= 0) {  // warp-uniform: ci/cj/comp/len are broadcast from lane 0 below
+        if (ci >= 1 && cj >= 1 && !wk.in_tile(ci, cj)) {
+            const int R0 = 1 + ((ci - 1) / kRowBlock) * kRowBlock;
+            const int C0 = 1 + ((cj - 1) / kStrip) * kStrip;
+            __syncwarp();
+            process_strip<P, kRowBlock, true>(W, prm, C0, R0, ci, tileA, tileB, nullptr, 0, lane);
+            __syncwarp();
+            wk.tv = TileView{R0, ci, C0};
+        }
+        if (lane == 0) {
+            // walk while the current cell is on the boundary or inside the recomputed tile
+            while (ci >= 0 && (ci == 0 || cj == 0 || wk.in_tile(ci, cj)) && len < cap) {
+                const int M = wk.cM(ci, cj);
+                if (comp == 0) {
+                    for (int k = 0; k < P; ++k) {
+                        if (M == wk.cI(ci, cj, k)) { comp = k + 1; break; }
+                        if (M == wk.cD(ci, cj, k)) { comp = -k - 1; break; }
+                    }
+                }
+                const uint32_t a0 = W.poff1[ci], a1 = W.poff1[ci + 1];  // empty for the boundary index 0
+                const uint32_t b0 = W.poff2[cj], b1 = W.poff2[cj + 1];
+                int ni = -1, nj = -1;
+                int32_t* o = aln + 2 * (int64_t)(cap - 1 - len);
+                if (comp == 0) {
+                    o[0] = ci - 1; o[1] = cj - 1;
+                    const int sub = ((W.info1[ci] & kInfoLabelMask) == (W.info2[cj] & kInfoLabelMask)) ? prm.match : -prm.mismatch;
+                    for (uint32_t a = a0; a < a1; ++a) {  // last prev1 with a match wins, with its first prev2
+                        const int p = (int)W.pidx1[a];
+                        for (uint32_t b = b0; b < b1; ++b) {
+                            const int q = (int)W.pidx2[b];
+                            if (wk.cM(p, q) + sub == M) { ni = p; nj = q; break; }
+                        }
+                    }
+                } else if (comp > 0) {
+                    o[0] = ci - 1; o[1] = -1;
+                    const int k = comp - 1;
+                    const int cur = wk.cI(ci, cj, k);
+                    for (uint32_t a = a0; a < a1; ++a) {
+                        const int p = (int)W.pidx1[a];
+                        if (cur == wk.cM(p, cj) - prm.oe[k]) { comp = 0; ni = p; nj = cj; break; }
+                        if (cur == wk.cI(p, cj, k) - prm.e[k]) { ni = p; nj = cj; break; }
+                    }
+                } else {
+                    o[0] = -1; o[1] = cj - 1;
+                    const int k = -comp - 1;
+                    const int cur = wk.cD(ci, cj, k);
+                    for (uint32_t b = b0; b < b1; ++b) {
+                        const int q = (int)W.pidx2[b];
+                        if (cur == wk.cM(ci, q) - prm.oe[k]) { comp = 0; ni = ci; nj = q; break; }
+                        if (cur == wk.cD(ci, q, k) - prm.e[k]) { ni = ci; nj = q; break; }
+                    }
+                }
+                ++len;
+                ci = ni; cj = nj;
+                if (ci == 0 && cj == 0) ci = -1;  // unreachable on valid input; the corner ends every path
+            }
+            if (len >= cap) ci = -1;
+        }
+        ci = __shfl_sync(kFull, ci, 0);
+        cj = __shfl_sync(kFull, cj, 0);
+    }
+    if (lane == 0) *len_out = (uint32_t)len;
+}
+
+// ------------------------------------------------------------------------------------------
+// Persistent kernel: fill + traceback per window.
+// ------------------------------------------------------------------------------------------
+constexpr int kFillRingInt4 = kWarps * 2 * kRingRows * 32;  // per-warp ringA + ringB
+constexpr int kTileInt4 = 2 * kRowBlock * 32;
+constexpr int kSmemInt4 = kFillRingInt4 > kTileInt4 ? kFillRingInt4 : kTileInt4;
+
+template <int P>
+__global__ void __launch_bounds__(kThreads, 1) popoa_kernel(const LaunchArgs A) {
+    extern __shared__ int4 smem[];
+    __shared__ Win W;
+    __shared__ int s_next;
+    __shared__ unsigned long long progress[64];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const Params prm = A.prm;
+
+    for (;;) {
+        if (tid == 0) s_next = atomicAdd(A.queue, 1);
+        if (tid < 64) progress[tid] = 0ull;
+        __syncthreads();
+        const int qi = s_next;
+        if (qi >= A.n_windows) break;
+        const int w = A.order[qi];
+        if (tid == 0) {
+            const WindowMeta m = A.meta[w];
+            W.n1 = (int)m.n1; W.n2 = (int)m.n2; W.nsnk1 = (int)m.nsnk1; W.nsnk2 = (int)m.nsnk2;
+            W.info1 = A.s1.info + m.node1; W.info2 = A.s2.info + m.node2;
+            W.slot1 = A.s1.slot + m.node1; W.slot2 = A.s2.slot + m.node2;
+            W.depth1 = A.s1.depth + m.node1; W.depth2 = A.s2.depth + m.node2;
+            W.poff1 = A.s1.poff + m.poff1; W.poff2 = A.s2.poff + m.poff2;
+            W.pidx1 = A.s1.pidx + m.pidx1; W.pidx2 = A.s2.pidx + m.pidx2;
+            W.snk1 = A.s1.sinks + m.snk1; W.snk2 = A.s2.sinks + m.snk2;
+            int4* ws = reinterpret_cast<int4*>(A.workspace + (int64_t)blockIdx.x * A.slot_bytes);
+            W.rowbuf = ws;
+            W.colbuf = W.rowbuf + (int64_t)m.nrslot * (m.n2 + 1);
+            W.brow = W.colbuf + (int64_t)m.ncslot * (m.n1 + 1);
+            W.bcol = W.brow + (m.n2 + 1);
+            W.out = m.out;
+        }
+        __syncthreads();
+        boundary_phase<P>(W, prm, tid, kThreads);
+        __syncthreads();
+        if (W.n1 >= 1) {
+            const int nstrips = (W.n2 + kStrip - 1) / kStrip;
+            int4* ringA = smem + warp * (2 * kRingRows * 32);
+            int4* ringB = ringA + kRingRows * 32;
+            for (int cs = warp; cs < nstrips; cs += kWarps)
+                process_strip<P, kRingRows, false>(W, prm, 1 + kStrip * cs, 1, W.n1, ringA, ringB, progress, cs, lane);
+        }
+        __syncthreads();
+        if (warp == 0)
+            traceback<P>(W, prm, smem, smem + kRowBlock * 32, lane, A.score + w, A.aln + 2 * W.out, A.aln_len + w);
+        __syncthreads();
+    }
+}
+
+int popoa_smem_bytes() { return kSmemInt4 * (int)sizeof(int4); }
+int popoa_threads() { return kThreads; }
+
+cudaError_t launch_popoa(int num_pw, const LaunchArgs& args, int grid, cudaStream_t stream) {
+    const int smem = popoa_smem_bytes();
+    cudaError_t err;
+    switch (num_pw) {
+        case 1:
+            err = cudaFuncSetAttribute(popoa_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (err != cudaSuccess) return err;
+            popoa_kernel<1><<<grid, kThreads, smem, stream>>>(args);
+            break;
+        case 2:
+            err = cudaFuncSetAttribute(popoa_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (err != cudaSuccess) return err;
+            popoa_kernel<2><<<grid, kThreads, smem, stream>>>(args);
+            break;
+        case 3:
+            err = cudaFuncSetAttribute(popoa_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (err != cudaSuccess) return err;
+            popoa_kernel<3><<<grid, kThreads, smem, stream>>>(args);
+            break;
+        default:
+            return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// INT32 issue-rate probe: independent add/max chains, no memory traffic.  use_dpx=1 issues the
+// fused DPX form (VIADDMNMX), use_dpx=0 plain IADD + IMNMX pairs.  One "op" = one add or max.
+// ------------------------------------------------------------------------------------------
+template <bool DPX>
+__global__ void __launch_bounds__(256) int32_probe_kernel(int* out, int iters, int seed) {
+    int a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = seed + k * 7 + threadIdx.x;
+    const int d = seed | 1;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (DPX) a[k] = __viaddmax_s32(a[k], d, a[(k + 1) & 7]);
+                else a[k] = max(a[k] + d, a[(k + 1) & 7] - it);
+            }
+        }
+    }
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s ^= a[k];
+    if (s == 0x7fffffff) out[0] = s;
+}
+
+double int32_probe(int use_dpx, int sm_count) {
+    int* d = nullptr;
+    if (cudaMalloc(&d, 4) != cudaSuccess) return -1.0;
+    const int iters = 4096, grid = sm_count * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        if (use_dpx) int32_probe_kernel<true><<<grid, threads>>>(d, iters, 12345);
+        else int32_probe_kernel<false><<<grid, threads>>>(d, iters, 12345);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1.f; break; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    if (best <= 0) return -1.0;
+    // per thread per iteration: 4*8 updates, each 1 add + 1 max (DPX fuses them) -> 2 ops; the plain
+    // variant has one more subtraction per update that is not counted.
+    const double ops = (double)grid * threads * iters * 4.0 * 8.0 * 2.0;
+    return ops / (best * 1e-3) / 1e12;
+}
+
+}  // namespace clb

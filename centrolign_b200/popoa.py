@@ -1,0 +1,197 @@
+"""Python front for the C ABI (include/centrolign_b200.h) -- harness plumbing only.
+
+``po_poa_batch`` is the batched counterpart of the reference's ``po_poa``
+(include/centrolign/alignment.hpp:78-85): same inputs (two PO graphs with source / sink sets,
+``AlignmentParameters``), same outputs (optimal score, alignment as node-id pairs with a gap
+sentinel), for many windows at once.  All compute happens in ``libcentrolign_b200.so``
+(hand-written sm_100a kernels); there is no CPU path here -- if the library or a CUDA device
+is missing these calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from .batch import AlignmentParameters, GraphSide, WindowBatch
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libcentrolign_b200.so")
+
+EXPORTS = ["clb_popoa_batch", "clb_batch_create", "clb_batch_upload", "clb_batch_run", "clb_batch_download",
+           "clb_batch_destroy", "clb_batch_get_stats", "clb_int32_peak_tops", "clb_last_error", "clb_device_count"]
+ERROR_NAMES = {0: "CLB_OK", 1: "CLB_EINVAL", 2: "CLB_ECYCLE", 3: "CLB_ECUDA", 4: "CLB_ENOMEM", 5: "CLB_ESTATE"}
+
+
+class ClbError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"{ERROR_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+class _Params(ctypes.Structure):
+    _fields_ = [("num_pw", ctypes.c_int32), ("match", ctypes.c_uint32), ("mismatch", ctypes.c_uint32),
+                ("gap_open", ctypes.c_uint32 * 3), ("gap_extend", ctypes.c_uint32 * 3)]
+
+
+class _GraphBatch(ctypes.Structure):
+    _fields_ = [("node_off", ctypes.c_void_p), ("label", ctypes.c_void_p), ("edge_off", ctypes.c_void_p),
+                ("pred_off", ctypes.c_void_p), ("pred", ctypes.c_void_p), ("src_off", ctypes.c_void_p),
+                ("src", ctypes.c_void_p), ("snk_off", ctypes.c_void_p), ("snk", ctypes.c_void_p)]
+
+
+class BatchStats(ctypes.Structure):
+    _fields_ = [("cells", ctypes.c_double), ("kernel_ms", ctypes.c_double), ("fill_ms", ctypes.c_double),
+                ("kernel_launches", ctypes.c_int64), ("h2d_bytes", ctypes.c_int64), ("d2h_bytes", ctypes.c_int64),
+                ("workspace_bytes", ctypes.c_int64), ("int_ops", ctypes.c_int64)]
+
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+    """Load ``libcentrolign_b200.so`` (built in-tree by ``__graft_entry__.build()``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise ClbError(3, f"{_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`; "
+                          "there is no CPU fallback for the gap-fill path")
+    lib = ctypes.CDLL(_LIB_PATH)
+    vp, i32 = ctypes.c_void_p, ctypes.c_int32
+    gp, pp = ctypes.POINTER(_GraphBatch), ctypes.POINTER(_Params)
+    lib.clb_popoa_batch.restype = ctypes.c_int
+    lib.clb_popoa_batch.argtypes = [ctypes.c_int, i32, gp, gp, pp, vp, vp, vp, vp]
+    lib.clb_batch_create.restype = ctypes.c_int
+    lib.clb_batch_create.argtypes = [ctypes.c_int, i32, gp, gp, pp, ctypes.POINTER(vp)]
+    for name in ("clb_batch_upload", "clb_batch_run"):
+        getattr(lib, name).restype = ctypes.c_int
+        getattr(lib, name).argtypes = [vp]
+    lib.clb_batch_download.restype = ctypes.c_int
+    lib.clb_batch_download.argtypes = [vp, vp, vp, vp, vp]
+    lib.clb_batch_destroy.restype = None
+    lib.clb_batch_destroy.argtypes = [vp]
+    lib.clb_batch_get_stats.restype = ctypes.c_int
+    lib.clb_batch_get_stats.argtypes = [vp, ctypes.POINTER(BatchStats)]
+    lib.clb_int32_peak_tops.restype = ctypes.c_double
+    lib.clb_int32_peak_tops.argtypes = [ctypes.c_int, ctypes.c_int]
+    lib.clb_last_error.restype = ctypes.c_char_p
+    lib.clb_device_count.restype = ctypes.c_int
+    _lib = lib
+    return lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise ClbError(rc, load_library().clb_last_error().decode())
+
+
+def _c_params(p: AlignmentParameters) -> _Params:
+    if not 1 <= p.num_pw <= 3 or len(p.gap_extend) != p.num_pw:
+        raise ClbError(1, "NumPW must be 1..3 with matching open/extend lists")
+    cp = _Params()
+    cp.num_pw, cp.match, cp.mismatch = p.num_pw, p.match, p.mismatch
+    for k in range(p.num_pw):
+        cp.gap_open[k], cp.gap_extend[k] = p.gap_open[k], p.gap_extend[k]
+    return cp
+
+
+def _c_side(side: GraphSide):
+    arrs = [np.ascontiguousarray(side.node_off, np.int64), np.ascontiguousarray(side.label, np.uint8),
+            np.ascontiguousarray(side.edge_off, np.int64), np.ascontiguousarray(side.pred_off, np.uint32),
+            np.ascontiguousarray(side.pred, np.uint32), np.ascontiguousarray(side.src_off, np.int64),
+            np.ascontiguousarray(side.src, np.uint32), np.ascontiguousarray(side.snk_off, np.int64),
+            np.ascontiguousarray(side.snk, np.uint32)]
+    gb = _GraphBatch(*[a.ctypes.data for a in arrs])
+    return gb, arrs  # keep arrs alive
+
+
+class DeviceBatch:
+    """Staged form of the call (create -> upload -> run -> download); bench.py keeps one of
+    these resident in HBM and times ``run`` alone."""
+
+    def __init__(self, batch: WindowBatch, params: AlignmentParameters, device: int = 0):
+        self.lib = load_library()
+        self.batch = batch
+        self.params = params
+        self.handle = ctypes.c_void_p()
+        self._p = _c_params(params)
+        self._g1, self._k1 = _c_side(batch.g1)
+        self._g2, self._k2 = _c_side(batch.g2)
+        _check(self.lib.clb_batch_create(device, batch.n_windows, ctypes.byref(self._g1), ctypes.byref(self._g2),
+                                         ctypes.byref(self._p), ctypes.byref(self.handle)))
+        cap = batch.aln_capacity()
+        self.aln_off = np.zeros(batch.n_windows + 1, np.int64)
+        np.cumsum(cap, out=self.aln_off[1:])
+        self.score = np.zeros(batch.n_windows, np.int64)
+        self.aln_len = np.zeros(batch.n_windows, np.uint32)
+        self.aln_pairs = np.empty((max(1, int(self.aln_off[-1])), 2), np.int32)
+
+    def upload(self):
+        _check(self.lib.clb_batch_upload(self.handle))
+
+    def run(self):
+        _check(self.lib.clb_batch_run(self.handle))
+
+    def download(self):
+        _check(self.lib.clb_batch_download(self.handle, self.score.ctypes.data, self.aln_off.ctypes.data,
+                                           self.aln_pairs.ctypes.data, self.aln_len.ctypes.data))
+        return self.score, self.alignments()
+
+    def alignments(self) -> List[np.ndarray]:
+        return [self.aln_pairs[int(self.aln_off[w]): int(self.aln_off[w]) + int(self.aln_len[w])]
+                for w in range(self.batch.n_windows)]
+
+    def stats(self) -> BatchStats:
+        st = BatchStats()
+        _check(self.lib.clb_batch_get_stats(self.handle, ctypes.byref(st)))
+        return st
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.clb_batch_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def po_poa_batch(batch: WindowBatch, params: AlignmentParameters, device: int = 0,
+                 out: Optional[Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]] = None):
+    """One-shot ``clb_popoa_batch``: host arrays in, (scores, [alignment per window]) out."""
+    lib = load_library()
+    p = _c_params(params)
+    g1, k1 = _c_side(batch.g1)
+    g2, k2 = _c_side(batch.g2)
+    nw = batch.n_windows
+    if out is None:
+        aln_off = np.zeros(nw + 1, np.int64)
+        np.cumsum(batch.aln_capacity(), out=aln_off[1:])
+        score = np.zeros(nw, np.int64)
+        aln_len = np.zeros(nw, np.uint32)
+        pairs = np.empty((max(1, int(aln_off[-1])), 2), np.int32)
+    else:
+        score, aln_off, pairs, aln_len = out
+    _check(lib.clb_popoa_batch(device, nw, ctypes.byref(g1), ctypes.byref(g2), ctypes.byref(p), score.ctypes.data,
+                               aln_off.ctypes.data, pairs.ctypes.data, aln_len.ctypes.data))
+    del k1, k2
+    return score, [pairs[int(aln_off[w]): int(aln_off[w]) + int(aln_len[w])] for w in range(nw)]
+
+
+def po_poa(graph1, graph2, params: AlignmentParameters, device: int = 0):
+    """Single-window convenience with the reference's argument order:
+    ``graph = (labels, predecessor lists, sources, sinks)``; returns (alignment, score)."""
+    from .batch import batch_from_graph_pairs
+
+    score, alns = po_poa_batch(batch_from_graph_pairs([(graph1, graph2)]), params, device)
+    return alns[0], int(score[0])
