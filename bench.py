@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- GCUPS of the batched PO-to-PO gap-fill DP (BASELINE.json metric, configs[1]).
+
+A "step" is one pass of the hot path (DP fill + traceback of every window) over one batch of
+synthetic inter-anchor windows (PO graph pairs, ~1-20 k nodes per side,
+SNP + 171-node bubbles, production 3-piece parameters), `--windows` of them per GPU.
+
+  value      device-resident throughput: cells of all ranks / max-over-ranks CUDA-event time of K
+             `clb_batch_run` calls on a batch already in HBM
+  e2e        the same K steps through the reference-facing call `clb_popoa_batch` with HOST buffers:
+             host flattening, H2D, kernels, D2H and id translation all inside the timed region
+  roofline   the dominant kernel (`popoa_kernel`, INT32/DPX issue bound -- SURVEY.md 8d) + HBM side
+  cpu_baseline  the unmodified reference's po_poa (oracle/_ref/libclref.so) or the C port, one
+             thread, on a bounded sample of the same windows, parity-checked against the GPU result
+
+`--impl reference` times the reference's own CPU implementation on all host threads instead.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "GCUPS (graph DP cell updates/s), batched PO-to-PO gap-fill windows"
+UNIT = "GCUPS"
+SEED = 20261017
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--windows", type=int, default=int(os.environ.get("CLB_BENCH_WINDOWS", "50000")),
+                    help="windows per GPU per step (configs[1]: 50000)")
+    ap.add_argument("--len-min", type=float, default=880.0)
+    ap.add_argument("--len-max", type=float, default=17600.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, world):
+    return {"workload": f"configs[1]: batched inter-anchor windows, {args.windows} synthetic PO-to-PO gap-fill problems per GPU, "
+                        f"backbone {args.len_min:.0f}-{args.len_max:.0f} bp log-uniform (~1-20 k nodes/side), 5% SNP bubbles, "
+                        "171-node bubble per 2 kbp, NumPW=3 production parameters 20/80/{60,800,2500}/{30,5,1}",
+            "windows_per_gpu": args.windows, "num_pw": 3, "seed": SEED, "sharding": f"independent windows, {world} rank(s), no collective",
+            "l2_policy": "inputs (GBs of CSR + workspace) exceed the 126 MB L2; no flush needed"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 8 for k in range(4) if r[4 + k].lower().startswith("active")})
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def cpu_sample(batch, cells, budget_cells, max_cells):
+    """Bounded, size-stratified sample of window ids: evenly spaced in the size-sorted order."""
+    order = np.argsort(cells, kind="stable")
+    order = order[cells[order] <= max_cells]
+    if len(order) == 0:
+        order = np.argsort(cells, kind="stable")[:1]
+    picks, total = [], 0
+    for q in np.linspace(0.05, 0.95, 12):
+        w = int(order[int(q * (len(order) - 1))])
+        if w in picks:
+            continue
+        if total + int(cells[w]) > budget_cells and picks:
+            continue
+        picks.append(w)
+        total += int(cells[w])
+    return picks
+
+
+def run_reference_arm(args, rank, world):
+    """The reference's own CPU implementation of the path, all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    from concurrent.futures import ThreadPoolExecutor
+
+    from centrolign_b200.batch import AlignmentParameters, CpuChecker, select_windows, synth_windows
+
+    kind = "reference" if CpuChecker.available("reference") else "port"
+    chk = CpuChecker(kind)
+    cores = os.cpu_count() or 1
+    params = AlignmentParameters()
+    # bounded sample of the workload: windows small enough that `cores` tables fit in RAM (28 B/cell),
+    # ~1.5 s of work per thread per step
+    pool_n = max(4 * cores, 64)
+    full = synth_windows(pool_n, first_index=0, seed=SEED, len_min=args.len_min, len_max=min(args.len_max, 3000.0))
+    cells = full.cells()
+    budget = int(0.03e9 * 1.5 * cores)
+    order = np.argsort(-cells, kind="stable")
+    picks, tot = [], 0
+    for w in order:
+        if tot >= budget:
+            break
+        picks.append(int(w))
+        tot += int(cells[w])
+    sample = select_windows(full, picks)
+    scells = float(sample.cells().sum())
+
+    def one(w):
+        return chk.po_poa(sample, w, params)[0]
+
+    def step():
+        with ThreadPoolExecutor(max_workers=cores) as ex:
+            list(ex.map(one, range(sample.n_windows)))
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = scells * args.steps / dt / 1e9
+    sample_desc = (f"{sample.n_windows} windows of the same generator (backbone <= 3 kbp so {cores} concurrent 28 B/cell tables fit), "
+                   f"{scells:.3g} cells per step, {cores} threads each running the single-threaded reference po_poa")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": workload_config(args, world),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample_desc},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank, world, local = dist_env()
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+
+    from centrolign_b200.batch import AlignmentParameters, CpuChecker, select_windows, synth_windows
+    from centrolign_b200.popoa import DeviceBatch, load_library, po_poa_batch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the gap-fill path)")
+    torch.cuda.set_device(local)
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = load_library()
+    params = AlignmentParameters()
+
+    t_gen = time.perf_counter()
+    batch = synth_windows(args.windows, first_index=rank * args.windows, seed=SEED, len_min=args.len_min, len_max=args.len_max)
+    t_gen = time.perf_counter() - t_gen
+    cells = batch.cells()
+    my_cells = float(cells.sum())
+
+    db = DeviceBatch(batch, params, device=local)
+    db.upload()
+
+    def barrier():
+        if use_dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        db.run()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    kernel_ms = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        db.run()
+        kernel_ms += db.stats().kernel_ms  # CUDA events on the library's own stream
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop() if rank == 0 else None
+    st = db.stats()
+    launches_per_step = int(st.kernel_launches)
+
+    # results of the resident run (for the parity check of the CPU sample)
+    scores, alns = db.download()
+    scores = scores.copy()
+    db.close()
+
+    # ---- e2e: the reference-facing one-shot call with host buffers ----
+    e2e_ms, h2d, d2h = None, int(st.h2d_bytes), int(st.d2h_bytes)
+    if not args.no_e2e:
+        out = (np.zeros(batch.n_windows, np.int64), db.aln_off, db.aln_pairs, np.zeros(batch.n_windows, np.uint32))
+        po_poa_batch(batch, params, device=local, out=out)  # one warm-up pass (page-in, pinned pools)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            po_poa_batch(batch, params, device=local, out=out)
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+        assert np.array_equal(out[0], scores), "e2e scores differ from the resident run"
+
+    def allmax(x):
+        if not use_dist:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if not use_dist:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    kernel_ms_max = allmax(kernel_ms)
+    total_cells = allsum(my_cells)
+    e2e_ms_max = allmax(e2e_ms) if e2e_ms is not None else None
+    value = total_cells * args.steps / (kernel_ms_max * 1e-3) / 1e9
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel ----
+        peak_dpx = lib.clb_int32_peak_tops(local, 1)
+        peak_plain = lib.clb_int32_peak_tops(local, 0)
+        peak = max(peak_dpx, peak_plain)
+        step_s = kernel_ms / args.steps * 1e-3
+        achieved = st.int_ops / step_s / 1e12
+        peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        hbm_peak, hbm_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+        if os.path.exists(peaks_file):
+            hbm_peak, hbm_src = float(json.load(open(peaks_file))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+        hbm_bytes = float(st.persist_bytes + st.h2d_bytes)
+        roofline = {"bound": "int32", "kernel": "popoa_kernel<3> (fused DP fill + traceback, 1 launch per step)",
+                    "achieved": achieved, "peak": peak, "unit": "TOP/s", "frac": achieved / peak if peak > 0 else None,
+                    "traffic": None,
+                    "ops_per_launch": int(st.int_ops), "ops_model": "SURVEY 8d: a*b+1+4P(a+b)+2P INT32 add/max per cell (32 for a linear cell at P=3)",
+                    "peak_source": f"measured in this run by clb_int32_peak_tops: DPX viaddmax {peak_dpx:.1f}, add+max {peak_plain:.1f} TOP/s "
+                                   "(nominal 148 SM x 128 lanes x 1.965 GHz = 37.2)",
+                    "hbm": {"bound": "hbm", "achieved": hbm_bytes / step_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": hbm_bytes / step_s / 1e9 / hbm_peak, "traffic": None,
+                            "bytes_model": "persisted rows/columns written once + flattened graph arrays read once", "peak_source": hbm_src}}
+        # ---- CPU baseline on a bounded sample, parity-checked against the GPU result ----
+        cpu = None
+        if not args.no_cpu_baseline:
+            kind = "reference" if CpuChecker.available("reference") else "port"
+            chk = CpuChecker(kind)
+            picks = cpu_sample(batch, cells, budget_cells=int(5e8), max_cells=int(1.2e8))
+            t_cpu, c_cpu = 0.0, 0.0
+            for w in picks:
+                t1 = time.perf_counter()
+                s, a = chk.po_poa(batch, w, params)
+                t_cpu += time.perf_counter() - t1
+                c_cpu += float(cells[w])
+                assert s == scores[w] and np.array_equal(a, alns[w]), f"GPU result differs from the CPU {kind} on window {w}"
+            cpu = {"value": c_cpu / t_cpu / 1e9, "unit": UNIT, "cores": 1, "kind": kind,
+                   "sample": f"{len(picks)} windows evenly spaced in the size-sorted batch (<=1.2e8 cells each), {c_cpu:.3g} cells, "
+                             f"{t_cpu:.1f} s single-threaded; score+alignment of every sampled window equal to the GPU's",
+                   "host_cores": os.cpu_count()}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": kernel_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "int32", "data": "synthetic", "config": workload_config(args, world),
+                "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+                "e2e": None if e2e_ms_max is None else {"value": total_cells * args.steps / (e2e_ms_max * 1e-3) / 1e9, "unit": UNIT,
+                                                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                                                         "ms_per_step": e2e_ms_max / args.steps,
+                                                         "includes": "host topological flattening, pinned staging, H2D, kernels, D2H, id translation"},
+                "gpu_launches": launches_per_step * args.steps,
+                "wall_ms_per_step": wall_ms / args.steps, "cells_per_step": total_cells, "windows_gen_s": t_gen,
+                "workspace_bytes": int(st.workspace_bytes)}
+        print(json.dumps(line), flush=True)
+    if use_dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

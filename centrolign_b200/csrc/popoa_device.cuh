@@ -21,6 +21,9 @@ constexpr int kRingRows = 8;            // fill-kernel ring depth (>= 2*kNear+2)
 constexpr uint32_t kInfoLabelMask = 0xffu;
 constexpr uint32_t kInfoRegular = 1u << 8;  // exactly one predecessor and it is index-1
 constexpr uint32_t kInfoPersist = 1u << 9;  // row / column is kept in the window workspace
+constexpr uint32_t kInfoNearShift = 10;     // bits 10..12: predecessor index-d present, d = 1..kNear (index-d >= 1)
+constexpr uint32_t kInfoNearMask = 7u << kInfoNearShift;
+constexpr uint32_t kInfoFar = 1u << 13;     // has a predecessor not covered by the near bits (far back, or the boundary 0)
 
 // One side (graph 1 = rows, graph 2 = columns) of all windows, concatenated on the device.
 struct SideArrays {
@@ -63,9 +66,13 @@ struct LaunchArgs {
     Params prm;
 };
 
+// Workspace of one window: rowbuf {M,I_k} + colbuf {M,D_k} + boundary row + boundary column (16 B per
+// entry), then coleff (4 B per persisted-column entry: the column's effective diagonal input per row).
+inline int64_t workspace_int4(uint32_t n1, uint32_t n2, uint32_t nrslot, uint32_t ncslot) {
+    return (int64_t)nrslot * (n2 + 1) + (int64_t)ncslot * (n1 + 1) + (n2 + 1) + (n1 + 1);
+}
 inline int64_t workspace_bytes(uint32_t n1, uint32_t n2, uint32_t nrslot, uint32_t ncslot) {
-    // rowbuf + colbuf + boundary row + boundary column, 16 bytes per entry
-    return 16 * ((int64_t)nrslot * (n2 + 1) + (int64_t)ncslot * (n1 + 1) + (n2 + 1) + (n1 + 1));
+    return 16 * workspace_int4(n1, n2, nrslot, ncslot) + ((4 * (int64_t)ncslot * (n1 + 1) + 15) & ~int64_t(15));
 }
 
 }  // namespace clb

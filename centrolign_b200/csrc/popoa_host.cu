@@ -185,15 +185,22 @@ int flatten_side(const clb_graph_batch& g, int64_t w, int side, SideStage& st, c
             pidx[fill++] = p;
             if (depth[p] && (dmin == 0 || depth[p] + 1 < dmin)) dmin = depth[p] + 1;
             if (i - p > (uint32_t)clb::kNear || (i - 1) / block != (p - 1) / block) info[p] |= clb::kInfoPersist;
+            if (i - p <= (uint32_t)clb::kNear) info[i] |= 1u << (clb::kInfoNearShift + (i - p - 1));
+            else info[i] |= clb::kInfoFar;
         }
         if (sc.is_src[v]) {
             pidx[fill++] = 0;
             dmin = 1;
+            info[i] |= clb::kInfoFar;
         }
         depth[i] = dmin;
         poff[i + 1] = fill;
         uint32_t word = (uint32_t)g.label[n0 + v];
-        if (fill - first == 1 && pidx[first] == i - 1) word |= clb::kInfoRegular;
+        if (fill - first == 1 && pidx[first] == i - 1) {  // regular: also for i == 1 with the boundary as its only predecessor
+            word |= clb::kInfoRegular;
+            info[i] &= ~(clb::kInfoFar | clb::kInfoNearMask);
+            if (i > 1) info[i] |= 1u << clb::kInfoNearShift;
+        }
         info[i] |= word;
         int_ops_deg += fill - first;
     }
@@ -350,9 +357,12 @@ int clb_batch_create(int device, int32_t n_windows, const clb_graph_batch* g1, c
     });
     if (nw) memcpy(b->order.h, ord.data(), nw * sizeof(int32_t));
     b->slot_bytes = 16;
+    b->stats.persist_bytes = 0;
     for (int64_t w = 0; w < nw; ++w) {
         const clb::WindowMeta& m = b->meta.h[w];
-        b->slot_bytes = std::max(b->slot_bytes, clb::workspace_bytes(m.n1, m.n2, m.nrslot, m.ncslot));
+        const int64_t ws = clb::workspace_bytes(m.n1, m.n2, m.nrslot, m.ncslot);
+        b->slot_bytes = std::max(b->slot_bytes, ws);
+        b->stats.persist_bytes += ws;
     }
     b->slot_bytes = (b->slot_bytes + 255) & ~int64_t(255);
     if (b->aln.alloc_host(2 * tot_pairs) != CLB_OK) {

@@ -45,6 +45,7 @@ struct Win {
     const uint32_t *pidx1, *pidx2;
     const uint32_t *snk1, *snk2;
     int4 *rowbuf, *colbuf, *brow, *bcol;
+    int* coleff;  // per persisted column and row r: max over pred1(r) of M(p, column) -- the diagonal input of its right neighbours
     int64_t out;
 };
 
@@ -215,6 +216,169 @@ __device__ __forceinline__ void process_strip(const Win& Wsh, const Params& prm,
 }
 
 // ------------------------------------------------------------------------------------------
+// DP fill of one strip, rows 1..n1 -- the hot loop.  Same recurrence as process_strip, tuned:
+// predecessors at distance 1..kNear (SNP-sized bubbles, the common irregular case) are named by
+// bits of the node's info word and served branch-light from registers (distance 1) or the
+// shared-memory ring; only genuinely far predecessors (long bubbles, deletion edges, the
+// boundary) walk the predecessor list.  The diagonal input of a column's right neighbours is
+// kept explicitly (ringE in shared memory, coleff for persisted columns).
+// ------------------------------------------------------------------------------------------
+template <int P>
+__device__ __forceinline__ void fill_strip(const Win& Wsh, const Params& prm, const int C0, int4* __restrict__ ringA,
+                                           int4* __restrict__ ringB, int* __restrict__ ringE,
+                                           volatile unsigned long long* progress, const int cs, const int lane) {
+    constexpr int H = kRingRows;
+    const int n1 = Wsh.n1, n2 = Wsh.n2;
+    const uint32_t* __restrict__ info1 = Wsh.info1;
+    const int32_t* __restrict__ slot1 = Wsh.slot1;
+    const uint32_t* __restrict__ poff1 = Wsh.poff1;
+    const uint32_t* __restrict__ pidx1 = Wsh.pidx1;
+    const int32_t* __restrict__ slot2 = Wsh.slot2;
+    const uint32_t* __restrict__ pidx2 = Wsh.pidx2;
+    int4* rowbuf = Wsh.rowbuf;
+    int4* colbuf = Wsh.colbuf;
+    int* coleff = Wsh.coleff;
+    const int64_t rstride = (int64_t)n2 + 1, cstride = (int64_t)n1 + 1;
+
+    const int j = C0 + lane;
+    const bool jvalid = j <= n2;
+    const uint32_t cinfo = jvalid ? Wsh.info2[j] : (kInfoRegular | (1u << kInfoNearShift));
+    const int clabel = (int)(cinfo & kInfoLabelMask);
+    const bool creg = (cinfo & kInfoRegular) != 0;
+    const uint32_t cmask = (cinfo >> kInfoNearShift) & 7u;
+    const bool cfar = (cinfo & kInfoFar) != 0;
+    const uint32_t cp0 = (jvalid && cfar) ? Wsh.poff2[j] : 0u, cp1 = (jvalid && cfar) ? Wsh.poff2[j + 1] : 0u;
+    // near predecessor columns that live in the previous strip (lanes 0..2 only), and lane 0's regular left column
+    int64_t xoff[3] = {0, 0, 0};
+#pragma unroll
+    for (int d = 1; d <= 3; ++d) {
+        const bool need = jvalid && lane < d && (((cmask >> (d - 1)) & 1u) || (d == 1 && creg));
+        if (need) xoff[d - 1] = (int64_t)slot2[j - d] * cstride;
+    }
+    int64_t myoff = -1;
+    if (jvalid && (cinfo & kInfoPersist)) myoff = (int64_t)slot2[j] * cstride;
+
+    int upM = kMinInf, upI[3] = {kMinInf, kMinInf, kMinInf};
+    if (jvalid) {
+        const int4 a = rowbuf[j];  // row 0 = boundary row (slot 0)
+        upM = a.x; upI[0] = a.y; upI[1] = a.z; upI[2] = a.w;
+    }
+    int outM = kMinInf, outD[3] = {kMinInf, kMinInf, kMinInf}, outEff = kMinInf;
+    int avail = cs == 0 ? INT_MAX : 0;
+    const int nsteps = n1 + 31;
+    uint32_t rinfo_next = (lane == 0 && jvalid) ? info1[1] : 0u;  // software-pipelined row info
+
+    for (int s = 0; s < nsteps; ++s) {
+        const int r = 1 + s - lane;
+        const bool active = jvalid && r >= 1 && r <= n1;
+        {
+            const int need = min(1 + s, n1);
+            if (avail < need) {
+                const int want = min(need + 24, n1);
+                for (;;) {
+                    const unsigned long long v = progress[(cs - 1) & 63];
+                    avail = ((int)(v >> 32) == cs) ? (int)(v & 0xffffffffu) : 0;
+                    if (avail >= want) break;
+                    __nanosleep(100);
+                }
+                __threadfence_block();
+            }
+        }
+        int lM = __shfl_up_sync(kFull, outM, 1);
+        int lD[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) lD[k] = (k < P) ? __shfl_up_sync(kFull, outD[k], 1) : kMinInf;
+        int lEff = __shfl_up_sync(kFull, outEff, 1);
+        const uint32_t rinfo = rinfo_next;
+        {
+            const int rn = r + 1;
+            rinfo_next = (jvalid && rn >= 1 && rn <= n1) ? info1[rn] : 0u;
+        }
+
+        if (active) {
+            const int rlabel = (int)(rinfo & kInfoLabelMask);
+            const int slotr = (r & (H - 1)) * 32;
+            // ---- effective predecessor row ----
+            int eM = upM, eI[3] = {upI[0], upI[1], upI[2]};
+            if (!(rinfo & kInfoRegular)) {
+                const uint32_t rmask = (rinfo >> kInfoNearShift) & 7u;
+                if (!(rmask & 1u)) { eM = kMinInf; eI[0] = eI[1] = eI[2] = kMinInf; }
+                if (rmask & 2u) max4(eM, eI, ringA[((r - 2) & (H - 1)) * 32 + lane]);
+                if (rmask & 4u) max4(eM, eI, ringA[((r - 3) & (H - 1)) * 32 + lane]);
+                if (rinfo & kInfoFar) {
+                    const uint32_t rp1 = poff1[r + 1];
+                    for (uint32_t a = poff1[r]; a < rp1; ++a) {
+                        const int p = (int)pidx1[a];
+                        if (p >= 1 && r - p <= kNear) continue;
+                        max4(eM, eI, rowbuf[(int64_t)slot1[p] * rstride + j]);
+                    }
+                }
+            }
+            // ---- effective predecessor column + diagonal input ----
+            if (creg) {
+                if (lane == 0) {
+                    const int4 b = colbuf[xoff[0] + r];
+                    lM = b.x; lD[0] = b.y; lD[1] = b.z; lD[2] = b.w;
+                    lEff = coleff[xoff[0] + r];
+                }
+            } else {
+                if (!(cmask & 1u)) { lM = kMinInf; lD[0] = lD[1] = lD[2] = kMinInf; lEff = kMinInf; }
+                else if (lane == 0) {
+                    const int4 b = colbuf[xoff[0] + r];
+                    lM = b.x; lD[0] = b.y; lD[1] = b.z; lD[2] = b.w;
+                    lEff = coleff[xoff[0] + r];
+                }
+#pragma unroll
+                for (int d = 2; d <= 3; ++d) {
+                    if (cmask & (1u << (d - 1))) {
+                        int4 v;
+                        int e;
+                        if (lane >= d) { v = ringB[slotr + lane - d]; e = ringE[slotr + lane - d]; }
+                        else { v = colbuf[xoff[d - 1] + r]; e = coleff[xoff[d - 1] + r]; }
+                        max4(lM, lD, v);
+                        lEff = imax(lEff, e);
+                    }
+                }
+                if (cfar) {
+                    for (uint32_t b = cp0; b < cp1; ++b) {
+                        const int q = (int)pidx2[b];
+                        if (q >= 1 && j - q <= kNear) continue;
+                        const int64_t o = (int64_t)slot2[q] * cstride + r;
+                        max4(lM, lD, colbuf[o]);
+                        lEff = imax(lEff, coleff[o]);
+                    }
+                }
+            }
+            // ---- the cell ----
+            const int sub = (rlabel == clabel) ? prm.match : -prm.mismatch;
+            int I[3] = {kMinInf, kMinInf, kMinInf}, D[3] = {kMinInf, kMinInf, kMinInf};
+            int M = __viaddmax_s32(lEff, sub, kMinInf);
+#pragma unroll
+            for (int k = 0; k < P; ++k) {
+                I[k] = __viaddmax_s32(eI[k], -prm.e[k], eM - prm.oe[k]);
+                D[k] = __viaddmax_s32(lD[k], -prm.e[k], lM - prm.oe[k]);
+                M = __vimax3_s32(M, I[k], D[k]);
+            }
+            const int4 cellA = make_int4(M, I[0], I[1], I[2]);
+            const int4 cellB = make_int4(M, D[0], D[1], D[2]);
+            ringA[slotr + lane] = cellA;
+            ringB[slotr + lane] = cellB;
+            ringE[slotr + lane] = eM;
+            if (rinfo & kInfoPersist) rowbuf[(int64_t)slot1[r] * rstride + j] = cellA;
+            if (myoff >= 0) { colbuf[myoff + r] = cellB; coleff[myoff + r] = eM; }
+            upM = M; upI[0] = I[0]; upI[1] = I[1]; upI[2] = I[2];
+            outM = M; outD[0] = D[0]; outD[1] = D[1]; outD[2] = D[2];
+            outEff = eM;
+        }
+        __syncwarp();
+        if (lane == 31 && active && ((r & 7) == 0 || r == n1)) {
+            __threadfence_block();
+            progress[cs & 63] = ((unsigned long long)(cs + 1) << 32) | (unsigned)r;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Boundary row / column (alignment.hpp:814-894).  In the boundary column only the lead
 // insertion is extended, so I_k(i,0) = -(o_k + e_k * depth(i)) with depth = fewest nodes on a
 // path from a source; the host supplies depth, which makes this pass embarrassingly parallel.
@@ -248,6 +412,13 @@ __device__ void boundary_phase(const Win& W, const Params& prm, int tid, int nth
         W.bcol[i] = b;
         W.colbuf[i] = make_int4(b.x, kMinInf, kMinInf, kMinInf);  // column slot 0
         if (W.info1[i] & kInfoPersist) W.rowbuf[(int64_t)W.slot1[i] * rstride] = b;
+        // diagonal input that column 0 offers to row i: max over pred1(i) of M(p,0), the corner counting as 0
+        int e = kMinInf;
+        for (uint32_t a = W.poff1[i]; a < W.poff1[i + 1]; ++a) {
+            const uint32_t p = W.pidx1[a];
+            e = imax(e, p == 0 ? 0 : boundary_cell<P>(W.depth1[p], prm).x);
+        }
+        W.coleff[i] = e;
     }
 }
 
@@ -406,7 +577,8 @@ __device__ void traceback(const Win& W, const Params& prm, int4* tileA, int4* ti
 // ------------------------------------------------------------------------------------------
 // Persistent kernel: fill + traceback per window.
 // ------------------------------------------------------------------------------------------
-constexpr int kFillRingInt4 = kWarps * 2 * kRingRows * 32;  // per-warp ringA + ringB
+constexpr int kWarpRingInt4 = 2 * kRingRows * 32 + kRingRows * 32 / 4;  // per-warp ringA + ringB + ringE
+constexpr int kFillRingInt4 = kWarps * kWarpRingInt4;
 constexpr int kTileInt4 = 2 * kRowBlock * 32;
 constexpr int kSmemInt4 = kFillRingInt4 > kTileInt4 ? kFillRingInt4 : kTileInt4;
 
@@ -440,6 +612,7 @@ __global__ void __launch_bounds__(kThreads, 1) popoa_kernel(const LaunchArgs A) 
             W.colbuf = W.rowbuf + (int64_t)m.nrslot * (m.n2 + 1);
             W.brow = W.colbuf + (int64_t)m.ncslot * (m.n1 + 1);
             W.bcol = W.brow + (m.n2 + 1);
+            W.coleff = reinterpret_cast<int*>(W.bcol + (m.n1 + 1));
             W.out = m.out;
         }
         __syncthreads();
@@ -447,10 +620,11 @@ __global__ void __launch_bounds__(kThreads, 1) popoa_kernel(const LaunchArgs A) 
         __syncthreads();
         if (W.n1 >= 1) {
             const int nstrips = (W.n2 + kStrip - 1) / kStrip;
-            int4* ringA = smem + warp * (2 * kRingRows * 32);
+            int4* ringA = smem + warp * kWarpRingInt4;
             int4* ringB = ringA + kRingRows * 32;
+            int* ringE = reinterpret_cast<int*>(ringB + kRingRows * 32);
             for (int cs = warp; cs < nstrips; cs += kWarps)
-                process_strip<P, kRingRows, false>(W, prm, 1 + kStrip * cs, 1, W.n1, ringA, ringB, progress, cs, lane);
+                fill_strip<P>(W, prm, 1 + kStrip * cs, ringA, ringB, ringE, progress, cs, lane);
         }
         __syncthreads();
         if (warp == 0)

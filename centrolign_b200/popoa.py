@@ -44,7 +44,7 @@ class _GraphBatch(ctypes.Structure):
 class BatchStats(ctypes.Structure):
     _fields_ = [("cells", ctypes.c_double), ("kernel_ms", ctypes.c_double), ("fill_ms", ctypes.c_double),
                 ("kernel_launches", ctypes.c_int64), ("h2d_bytes", ctypes.c_int64), ("d2h_bytes", ctypes.c_int64),
-                ("workspace_bytes", ctypes.c_int64), ("int_ops", ctypes.c_int64)]
+                ("workspace_bytes", ctypes.c_int64), ("int_ops", ctypes.c_int64), ("persist_bytes", ctypes.c_int64)]
 
 
 _lib = None

@@ -114,6 +114,7 @@ typedef struct clb_batch_stats {
     int64_t d2h_bytes;       /* bytes clb_batch_download copies */
     int64_t workspace_bytes; /* device workspace held by the batch */
     int64_t int_ops;         /* algorithmic INT32 add/max count of the fill (SURVEY.md 8d formula) */
+    int64_t persist_bytes;   /* bytes of persisted rows/columns the fill writes to HBM (its algorithmic traffic) */
 } clb_batch_stats;
 int clb_batch_get_stats(const clb_batch* b, clb_batch_stats* out);
 

@@ -31,7 +31,7 @@ def test_header_symbols_exported():
 def test_struct_layout_matches_header():
     assert ctypes.sizeof(popoa._Params) == 4 + 4 + 4 + 12 + 12
     assert ctypes.sizeof(popoa._GraphBatch) == 9 * 8
-    assert ctypes.sizeof(popoa.BatchStats) == 8 * 8
+    assert ctypes.sizeof(popoa.BatchStats) == 9 * 8
 
 
 def test_argument_validation_and_no_cpu_fallback():
