@@ -405,12 +405,14 @@ int clb_batch_upload(clb_batch* b) {
     int grid = std::max(1, std::min<int>(b->nw, prop.multiProcessorCount));
     const int64_t budget = (int64_t)(free_b * 0.92);
     if (b->slot_bytes > budget) return fail(CLB_ENOMEM, "a single window's workspace exceeds device memory");
-    grid = (int)std::min<int64_t>(grid, budget / b->slot_bytes);
+    // two workspace slots per CTA: one window being filled, the previous one being traced back
+    if (2 * b->slot_bytes > budget) return fail(CLB_ENOMEM, "a single window's workspace exceeds device memory");
+    grid = (int)std::min<int64_t>(grid, budget / (2 * b->slot_bytes));
     b->grid = std::max(1, grid);
-    CUDA_TRY(cudaMalloc((void**)&b->d_workspace, (size_t)b->grid * b->slot_bytes));
+    CUDA_TRY(cudaMalloc((void**)&b->d_workspace, (size_t)b->grid * 2 * b->slot_bytes));
     CUDA_TRY(cudaStreamSynchronize(b->stream));
     b->stats.h2d_bytes = h2d;
-    b->stats.workspace_bytes = (int64_t)b->grid * b->slot_bytes;
+    b->stats.workspace_bytes = (int64_t)b->grid * 2 * b->slot_bytes;
     b->uploaded = true;
     return CLB_OK;
 }

@@ -47,6 +47,7 @@ struct Win {
     int4 *rowbuf, *colbuf, *brow, *bcol;
     int* coleff;  // per persisted column and row r: max over pred1(r) of M(p, column) -- the diagonal input of its right neighbours
     int64_t out;
+    int id;
 };
 
 __device__ __forceinline__ int imax(int a, int b) { return a > b ? a : b; }
@@ -216,18 +217,49 @@ __device__ __forceinline__ void process_strip(const Win& Wsh, const Params& prm,
 }
 
 // ------------------------------------------------------------------------------------------
+// Asynchronous global->shared copies (LDGSTS) for the left-column prefetch.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// per-fill-warp shared memory
+constexpr int kFillRing = 4;  // ring rows: a row is read at most kNear steps after it was written
+struct __align__(16) FillSmem {
+    int4 ringA[kFillRing * 32];  // {M, I_k} of the last rows, own column
+    int4 ringB[kFillRing * 32];  // {M, D_k} of the current row, columns to the left
+    int4 leftv[3][2][32];        // prefetched {M, D_k} of the up-to-3 columns just left of the strip, 32-row blocks
+    int ringE[kFillRing * 32];   // diagonal input (max over predecessor rows of M) per column
+    int lefte[3][2][32];         // prefetched diagonal input of the left columns
+};
+
+template <int P>
+__device__ __forceinline__ int4 boundary_cell(uint32_t depth, const Params& prm);
+
+// ------------------------------------------------------------------------------------------
 // DP fill of one strip, rows 1..n1 -- the hot loop.  Same recurrence as process_strip, tuned:
-// predecessors at distance 1..kNear (SNP-sized bubbles, the common irregular case) are named by
-// bits of the node's info word and served branch-light from registers (distance 1) or the
-// shared-memory ring; only genuinely far predecessors (long bubbles, deletion edges, the
-// boundary) walk the predecessor list.  The diagonal input of a column's right neighbours is
-// kept explicitly (ringE in shared memory, coleff for persisted columns).
+//  * predecessors at distance 1..kNear (SNP-sized bubbles, the common irregular case) are named
+//    by bits of the node's info word and served branch-light from registers (distance 1) or the
+//    shared-memory ring; only genuinely far predecessors (long bubbles, deletion edges, the
+//    boundary) walk the predecessor list;
+//  * the diagonal input of a column's right neighbours is kept explicitly (ringE / coleff);
+//  * the columns just left of the strip (written by another warp) are prefetched 32 rows at a
+//    time with cp.async, so no global-memory latency sits on the per-row critical path and the
+//    producer's progress word is polled once per 32 rows.
+// `g` is the CTA-wide running strip number (progress tag), `cs` the strip index in the window.
 // ------------------------------------------------------------------------------------------
 template <int P>
-__device__ __forceinline__ void fill_strip(const Win& Wsh, const Params& prm, const int C0, int4* __restrict__ ringA,
-                                           int4* __restrict__ ringB, int* __restrict__ ringE,
-                                           volatile unsigned long long* progress, const int cs, const int lane) {
-    constexpr int H = kRingRows;
+__device__ __forceinline__ void fill_strip(const Win& Wsh, const Params& prm, const int cs, const int g, FillSmem& sm,
+                                           volatile unsigned long long* progress, const int lane) {
+    constexpr int H = kFillRing;
+    const int C0 = 1 + kStrip * cs;
     const int n1 = Wsh.n1, n2 = Wsh.n2;
     const uint32_t* __restrict__ info1 = Wsh.info1;
     const int32_t* __restrict__ slot1 = Wsh.slot1;
@@ -248,40 +280,85 @@ __device__ __forceinline__ void fill_strip(const Win& Wsh, const Params& prm, co
     const uint32_t cmask = (cinfo >> kInfoNearShift) & 7u;
     const bool cfar = (cinfo & kInfoFar) != 0;
     const uint32_t cp0 = (jvalid && cfar) ? Wsh.poff2[j] : 0u, cp1 = (jvalid && cfar) ? Wsh.poff2[j + 1] : 0u;
-    // near predecessor columns that live in the previous strip (lanes 0..2 only), and lane 0's regular left column
-    int64_t xoff[3] = {0, 0, 0};
-#pragma unroll
-    for (int d = 1; d <= 3; ++d) {
-        const bool need = jvalid && lane < d && (((cmask >> (d - 1)) & 1u) || (d == 1 && creg));
-        if (need) xoff[d - 1] = (int64_t)slot2[j - d] * cstride;
-    }
     int64_t myoff = -1;
     if (jvalid && (cinfo & kInfoPersist)) myoff = (int64_t)slot2[j] * cstride;
 
+    // ---- boundary data owned by this strip (alignment.hpp:814-894, see boundary_cell) ----
     int upM = kMinInf, upI[3] = {kMinInf, kMinInf, kMinInf};
     if (jvalid) {
-        const int4 a = rowbuf[j];  // row 0 = boundary row (slot 0)
-        upM = a.x; upI[0] = a.y; upI[1] = a.z; upI[2] = a.w;
+        upM = boundary_cell<P>(Wsh.depth2[j], prm).x;  // M(0,j); I_k(0,j) = -inf
+        rowbuf[j] = make_int4(upM, kMinInf, kMinInf, kMinInf);
     }
-    int outM = kMinInf, outD[3] = {kMinInf, kMinInf, kMinInf}, outEff = kMinInf;
+    if (cs == 0) {  // boundary column as a predecessor column: {M(i,0), -inf} and its diagonal input
+        for (int i = lane; i <= n1; i += 32) {
+            const int m = i == 0 ? 0 : boundary_cell<P>(Wsh.depth1[i], prm).x;  // M(0,0)=0 seeds the sources
+            colbuf[i] = make_int4(m, kMinInf, kMinInf, kMinInf);
+            int e = kMinInf;
+            const uint32_t a1 = poff1[i + 1];
+            for (uint32_t a = poff1[i]; a < a1; ++a) {
+                const uint32_t p = pidx1[a];
+                e = imax(e, p == 0 ? 0 : boundary_cell<P>(Wsh.depth1[p], prm).x);
+            }
+            coleff[i] = e;
+        }
+    }
+    // ---- which of the three columns left of the strip are needed (warp-uniform) ----
+    // lane t with near bit d' (> t) reads left column d = d' - t, i.e. matrix column C0 - d
+    unsigned needbits = 0;
+    if (jvalid) {
+#pragma unroll
+        for (int dd = 1; dd <= 3; ++dd)
+            if (dd > lane && ((cmask >> (dd - 1)) & 1u)) needbits |= 1u << (dd - lane - 1);
+        if (lane == 0 && creg) needbits |= 1u;  // column 1's only predecessor is the boundary column
+    }
+    needbits = __reduce_or_sync(kFull, needbits);
+    int64_t xoffw[3] = {0, 0, 0};
+#pragma unroll
+    for (int d = 1; d <= 3; ++d)
+        if (needbits & (1u << (d - 1))) xoffw[d - 1] = (int64_t)slot2[C0 - d] * cstride;
+    __syncwarp();
+
     int avail = cs == 0 ? INT_MAX : 0;
+    auto wait_rows = [&](int want) {
+        if (avail < want) {
+            for (;;) {
+                const unsigned long long v = progress[(g - 1) & 63];
+                avail = ((int)(v >> 32) == g) ? (int)(v & 0xffffffffu) : 0;
+                if (avail >= want) break;
+                __nanosleep(200);
+            }
+            __threadfence_block();
+        }
+    };
+    auto prefetch_block = [&](int b) {  // rows 32b+1 .. 32b+32 of the needed left columns -> buffer b&1
+        const int row = 32 * b + 1 + lane;
+        if (row <= n1) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+                if (needbits & (1u << d)) {
+                    cp_async_16(&sm.leftv[d][b & 1][lane], colbuf + xoffw[d] + row);
+                    cp_async_4(&sm.lefte[d][b & 1][lane], coleff + xoffw[d] + row);
+                }
+        }
+        cp_async_commit();
+    };
+    wait_rows(min(32, n1));
+    prefetch_block(0);
+    cp_async_wait_all();
+    __syncwarp();
+
+    int outM = kMinInf, outD[3] = {kMinInf, kMinInf, kMinInf}, outEff = kMinInf;
     const int nsteps = n1 + 31;
     uint32_t rinfo_next = (lane == 0 && jvalid) ? info1[1] : 0u;  // software-pipelined row info
 
     for (int s = 0; s < nsteps; ++s) {
         const int r = 1 + s - lane;
         const bool active = jvalid && r >= 1 && r <= n1;
-        {
-            const int need = min(1 + s, n1);
-            if (avail < need) {
-                const int want = min(need + 24, n1);
-                for (;;) {
-                    const unsigned long long v = progress[(cs - 1) & 63];
-                    avail = ((int)(v >> 32) == cs) ? (int)(v & 0xffffffffu) : 0;
-                    if (avail >= want) break;
-                    __nanosleep(100);
-                }
-                __threadfence_block();
+        if ((s & 31) == 3) {  // lanes 1,2 have left block b-1: refill its buffer with block b+1
+            const int b = (s >> 5) + 1;
+            if (32 * b + 1 <= n1) {
+                wait_rows(min(32 * b + 32, n1));
+                prefetch_block(b);
             }
         }
         int lM = __shfl_up_sync(kFull, outM, 1);
@@ -298,13 +375,14 @@ __device__ __forceinline__ void fill_strip(const Win& Wsh, const Params& prm, co
         if (active) {
             const int rlabel = (int)(rinfo & kInfoLabelMask);
             const int slotr = (r & (H - 1)) * 32;
+            const int lb = ((r - 1) >> 5) & 1, li = (r - 1) & 31;  // left-column prefetch buffer / index of row r
             // ---- effective predecessor row ----
             int eM = upM, eI[3] = {upI[0], upI[1], upI[2]};
             if (!(rinfo & kInfoRegular)) {
                 const uint32_t rmask = (rinfo >> kInfoNearShift) & 7u;
                 if (!(rmask & 1u)) { eM = kMinInf; eI[0] = eI[1] = eI[2] = kMinInf; }
-                if (rmask & 2u) max4(eM, eI, ringA[((r - 2) & (H - 1)) * 32 + lane]);
-                if (rmask & 4u) max4(eM, eI, ringA[((r - 3) & (H - 1)) * 32 + lane]);
+                if (rmask & 2u) max4(eM, eI, sm.ringA[((r - 2) & (H - 1)) * 32 + lane]);
+                if (rmask & 4u) max4(eM, eI, sm.ringA[((r - 3) & (H - 1)) * 32 + lane]);
                 if (rinfo & kInfoFar) {
                     const uint32_t rp1 = poff1[r + 1];
                     for (uint32_t a = poff1[r]; a < rp1; ++a) {
@@ -317,24 +395,24 @@ __device__ __forceinline__ void fill_strip(const Win& Wsh, const Params& prm, co
             // ---- effective predecessor column + diagonal input ----
             if (creg) {
                 if (lane == 0) {
-                    const int4 b = colbuf[xoff[0] + r];
+                    const int4 b = sm.leftv[0][lb][li];
                     lM = b.x; lD[0] = b.y; lD[1] = b.z; lD[2] = b.w;
-                    lEff = coleff[xoff[0] + r];
+                    lEff = sm.lefte[0][lb][li];
                 }
             } else {
                 if (!(cmask & 1u)) { lM = kMinInf; lD[0] = lD[1] = lD[2] = kMinInf; lEff = kMinInf; }
                 else if (lane == 0) {
-                    const int4 b = colbuf[xoff[0] + r];
+                    const int4 b = sm.leftv[0][lb][li];
                     lM = b.x; lD[0] = b.y; lD[1] = b.z; lD[2] = b.w;
-                    lEff = coleff[xoff[0] + r];
+                    lEff = sm.lefte[0][lb][li];
                 }
 #pragma unroll
                 for (int d = 2; d <= 3; ++d) {
                     if (cmask & (1u << (d - 1))) {
                         int4 v;
                         int e;
-                        if (lane >= d) { v = ringB[slotr + lane - d]; e = ringE[slotr + lane - d]; }
-                        else { v = colbuf[xoff[d - 1] + r]; e = coleff[xoff[d - 1] + r]; }
+                        if (lane >= d) { v = sm.ringB[slotr + lane - d]; e = sm.ringE[slotr + lane - d]; }
+                        else { v = sm.leftv[d - lane - 1][lb][li]; e = sm.lefte[d - lane - 1][lb][li]; }
                         max4(lM, lD, v);
                         lEff = imax(lEff, e);
                     }
@@ -361,19 +439,20 @@ __device__ __forceinline__ void fill_strip(const Win& Wsh, const Params& prm, co
             }
             const int4 cellA = make_int4(M, I[0], I[1], I[2]);
             const int4 cellB = make_int4(M, D[0], D[1], D[2]);
-            ringA[slotr + lane] = cellA;
-            ringB[slotr + lane] = cellB;
-            ringE[slotr + lane] = eM;
+            sm.ringA[slotr + lane] = cellA;
+            sm.ringB[slotr + lane] = cellB;
+            sm.ringE[slotr + lane] = eM;
             if (rinfo & kInfoPersist) rowbuf[(int64_t)slot1[r] * rstride + j] = cellA;
             if (myoff >= 0) { colbuf[myoff + r] = cellB; coleff[myoff + r] = eM; }
             upM = M; upI[0] = I[0]; upI[1] = I[1]; upI[2] = I[2];
             outM = M; outD[0] = D[0]; outD[1] = D[1]; outD[2] = D[2];
             outEff = eM;
         }
+        if ((s & 31) == 31) cp_async_wait_all();  // next block's left columns have landed
         __syncwarp();
         if (lane == 31 && active && ((r & 7) == 0 || r == n1)) {
             __threadfence_block();
-            progress[cs & 63] = ((unsigned long long)(cs + 1) << 32) | (unsigned)r;
+            progress[g & 63] = ((unsigned long long)(g + 1) << 32) | (unsigned)r;
         }
     }
 }
@@ -397,33 +476,29 @@ __device__ __forceinline__ int4 boundary_cell(uint32_t depth, const Params& prm)
     return make_int4(m, v[0], v[1], v[2]);
 }
 
+// Boundary data that only the traceback reads: the full boundary row {M,D_k} / column {M,I_k}
+// and the boundary entries of persisted rows / columns.  Run by the traceback warp.
 template <int P>
-__device__ void boundary_phase(const Win& W, const Params& prm, int tid, int nthreads) {
+__device__ void tb_boundary(const Win& W, const Params& prm, int lane) {
     const int64_t rstride = (int64_t)W.n2 + 1, cstride = (int64_t)W.n1 + 1;
-    const int4 corner = make_int4(0, kMinInf, kMinInf, kMinInf);  // M(0,0)=0 seeds the sources (alignment.hpp:814-829)
-    for (int j = tid; j <= W.n2; j += nthreads) {
+    const int4 corner = make_int4(0, kMinInf, kMinInf, kMinInf);
+    for (int j = lane; j <= W.n2; j += 32) {
         const int4 b = j == 0 ? corner : boundary_cell<P>(W.depth2[j], prm);
         W.brow[j] = b;
-        W.rowbuf[j] = make_int4(b.x, kMinInf, kMinInf, kMinInf);  // row slot 0 = boundary row seen as a predecessor row
+        if (j == 0 || W.n1 == 0) W.rowbuf[j] = make_int4(b.x, kMinInf, kMinInf, kMinInf);
         if (W.info2[j] & kInfoPersist) W.colbuf[(int64_t)W.slot2[j] * cstride] = b;
     }
-    for (int i = tid; i <= W.n1; i += nthreads) {
+    for (int i = lane; i <= W.n1; i += 32) {
         const int4 b = i == 0 ? corner : boundary_cell<P>(W.depth1[i], prm);
         W.bcol[i] = b;
-        W.colbuf[i] = make_int4(b.x, kMinInf, kMinInf, kMinInf);  // column slot 0
+        if (W.n2 == 0) W.colbuf[i] = make_int4(b.x, kMinInf, kMinInf, kMinInf);
         if (W.info1[i] & kInfoPersist) W.rowbuf[(int64_t)W.slot1[i] * rstride] = b;
-        // diagonal input that column 0 offers to row i: max over pred1(i) of M(p,0), the corner counting as 0
-        int e = kMinInf;
-        for (uint32_t a = W.poff1[i]; a < W.poff1[i + 1]; ++a) {
-            const uint32_t p = W.pidx1[a];
-            e = imax(e, p == 0 ? 0 : boundary_cell<P>(W.depth1[p], prm).x);
-        }
-        W.coleff[i] = e;
     }
+    __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------
-// Traceback (warp 0).  Mirrors alignment.hpp:979-1138 on recomputed cell values.
+// Traceback (the CTA's traceback warp).  Mirrors alignment.hpp:979-1138 on recomputed cell values.
 // ------------------------------------------------------------------------------------------
 struct TileView {
     int R0, R1, C0;  // tile rows R0..R1, columns C0..C0+31; R0 = 0 means "no tile"
@@ -575,65 +650,118 @@ __device__ void traceback(const Win& W, const Params& prm, int4* tileA, int4* ti
 }
 
 // ------------------------------------------------------------------------------------------
-// Persistent kernel: fill + traceback per window.
+// Persistent kernel.  Each CTA works through its own sequence of windows (pulled from the
+// global queue, largest first) with kFillWarps fill warps and one traceback warp:
+//   * fill warps take strips round-robin by a CTA-wide running strip number, so they flow
+//     from one window into the next without any CTA-wide barrier;
+//   * the traceback warp fetches windows (which also hands out the workspace slot: two slots
+//     per CTA, window k uses slot k&1), waits until all strips of a window are filled, then
+//     traces it back while the fill warps are already on the next window.
 // ------------------------------------------------------------------------------------------
-constexpr int kWarpRingInt4 = 2 * kRingRows * 32 + kRingRows * 32 / 4;  // per-warp ringA + ringB + ringE
-constexpr int kFillRingInt4 = kWarps * kWarpRingInt4;
+constexpr int kFillWarps = kWarps - 1;
 constexpr int kTileInt4 = 2 * kRowBlock * 32;
-constexpr int kSmemInt4 = kFillRingInt4 > kTileInt4 ? kFillRingInt4 : kTileInt4;
+
+struct CtaState {
+    Win win[2];
+    unsigned long long progress[64];
+    int seq_win[8];      // window id of the CTA's k-th window (-1 = queue exhausted)
+    int seq_nstrips[8];
+    int seq_tag[8];      // k+1 once entry k is published
+    int strips_done[2];  // per workspace slot
+};
+
+__device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 
 template <int P>
 __global__ void __launch_bounds__(kThreads, 1) popoa_kernel(const LaunchArgs A) {
     extern __shared__ int4 smem[];
-    __shared__ Win W;
-    __shared__ int s_next;
-    __shared__ unsigned long long progress[64];
+    __shared__ CtaState S;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const Params prm = A.prm;
+    if (tid < 64) S.progress[tid] = 0ull;
+    if (tid < 8) S.seq_tag[tid] = 0;
+    __syncthreads();
 
-    for (;;) {
-        if (tid == 0) s_next = atomicAdd(A.queue, 1);
-        if (tid < 64) progress[tid] = 0ull;
-        __syncthreads();
-        const int qi = s_next;
-        if (qi >= A.n_windows) break;
-        const int w = A.order[qi];
-        if (tid == 0) {
-            const WindowMeta m = A.meta[w];
-            W.n1 = (int)m.n1; W.n2 = (int)m.n2; W.nsnk1 = (int)m.nsnk1; W.nsnk2 = (int)m.nsnk2;
-            W.info1 = A.s1.info + m.node1; W.info2 = A.s2.info + m.node2;
-            W.slot1 = A.s1.slot + m.node1; W.slot2 = A.s2.slot + m.node2;
-            W.depth1 = A.s1.depth + m.node1; W.depth2 = A.s2.depth + m.node2;
-            W.poff1 = A.s1.poff + m.poff1; W.poff2 = A.s2.poff + m.poff2;
-            W.pidx1 = A.s1.pidx + m.pidx1; W.pidx2 = A.s2.pidx + m.pidx2;
-            W.snk1 = A.s1.sinks + m.snk1; W.snk2 = A.s2.sinks + m.snk2;
-            int4* ws = reinterpret_cast<int4*>(A.workspace + (int64_t)blockIdx.x * A.slot_bytes);
-            W.rowbuf = ws;
-            W.colbuf = W.rowbuf + (int64_t)m.nrslot * (m.n2 + 1);
-            W.brow = W.colbuf + (int64_t)m.ncslot * (m.n1 + 1);
-            W.bcol = W.brow + (m.n2 + 1);
-            W.coleff = reinterpret_cast<int*>(W.bcol + (m.n1 + 1));
-            W.out = m.out;
+    if (warp < kFillWarps) {
+        // ================= fill warps =================
+        FillSmem& sm = *reinterpret_cast<FillSmem*>(smem + kTileInt4 + warp * (int)(sizeof(FillSmem) / sizeof(int4)));
+        int G = 0;  // running strip number at the start of window k
+        for (int k = 0;; ++k) {
+            while (ld_volatile(&S.seq_tag[k & 7]) != k + 1) __nanosleep(200);
+            __threadfence_block();
+            const int w = ld_volatile(&S.seq_win[k & 7]);
+            if (w < 0) break;
+            const int nstrips = ld_volatile(&S.seq_nstrips[k & 7]);
+            const Win& W = S.win[k & 1];
+            int first = (warp - G % kFillWarps + kFillWarps) % kFillWarps;  // my first strip of this window
+            for (int cs = first; cs < nstrips; cs += kFillWarps) {
+                fill_strip<P>(W, prm, cs, G + cs, sm, S.progress, lane);
+                if (lane == 0) {
+                    __threadfence_block();
+                    atomicAdd(&S.strips_done[k & 1], 1);
+                }
+                __syncwarp();
+            }
+            G += nstrips;
         }
-        __syncthreads();
-        boundary_phase<P>(W, prm, tid, kThreads);
-        __syncthreads();
-        if (W.n1 >= 1) {
-            const int nstrips = (W.n2 + kStrip - 1) / kStrip;
-            int4* ringA = smem + warp * kWarpRingInt4;
-            int4* ringB = ringA + kRingRows * 32;
-            int* ringE = reinterpret_cast<int*>(ringB + kRingRows * 32);
-            for (int cs = warp; cs < nstrips; cs += kWarps)
-                fill_strip<P>(W, prm, 1 + kStrip * cs, ringA, ringB, ringE, progress, cs, lane);
-        }
-        __syncthreads();
-        if (warp == 0)
+    } else {
+        // ================= traceback warp =================
+        int fetched = 0;
+        bool ended = false;
+        auto fetch = [&]() {
+            const int k = fetched++;
+            int w = -1;
+            if (lane == 0) {
+                const int qi = atomicAdd(A.queue, 1);
+                w = qi < A.n_windows ? A.order[qi] : -1;
+                int nstrips = 0;
+                if (w >= 0) {
+                    const WindowMeta m = A.meta[w];
+                    Win& W = S.win[k & 1];
+                    W.n1 = (int)m.n1; W.n2 = (int)m.n2; W.nsnk1 = (int)m.nsnk1; W.nsnk2 = (int)m.nsnk2;
+                    W.info1 = A.s1.info + m.node1; W.info2 = A.s2.info + m.node2;
+                    W.slot1 = A.s1.slot + m.node1; W.slot2 = A.s2.slot + m.node2;
+                    W.depth1 = A.s1.depth + m.node1; W.depth2 = A.s2.depth + m.node2;
+                    W.poff1 = A.s1.poff + m.poff1; W.poff2 = A.s2.poff + m.poff2;
+                    W.pidx1 = A.s1.pidx + m.pidx1; W.pidx2 = A.s2.pidx + m.pidx2;
+                    W.snk1 = A.s1.sinks + m.snk1; W.snk2 = A.s2.sinks + m.snk2;
+                    int4* ws = reinterpret_cast<int4*>(A.workspace + ((int64_t)blockIdx.x * 2 + (k & 1)) * A.slot_bytes);
+                    W.rowbuf = ws;
+                    W.colbuf = W.rowbuf + (int64_t)m.nrslot * (m.n2 + 1);
+                    W.brow = W.colbuf + (int64_t)m.ncslot * (m.n1 + 1);
+                    W.bcol = W.brow + (m.n2 + 1);
+                    W.coleff = reinterpret_cast<int*>(W.bcol + (m.n1 + 1));
+                    W.out = m.out;
+                    W.id = w;
+                    nstrips = m.n1 >= 1 ? (int)((m.n2 + kStrip - 1) / kStrip) : 0;
+                }
+                S.strips_done[k & 1] = 0;
+                S.seq_nstrips[k & 7] = nstrips;
+                S.seq_win[k & 7] = w;
+                __threadfence_block();
+                *reinterpret_cast<volatile int*>(&S.seq_tag[k & 7]) = k + 1;
+            }
+            w = __shfl_sync(kFull, w, 0);
+            if (w < 0) ended = true;
+        };
+        fetch();
+        if (!ended) fetch();
+        for (int t = 0;; ++t) {
+            const int w = ld_volatile(&S.seq_win[t & 7]);  // written by this warp
+            if (w < 0) break;
+            const int nstrips = ld_volatile(&S.seq_nstrips[t & 7]);
+            while (ld_volatile(&S.strips_done[t & 1]) < nstrips) __nanosleep(500);
+            __threadfence_block();
+            const Win& W = S.win[t & 1];
+            tb_boundary<P>(W, prm, lane);
             traceback<P>(W, prm, smem, smem + kRowBlock * 32, lane, A.score + w, A.aln + 2 * W.out, A.aln_len + w);
-        __syncthreads();
+            __syncwarp();
+            if (!ended) fetch();  // hands slot t&1 to window t+2
+        }
     }
 }
 
-int popoa_smem_bytes() { return kSmemInt4 * (int)sizeof(int4); }
+int popoa_smem_bytes() { return (kTileInt4 + kFillWarps * (int)(sizeof(FillSmem) / sizeof(int4))) * (int)sizeof(int4); }
 int popoa_threads() { return kThreads; }
 
 cudaError_t launch_popoa(int num_pw, const LaunchArgs& args, int grid, cudaStream_t stream) {
