@@ -43,6 +43,8 @@ def parse_args():
                     help="windows per GPU per step (configs[1]: 50000)")
     ap.add_argument("--len-min", type=float, default=880.0)
     ap.add_argument("--len-max", type=float, default=17600.0)
+    ap.add_argument("--alt-period", type=int, default=2000, help="one 171-node alternate-path bubble per this many bp (0 = none)")
+    ap.add_argument("--snp-rate", type=float, default=0.05)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -194,7 +196,8 @@ def main():
     params = AlignmentParameters()
 
     t_gen = time.perf_counter()
-    batch = synth_windows(args.windows, first_index=rank * args.windows, seed=SEED, len_min=args.len_min, len_max=args.len_max)
+    batch = synth_windows(args.windows, first_index=rank * args.windows, seed=SEED, len_min=args.len_min, len_max=args.len_max,
+                          snp_rate=args.snp_rate, alt_period=args.alt_period)
     t_gen = time.perf_counter() - t_gen
     cells = batch.cells()
     my_cells = float(cells.sum())

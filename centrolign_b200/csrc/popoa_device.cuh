@@ -24,6 +24,8 @@ constexpr uint32_t kInfoPersist = 1u << 9;  // row / column is kept in the windo
 constexpr uint32_t kInfoNearShift = 10;     // bits 10..12: predecessor index-d present, d = 1..kNear (index-d >= 1)
 constexpr uint32_t kInfoNearMask = 7u << kInfoNearShift;
 constexpr uint32_t kInfoFar = 1u << 13;     // has a predecessor not covered by the near bits (far back, or the boundary 0)
+constexpr uint32_t kInfoSlotShift = 14;     // bits 14..31: workspace slot of a persisted row / column ...
+constexpr uint32_t kInfoSlotEscape = 0x3ffffu;  // ... or this value: look the slot up in the slot array
 
 // One side (graph 1 = rows, graph 2 = columns) of all windows, concatenated on the device.
 struct SideArrays {

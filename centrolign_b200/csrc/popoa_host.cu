@@ -210,7 +210,14 @@ int flatten_side(const clb_graph_batch& g, int64_t w, int side, SideStage& st, c
         if (side == 0) info[sinks[k]] |= clb::kInfoPersist;  // M at (sink1, sink2) is read from the persisted row
     }
     uint32_t nslot = 0;
-    for (uint32_t i = 0; i <= n; ++i) slot[i] = (info[i] & clb::kInfoPersist) ? (int32_t)nslot++ : -1;
+    for (uint32_t i = 0; i <= n; ++i) {
+        if (info[i] & clb::kInfoPersist) {
+            info[i] |= std::min<uint32_t>(nslot, clb::kInfoSlotEscape) << clb::kInfoSlotShift;
+            slot[i] = (int32_t)nslot++;
+        } else {
+            slot[i] = -1;
+        }
+    }
     if (side == 0) { m.n1 = n; m.nsnk1 = nsnk; m.nrslot = nslot; }
     else { m.n2 = n; m.nsnk2 = nsnk; m.ncslot = nslot; }
     return CLB_OK;
@@ -273,7 +280,7 @@ int clb_batch_create(int device, int32_t n_windows, const clb_graph_batch* g1, c
         const int64_t S = nw ? gs[sd]->src_off[nw] : 0, K = nw ? gs[sd]->snk_off[nw] : 0;
         if (N < 0 || E < 0 || S < 0 || K < 0) rc = CLB_EINVAL;
         SideStage& st = b->s[sd];
-        rc |= st.info.alloc_host(N + nw) | st.slot.alloc_host(N + nw) | st.depth.alloc_host(N + nw) |
+        rc |= st.info.alloc_host(N + nw + 1) | st.slot.alloc_host(N + nw) | st.depth.alloc_host(N + nw) |  // info: +1 pad, read one past
               st.poff.alloc_host(N + 2 * nw) | st.pidx.alloc_host(E + S) | st.sinks.alloc_host(K);
         st.orig.resize(N + nw);
     }
@@ -361,6 +368,10 @@ int clb_batch_create(int device, int32_t n_windows, const clb_graph_batch* g1, c
     for (int64_t w = 0; w < nw; ++w) {
         const clb::WindowMeta& m = b->meta.h[w];
         const int64_t ws = clb::workspace_bytes(m.n1, m.n2, m.nrslot, m.ncslot);
+        if (clb::workspace_int4(m.n1, m.n2, m.nrslot, m.ncslot) >= (int64_t(1) << 31)) {
+            clb_batch_destroy(b);
+            return fail(CLB_ENOMEM, "window " + std::to_string(w) + " needs a workspace beyond the 32-bit offset range (32 GB)");
+        }
         b->slot_bytes = std::max(b->slot_bytes, ws);
         b->stats.persist_bytes += ws;
     }

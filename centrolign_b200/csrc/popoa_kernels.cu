@@ -26,6 +26,8 @@
 #include <cuda_runtime.h>
 #include <limits.h>
 
+#include <type_traits>
+
 #include "popoa_device.cuh"
 
 namespace clb {
@@ -231,13 +233,13 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 // per-fill-warp shared memory
-constexpr int kFillRing = 4;  // ring rows: a row is read at most kNear steps after it was written
+constexpr int kStartLag = 192;  // rows a strip stays behind its left neighbour (lane 31 of it)
+constexpr int kFillRing = 4;    // ring rows: a row is read at most kNear steps after it was written
 struct __align__(16) FillSmem {
     int4 ringA[kFillRing * 32];  // {M, I_k} of the last rows, own column
-    int4 ringB[kFillRing * 32];  // {M, D_k} of the current row, columns to the left
+    int4 ringB[kFillRing * 32];  // {diagonal input, D_k} of the current row, for the columns to the right
     int4 leftv[3][2][32];        // prefetched {M, D_k} of the up-to-3 columns just left of the strip, 32-row blocks
-    int ringE[kFillRing * 32];   // diagonal input (max over predecessor rows of M) per column
-    int lefte[3][2][32];         // prefetched diagonal input of the left columns
+    int lefte[3][2][32];         // prefetched diagonal input of those columns
 };
 
 template <int P>
@@ -249,10 +251,11 @@ __device__ __forceinline__ int4 boundary_cell(uint32_t depth, const Params& prm)
 //    by bits of the node's info word and served branch-light from registers (distance 1) or the
 //    shared-memory ring; only genuinely far predecessors (long bubbles, deletion edges, the
 //    boundary) walk the predecessor list;
-//  * the diagonal input of a column's right neighbours is kept explicitly (ringE / coleff);
+//  * the diagonal input of a column's right neighbours is kept explicitly (ringB.x / coleff);
 //  * the columns just left of the strip (written by another warp) are prefetched 32 rows at a
 //    time with cp.async, so no global-memory latency sits on the per-row critical path and the
-//    producer's progress word is polled once per 32 rows.
+//    producer's progress word is polled once per 32 rows;
+//  * 32-bit element offsets into the window workspace, workspace slot packed in the info word.
 // `g` is the CTA-wide running strip number (progress tag), `cs` the strip index in the window.
 // ------------------------------------------------------------------------------------------
 template <int P>
@@ -267,21 +270,23 @@ __device__ __forceinline__ void fill_strip(const Win& Wsh, const Params& prm, co
     const uint32_t* __restrict__ pidx1 = Wsh.pidx1;
     const int32_t* __restrict__ slot2 = Wsh.slot2;
     const uint32_t* __restrict__ pidx2 = Wsh.pidx2;
-    int4* rowbuf = Wsh.rowbuf;
-    int4* colbuf = Wsh.colbuf;
-    int* coleff = Wsh.coleff;
-    const int64_t rstride = (int64_t)n2 + 1, cstride = (int64_t)n1 + 1;
+    int4* const rowbuf = Wsh.rowbuf;
+    int4* const colbuf = Wsh.colbuf;
+    int* const coleff = Wsh.coleff;
+    const uint32_t rstride = (uint32_t)n2 + 1u, cstride = (uint32_t)n1 + 1u;  // host guarantees 32-bit offsets
 
     const int j = C0 + lane;
     const bool jvalid = j <= n2;
-    const uint32_t cinfo = jvalid ? Wsh.info2[j] : (kInfoRegular | (1u << kInfoNearShift));
+    const uint32_t cinfo = jvalid ? Wsh.info2[j] : (kInfoRegular | (1u << kInfoNearShift) | 0xffu);
     const int clabel = (int)(cinfo & kInfoLabelMask);
     const bool creg = (cinfo & kInfoRegular) != 0;
     const uint32_t cmask = (cinfo >> kInfoNearShift) & 7u;
     const bool cfar = (cinfo & kInfoFar) != 0;
+    const bool colpath = !creg || lane == 0;  // lanes whose left state does not simply come from the shuffle
     const uint32_t cp0 = (jvalid && cfar) ? Wsh.poff2[j] : 0u, cp1 = (jvalid && cfar) ? Wsh.poff2[j + 1] : 0u;
-    int64_t myoff = -1;
-    if (jvalid && (cinfo & kInfoPersist)) myoff = (int64_t)slot2[j] * cstride;
+    const bool hascol = jvalid && (cinfo & kInfoPersist);
+    const uint32_t myoff = hascol ? (uint32_t)slot2[j] * cstride : 0u;
+    const uint32_t persist_mask = jvalid ? kInfoPersist : 0u;  // lanes beyond n2 never store rows
 
     // ---- boundary data owned by this strip (alignment.hpp:814-894, see boundary_cell) ----
     int upM = kMinInf, upI[3] = {kMinInf, kMinInf, kMinInf};
@@ -312,10 +317,10 @@ __device__ __forceinline__ void fill_strip(const Win& Wsh, const Params& prm, co
         if (lane == 0 && creg) needbits |= 1u;  // column 1's only predecessor is the boundary column
     }
     needbits = __reduce_or_sync(kFull, needbits);
-    int64_t xoffw[3] = {0, 0, 0};
+    uint32_t xoffw[3] = {0, 0, 0};
 #pragma unroll
     for (int d = 1; d <= 3; ++d)
-        if (needbits & (1u << (d - 1))) xoffw[d - 1] = (int64_t)slot2[C0 - d] * cstride;
+        if (needbits & (1u << (d - 1))) xoffw[d - 1] = (uint32_t)slot2[C0 - d] * cstride;
     __syncwarp();
 
     int avail = cs == 0 ? INT_MAX : 0;
@@ -336,99 +341,97 @@ __device__ __forceinline__ void fill_strip(const Win& Wsh, const Params& prm, co
 #pragma unroll
             for (int d = 0; d < 3; ++d)
                 if (needbits & (1u << d)) {
-                    cp_async_16(&sm.leftv[d][b & 1][lane], colbuf + xoffw[d] + row);
-                    cp_async_4(&sm.lefte[d][b & 1][lane], coleff + xoffw[d] + row);
+                    cp_async_16(&sm.leftv[d][b & 1][lane], colbuf + (xoffw[d] + (uint32_t)row));
+                    cp_async_4(&sm.lefte[d][b & 1][lane], coleff + (xoffw[d] + (uint32_t)row));
                 }
         }
         cp_async_commit();
     };
-    wait_rows(min(32, n1));
+    // Start well behind the producer strip: the lag set here persists (all strips advance at the same
+    // rate), and the slack absorbs scheduling jitter so the per-block waits below rarely spin.
+    wait_rows(min(max(kStartLag, 32), n1));
     prefetch_block(0);
     cp_async_wait_all();
     __syncwarp();
 
     int outM = kMinInf, outD[3] = {kMinInf, kMinInf, kMinInf}, outEff = kMinInf;
-    const int nsteps = n1 + 31;
-    uint32_t rinfo_next = (lane == 0 && jvalid) ? info1[1] : 0u;  // software-pipelined row info
+    uint32_t rinfo_next = (lane == 0) ? info1[1] : 0u;  // software-pipelined row info
+    int4* const myA = sm.ringA + lane;
+    int4* const myB = sm.ringB + lane;
 
-    for (int s = 0; s < nsteps; ++s) {
+    // one wavefront step; GUARD = some lanes may be outside rows 1..n1 (pipeline fill / drain)
+    auto step = [&](const int s, auto guard_tag) {
+        constexpr bool GUARD = decltype(guard_tag)::value;
         const int r = 1 + s - lane;
-        const bool active = jvalid && r >= 1 && r <= n1;
-        if ((s & 31) == 3) {  // lanes 1,2 have left block b-1: refill its buffer with block b+1
-            const int b = (s >> 5) + 1;
-            if (32 * b + 1 <= n1) {
-                wait_rows(min(32 * b + 32, n1));
-                prefetch_block(b);
-            }
-        }
+        bool act = true;
+        if (GUARD) act = r >= 1 && r <= n1;
         int lM = __shfl_up_sync(kFull, outM, 1);
         int lD[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) lD[k] = (k < P) ? __shfl_up_sync(kFull, outD[k], 1) : kMinInf;
         int lEff = __shfl_up_sync(kFull, outEff, 1);
         const uint32_t rinfo = rinfo_next;
-        {
-            const int rn = r + 1;
-            rinfo_next = (jvalid && rn >= 1 && rn <= n1) ? info1[rn] : 0u;
-        }
-
-        if (active) {
-            const int rlabel = (int)(rinfo & kInfoLabelMask);
-            const int slotr = (r & (H - 1)) * 32;
-            const int lb = ((r - 1) >> 5) & 1, li = (r - 1) & 31;  // left-column prefetch buffer / index of row r
+        if (GUARD) rinfo_next = (r >= 0 && r < n1) ? info1[r + 1] : 0u;
+        else rinfo_next = info1[r + 1];  // r+1 <= n1+1: the info array is padded by one entry
+        if (act) {
+            const int rs = (r & (H - 1)) * 32;
             // ---- effective predecessor row ----
             int eM = upM, eI[3] = {upI[0], upI[1], upI[2]};
             if (!(rinfo & kInfoRegular)) {
-                const uint32_t rmask = (rinfo >> kInfoNearShift) & 7u;
-                if (!(rmask & 1u)) { eM = kMinInf; eI[0] = eI[1] = eI[2] = kMinInf; }
-                if (rmask & 2u) max4(eM, eI, sm.ringA[((r - 2) & (H - 1)) * 32 + lane]);
-                if (rmask & 4u) max4(eM, eI, sm.ringA[((r - 3) & (H - 1)) * 32 + lane]);
-                if (rinfo & kInfoFar) {
-                    const uint32_t rp1 = poff1[r + 1];
-                    for (uint32_t a = poff1[r]; a < rp1; ++a) {
-                        const int p = (int)pidx1[a];
-                        if (p >= 1 && r - p <= kNear) continue;
-                        max4(eM, eI, rowbuf[(int64_t)slot1[p] * rstride + j]);
+                if (!(rinfo & (1u << kInfoNearShift))) { eM = kMinInf; eI[0] = eI[1] = eI[2] = kMinInf; }
+                if (rinfo & (2u << kInfoNearShift)) max4(eM, eI, myA[rs ^ 64]);  // row r-2
+                if (rinfo & ((4u << kInfoNearShift) | kInfoFar)) {
+                    if (rinfo & (4u << kInfoNearShift)) max4(eM, eI, myA[((r - 3) & (H - 1)) * 32]);
+                    if (rinfo & kInfoFar) {
+                        const uint32_t rp1 = poff1[r + 1];
+                        for (uint32_t a = poff1[r]; a < rp1; ++a) {
+                            const int p = (int)pidx1[a];
+                            if (p >= 1 && r - p <= kNear) continue;
+                            max4(eM, eI, rowbuf[(uint32_t)slot1[p] * rstride + (uint32_t)j]);
+                        }
                     }
                 }
             }
             // ---- effective predecessor column + diagonal input ----
-            if (creg) {
-                if (lane == 0) {
-                    const int4 b = sm.leftv[0][lb][li];
-                    lM = b.x; lD[0] = b.y; lD[1] = b.z; lD[2] = b.w;
-                    lEff = sm.lefte[0][lb][li];
-                }
-            } else {
-                if (!(cmask & 1u)) { lM = kMinInf; lD[0] = lD[1] = lD[2] = kMinInf; lEff = kMinInf; }
+            if (colpath) {
+                const int lb = ((r - 1) >> 5) & 1, li = (r - 1) & 31;  // prefetch buffer / index of row r
+                if (!(cmask & 1u) && !creg) { lM = kMinInf; lD[0] = lD[1] = lD[2] = kMinInf; lEff = kMinInf; }
                 else if (lane == 0) {
                     const int4 b = sm.leftv[0][lb][li];
                     lM = b.x; lD[0] = b.y; lD[1] = b.z; lD[2] = b.w;
                     lEff = sm.lefte[0][lb][li];
                 }
+                if (cmask & 6u) {
 #pragma unroll
-                for (int d = 2; d <= 3; ++d) {
-                    if (cmask & (1u << (d - 1))) {
-                        int4 v;
-                        int e;
-                        if (lane >= d) { v = sm.ringB[slotr + lane - d]; e = sm.ringE[slotr + lane - d]; }
-                        else { v = sm.leftv[d - lane - 1][lb][li]; e = sm.lefte[d - lane - 1][lb][li]; }
-                        max4(lM, lD, v);
-                        lEff = imax(lEff, e);
+                    for (int d = 2; d <= 3; ++d) {
+                        if (cmask & (1u << (d - 1))) {
+                            int4 v;
+                            int m;
+                            if (lane >= d) {
+                                v = sm.ringB[rs + lane - d];           // {diag input, D_k}
+                                m = sm.ringA[rs + lane - d].x;          // M
+                            } else {
+                                const int4 t = sm.leftv[d - lane - 1][lb][li];  // {M, D_k}
+                                m = t.x;
+                                v = make_int4(sm.lefte[d - lane - 1][lb][li], t.y, t.z, t.w);
+                            }
+                            lM = imax(lM, m);
+                            max4(lEff, lD, v);
+                        }
                     }
                 }
                 if (cfar) {
                     for (uint32_t b = cp0; b < cp1; ++b) {
                         const int q = (int)pidx2[b];
                         if (q >= 1 && j - q <= kNear) continue;
-                        const int64_t o = (int64_t)slot2[q] * cstride + r;
+                        const uint32_t o = (uint32_t)slot2[q] * cstride + (uint32_t)r;
                         max4(lM, lD, colbuf[o]);
                         lEff = imax(lEff, coleff[o]);
                     }
                 }
             }
             // ---- the cell ----
-            const int sub = (rlabel == clabel) ? prm.match : -prm.mismatch;
+            const int sub = ((int)(rinfo & kInfoLabelMask) == clabel) ? prm.match : -prm.mismatch;
             int I[3] = {kMinInf, kMinInf, kMinInf}, D[3] = {kMinInf, kMinInf, kMinInf};
             int M = __viaddmax_s32(lEff, sub, kMinInf);
 #pragma unroll
@@ -438,22 +441,56 @@ __device__ __forceinline__ void fill_strip(const Win& Wsh, const Params& prm, co
                 M = __vimax3_s32(M, I[k], D[k]);
             }
             const int4 cellA = make_int4(M, I[0], I[1], I[2]);
-            const int4 cellB = make_int4(M, D[0], D[1], D[2]);
-            sm.ringA[slotr + lane] = cellA;
-            sm.ringB[slotr + lane] = cellB;
-            sm.ringE[slotr + lane] = eM;
-            if (rinfo & kInfoPersist) rowbuf[(int64_t)slot1[r] * rstride + j] = cellA;
-            if (myoff >= 0) { colbuf[myoff + r] = cellB; coleff[myoff + r] = eM; }
+            myA[rs] = cellA;
+            myB[rs] = make_int4(eM, D[0], D[1], D[2]);
+            if (rinfo & persist_mask) {
+                uint32_t slot = rinfo >> kInfoSlotShift;
+                if (slot == kInfoSlotEscape) slot = (uint32_t)slot1[r];
+                rowbuf[slot * rstride + (uint32_t)j] = cellA;
+            }
+            if (hascol) {
+                colbuf[myoff + (uint32_t)r] = make_int4(M, D[0], D[1], D[2]);
+                coleff[myoff + (uint32_t)r] = eM;
+            }
             upM = M; upI[0] = I[0]; upI[1] = I[1]; upI[2] = I[2];
             outM = M; outD[0] = D[0]; outD[1] = D[1]; outD[2] = D[2];
             outEff = eM;
         }
-        if ((s & 31) == 31) cp_async_wait_all();  // next block's left columns have landed
         __syncwarp();
-        if (lane == 31 && active && ((r & 7) == 0 || r == n1)) {
-            __threadfence_block();
-            progress[g & 63] = ((unsigned long long)(g + 1) << 32) | (unsigned)r;
+    };
+    auto publish = [&](int r31) {  // rows 1..r31 of this strip are complete (called by lane 31)
+        __threadfence_block();
+        progress[g & 63] = ((unsigned long long)(g + 1) << 32) | (unsigned)r31;
+    };
+
+    const int nsteps = n1 + 31;
+    for (int s0 = 0; s0 < nsteps; s0 += 32) {  // 32-step blocks; lane 0 is on rows s0+1 .. s0+32
+        const int s1 = min(s0 + 32, nsteps);
+        const bool inner = s0 >= 31 && s1 <= n1;  // every lane is inside rows 1..n1 for the whole block
+#pragma unroll 1
+        for (int q8 = s0; q8 < s1; q8 += 8) {
+            const int e8 = min(q8 + 8, s1);
+            if (inner) {
+#pragma unroll 1
+                for (int s = q8; s < e8; ++s) step(s, std::false_type{});
+            } else {
+#pragma unroll 1
+                for (int s = q8; s < e8; ++s) step(s, std::true_type{});
+            }
+            if (q8 == s0) {  // lanes 1,2 have left block b-1 by now: refill its buffer with block b+1
+                const int b = (s0 >> 5) + 1;
+                if (32 * b + 1 <= n1) {
+                    wait_rows(min(32 * b + 32, n1));
+                    prefetch_block(b);
+                }
+            }
+            if (lane == 31) {
+                const int r31 = e8 - 31;  // last row lane 31 finished
+                if (r31 >= 1) publish(min(r31, n1));
+            }
         }
+        cp_async_wait_all();  // next block's left columns have landed
+        __syncwarp();
     }
 }
 
