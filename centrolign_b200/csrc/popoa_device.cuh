@@ -66,6 +66,7 @@ struct LaunchArgs {
     int32_t* aln;           // pairs, written backwards from the end of each window's region
     uint32_t* aln_len;      // [n_windows]
     Params prm;
+    int debug_flags;        // bit0: skip the traceback walk (profiling the fill alone; results are then invalid)
 };
 
 // Workspace of one window: rowbuf {M,I_k} + colbuf {M,D_k} + boundary row + boundary column (16 B per

@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -451,6 +452,7 @@ int clb_batch_run(clb_batch* b) {
             a.prm.oe[k] = k < b->params.num_pw ? (int)(b->params.gap_open[k] + b->params.gap_extend[k]) : 0;
             a.prm.e[k] = k < b->params.num_pw ? (int)b->params.gap_extend[k] : 0;
         }
+        a.debug_flags = getenv("CLB_DEBUG_FLAGS") ? atoi(getenv("CLB_DEBUG_FLAGS")) : 0;
         CUDA_TRY(clb::launch_popoa(b->params.num_pw, a, b->grid, b->stream));
         b->stats.kernel_launches = 1;
     }

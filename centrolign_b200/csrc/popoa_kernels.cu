@@ -50,6 +50,7 @@ struct Win {
     int* coleff;  // per persisted column and row r: max over pred1(r) of M(p, column) -- the diagonal input of its right neighbours
     int64_t out;
     int id;
+    int cw;  // columns per lane of the fill (1: 32-column strips, 4: 128-column strips)
 };
 
 __device__ __forceinline__ int imax(int a, int b) { return a > b ? a : b; }
@@ -495,6 +496,288 @@ __device__ __forceinline__ void fill_strip(const Win& Wsh, const Params& prm, co
 }
 
 // ------------------------------------------------------------------------------------------
+// DP fill, wide variant: strips of 128 columns, FOUR consecutive columns per lane.
+// The per-step overhead (shuffles, row info, loop, waits) is shared by 128 cells instead of 32,
+// a column's near predecessors inside the lane are plain registers, and the ones that fall into
+// the previous lane come over warp shuffles (lane-1 finished the same row one step earlier), so
+// no shared-memory traffic is needed for columns at all; rows still use a small ring.
+// ------------------------------------------------------------------------------------------
+constexpr int kWideCols = 4;
+struct __align__(16) FillSmemWide {
+    int4 ringA[kFillRing * kWideCols * 32];  // [row & 3][c][lane]: {M, I_k} of the last rows, own columns
+    int4 leftv[3][2][16];                    // prefetched {M, D_k} of the 3 columns left of the strip, 16-row blocks
+    int lefte[3][2][16];
+};
+
+struct ColState {  // what a column offers to the columns right of it, for the current row
+    int M, D[3], E;  // E = diagonal input = max over predecessor rows of M
+};
+
+template <int P>
+__device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& prm, const int cs, const int g,
+                                                FillSmemWide& sm, volatile unsigned long long* progress, const int lane) {
+    constexpr int H = kFillRing, C = kWideCols, W = 32 * C, PB = 16;  // PB = rows per left-column prefetch block
+    const int C0 = 1 + W * cs;
+    const int n1 = Wsh.n1, n2 = Wsh.n2;
+    const uint32_t* __restrict__ info1 = Wsh.info1;
+    const int32_t* __restrict__ slot1 = Wsh.slot1;
+    const uint32_t* __restrict__ poff1 = Wsh.poff1;
+    const uint32_t* __restrict__ pidx1 = Wsh.pidx1;
+    const int32_t* __restrict__ slot2 = Wsh.slot2;
+    const uint32_t* __restrict__ poff2 = Wsh.poff2;
+    const uint32_t* __restrict__ pidx2 = Wsh.pidx2;
+    int4* const rowbuf = Wsh.rowbuf;
+    int4* const colbuf = Wsh.colbuf;
+    int* const coleff = Wsh.coleff;
+    const uint32_t rstride = (uint32_t)n2 + 1u, cstride = (uint32_t)n1 + 1u;
+    const int j0 = C0 + C * lane;
+
+    // ---- per-column constants ----
+    uint32_t cinfo[C], coff[C];
+    int upM[C], upI[C][3];
+    uint32_t nvalid = 0;  // number of this lane's columns that exist
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const int j = j0 + c;
+        const bool jv = j <= n2;
+        nvalid += jv ? 1u : 0u;
+        cinfo[c] = jv ? Wsh.info2[j] : (kInfoRegular | (1u << kInfoNearShift) | 0xffu);
+        coff[c] = (jv && (cinfo[c] & kInfoPersist)) ? (uint32_t)slot2[j] * cstride : 0xffffffffu;
+        upM[c] = kMinInf; upI[c][0] = upI[c][1] = upI[c][2] = kMinInf;
+        if (jv) {  // boundary row (alignment.hpp:814-894): M(0,j), I_k(0,j) = -inf
+            upM[c] = boundary_cell<P>(Wsh.depth2[j], prm).x;
+            rowbuf[j] = make_int4(upM[c], kMinInf, kMinInf, kMinInf);
+        }
+    }
+    if (cs == 0) {  // boundary column as a predecessor column, and its diagonal input
+        for (int i = lane; i <= n1; i += 32) {
+            const int m = i == 0 ? 0 : boundary_cell<P>(Wsh.depth1[i], prm).x;
+            colbuf[i] = make_int4(m, kMinInf, kMinInf, kMinInf);
+            int e = kMinInf;
+            const uint32_t a1 = poff1[i + 1];
+#pragma unroll 1
+            for (uint32_t a = poff1[i]; a < a1; ++a) {
+                const uint32_t p = pidx1[a];
+                e = imax(e, p == 0 ? 0 : boundary_cell<P>(Wsh.depth1[p], prm).x);
+            }
+            coleff[i] = e;
+        }
+    }
+    // ---- which neighbour columns are needed ----
+    // column c with near bit d (distance d) and c-d < 0 needs column 4+c-d (= 3,2,1) of the previous lane;
+    // for lane 0 that is the column C0-(d-c) left of the strip.
+    unsigned nb = 1u;  // bit0: previous lane's column 3 (always: column 0's distance-1 predecessor, if any)
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+        for (int d = 1; d <= 3; ++d)
+            if (d > c && ((cinfo[c] >> (kInfoNearShift + d - 1)) & 1u)) nb |= 1u << (d - c - 1);
+    const unsigned needS = __reduce_or_sync(kFull, nb);           // shuffles needed by any lane
+    const unsigned needL = __shfl_sync(kFull, nb, 0);             // left columns needed by lane 0
+    uint32_t xoffw[3] = {0, 0, 0};
+#pragma unroll
+    for (int d = 1; d <= 3; ++d)
+        if ((needL & (1u << (d - 1))) && C0 - d >= 0 && slot2[C0 - d] >= 0) xoffw[d - 1] = (uint32_t)slot2[C0 - d] * cstride;
+    __syncwarp();
+
+    int avail = cs == 0 ? INT_MAX : 0;
+    auto wait_rows = [&](int want) {
+        if (avail < want) {
+            for (;;) {
+                const unsigned long long v = progress[(g - 1) & 63];
+                avail = ((int)(v >> 32) == g) ? (int)(v & 0xffffffffu) : 0;
+                if (avail >= want) break;
+                __nanosleep(200);
+            }
+            __threadfence_block();
+        }
+    };
+    auto prefetch_block = [&](int b) {  // rows PB*b+1 .. PB*b+PB of the needed left columns -> buffer b&1
+        const int row = PB * b + 1 + lane;
+        if (lane < PB && row <= n1) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+                if (needL & (1u << d)) {
+                    cp_async_16(&sm.leftv[d][b & 1][lane], colbuf + (xoffw[d] + (uint32_t)row));
+                    cp_async_4(&sm.lefte[d][b & 1][lane], coleff + (xoffw[d] + (uint32_t)row));
+                }
+        }
+        cp_async_commit();
+    };
+    wait_rows(min(max(kStartLag, PB), n1));
+    prefetch_block(0);
+    cp_async_wait_all();
+    __syncwarp();
+
+    ColState out[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) { out[c].M = kMinInf; out[c].D[0] = out[c].D[1] = out[c].D[2] = kMinInf; out[c].E = kMinInf; }
+    uint32_t rinfo_next = (lane == 0) ? info1[1] : 0u;
+    int4* const myA = sm.ringA + lane;
+
+    auto shfl_col = [&](const ColState& v) {
+        ColState o;
+        o.M = __shfl_up_sync(kFull, v.M, 1);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) o.D[k] = (k < P) ? __shfl_up_sync(kFull, v.D[k], 1) : kMinInf;
+        o.E = __shfl_up_sync(kFull, v.E, 1);
+        return o;
+    };
+    auto load_left = [&](int d, int lb, int li) {  // left column C0-1-d at the current row (lane 0)
+        ColState o;
+        const int4 t = sm.leftv[d][lb][li];
+        o.M = t.x; o.D[0] = t.y; o.D[1] = t.z; o.D[2] = t.w;
+        o.E = sm.lefte[d][lb][li];
+        return o;
+    };
+    auto fold = [&](ColState& a, const ColState& b) {
+        a.M = imax(a.M, b.M);
+#pragma unroll
+        for (int k = 0; k < P; ++k) a.D[k] = imax(a.D[k], b.D[k]);
+        a.E = imax(a.E, b.E);
+    };
+
+    auto step = [&](const int s, auto guard_tag) {
+        constexpr bool GUARD = decltype(guard_tag)::value;
+        const int r = 1 + s - lane;
+        bool act = true;
+        if (GUARD) act = r >= 1 && r <= n1;
+        // previous lane's columns for this row (it finished the row one step ago)
+        ColState S[3];  // S[0] = its column 3, S[1] = column 2, S[2] = column 1
+        S[0] = shfl_col(out[3]);
+        if (needS & 2u) S[1] = shfl_col(out[2]);
+        if (needS & 4u) S[2] = shfl_col(out[1]);
+        const uint32_t rinfo = rinfo_next;
+        if (GUARD) rinfo_next = (r >= 0 && r < n1) ? info1[(uint32_t)(r + 1)] : 0u;
+        else rinfo_next = info1[(uint32_t)(r + 1)];  // the info array is padded by one entry
+        if (act) {
+            const int rs = (r & (H - 1)) * (C * 32);
+            if (lane == 0) {
+                const int lb = ((r - 1) / PB) & 1, li = (r - 1) % PB;
+                if (needL & 1u) S[0] = load_left(0, lb, li);
+                if (needL & 2u) S[1] = load_left(1, lb, li);
+                if (needL & 4u) S[2] = load_left(2, lb, li);
+            }
+            const int rlabel = (int)(rinfo & kInfoLabelMask);
+            const bool rirr = !(rinfo & kInfoRegular);
+            uint32_t rslot = 0;
+            const bool rpers = (rinfo & kInfoPersist) != 0;
+            if (rpers) {
+                rslot = rinfo >> kInfoSlotShift;
+                if (rslot == kInfoSlotEscape) rslot = (uint32_t)slot1[r];
+                rslot = rslot * rstride + (uint32_t)j0;
+            }
+            ColState cur[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                // ---- effective predecessor row for this column ----
+                int eM = upM[c], eI[3] = {upI[c][0], upI[c][1], upI[c][2]};
+                if (rirr) {
+                    if (!(rinfo & (1u << kInfoNearShift))) { eM = kMinInf; eI[0] = eI[1] = eI[2] = kMinInf; }
+                    if (rinfo & (2u << kInfoNearShift)) max4(eM, eI, myA[(rs ^ (2 * C * 32)) + c * 32]);
+                    if (rinfo & ((4u << kInfoNearShift) | kInfoFar)) {
+                        if (rinfo & (4u << kInfoNearShift)) max4(eM, eI, myA[((r - 3) & (H - 1)) * (C * 32) + c * 32]);
+                        if ((rinfo & kInfoFar) && c < (int)nvalid) {
+                            const uint32_t rp1 = poff1[r + 1];
+#pragma unroll 1
+                            for (uint32_t a = poff1[r]; a < rp1; ++a) {
+                                const int p = (int)pidx1[a];
+                                if (p >= 1 && r - p <= kNear) continue;
+                                max4(eM, eI, rowbuf[(uint32_t)slot1[p] * rstride + (uint32_t)(j0 + c)]);
+                            }
+                        }
+                    }
+                }
+                // ---- effective predecessor column ----
+                ColState L;
+                if (c == 0) L = S[0]; else L = cur[c - 1];
+                const uint32_t ci = cinfo[c];
+                if (!(ci & kInfoRegular)) {
+                    if (!(ci & (1u << kInfoNearShift))) { L.M = kMinInf; L.D[0] = L.D[1] = L.D[2] = kMinInf; L.E = kMinInf; }
+                    if (ci & (2u << kInfoNearShift)) {  // distance 2
+                        if (c >= 2) fold(L, cur[c - 2]); else fold(L, S[1 - c]);
+                    }
+                    if (ci & (4u << kInfoNearShift)) {  // distance 3
+                        if (c >= 3) fold(L, cur[c - 3]); else fold(L, S[2 - c]);
+                    }
+                    if (ci & kInfoFar) {
+                        const int j = j0 + c;
+                        const uint32_t b1 = poff2[j + 1];
+#pragma unroll 1
+                        for (uint32_t b = poff2[j]; b < b1; ++b) {
+                            const int q = (int)pidx2[b];
+                            if (q >= 1 && j - q <= kNear) continue;
+                            const uint32_t o = (uint32_t)slot2[q] * cstride + (uint32_t)r;
+                            const int4 t = colbuf[o];
+                            L.M = imax(L.M, t.x); L.D[0] = imax(L.D[0], t.y); L.D[1] = imax(L.D[1], t.z); L.D[2] = imax(L.D[2], t.w);
+                            L.E = imax(L.E, coleff[o]);
+                        }
+                    }
+                }
+                // ---- the cell ----
+                const int sub = (rlabel == (int)(ci & kInfoLabelMask)) ? prm.match : -prm.mismatch;
+                int I[3] = {kMinInf, kMinInf, kMinInf};
+                cur[c].D[0] = cur[c].D[1] = cur[c].D[2] = kMinInf;
+                int M = __viaddmax_s32(L.E, sub, kMinInf);
+#pragma unroll
+                for (int k = 0; k < P; ++k) {
+                    I[k] = __viaddmax_s32(eI[k], -prm.e[k], eM - prm.oe[k]);
+                    cur[c].D[k] = __viaddmax_s32(L.D[k], -prm.e[k], L.M - prm.oe[k]);
+                    M = __vimax3_s32(M, I[k], cur[c].D[k]);
+                }
+                cur[c].M = M;
+                cur[c].E = eM;
+                const int4 cellA = make_int4(M, I[0], I[1], I[2]);
+                myA[rs + c * 32] = cellA;
+                if (rpers && c < (int)nvalid) rowbuf[rslot + c] = cellA;
+                if (coff[c] != 0xffffffffu) {
+                    colbuf[coff[c] + (uint32_t)r] = make_int4(M, cur[c].D[0], cur[c].D[1], cur[c].D[2]);
+                    coleff[coff[c] + (uint32_t)r] = eM;
+                }
+                upM[c] = M; upI[c][0] = I[0]; upI[c][1] = I[1]; upI[c][2] = I[2];
+            }
+#pragma unroll
+            for (int c = 0; c < C; ++c) out[c] = cur[c];
+        }
+        __syncwarp();
+    };
+    auto publish = [&](int r31) {
+        __threadfence_block();
+        progress[g & 63] = ((unsigned long long)(g + 1) << 32) | (unsigned)r31;
+    };
+
+    const int nsteps = n1 + 31;
+    for (int s0 = 0; s0 < nsteps; s0 += PB) {  // PB-step blocks; lane 0 is on rows s0+1 .. s0+PB
+        const int s1 = min(s0 + PB, nsteps);
+        {  // only lane 0 reads the prefetch buffers, so the next block can be requested right away
+            const int b = s0 / PB + 1;
+            if (PB * b + 1 <= n1) {
+                wait_rows(min(PB * b + PB, n1));
+                prefetch_block(b);
+            }
+        }
+        const bool inner = s0 >= 31 && s1 <= n1;
+#pragma unroll 1
+        for (int q8 = s0; q8 < s1; q8 += 8) {
+            const int e8 = min(q8 + 8, s1);
+            if (inner) {
+#pragma unroll 1
+                for (int s = q8; s < e8; ++s) step(s, std::false_type{});
+            } else {
+#pragma unroll 1
+                for (int s = q8; s < e8; ++s) step(s, std::true_type{});
+            }
+            if (lane == 31) {
+                const int r31 = e8 - 31;
+                if (r31 >= 1) publish(min(r31, n1));
+            }
+        }
+        cp_async_wait_all();
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Boundary row / column (alignment.hpp:814-894).  In the boundary column only the lead
 // insertion is extended, so I_k(i,0) = -(o_k + e_k * depth(i)) with depth = fewest nodes on a
 // path from a source; the host supplies depth, which makes this pass embarrassingly parallel.
@@ -696,6 +979,11 @@ __device__ void traceback(const Win& W, const Params& prm, int4* tileA, int4* ti
 //     traces it back while the fill warps are already on the next window.
 // ------------------------------------------------------------------------------------------
 constexpr int kFillWarps = kWarps - 1;
+constexpr int kWideMinCols = 384;  // windows at least this wide use 128-column strips
+union FillSmemAny {
+    FillSmem narrow;
+    FillSmemWide wide;
+};
 constexpr int kTileInt4 = 2 * kRowBlock * 32;
 
 struct CtaState {
@@ -721,7 +1009,7 @@ __global__ void __launch_bounds__(kThreads, 1) popoa_kernel(const LaunchArgs A) 
 
     if (warp < kFillWarps) {
         // ================= fill warps =================
-        FillSmem& sm = *reinterpret_cast<FillSmem*>(smem + kTileInt4 + warp * (int)(sizeof(FillSmem) / sizeof(int4)));
+        FillSmemAny& sm = *reinterpret_cast<FillSmemAny*>(smem + kTileInt4 + warp * (int)(sizeof(FillSmemAny) / sizeof(int4)));
         int G = 0;  // running strip number at the start of window k
         for (int k = 0;; ++k) {
             while (ld_volatile(&S.seq_tag[k & 7]) != k + 1) __nanosleep(200);
@@ -732,7 +1020,8 @@ __global__ void __launch_bounds__(kThreads, 1) popoa_kernel(const LaunchArgs A) 
             const Win& W = S.win[k & 1];
             int first = (warp - G % kFillWarps + kFillWarps) % kFillWarps;  // my first strip of this window
             for (int cs = first; cs < nstrips; cs += kFillWarps) {
-                fill_strip<P>(W, prm, cs, G + cs, sm, S.progress, lane);
+                if (W.cw == kWideCols) fill_strip_wide<P>(W, prm, cs, G + cs, *reinterpret_cast<FillSmemWide*>(&sm), S.progress, lane);
+                else fill_strip<P>(W, prm, cs, G + cs, *reinterpret_cast<FillSmem*>(&sm), S.progress, lane);
                 if (lane == 0) {
                     __threadfence_block();
                     atomicAdd(&S.strips_done[k & 1], 1);
@@ -770,7 +1059,9 @@ __global__ void __launch_bounds__(kThreads, 1) popoa_kernel(const LaunchArgs A) 
                     W.coleff = reinterpret_cast<int*>(W.bcol + (m.n1 + 1));
                     W.out = m.out;
                     W.id = w;
-                    nstrips = m.n1 >= 1 ? (int)((m.n2 + kStrip - 1) / kStrip) : 0;
+                    W.cw = (int)m.n2 >= kWideMinCols ? kWideCols : 1;
+                    const int sw = kStrip * W.cw;
+                    nstrips = m.n1 >= 1 ? (int)((m.n2 + sw - 1) / sw) : 0;
                 }
                 S.strips_done[k & 1] = 0;
                 S.seq_nstrips[k & 7] = nstrips;
@@ -791,14 +1082,14 @@ __global__ void __launch_bounds__(kThreads, 1) popoa_kernel(const LaunchArgs A) 
             __threadfence_block();
             const Win& W = S.win[t & 1];
             tb_boundary<P>(W, prm, lane);
-            traceback<P>(W, prm, smem, smem + kRowBlock * 32, lane, A.score + w, A.aln + 2 * W.out, A.aln_len + w);
+            if (!(A.debug_flags & 1)) traceback<P>(W, prm, smem, smem + kRowBlock * 32, lane, A.score + w, A.aln + 2 * W.out, A.aln_len + w);
             __syncwarp();
             if (!ended) fetch();  // hands slot t&1 to window t+2
         }
     }
 }
 
-int popoa_smem_bytes() { return (kTileInt4 + kFillWarps * (int)(sizeof(FillSmem) / sizeof(int4))) * (int)sizeof(int4); }
+int popoa_smem_bytes() { return (kTileInt4 + kFillWarps * (int)(sizeof(FillSmemAny) / sizeof(int4))) * (int)sizeof(int4); }
 int popoa_threads() { return kThreads; }
 
 cudaError_t launch_popoa(int num_pw, const LaunchArgs& args, int grid, cudaStream_t stream) {
