@@ -824,14 +824,179 @@ struct TileView {
     int R0, R1, C0;  // tile rows R0..R1, columns C0..C0+31; R0 = 0 means "no tile"
 };
 
+// shared memory of the traceback warp
+struct __align__(16) TileSmem {
+    int4 A[kRowBlock * 32];       // {M, I_k}       [row & 63][lane]
+    int4 B[kRowBlock * 32];       // {diag in, D_k} [row & 63][lane]
+    int4 leftv[3][kRowBlock];     // {M, D_k} of the 3 columns left of the tile, rows R0..R1
+    int lefte[3][kRowBlock];      // their diagonal input
+    uint32_t rinfo[kRowBlock];    // info words of the tile's rows
+    uint32_t cinfo[kStrip];       // info words of the tile's columns
+};
+
+// Recompute one tile: rows R0..R1 (same 64-row block) x 32 columns from C0, every cell kept in
+// shared memory.  Same recurrence and same near / far predecessor handling as fill_strip; what
+// lies outside the tile comes from the persisted rows / columns of the window workspace.
+template <int P>
+__device__ __forceinline__ void tile_strip(const Win& Wsh, const Params& prm, const int C0, const int R0, const int R1,
+                                           TileSmem& sm, const int lane) {
+    constexpr int H = kRowBlock;
+    const int n1 = Wsh.n1, n2 = Wsh.n2;
+    const uint32_t* __restrict__ info1 = Wsh.info1;
+    const int32_t* __restrict__ slot1 = Wsh.slot1;
+    const uint32_t* __restrict__ poff1 = Wsh.poff1;
+    const uint32_t* __restrict__ pidx1 = Wsh.pidx1;
+    const int32_t* __restrict__ slot2 = Wsh.slot2;
+    const uint32_t* __restrict__ pidx2 = Wsh.pidx2;
+    const int4* const rowbuf = Wsh.rowbuf;
+    const int4* const colbuf = Wsh.colbuf;
+    const int* const coleff = Wsh.coleff;
+    const uint32_t rstride = (uint32_t)n2 + 1u, cstride = (uint32_t)n1 + 1u;
+    const int nrows = R1 - R0 + 1;
+
+    const int j = C0 + lane;
+    const bool jvalid = j <= n2;
+    const uint32_t cinfo = jvalid ? Wsh.info2[j] : (kInfoRegular | (1u << kInfoNearShift) | 0xffu);
+    sm.cinfo[lane] = cinfo;
+    const int clabel = (int)(cinfo & kInfoLabelMask);
+    const bool creg = (cinfo & kInfoRegular) != 0;
+    const uint32_t cmask = (cinfo >> kInfoNearShift) & 7u;
+    const bool cfar = (cinfo & kInfoFar) != 0;
+    const bool colpath = !creg || lane == 0;
+    const uint32_t cp0 = (jvalid && cfar) ? Wsh.poff2[j] : 0u, cp1 = (jvalid && cfar) ? Wsh.poff2[j + 1] : 0u;
+
+    unsigned needbits = 0;
+    if (jvalid) {
+#pragma unroll
+        for (int dd = 1; dd <= 3; ++dd)
+            if (dd > lane && ((cmask >> (dd - 1)) & 1u)) needbits |= 1u << (dd - lane - 1);
+        if (lane == 0 && creg) needbits |= 1u;
+    }
+    needbits = __reduce_or_sync(kFull, needbits);
+    // cache the left columns and the row info words of the tile
+    for (int idx = lane; idx < nrows; idx += 32) {
+        const int r = R0 + idx;
+        sm.rinfo[idx] = info1[r];
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+            if (needbits & (1u << d)) {
+                const uint32_t o = (uint32_t)slot2[C0 - 1 - d] * cstride + (uint32_t)r;
+                sm.leftv[d][idx] = colbuf[o];
+                sm.lefte[d][idx] = coleff[o];
+            }
+    }
+    int upM = kMinInf, upI[3] = {kMinInf, kMinInf, kMinInf};
+    if (jvalid) {
+        const int s0 = slot1[R0 - 1];
+        if (s0 >= 0) {
+            const int4 a = rowbuf[(uint32_t)s0 * rstride + (uint32_t)j];
+            upM = a.x; upI[0] = a.y; upI[1] = a.z; upI[2] = a.w;
+        }
+    }
+    __syncwarp();
+
+    int outM = kMinInf, outD[3] = {kMinInf, kMinInf, kMinInf}, outEff = kMinInf;
+    int4* const myA = sm.A + lane;
+    int4* const myB = sm.B + lane;
+    const int nsteps = nrows + 31;
+#pragma unroll 1
+    for (int s = 0; s < nsteps; ++s) {
+        const int r = R0 + s - lane;
+        const bool act = jvalid && r >= R0 && r <= R1;
+        int lM = __shfl_up_sync(kFull, outM, 1);
+        int lD[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) lD[k] = (k < P) ? __shfl_up_sync(kFull, outD[k], 1) : kMinInf;
+        int lEff = __shfl_up_sync(kFull, outEff, 1);
+        if (act) {
+            const int li = r - R0;
+            const uint32_t rinfo = sm.rinfo[li];
+            const int rs = (r & (H - 1)) * 32;
+            // ---- effective predecessor row ----
+            int eM = upM, eI[3] = {upI[0], upI[1], upI[2]};
+            if (!(rinfo & kInfoRegular)) {
+                if (!(rinfo & (1u << kInfoNearShift))) { eM = kMinInf; eI[0] = eI[1] = eI[2] = kMinInf; }
+#pragma unroll
+                for (int d = 2; d <= 3; ++d) {
+                    if (rinfo & ((1u << (d - 1)) << kInfoNearShift)) {
+                        const int p = r - d;
+                        const int4 v = p >= R0 ? myA[(p & (H - 1)) * 32] : rowbuf[(uint32_t)slot1[p] * rstride + (uint32_t)j];
+                        max4(eM, eI, v);
+                    }
+                }
+                if (rinfo & kInfoFar) {
+                    const uint32_t rp1 = poff1[r + 1];
+#pragma unroll 1
+                    for (uint32_t a = poff1[r]; a < rp1; ++a) {
+                        const int p = (int)pidx1[a];
+                        if (p >= 1 && r - p <= kNear) continue;
+                        max4(eM, eI, rowbuf[(uint32_t)slot1[p] * rstride + (uint32_t)j]);
+                    }
+                }
+            }
+            // ---- effective predecessor column + diagonal input ----
+            if (colpath) {
+                if (!(cmask & 1u) && !creg) { lM = kMinInf; lD[0] = lD[1] = lD[2] = kMinInf; lEff = kMinInf; }
+                else if (lane == 0) {
+                    const int4 b = sm.leftv[0][li];
+                    lM = b.x; lD[0] = b.y; lD[1] = b.z; lD[2] = b.w;
+                    lEff = sm.lefte[0][li];
+                }
+#pragma unroll
+                for (int d = 2; d <= 3; ++d) {
+                    if (cmask & (1u << (d - 1))) {
+                        int4 v;
+                        int m;
+                        if (lane >= d) {
+                            v = sm.B[rs + lane - d];
+                            m = sm.A[rs + lane - d].x;
+                        } else {
+                            const int4 t = sm.leftv[d - lane - 1][li];
+                            m = t.x;
+                            v = make_int4(sm.lefte[d - lane - 1][li], t.y, t.z, t.w);
+                        }
+                        lM = imax(lM, m);
+                        max4(lEff, lD, v);
+                    }
+                }
+                if (cfar) {
+#pragma unroll 1
+                    for (uint32_t b = cp0; b < cp1; ++b) {
+                        const int q = (int)pidx2[b];
+                        if (q >= 1 && j - q <= kNear) continue;
+                        const uint32_t o = (uint32_t)slot2[q] * cstride + (uint32_t)r;
+                        max4(lM, lD, colbuf[o]);
+                        lEff = imax(lEff, coleff[o]);
+                    }
+                }
+            }
+            // ---- the cell ----
+            const int sub = ((int)(rinfo & kInfoLabelMask) == clabel) ? prm.match : -prm.mismatch;
+            int I[3] = {kMinInf, kMinInf, kMinInf}, D[3] = {kMinInf, kMinInf, kMinInf};
+            int M = __viaddmax_s32(lEff, sub, kMinInf);
+#pragma unroll
+            for (int k = 0; k < P; ++k) {
+                I[k] = __viaddmax_s32(eI[k], -prm.e[k], eM - prm.oe[k]);
+                D[k] = __viaddmax_s32(lD[k], -prm.e[k], lM - prm.oe[k]);
+                M = __vimax3_s32(M, I[k], D[k]);
+            }
+            myA[rs] = make_int4(M, I[0], I[1], I[2]);
+            myB[rs] = make_int4(eM, D[0], D[1], D[2]);
+            upM = M; upI[0] = I[0]; upI[1] = I[1]; upI[2] = I[2];
+            outM = M; outD[0] = D[0]; outD[1] = D[1]; outD[2] = D[2];
+            outEff = eM;
+        }
+        __syncwarp();
+    }
+}
+
 template <int P>
 struct Walker {
     const Win& W;
     const Params& prm;
-    const int4* tileA;
-    const int4* tileB;
+    const TileSmem& sm;
     TileView tv;
-    int64_t rstride, cstride;
+    uint32_t rstride, cstride;
 
     __device__ bool in_tile(int i, int j) const {
         return tv.R0 > 0 && i >= tv.R0 && i <= tv.R1 && j >= tv.C0 && j < tv.C0 + kStrip && j <= W.n2;
@@ -840,34 +1005,53 @@ struct Walker {
     __device__ int cM(int i, int j) const {
         if (i == 0) return j == 0 ? kMinInf : W.brow[j].x;
         if (j == 0) return W.bcol[i].x;
-        if (in_tile(i, j)) return tileA[(i & (kRowBlock - 1)) * 32 + (j - tv.C0)].x;
+        if (in_tile(i, j)) return sm.A[(i & (kRowBlock - 1)) * 32 + (j - tv.C0)].x;
         const int s = W.slot1[i];
-        if (s >= 0) return W.rowbuf[(int64_t)s * rstride + j].x;
-        return W.colbuf[(int64_t)W.slot2[j] * cstride + i].x;
+        if (s >= 0) return W.rowbuf[(uint32_t)s * rstride + (uint32_t)j].x;
+        return W.colbuf[(uint32_t)W.slot2[j] * cstride + (uint32_t)i].x;
     }
     __device__ int cI(int i, int j, int k) const {
         if (i == 0) return kMinInf;
         int4 v;
         if (j == 0) v = W.bcol[i];
-        else if (in_tile(i, j)) v = tileA[(i & (kRowBlock - 1)) * 32 + (j - tv.C0)];
-        else v = W.rowbuf[(int64_t)W.slot1[i] * rstride + j];
+        else if (in_tile(i, j)) v = sm.A[(i & (kRowBlock - 1)) * 32 + (j - tv.C0)];
+        else v = W.rowbuf[(uint32_t)W.slot1[i] * rstride + (uint32_t)j];
         return k == 0 ? v.y : (k == 1 ? v.z : v.w);
     }
     __device__ int cD(int i, int j, int k) const {
         if (j == 0) return kMinInf;
         int4 v;
         if (i == 0) v = W.brow[j];
-        else if (in_tile(i, j)) v = tileB[(i & (kRowBlock - 1)) * 32 + (j - tv.C0)];
-        else v = W.colbuf[(int64_t)W.slot2[j] * cstride + i];
+        else if (in_tile(i, j)) v = sm.B[(i & (kRowBlock - 1)) * 32 + (j - tv.C0)];
+        else v = W.colbuf[(uint32_t)W.slot2[j] * cstride + (uint32_t)i];
         return k == 0 ? v.y : (k == 1 ? v.z : v.w);
     }
+    __device__ uint32_t rinfo(int i) const { return (tv.R0 > 0 && i >= tv.R0 && i <= tv.R1) ? sm.rinfo[i - tv.R0] : W.info1[i]; }
+    __device__ uint32_t cinfo(int j) const { return (tv.R0 > 0 && j >= tv.C0 && j < tv.C0 + kStrip && j <= W.n2) ? sm.cinfo[j - tv.C0] : W.info2[j]; }
 };
 
+// predecessor list of a node in previous() order; regular nodes (one predecessor = index-1) need no memory access
+struct PredList {
+    const uint32_t* ptr;
+    int n, single;
+    __device__ int at(int k) const { return ptr ? (int)ptr[k] : single; }
+};
+__device__ __forceinline__ PredList pred_list(uint32_t info, int idx, const uint32_t* poff, const uint32_t* pidx) {
+    PredList pl;
+    if (info & kInfoRegular) {
+        pl.ptr = nullptr; pl.n = 1; pl.single = idx - 1;
+    } else {
+        const uint32_t a = poff[idx];
+        pl.ptr = pidx + a; pl.n = (int)(poff[idx + 1] - a); pl.single = 0;
+    }
+    return pl;
+}
+
 template <int P>
-__device__ void traceback(const Win& W, const Params& prm, int4* tileA, int4* tileB, int lane, int64_t* score_out,
-                          int32_t* aln, uint32_t* len_out) {
+__device__ void traceback(const Win& W, const Params& prm, TileSmem& sm, int lane, int64_t* score_out, int32_t* aln,
+                          uint32_t* len_out) {
     const int n1 = W.n1, n2 = W.n2;
-    const int64_t rstride = (int64_t)n2 + 1;
+    const uint32_t rstride = (uint32_t)n2 + 1u;
     // ---- best sink pair: first maximum in caller order, strict '>' (alignment.hpp:979-1008) ----
     long long npairs;
     if (n1 != 0 && n2 != 0) npairs = (long long)W.nsnk1 * W.nsnk2;
@@ -880,7 +1064,7 @@ __device__ void traceback(const Win& W, const Params& prm, int4* tileA, int4* ti
         int v;
         if (n1 != 0 && n2 != 0) {
             const int i = (int)W.snk1[x / W.nsnk2], j = (int)W.snk2[x % W.nsnk2];
-            v = W.rowbuf[(int64_t)W.slot1[i] * rstride + j].x;
+            v = W.rowbuf[(uint32_t)W.slot1[i] * rstride + (uint32_t)j].x;
         } else if (n1 != 0) {
             v = W.bcol[W.snk1[x]].x;
         } else {
@@ -902,15 +1086,15 @@ __device__ void traceback(const Win& W, const Params& prm, int4* tileA, int4* ti
     }
     if (lane == 0) *score_out = (ci >= 0) ? (long long)best : 0;
 
-    Walker<P> wk{W, prm, tileA, tileB, TileView{0, 0, 0}, rstride, (int64_t)n1 + 1};
+    Walker<P> wk{W, prm, sm, TileView{0, 0, 0}, rstride, (uint32_t)n1 + 1u};
     const int cap = n1 + n2;
     int len = 0, comp = 0;
-    while (ci >= 0) {  // warp-uniform: ci/cj/comp/len are broadcast from lane 0 below
+    while (ci >= 0) {  // warp-uniform: ci/cj are broadcast from lane 0 below
         if (ci >= 1 && cj >= 1 && !wk.in_tile(ci, cj)) {
             const int R0 = 1 + ((ci - 1) / kRowBlock) * kRowBlock;
             const int C0 = 1 + ((cj - 1) / kStrip) * kStrip;
             __syncwarp();
-            process_strip<P, kRowBlock, true>(W, prm, C0, R0, ci, tileA, tileB, nullptr, 0, lane);
+            tile_strip<P>(W, prm, C0, R0, ci, sm, lane);
             __syncwarp();
             wk.tv = TileView{R0, ci, C0};
         }
@@ -924,17 +1108,17 @@ __device__ void traceback(const Win& W, const Params& prm, int4* tileA, int4* ti
                         if (M == wk.cD(ci, cj, k)) { comp = -k - 1; break; }
                     }
                 }
-                const uint32_t a0 = W.poff1[ci], a1 = W.poff1[ci + 1];  // empty for the boundary index 0
-                const uint32_t b0 = W.poff2[cj], b1 = W.poff2[cj + 1];
                 int ni = -1, nj = -1;
                 int32_t* o = aln + 2 * (int64_t)(cap - 1 - len);
                 if (comp == 0) {
                     o[0] = ci - 1; o[1] = cj - 1;
-                    const int sub = ((W.info1[ci] & kInfoLabelMask) == (W.info2[cj] & kInfoLabelMask)) ? prm.match : -prm.mismatch;
-                    for (uint32_t a = a0; a < a1; ++a) {  // last prev1 with a match wins, with its first prev2
-                        const int p = (int)W.pidx1[a];
-                        for (uint32_t b = b0; b < b1; ++b) {
-                            const int q = (int)W.pidx2[b];
+                    const uint32_t ri = wk.rinfo(ci), cf = wk.cinfo(cj);
+                    const PredList p1 = pred_list(ri, ci, W.poff1, W.pidx1), p2 = pred_list(cf, cj, W.poff2, W.pidx2);
+                    const int sub = ((ri & kInfoLabelMask) == (cf & kInfoLabelMask)) ? prm.match : -prm.mismatch;
+                    for (int a = 0; a < p1.n; ++a) {  // last prev1 with a match wins, with its first prev2
+                        const int p = p1.at(a);
+                        for (int b = 0; b < p2.n; ++b) {
+                            const int q = p2.at(b);
                             if (wk.cM(p, q) + sub == M) { ni = p; nj = q; break; }
                         }
                     }
@@ -942,8 +1126,9 @@ __device__ void traceback(const Win& W, const Params& prm, int4* tileA, int4* ti
                     o[0] = ci - 1; o[1] = -1;
                     const int k = comp - 1;
                     const int cur = wk.cI(ci, cj, k);
-                    for (uint32_t a = a0; a < a1; ++a) {
-                        const int p = (int)W.pidx1[a];
+                    const PredList p1 = pred_list(wk.rinfo(ci), ci, W.poff1, W.pidx1);
+                    for (int a = 0; a < p1.n; ++a) {
+                        const int p = p1.at(a);
                         if (cur == wk.cM(p, cj) - prm.oe[k]) { comp = 0; ni = p; nj = cj; break; }
                         if (cur == wk.cI(p, cj, k) - prm.e[k]) { ni = p; nj = cj; break; }
                     }
@@ -951,8 +1136,9 @@ __device__ void traceback(const Win& W, const Params& prm, int4* tileA, int4* ti
                     o[0] = -1; o[1] = cj - 1;
                     const int k = -comp - 1;
                     const int cur = wk.cD(ci, cj, k);
-                    for (uint32_t b = b0; b < b1; ++b) {
-                        const int q = (int)W.pidx2[b];
+                    const PredList p2 = pred_list(wk.cinfo(cj), cj, W.poff2, W.pidx2);
+                    for (int b = 0; b < p2.n; ++b) {
+                        const int q = p2.at(b);
                         if (cur == wk.cM(ci, q) - prm.oe[k]) { comp = 0; ni = ci; nj = q; break; }
                         if (cur == wk.cD(ci, q, k) - prm.e[k]) { ni = ci; nj = q; break; }
                     }
@@ -984,7 +1170,7 @@ union FillSmemAny {
     FillSmem narrow;
     FillSmemWide wide;
 };
-constexpr int kTileInt4 = 2 * kRowBlock * 32;
+constexpr int kTileInt4 = (int)(sizeof(TileSmem) / sizeof(int4));
 
 struct CtaState {
     Win win[2];
@@ -1082,7 +1268,8 @@ __global__ void __launch_bounds__(kThreads, 1) popoa_kernel(const LaunchArgs A) 
             __threadfence_block();
             const Win& W = S.win[t & 1];
             tb_boundary<P>(W, prm, lane);
-            if (!(A.debug_flags & 1)) traceback<P>(W, prm, smem, smem + kRowBlock * 32, lane, A.score + w, A.aln + 2 * W.out, A.aln_len + w);
+            if (!(A.debug_flags & 1))
+                traceback<P>(W, prm, *reinterpret_cast<TileSmem*>(smem), lane, A.score + w, A.aln + 2 * W.out, A.aln_len + w);
             __syncwarp();
             if (!ended) fetch();  // hands slot t&1 to window t+2
         }
