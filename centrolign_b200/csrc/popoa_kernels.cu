@@ -32,7 +32,7 @@
 
 namespace clb {
 
-constexpr int kWarps = 16;
+constexpr int kWarps = 12;
 constexpr int kThreads = kWarps * 32;
 constexpr unsigned kFull = 0xffffffffu;
 
