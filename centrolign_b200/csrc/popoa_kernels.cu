@@ -230,6 +230,19 @@ __device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ int4 lds_128(uint32_t saddr) {
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ int lds_32(uint32_t saddr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];\n" : "=r"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts_128(uint32_t saddr, const int4 v) {
+    asm volatile("st.shared.v4.s32 [%0], {%1,%2,%3,%4};\n" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
@@ -520,12 +533,9 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
     const int C0 = 1 + W * cs;
     const int n1 = Wsh.n1, n2 = Wsh.n2;
     const uint32_t* __restrict__ info1 = Wsh.info1;
-    const int32_t* __restrict__ slot1 = Wsh.slot1;
     const uint32_t* __restrict__ poff1 = Wsh.poff1;
     const uint32_t* __restrict__ pidx1 = Wsh.pidx1;
     const int32_t* __restrict__ slot2 = Wsh.slot2;
-    const uint32_t* __restrict__ poff2 = Wsh.poff2;
-    const uint32_t* __restrict__ pidx2 = Wsh.pidx2;
     int4* const rowbuf = Wsh.rowbuf;
     int4* const colbuf = Wsh.colbuf;
     int* const coleff = Wsh.coleff;
@@ -613,7 +623,20 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
 #pragma unroll
     for (int c = 0; c < C; ++c) { out[c].M = kMinInf; out[c].D[0] = out[c].D[1] = out[c].D[2] = kMinInf; out[c].E = kMinInf; }
     uint32_t rinfo_next = (lane == 0) ? info1[1] : 0u;
-    int4* const myA = sm.ringA + lane;
+    // explicit 32-bit shared-window addresses: keeps ptxas from re-deriving them every step
+    const uint32_t saA = (uint32_t)__cvta_generic_to_shared(sm.ringA) + (uint32_t)lane * 16u;
+    const uint32_t saLv = (uint32_t)__cvta_generic_to_shared(&sm.leftv[0][0][0]);
+    const uint32_t saLe = (uint32_t)__cvta_generic_to_shared(&sm.lefte[0][0][0]);
+    // per-column constant predicates
+    bool cb1[C], cb2[C], crare[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        cb1[c] = (cinfo[c] & ((1u << kInfoNearShift) | kInfoRegular)) != 0 &&
+                 ((cinfo[c] & (1u << kInfoNearShift)) != 0 || (cinfo[c] & kInfoRegular) != 0);
+        // a regular column always takes its distance-1 neighbour (column 1's is the boundary column)
+        cb2[c] = (cinfo[c] & (2u << kInfoNearShift)) != 0;
+        crare[c] = (cinfo[c] & ((4u << kInfoNearShift) | kInfoFar)) != 0;
+    }
 
     auto shfl_col = [&](const ColState& v) {
         ColState o;
@@ -623,18 +646,18 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
         o.E = __shfl_up_sync(kFull, v.E, 1);
         return o;
     };
-    auto load_left = [&](int d, int lb, int li) {  // left column C0-1-d at the current row (lane 0)
-        ColState o;
-        const int4 t = sm.leftv[d][lb][li];
-        o.M = t.x; o.D[0] = t.y; o.D[1] = t.z; o.D[2] = t.w;
-        o.E = sm.lefte[d][lb][li];
-        return o;
-    };
     auto fold = [&](ColState& a, const ColState& b) {
         a.M = imax(a.M, b.M);
 #pragma unroll
         for (int k = 0; k < P; ++k) a.D[k] = imax(a.D[k], b.D[k]);
         a.E = imax(a.E, b.E);
+    };
+    // all lanes read lane 0's left-column entry (a broadcast, no divergence); lane 0 keeps it
+    auto take_left = [&](ColState& S, int d, int s) {
+        const uint32_t slot = (uint32_t)(d * 2 + ((s / PB) & 1)) * PB + (uint32_t)(s % PB);
+        const int4 t = lds_128(saLv + slot * 16u);
+        const int e = lds_32(saLe + slot * 4u);
+        if (lane == 0) { S.M = t.x; S.D[0] = t.y; S.D[1] = t.z; S.D[2] = t.w; S.E = e; }
     };
 
     auto step = [&](const int s, auto guard_tag) {
@@ -643,71 +666,84 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
         bool act = true;
         if (GUARD) act = r >= 1 && r <= n1;
         // previous lane's columns for this row (it finished the row one step ago)
-        ColState S[3];  // S[0] = its column 3, S[1] = column 2, S[2] = column 1
-        S[0] = shfl_col(out[3]);
-        if (needS & 2u) S[1] = shfl_col(out[2]);
-        if (needS & 4u) S[2] = shfl_col(out[1]);
+        ColState S0, S1, S2;  // its column 3, 2, 1
+        S0 = shfl_col(out[3]);
+        if (needS & 2u) S1 = shfl_col(out[2]);
+        if (needS & 4u) S2 = shfl_col(out[1]);
+        // lane 0 is on row s+1: rows PB*b+1.. live in buffer b&1 at index (row-1) % PB
+        if (needL & 1u) take_left(S0, 0, s);
+        if (needL & 6u) {
+            if (needL & 2u) take_left(S1, 1, s);
+            if (needL & 4u) take_left(S2, 2, s);
+        }
         const uint32_t rinfo = rinfo_next;
         if (GUARD) rinfo_next = (r >= 0 && r < n1) ? info1[(uint32_t)(r + 1)] : 0u;
         else rinfo_next = info1[(uint32_t)(r + 1)];  // the info array is padded by one entry
         if (act) {
-            const int rs = (r & (H - 1)) * (C * 32);
-            if (lane == 0) {
-                const int lb = ((r - 1) / PB) & 1, li = (r - 1) % PB;
-                if (needL & 1u) S[0] = load_left(0, lb, li);
-                if (needL & 2u) S[1] = load_left(1, lb, li);
-                if (needL & 4u) S[2] = load_left(2, lb, li);
-            }
+            const uint32_t rsA = saA + (uint32_t)(r & (H - 1)) * (C * 32 * 16);
             const int rlabel = (int)(rinfo & kInfoLabelMask);
-            const bool rirr = !(rinfo & kInfoRegular);
+            // ---- effective predecessor row, folded in place into the up registers ----
+            if (!(rinfo & kInfoRegular)) {
+                const bool rb1 = (rinfo & (1u << kInfoNearShift)) != 0;
+                const uint32_t rs2 = saA + (uint32_t)((r - 2) & (H - 1)) * (C * 32 * 16);  // row r-2
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    if (!rb1) { upM[c] = kMinInf; upI[c][0] = upI[c][1] = upI[c][2] = kMinInf; }
+                    if (rinfo & (2u << kInfoNearShift)) max4(upM[c], upI[c], lds_128(rs2 + c * (32 * 16)));
+                }
+                if (rinfo & ((4u << kInfoNearShift) | kInfoFar)) {
+                    if (rinfo & (4u << kInfoNearShift)) {
+                        const uint32_t rs3 = saA + (uint32_t)((r - 3) & (H - 1)) * (C * 32 * 16);
+#pragma unroll
+                        for (int c = 0; c < C; ++c) max4(upM[c], upI[c], lds_128(rs3 + c * (32 * 16)));
+                    }
+                    if (rinfo & kInfoFar) {
+                        const uint32_t rp1 = Wsh.poff1[r + 1];
+#pragma unroll 1
+                        for (uint32_t a = Wsh.poff1[r]; a < rp1; ++a) {
+                            const int p = (int)Wsh.pidx1[a];
+                            if (p >= 1 && r - p <= kNear) continue;
+                            const uint32_t o = (uint32_t)Wsh.slot1[p] * rstride + (uint32_t)j0;
+#pragma unroll
+                            for (int c = 0; c < C; ++c)
+                                if (c < (int)nvalid) max4(upM[c], upI[c], rowbuf[o + c]);
+                        }
+                    }
+                }
+            }
             uint32_t rslot = 0;
             const bool rpers = (rinfo & kInfoPersist) != 0;
             if (rpers) {
                 rslot = rinfo >> kInfoSlotShift;
-                if (rslot == kInfoSlotEscape) rslot = (uint32_t)slot1[r];
+                if (rslot == kInfoSlotEscape) rslot = (uint32_t)Wsh.slot1[r];
                 rslot = rslot * rstride + (uint32_t)j0;
             }
             ColState cur[C];
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                // ---- effective predecessor row for this column ----
-                int eM = upM[c], eI[3] = {upI[c][0], upI[c][1], upI[c][2]};
-                if (rirr) {
-                    if (!(rinfo & (1u << kInfoNearShift))) { eM = kMinInf; eI[0] = eI[1] = eI[2] = kMinInf; }
-                    if (rinfo & (2u << kInfoNearShift)) max4(eM, eI, myA[(rs ^ (2 * C * 32)) + c * 32]);
-                    if (rinfo & ((4u << kInfoNearShift) | kInfoFar)) {
-                        if (rinfo & (4u << kInfoNearShift)) max4(eM, eI, myA[((r - 3) & (H - 1)) * (C * 32) + c * 32]);
-                        if ((rinfo & kInfoFar) && c < (int)nvalid) {
-                            const uint32_t rp1 = poff1[r + 1];
-#pragma unroll 1
-                            for (uint32_t a = poff1[r]; a < rp1; ++a) {
-                                const int p = (int)pidx1[a];
-                                if (p >= 1 && r - p <= kNear) continue;
-                                max4(eM, eI, rowbuf[(uint32_t)slot1[p] * rstride + (uint32_t)(j0 + c)]);
-                            }
-                        }
-                    }
-                }
-                // ---- effective predecessor column ----
+                // ---- effective predecessor column: distance 1 and 2 branch-free, the rest rarely ----
+                const ColState& d1 = (c == 0) ? S0 : cur[c > 0 ? c - 1 : 0];
+                const ColState& d2 = (c >= 2) ? cur[c >= 2 ? c - 2 : 0] : (c == 1 ? S0 : S1);
                 ColState L;
-                if (c == 0) L = S[0]; else L = cur[c - 1];
-                const uint32_t ci = cinfo[c];
-                if (!(ci & kInfoRegular)) {
-                    if (!(ci & (1u << kInfoNearShift))) { L.M = kMinInf; L.D[0] = L.D[1] = L.D[2] = kMinInf; L.E = kMinInf; }
-                    if (ci & (2u << kInfoNearShift)) {  // distance 2
-                        if (c >= 2) fold(L, cur[c - 2]); else fold(L, S[1 - c]);
-                    }
-                    if (ci & (4u << kInfoNearShift)) {  // distance 3
-                        if (c >= 3) fold(L, cur[c - 3]); else fold(L, S[2 - c]);
+                L.M = cb1[c] ? d1.M : kMinInf;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) L.D[k] = (k < P && cb1[c]) ? d1.D[k] : kMinInf;
+                L.E = cb1[c] ? d1.E : kMinInf;
+                if (cb2[c]) fold(L, d2);
+                if (crare[c]) {
+                    const uint32_t ci = cinfo[c];
+                    if (ci & (4u << kInfoNearShift)) {
+                        const ColState& d3 = (c >= 3) ? cur[0] : (c == 2 ? S0 : (c == 1 ? S1 : S2));
+                        fold(L, d3);
                     }
                     if (ci & kInfoFar) {
                         const int j = j0 + c;
-                        const uint32_t b1 = poff2[j + 1];
+                        const uint32_t b1 = Wsh.poff2[j + 1];
 #pragma unroll 1
-                        for (uint32_t b = poff2[j]; b < b1; ++b) {
-                            const int q = (int)pidx2[b];
+                        for (uint32_t b = Wsh.poff2[j]; b < b1; ++b) {
+                            const int q = (int)Wsh.pidx2[b];
                             if (q >= 1 && j - q <= kNear) continue;
-                            const uint32_t o = (uint32_t)slot2[q] * cstride + (uint32_t)r;
+                            const uint32_t o = (uint32_t)Wsh.slot2[q] * cstride + (uint32_t)r;
                             const int4 t = colbuf[o];
                             L.M = imax(L.M, t.x); L.D[0] = imax(L.D[0], t.y); L.D[1] = imax(L.D[1], t.z); L.D[2] = imax(L.D[2], t.w);
                             L.E = imax(L.E, coleff[o]);
@@ -715,20 +751,21 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
                     }
                 }
                 // ---- the cell ----
-                const int sub = (rlabel == (int)(ci & kInfoLabelMask)) ? prm.match : -prm.mismatch;
+                const int sub = (rlabel == (int)(cinfo[c] & kInfoLabelMask)) ? prm.match : -prm.mismatch;
+                const int eM = upM[c];
                 int I[3] = {kMinInf, kMinInf, kMinInf};
                 cur[c].D[0] = cur[c].D[1] = cur[c].D[2] = kMinInf;
                 int M = __viaddmax_s32(L.E, sub, kMinInf);
 #pragma unroll
                 for (int k = 0; k < P; ++k) {
-                    I[k] = __viaddmax_s32(eI[k], -prm.e[k], eM - prm.oe[k]);
+                    I[k] = __viaddmax_s32(upI[c][k], -prm.e[k], eM - prm.oe[k]);
                     cur[c].D[k] = __viaddmax_s32(L.D[k], -prm.e[k], L.M - prm.oe[k]);
                     M = __vimax3_s32(M, I[k], cur[c].D[k]);
                 }
                 cur[c].M = M;
                 cur[c].E = eM;
                 const int4 cellA = make_int4(M, I[0], I[1], I[2]);
-                myA[rs + c * 32] = cellA;
+                sts_128(rsA + c * (32 * 16), cellA);
                 if (rpers && c < (int)nvalid) rowbuf[rslot + c] = cellA;
                 if (coff[c] != 0xffffffffu) {
                     colbuf[coff[c] + (uint32_t)r] = make_int4(M, cur[c].D[0], cur[c].D[1], cur[c].D[2]);
