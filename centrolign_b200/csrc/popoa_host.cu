@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -512,12 +513,22 @@ int clb_batch_get_stats(const clb_batch* b, clb_batch_stats* out) {
 int clb_popoa_batch(int device, int32_t n_windows, const clb_graph_batch* g1, const clb_graph_batch* g2,
                     const clb_params* params, int64_t* score_out, const int64_t* aln_off, int32_t* aln_pairs,
                     uint32_t* aln_len) {
+    const bool timing = getenv("CLB_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t0 = now(), t1 = t0, t2 = t0, t3 = t0, t4 = t0;
     clb_batch* b = nullptr;
     int rc = clb_batch_create(device, n_windows, g1, g2, params, &b);
+    t1 = now();
     if (rc == CLB_OK) rc = clb_batch_upload(b);
+    t2 = now();
     if (rc == CLB_OK) rc = clb_batch_run(b);
+    t3 = now();
     if (rc == CLB_OK) rc = clb_batch_download(b, score_out, aln_off, aln_pairs, aln_len);
+    t4 = now();
     clb_batch_destroy(b);
+    if (timing)
+        fprintf(stderr, "[clb] create %.3f s, upload %.3f s, run %.3f s, download %.3f s, destroy %.3f s\n", t1 - t0, t2 - t1,
+                t3 - t2, t4 - t3, now() - t4);
     return rc;
 }
 
