@@ -230,6 +230,7 @@ def main():
     # results of the resident run (for the parity check of the CPU sample)
     scores, alns = db.download()
     scores = scores.copy()
+    st = db.stats()  # now includes the D2H byte count
     db.close()
 
     # ---- e2e: the reference-facing one-shot call with host buffers ----

@@ -15,6 +15,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -43,30 +45,110 @@ int fail(int code, const std::string& msg) {
                         std::string(#expr) + ": " + cudaGetErrorString(_e));                        \
     } while (0)
 
+// Process-wide cache of pinned-host and device blocks.  cudaHostAlloc / cudaFreeHost of the
+// multi-GB staging buffers cost seconds per call; a Stitcher calls the batch entry point once per
+// guide-tree node, so blocks are kept and reused (best fit) until clb_release_cached_memory().
+class MemCache {
+public:
+    void* host_alloc(size_t bytes, size_t* cap) {
+        bytes = round_up(bytes);
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            auto it = host_.lower_bound(bytes);
+            if (it != host_.end() && it->first <= 2 * bytes + (size_t(1) << 20)) {
+                void* p = it->second;
+                *cap = it->first;
+                host_.erase(it);
+                return p;
+            }
+        }
+        void* p = nullptr;
+        if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            trim();
+            if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        }
+        *cap = bytes;
+        return p;
+    }
+    void host_release(void* p, size_t cap) {
+        std::lock_guard<std::mutex> lk(mu_);
+        host_.emplace(cap, p);
+    }
+    void* dev_alloc(int device, size_t bytes, size_t* cap, bool any_larger) {
+        bytes = round_up(bytes);
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            auto& m = dev_[device];
+            auto it = m.lower_bound(bytes);
+            if (it != m.end() && (any_larger || it->first <= 2 * bytes + (size_t(1) << 20))) {
+                void* p = it->second;
+                *cap = it->first;
+                m.erase(it);
+                return p;
+            }
+        }
+        void* p = nullptr;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            trim();
+            if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        }
+        *cap = bytes;
+        return p;
+    }
+    void dev_release(int device, void* p, size_t cap) {
+        std::lock_guard<std::mutex> lk(mu_);
+        dev_[device].emplace(cap, p);
+    }
+    size_t dev_cached(int device) {
+        std::lock_guard<std::mutex> lk(mu_);
+        size_t t = 0;
+        for (auto& kv : dev_[device]) t += kv.first;
+        return t;
+    }
+    void trim() {
+        std::lock_guard<std::mutex> lk(mu_);
+        for (auto& kv : host_) cudaFreeHost(kv.second);
+        host_.clear();
+        int cur = 0;
+        cudaGetDevice(&cur);
+        for (auto& d : dev_) {
+            cudaSetDevice(d.first);
+            for (auto& kv : d.second) cudaFree(kv.second);
+            d.second.clear();
+        }
+        cudaSetDevice(cur);
+    }
+
+private:
+    static size_t round_up(size_t b) { return (std::max<size_t>(b, 1) + 4095) & ~size_t(4095); }
+    std::mutex mu_;
+    std::multimap<size_t, void*> host_;
+    std::map<int, std::multimap<size_t, void*>> dev_;
+};
+MemCache g_cache;
+
 template <class T>
-struct Pinned {  // pinned host + device twin
+struct Pinned {  // pinned host + device twin, both drawn from the cache
     T* h = nullptr;
     T* d = nullptr;
-    size_t n = 0;
+    size_t n = 0, cap_h = 0, cap_d = 0;
+    int dev = 0;
     int alloc_host(size_t count) {
         n = count;
-        if (cudaHostAlloc((void**)&h, std::max<size_t>(1, count) * sizeof(T), cudaHostAllocDefault) != cudaSuccess) {
-            h = nullptr;
-            return CLB_ENOMEM;
-        }
-        return CLB_OK;
+        h = (T*)g_cache.host_alloc(count * sizeof(T), &cap_h);
+        return h ? CLB_OK : CLB_ENOMEM;
     }
-    int alloc_dev() {
-        if (cudaMalloc((void**)&d, std::max<size_t>(1, n) * sizeof(T)) != cudaSuccess) {
-            d = nullptr;
-            return CLB_ENOMEM;
-        }
-        return CLB_OK;
+    int alloc_dev(int device) {
+        dev = device;
+        d = (T*)g_cache.dev_alloc(device, n * sizeof(T), &cap_d, false);
+        return d ? CLB_OK : CLB_ENOMEM;
     }
     size_t bytes() const { return n * sizeof(T); }
     void release() {
-        if (h) cudaFreeHost(h);
-        if (d) cudaFree(d);
+        if (h) g_cache.host_release(h, cap_h);
+        if (d) g_cache.dev_release(dev, d, cap_d);
         h = d = nullptr;
     }
 };
@@ -94,6 +176,7 @@ struct clb_batch {
     Pinned<uint32_t> aln_len;
     int32_t* d_queue = nullptr;
     char* d_workspace = nullptr;
+    size_t workspace_cap = 0;
     int64_t slot_bytes = 0;
     int grid = 0;
     cudaStream_t stream = nullptr;
@@ -247,8 +330,8 @@ void clb_batch_destroy(clb_batch* b) {
     cudaSetDevice(b->device);
     for (auto& s : b->s) s.release();
     b->meta.release(); b->order.release(); b->score.release(); b->aln.release(); b->aln_len.release();
-    if (b->d_queue) cudaFree(b->d_queue);
-    if (b->d_workspace) cudaFree(b->d_workspace);
+    if (b->d_queue) g_cache.dev_release(b->device, b->d_queue, 4096);
+    if (b->d_workspace) g_cache.dev_release(b->device, b->d_workspace, b->workspace_cap);
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
     if (b->stream) cudaStreamDestroy(b->stream);
@@ -309,6 +392,7 @@ int clb_batch_create(int device, int32_t n_windows, const clb_graph_batch* g1, c
     b->out_off[nw] = tot_pairs;
 
     // multi-threaded flatten
+    const double t_alloc_done = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
     std::atomic<int64_t> next(0);
     std::atomic<int> status(CLB_OK);
     std::atomic<int64_t> bad_window(-1);
@@ -353,6 +437,9 @@ int clb_batch_create(int device, int32_t n_windows, const clb_graph_batch* g1, c
         clb_batch_destroy(b);
         return fail(r, std::string(r == CLB_ECYCLE ? "cyclic graph" : "malformed graph") + " in window " + std::to_string(bw));
     }
+    if (getenv("CLB_TIMING"))
+        fprintf(stderr, "[clb] create: flatten %.3f s on %u threads\n",
+                std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count() - t_alloc_done, nthreads);
     b->stats.cells = 0;
     b->stats.int_ops = 0;
     for (unsigned t = 0; t < nthreads; ++t) { b->stats.cells += cells_part[t]; b->stats.int_ops += ops_part[t]; }
@@ -399,7 +486,7 @@ int clb_batch_upload(clb_batch* b) {
     int64_t h2d = 0;
 #define UP(P_)                                                                                               \
     do {                                                                                                     \
-        if ((P_).alloc_dev() != CLB_OK) return fail(CLB_ENOMEM, "device allocation failed (" #P_ ")");       \
+        if ((P_).alloc_dev(b->device) != CLB_OK) return fail(CLB_ENOMEM, "device allocation failed (" #P_ ")");       \
         if ((P_).n) CUDA_TRY(cudaMemcpyAsync((P_).d, (P_).h, (P_).bytes(), cudaMemcpyHostToDevice, b->stream)); \
         h2d += (int64_t)(P_).bytes();                                                                        \
     } while (0)
@@ -409,12 +496,15 @@ int clb_batch_upload(clb_batch* b) {
     UP(b->meta);
     UP(b->order);
 #undef UP
-    if (b->score.alloc_dev() || b->aln.alloc_dev() || b->aln_len.alloc_dev())
+    if (b->score.alloc_dev(b->device) || b->aln.alloc_dev(b->device) || b->aln_len.alloc_dev(b->device))
         return fail(CLB_ENOMEM, "device allocation failed (outputs)");
-    CUDA_TRY(cudaMalloc((void**)&b->d_queue, sizeof(int32_t)));
+    size_t qcap = 0;
+    b->d_queue = (int32_t*)g_cache.dev_alloc(b->device, sizeof(int32_t), &qcap, false);
+    if (!b->d_queue) return fail(CLB_ENOMEM, "device allocation failed (queue)");
     // one workspace slot per persistent CTA; shrink the grid if memory is short
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    free_b += g_cache.dev_cached(b->device);  // cached blocks are reusable (or trimmed on demand)
     int grid = std::max(1, std::min<int>(b->nw, prop.multiProcessorCount));
     const int64_t budget = (int64_t)(free_b * 0.92);
     if (b->slot_bytes > budget) return fail(CLB_ENOMEM, "a single window's workspace exceeds device memory");
@@ -422,7 +512,8 @@ int clb_batch_upload(clb_batch* b) {
     if (2 * b->slot_bytes > budget) return fail(CLB_ENOMEM, "a single window's workspace exceeds device memory");
     grid = (int)std::min<int64_t>(grid, budget / (2 * b->slot_bytes));
     b->grid = std::max(1, grid);
-    CUDA_TRY(cudaMalloc((void**)&b->d_workspace, (size_t)b->grid * 2 * b->slot_bytes));
+    b->d_workspace = (char*)g_cache.dev_alloc(b->device, (size_t)b->grid * 2 * b->slot_bytes, &b->workspace_cap, true);
+    if (!b->d_workspace) return fail(CLB_ENOMEM, "device allocation failed (workspace)");
     CUDA_TRY(cudaStreamSynchronize(b->stream));
     b->stats.h2d_bytes = h2d;
     b->stats.workspace_bytes = (int64_t)b->grid * 2 * b->slot_bytes;
@@ -485,7 +576,7 @@ int clb_batch_download(clb_batch* b, int64_t* score_out, const int64_t* aln_off,
     b->stats.d2h_bytes = (int64_t)(b->score.bytes() + b->aln_len.bytes() + b->aln.bytes());
     // translate topological ranks back to the caller's node ids; pairs were written backwards
     // from the end of each window's region, so they are already in forward order
-    for (int64_t w = 0; w < nw; ++w) {
+    auto translate = [&](int64_t w) {
         const clb::WindowMeta& m = b->meta.h[w];
         const uint32_t len = b->aln_len.h[w];
         const int64_t cap = b->out_off[w + 1] - b->out_off[w];
@@ -500,6 +591,23 @@ int clb_batch_download(clb_batch* b, int64_t* score_out, const int64_t* aln_off,
         }
         aln_len[w] = len;
         score_out[w] = b->score.h[w];
+    };
+    unsigned nthreads = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    if (nw < 64) nthreads = 1;
+    if (nthreads == 1) {
+        for (int64_t w = 0; w < nw; ++w) translate(w);
+    } else {
+        std::atomic<int64_t> next(0);
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < nthreads; ++t)
+            pool.emplace_back([&] {
+                for (;;) {
+                    const int64_t w0 = next.fetch_add(64);
+                    if (w0 >= nw) break;
+                    for (int64_t w = w0; w < std::min<int64_t>(nw, w0 + 64); ++w) translate(w);
+                }
+            });
+        for (auto& t : pool) t.join();
     }
     return CLB_OK;
 }
@@ -531,6 +639,8 @@ int clb_popoa_batch(int device, int32_t n_windows, const clb_graph_batch* g1, co
                 t3 - t2, t4 - t3, now() - t4);
     return rc;
 }
+
+void clb_release_cached_memory(void) { g_cache.trim(); }
 
 double clb_int32_peak_tops(int device, int use_dpx) {
     int ndev = 0;

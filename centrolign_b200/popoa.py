@@ -20,7 +20,8 @@ from .batch import AlignmentParameters, GraphSide, WindowBatch
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libcentrolign_b200.so")
 
 EXPORTS = ["clb_popoa_batch", "clb_batch_create", "clb_batch_upload", "clb_batch_run", "clb_batch_download",
-           "clb_batch_destroy", "clb_batch_get_stats", "clb_int32_peak_tops", "clb_last_error", "clb_device_count"]
+           "clb_batch_destroy", "clb_batch_get_stats", "clb_int32_peak_tops", "clb_last_error", "clb_device_count",
+           "clb_release_cached_memory"]
 ERROR_NAMES = {0: "CLB_OK", 1: "CLB_EINVAL", 2: "CLB_ECYCLE", 3: "CLB_ECUDA", 4: "CLB_ENOMEM", 5: "CLB_ESTATE"}
 
 
@@ -78,6 +79,7 @@ def load_library() -> ctypes.CDLL:
     lib.clb_int32_peak_tops.argtypes = [ctypes.c_int, ctypes.c_int]
     lib.clb_last_error.restype = ctypes.c_char_p
     lib.clb_device_count.restype = ctypes.c_int
+    lib.clb_release_cached_memory.restype = None
     _lib = lib
     return lib
 

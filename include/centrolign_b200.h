@@ -122,6 +122,9 @@ int clb_batch_get_stats(const clb_batch* b, clb_batch_stats* out);
  * returns achieved 10^12 INT32 lane-ops per second on `device`, <0 on error. */
 double clb_int32_peak_tops(int device, int use_dpx);
 
+/* Staging buffers (pinned host, device) are cached across calls; this frees the cache. */
+void clb_release_cached_memory(void);
+
 const char* clb_last_error(void);
 int clb_device_count(void);
 
