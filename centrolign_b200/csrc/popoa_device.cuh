@@ -67,6 +67,7 @@ struct LaunchArgs {
     uint32_t* aln_len;      // [n_windows]
     Params prm;
     int debug_flags;        // bit0: skip the traceback walk (profiling the fill alone; results are then invalid)
+    int start_lag;          // rows a strip stays behind its left neighbour when it starts
 };
 
 // Workspace of one window: rowbuf {M,I_k} + colbuf {M,D_k} + boundary row + boundary column (16 B per

@@ -545,6 +545,7 @@ int clb_batch_run(clb_batch* b) {
             a.prm.e[k] = k < b->params.num_pw ? (int)b->params.gap_extend[k] : 0;
         }
         a.debug_flags = getenv("CLB_DEBUG_FLAGS") ? atoi(getenv("CLB_DEBUG_FLAGS")) : 0;
+        a.start_lag = getenv("CLB_START_LAG") ? atoi(getenv("CLB_START_LAG")) : 64;
         CUDA_TRY(clb::launch_popoa(b->params.num_pw, a, b->grid, b->stream));
         b->stats.kernel_launches = 1;
     }

@@ -247,7 +247,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 // per-fill-warp shared memory
-constexpr int kStartLag = 192;  // rows a strip stays behind its left neighbour (lane 31 of it)
+// (the start lag between neighbouring strips is a launch parameter, LaunchArgs::start_lag; 64 rows measured best)
 constexpr int kFillRing = 4;    // ring rows: a row is read at most kNear steps after it was written
 struct __align__(16) FillSmem {
     int4 ringA[kFillRing * 32];  // {M, I_k} of the last rows, own column
@@ -274,7 +274,7 @@ __device__ __forceinline__ int4 boundary_cell(uint32_t depth, const Params& prm)
 // ------------------------------------------------------------------------------------------
 template <int P>
 __device__ __forceinline__ void fill_strip(const Win& Wsh, const Params& prm, const int cs, const int g, FillSmem& sm,
-                                           volatile unsigned long long* progress, const int lane) {
+                                           volatile unsigned long long* progress, const int lane, const int start_lag) {
     constexpr int H = kFillRing;
     const int C0 = 1 + kStrip * cs;
     const int n1 = Wsh.n1, n2 = Wsh.n2;
@@ -363,7 +363,7 @@ __device__ __forceinline__ void fill_strip(const Win& Wsh, const Params& prm, co
     };
     // Start well behind the producer strip: the lag set here persists (all strips advance at the same
     // rate), and the slack absorbs scheduling jitter so the per-block waits below rarely spin.
-    wait_rows(min(max(kStartLag, 32), n1));
+    wait_rows(min(max(start_lag, 32), n1));
     prefetch_block(0);
     cp_async_wait_all();
     __syncwarp();
@@ -528,7 +528,8 @@ struct ColState {  // what a column offers to the columns right of it, for the c
 
 template <int P>
 __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& prm, const int cs, const int g,
-                                                FillSmemWide& sm, volatile unsigned long long* progress, const int lane) {
+                                                FillSmemWide& sm, volatile unsigned long long* progress, const int lane,
+                                                const int start_lag) {
     constexpr int H = kFillRing, C = kWideCols, W = 32 * C, PB = 16;  // PB = rows per left-column prefetch block
     const int C0 = 1 + W * cs;
     const int n1 = Wsh.n1, n2 = Wsh.n2;
@@ -614,7 +615,7 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
         }
         cp_async_commit();
     };
-    wait_rows(min(max(kStartLag, PB), n1));
+    wait_rows(min(max(start_lag, PB), n1));
     prefetch_block(0);
     cp_async_wait_all();
     __syncwarp();
@@ -1243,8 +1244,8 @@ __global__ void __launch_bounds__(kThreads, 1) popoa_kernel(const LaunchArgs A) 
             const Win& W = S.win[k & 1];
             int first = (warp - G % kFillWarps + kFillWarps) % kFillWarps;  // my first strip of this window
             for (int cs = first; cs < nstrips; cs += kFillWarps) {
-                if (W.cw == kWideCols) fill_strip_wide<P>(W, prm, cs, G + cs, *reinterpret_cast<FillSmemWide*>(&sm), S.progress, lane);
-                else fill_strip<P>(W, prm, cs, G + cs, *reinterpret_cast<FillSmem*>(&sm), S.progress, lane);
+                if (W.cw == kWideCols) fill_strip_wide<P>(W, prm, cs, G + cs, *reinterpret_cast<FillSmemWide*>(&sm), S.progress, lane, A.start_lag);
+                else fill_strip<P>(W, prm, cs, G + cs, *reinterpret_cast<FillSmem*>(&sm), S.progress, lane, A.start_lag);
                 if (lane == 0) {
                     __threadfence_block();
                     atomicAdd(&S.strips_done[k & 1], 1);
