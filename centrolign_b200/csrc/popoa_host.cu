@@ -623,6 +623,15 @@ int clb_popoa_batch(int device, int32_t n_windows, const clb_graph_batch* g1, co
                     const clb_params* params, int64_t* score_out, const int64_t* aln_off, int32_t* aln_pairs,
                     uint32_t* aln_len) {
     const bool timing = getenv("CLB_TIMING") != nullptr;
+    if (getenv("CLB_COUNT_CALLS")) {  // evidence for integration tests that the GPU path really ran
+        static std::atomic<int64_t> calls(0), windows(0);
+        static std::once_flag once;
+        std::call_once(once, [] {
+            atexit([] { fprintf(stderr, "[clb] calls %lld windows %lld\n", (long long)calls.load(), (long long)windows.load()); });
+        });
+        calls += 1;
+        windows += n_windows;
+    }
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t0 = now(), t1 = t0, t2 = t0, t3 = t0, t4 = t0;
     clb_batch* b = nullptr;

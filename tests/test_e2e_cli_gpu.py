@@ -1,0 +1,34 @@
+"""End-to-end drop-in: the reference CLI, compiled from its own unmodified sources with only the include
+path changed so that Stitcher::do_alignment's po_poa call lands in libcentrolign_b200.so
+(integration/shadow/centrolign/stitcher.hpp), must print byte-identical CIGAR / GFA.  Expected md5s come
+from the unmodified CLI (tests/golden/e2e.json, written by integration/make_e2e_golden.py)."""
+import hashlib
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "oracle", "_ref", "centrolign_b200")
+GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "e2e.json")))
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.path.exists(CLI), reason="oracle/_ref/centrolign_b200 did not travel "
+                                                  "(build it with `make -C integration` where /root/reference exists)")]
+
+
+@pytest.mark.parametrize("name", sorted(GOLD))
+def test_cli_output_is_byte_identical(name, tmp_path):
+    case = GOLD[name]
+    fa = str(tmp_path / (name + ".fa"))
+    subprocess.run([sys.executable, os.path.join(ROOT, "integration", "make_hor_fasta.py"), fa] + [str(a) for a in case["fasta_args"]],
+                   check=True)
+    assert hashlib.md5(open(fa, "rb").read()).hexdigest() == case["fasta_md5"], "input generator drifted"
+    env = dict(os.environ, CLB_COUNT_CALLS="1")
+    res = subprocess.run([CLI, "-v", "0"] + case["options"] + [fa], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
+    assert res.returncode == 0, res.stderr.decode()[-2000:]
+    assert len(res.stdout) == case["output_bytes"]
+    assert hashlib.md5(res.stdout).hexdigest() == case["output_md5"], "CIGAR/GFA differs from the unmodified reference"
+    calls = [l for l in res.stderr.decode().splitlines() if l.startswith("[clb] calls")]
+    assert calls and int(calls[-1].split()[2]) > 0, "the GPU gap fill was never called"
