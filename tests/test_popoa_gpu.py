@@ -177,3 +177,21 @@ def assert_valid_and_rescore(batch, w, p, score, aln):
     if run:
         total -= gap_cost(run)
     assert total == score
+
+
+def test_repeated_runs_are_identical_and_valid():
+    """The fill warps of a CTA stream over windows and synchronise through progress words; any race
+    would show up as run-to-run differences.  Re-run a mixed batch (narrow + wide strips, several
+    windows per CTA) and demand identical bytes, plus the size-independent validity check."""
+    batch = concat_batches([
+        synth_windows(300, first_index=5000, seed=8, len_min=100, len_max=1200),
+        synth_windows(40, first_index=6000, seed=8, len_min=1500, len_max=2500),
+    ])
+    ref_s, ref_a = po_poa_batch(batch, PROD)
+    ref_s = ref_s.copy()
+    for _ in range(2):
+        s, a = po_poa_batch(batch, PROD)
+        assert np.array_equal(s, ref_s)
+        assert all(np.array_equal(x, y) for x, y in zip(a, ref_a))
+    for w in range(0, batch.n_windows, 17):
+        assert_valid_and_rescore(batch, w, PROD, int(ref_s[w]), ref_a[w])
