@@ -639,6 +639,16 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
         crare[c] = (cinfo[c] & ((4u << kInfoNearShift) | kInfoFar)) != 0;
     }
 
+    // warp-uniform: does any column of this strip have a distance-3 or far predecessor / a persisted column 0..2?
+    bool lane_rare = false, lane_pers012 = false;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        lane_rare |= crare[c];
+        if (c < C - 1) lane_pers012 |= coff[c] != 0xffffffffu;
+    }
+    const bool strip_rare = __any_sync(kFull, lane_rare);
+    const bool strip_pers012 = __any_sync(kFull, lane_pers012);
+
     auto shfl_col = [&](const ColState& v) {
         ColState o;
         o.M = __shfl_up_sync(kFull, v.M, 1);
@@ -712,13 +722,6 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
                     }
                 }
             }
-            uint32_t rslot = 0;
-            const bool rpers = (rinfo & kInfoPersist) != 0;
-            if (rpers) {
-                rslot = rinfo >> kInfoSlotShift;
-                if (rslot == kInfoSlotEscape) rslot = (uint32_t)Wsh.slot1[r];
-                rslot = rslot * rstride + (uint32_t)j0;
-            }
             ColState cur[C];
 #pragma unroll
             for (int c = 0; c < C; ++c) {
@@ -731,7 +734,7 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
                 for (int k = 0; k < 3; ++k) L.D[k] = (k < P && cb1[c]) ? d1.D[k] : kMinInf;
                 L.E = cb1[c] ? d1.E : kMinInf;
                 if (cb2[c]) fold(L, d2);
-                if (crare[c]) {
+                if (strip_rare && crare[c]) {
                     const uint32_t ci = cinfo[c];
                     if (ci & (4u << kInfoNearShift)) {
                         const ColState& d3 = (c >= 3) ? cur[0] : (c == 2 ? S0 : (c == 1 ? S1 : S2));
@@ -767,12 +770,19 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
                 cur[c].E = eM;
                 const int4 cellA = make_int4(M, I[0], I[1], I[2]);
                 sts_128(rsA + c * (32 * 16), cellA);
-                if (rpers && c < (int)nvalid) rowbuf[rslot + c] = cellA;
-                if (coff[c] != 0xffffffffu) {
+                if ((c == C - 1 || strip_pers012) && coff[c] != 0xffffffffu) {
                     colbuf[coff[c] + (uint32_t)r] = make_int4(M, cur[c].D[0], cur[c].D[1], cur[c].D[2]);
                     coleff[coff[c] + (uint32_t)r] = eM;
                 }
                 upM[c] = M; upI[c][0] = I[0]; upI[c][1] = I[1]; upI[c][2] = I[2];
+            }
+            if (rinfo & kInfoPersist) {  // persisted row: the new row is in the up registers
+                uint32_t rslot = rinfo >> kInfoSlotShift;
+                if (rslot == kInfoSlotEscape) rslot = (uint32_t)Wsh.slot1[r];
+                rslot = rslot * rstride + (uint32_t)j0;
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+                    if (c < (int)nvalid) rowbuf[rslot + c] = make_int4(upM[c], upI[c][0], upI[c][1], upI[c][2]);
             }
 #pragma unroll
             for (int c = 0; c < C; ++c) out[c] = cur[c];
