@@ -10,19 +10,21 @@
 // element-wise max and then applies the single-predecessor update: identical values, and the
 // common case (one predecessor = previous index) never leaves registers.
 //
-// Execution model.  One CTA per window (persistent CTAs pull windows, largest first, from an
-// atomic queue).  The matrix is cut into strips of 32 columns; a warp sweeps a strip top to
-// bottom as a skewed wavefront (lane t is on row r-t), neighbours exchange M / D_k / diagonal
-// through warp shuffles, and the warps of the CTA pipeline over consecutive strips, the hand-off
-// being the last column of a strip, published through the window workspace with a
-// fence + progress word in shared memory.  DPX instructions (__viaddmax_s32, __vimax3_s32) carry
+// Execution model.  One CTA per window at a time (persistent CTAs pull windows, largest first, from
+// an atomic queue): 11 fill warps + 1 traceback warp.  The matrix is cut into strips of 128 columns
+// (32 for narrow windows); a warp sweeps a strip top to bottom as a skewed wavefront (lane t is on
+// row r-t, 4 columns per lane), the row above lives in registers, neighbour columns arrive by warp
+// shuffles, and the warps pipeline over consecutive strips -- the hand-off being the last column of
+// a strip, published through the window workspace with a fence + progress word in shared memory and
+// prefetched by the consumer with cp.async.  DPX instructions (__viaddmax_s32, __vimax3_s32) carry
 // the three-piece affine recurrences.  No tensor cores: this is integer max-plus, not a GEMM.
 //
 // Traceback does not store the matrix.  The fill keeps only "persisted" rows {M,I_k} and
 // columns {M,D_k}: every 64th row / 32nd column plus any row / column that has a far successor.
-// The traceback warp re-computes the 64x32 tile the path is in (same strip routine, all cells
-// kept in shared memory) and applies the reference's own tests (alignment.hpp:1036-1138) to
-// the real cell values, so tie-breaking is the reference's by construction.
+// The traceback warp re-computes the 64x32 tile the path is in (tile_strip, all cells kept in
+// shared memory) and applies the reference's own tests (alignment.hpp:1036-1138) to the real cell
+// values, so tie-breaking is the reference's by construction.  It runs concurrently with the fill
+// of the next window (two workspace slots per CTA).
 #include <cuda_runtime.h>
 #include <limits.h>
 
@@ -60,163 +62,6 @@ __device__ __forceinline__ void max4(int& m, int (&v)[3], const int4 a) {
     v[0] = imax(v[0], a.y);
     v[1] = imax(v[1], a.z);
     v[2] = imax(v[2], a.w);
-}
-
-// ------------------------------------------------------------------------------------------
-// One strip (32 columns starting at C0) over rows R0..R1 as a skewed warp wavefront.
-//   TILE=false : DP fill. Ring of H rows in shared memory serves near predecessors; persisted
-//                rows / columns go to the window workspace; the last lane publishes progress.
-//   TILE=true  : traceback tile. H = kRowBlock, every cell of the tile stays in shared memory.
-// ------------------------------------------------------------------------------------------
-template <int P, int H, bool TILE>
-__device__ __forceinline__ void process_strip(const Win& Wsh, const Params& prm, const int C0, const int R0,
-                                              const int R1, int4* __restrict__ ringA, int4* __restrict__ ringB,
-                                              volatile unsigned long long* progress, const int cs, const int lane) {
-    const int n1 = Wsh.n1, n2 = Wsh.n2;
-    const uint32_t* __restrict__ info1 = Wsh.info1;
-    const int32_t* __restrict__ slot1 = Wsh.slot1;
-    const uint32_t* __restrict__ poff1 = Wsh.poff1;
-    const uint32_t* __restrict__ pidx1 = Wsh.pidx1;
-    const int32_t* __restrict__ slot2 = Wsh.slot2;
-    const uint32_t* __restrict__ pidx2 = Wsh.pidx2;
-    int4* rowbuf = Wsh.rowbuf;
-    int4* colbuf = Wsh.colbuf;
-    const int64_t rstride = (int64_t)n2 + 1, cstride = (int64_t)n1 + 1;
-
-    const int j = C0 + lane;
-    const bool jvalid = j <= n2;
-    const uint32_t cinfo = jvalid ? Wsh.info2[j] : 0u;
-    const int clabel = (int)(cinfo & kInfoLabelMask);
-    const bool creg = (cinfo & kInfoRegular) != 0;
-    const int cslot = (cinfo & kInfoPersist) ? slot2[j] : -1;
-    const uint32_t cp0 = jvalid ? Wsh.poff2[j] : 0u, cp1 = jvalid ? Wsh.poff2[j + 1] : 0u;
-    const int4* leftcol = nullptr;  // persisted column C0-1 (lane 0 only)
-    if (lane == 0) {
-        const int ls = slot2[C0 - 1];
-        if (ls >= 0) leftcol = colbuf + (int64_t)ls * cstride;
-    }
-    int4* mycol = cslot >= 0 ? colbuf + (int64_t)cslot * cstride : nullptr;
-
-    int upM = kMinInf, upI[3] = {kMinInf, kMinInf, kMinInf};
-    if (jvalid) {
-        const int s0 = slot1[R0 - 1];
-        if (s0 >= 0) {
-            const int4 a = rowbuf[(int64_t)s0 * rstride + j];
-            upM = a.x; upI[0] = a.y; upI[1] = a.z; upI[2] = a.w;
-        }
-    }
-    int outM = kMinInf, outD[3] = {kMinInf, kMinInf, kMinInf}, outEff = kMinInf;
-    int avail = (TILE || cs == 0) ? INT_MAX : 0;
-    const int nsteps = (R1 - R0 + 1) + 31;
-
-    for (int s = 0; s < nsteps; ++s) {
-        const int r = R0 + s - lane;
-        const bool active = jvalid && r >= R0 && r <= R1;
-        if (!TILE) {
-            const int need = min(R0 + s, R1);
-            if (avail < need) {
-                do {
-                    const unsigned long long v = progress[(cs - 1) & 63];
-                    avail = ((int)(v >> 32) == cs) ? (int)(v & 0xffffffffu) : 0;
-                } while (avail < need);
-                __threadfence_block();
-            }
-        }
-        int lM = __shfl_up_sync(kFull, outM, 1);
-        int lD[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) lD[k] = (k < P) ? __shfl_up_sync(kFull, outD[k], 1) : kMinInf;
-        int lEff = __shfl_up_sync(kFull, outEff, 1);
-
-        if (active) {
-            const uint32_t rinfo = info1[r];
-            const int rlabel = (int)(rinfo & kInfoLabelMask);
-            const bool rreg = (rinfo & kInfoRegular) != 0;
-            uint32_t rp0 = 0, rp1 = 0;
-            if (!rreg) { rp0 = poff1[r]; rp1 = poff1[r + 1]; }
-
-            // ---- effective predecessor row (same column) ----
-            int eM, eI[3];
-            if (rreg) {
-                eM = upM; eI[0] = upI[0]; eI[1] = upI[1]; eI[2] = upI[2];
-            } else {
-                eM = kMinInf; eI[0] = eI[1] = eI[2] = kMinInf;
-                for (uint32_t a = rp0; a < rp1; ++a) {
-                    const int p = (int)pidx1[a];
-                    const bool pin = TILE ? (p >= R0) : (p >= 1 && r - p <= kNear);
-                    const int4 v = pin ? ringA[(p & (H - 1)) * 32 + lane] : rowbuf[(int64_t)slot1[p] * rstride + j];
-                    max4(eM, eI, v);
-                }
-            }
-            // ---- effective predecessor column (same row) and diagonal ----
-            if (creg) {
-                if (lane == 0) {
-                    const int4 b = leftcol[r];
-                    lM = b.x; lD[0] = b.y; lD[1] = b.z; lD[2] = b.w;
-                    if (rreg) {
-                        lEff = leftcol[r - 1].x;
-                    } else {
-                        lEff = kMinInf;
-                        for (uint32_t a = rp0; a < rp1; ++a) lEff = imax(lEff, leftcol[pidx1[a]].x);
-                    }
-                }
-            } else {
-                lM = kMinInf; lD[0] = lD[1] = lD[2] = kMinInf; lEff = kMinInf;
-                for (uint32_t b = cp0; b < cp1; ++b) {
-                    const int q = (int)pidx2[b];
-                    const bool qin = (q >= C0) && (TILE || j - q <= kNear);
-                    const int4* colp = nullptr;
-                    int4 v;
-                    if (qin) {
-                        v = ringB[(r & (H - 1)) * 32 + (q - C0)];
-                    } else {
-                        colp = colbuf + (int64_t)slot2[q] * cstride;
-                        v = colp[r];
-                    }
-                    max4(lM, lD, v);
-                    // diagonal: max over predecessor rows p of M(p,q)
-                    const uint32_t a0 = rreg ? 0u : rp0, a1 = rreg ? 1u : rp1;
-                    for (uint32_t a = a0; a < a1; ++a) {
-                        const int p = rreg ? r - 1 : (int)pidx1[a];
-                        int m;
-                        if (!qin) {
-                            m = colp[p].x;
-                        } else {
-                            const bool pin = TILE ? (p >= R0) : (p >= 1 && r - p <= kNear);
-                            m = pin ? ringA[(p & (H - 1)) * 32 + (q - C0)].x : rowbuf[(int64_t)slot1[p] * rstride + q].x;
-                        }
-                        lEff = imax(lEff, m);
-                    }
-                }
-            }
-            // ---- the cell ----
-            const int sub = (rlabel == clabel) ? prm.match : -prm.mismatch;
-            int I[3] = {kMinInf, kMinInf, kMinInf}, D[3] = {kMinInf, kMinInf, kMinInf};
-            int M = __viaddmax_s32(lEff, sub, kMinInf);
-#pragma unroll
-            for (int k = 0; k < P; ++k) {
-                I[k] = __viaddmax_s32(eI[k], -prm.e[k], eM - prm.oe[k]);
-                D[k] = __viaddmax_s32(lD[k], -prm.e[k], lM - prm.oe[k]);
-                M = __vimax3_s32(M, I[k], D[k]);
-            }
-            const int4 cellA = make_int4(M, I[0], I[1], I[2]);
-            const int4 cellB = make_int4(M, D[0], D[1], D[2]);
-            ringA[(r & (H - 1)) * 32 + lane] = cellA;
-            ringB[(r & (H - 1)) * 32 + lane] = cellB;
-            if (!TILE) {
-                if (rinfo & kInfoPersist) rowbuf[(int64_t)slot1[r] * rstride + j] = cellA;
-                if (mycol) mycol[r] = cellB;
-            }
-            upM = M; upI[0] = I[0]; upI[1] = I[1]; upI[2] = I[2];
-            outM = M; outD[0] = D[0]; outD[1] = D[1]; outD[2] = D[2];
-            outEff = eM;
-        }
-        __syncwarp();
-        if (!TILE && lane == 31 && active && ((r & 3) == 0 || r == R1)) {
-            __threadfence_block();
-            progress[cs & 63] = ((unsigned long long)(cs + 1) << 32) | (unsigned)r;
-        }
-    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -625,9 +470,13 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
     for (int c = 0; c < C; ++c) { out[c].M = kMinInf; out[c].D[0] = out[c].D[1] = out[c].D[2] = kMinInf; out[c].E = kMinInf; }
     uint32_t rinfo_next = (lane == 0) ? info1[1] : 0u;
     // explicit 32-bit shared-window addresses: keeps ptxas from re-deriving them every step
-    const uint32_t saA = (uint32_t)__cvta_generic_to_shared(sm.ringA) + (uint32_t)lane * 16u;
-    const uint32_t saLv = (uint32_t)__cvta_generic_to_shared(&sm.leftv[0][0][0]);
-    const uint32_t saLe = (uint32_t)__cvta_generic_to_shared(&sm.lefte[0][0][0]);
+    uint32_t saA = (uint32_t)__cvta_generic_to_shared(sm.ringA) + (uint32_t)lane * 16u;
+    uint32_t saLv = (uint32_t)__cvta_generic_to_shared(&sm.leftv[0][0][0]);
+    uint32_t saLe = (uint32_t)__cvta_generic_to_shared(&sm.lefte[0][0][0]);
+    // opaque copies: stops ptxas from re-deriving the addresses (S2R + LEA + IMAD) inside the row loop
+    asm volatile("mov.u32 %0, %0;" : "+r"(saA));
+    asm volatile("mov.u32 %0, %0;" : "+r"(saLv));
+    asm volatile("mov.u32 %0, %0;" : "+r"(saLe));
     // per-column constant predicates
     bool cb1[C], cb2[C], crare[C];
 #pragma unroll
