@@ -1,0 +1,119 @@
+// stitch_recorder.hpp -- turns the reference's serial gap-fill loop into ONE batched GPU call.
+//
+// Stitcher::stitch (reference: include/centrolign/stitcher.hpp:104-206) calls po_poa once per
+// inter-anchor window and never looks at the result again: subalign() translates it to parent node ids
+// (src/stitcher.cpp:66) and appends it to the stitched alignment (:75-77).  So while the reference's
+// loop runs unchanged, the redirected po_poa call only RECORDS the window and hands back a one-pair
+// marker (gap, gap) -- a pair the reference never produces -- and the redirected translate() call notes
+// the window's back-translation tables.  When the loop is done, all recorded windows go to the GPU in
+// one clb_popoa_batch per NumPW, and every marker is replaced, in order, by the translated alignment of
+// its window.  Routing, gap-piece truncation, anchor copies and every non-po_poa route are the
+// reference's own code, executed as is.
+#ifndef CENTROLIGN_B200_STITCH_RECORDER_HPP
+#define CENTROLIGN_B200_STITCH_RECORDER_HPP
+
+#include <cstdint>
+#include <utility>
+#include <vector>
+
+#include "po_poa_b200.hpp"
+
+namespace centrolign_b200 {
+
+template <class AlignmentT>
+class StitchRecorder {
+public:
+    typedef typename AlignmentT::value_type Pair;
+
+    static StitchRecorder& instance() {
+        static thread_local StitchRecorder rec;
+        return rec;
+    }
+
+    bool active() const { return active_; }
+
+    void begin() {
+        active_ = true;
+        for (int k = 0; k < CLB_MAX_PW; ++k) {
+            batch_[k] = PoPoaBatch();
+            have_params_[k] = false;
+        }
+        windows_.clear();
+        translations_.clear();
+    }
+
+    // the redirected po_poa call: remember the window, return the marker
+    template <int NumPW, class Graph, class Params>
+    AlignmentT record(const Graph& graph1, const Graph& graph2, const std::vector<uint64_t>& sources1,
+                      const std::vector<uint64_t>& sources2, const std::vector<uint64_t>& sinks1,
+                      const std::vector<uint64_t>& sinks2, const Params& params) {
+        windows_.push_back(std::make_pair(NumPW, batch_[NumPW - 1].size()));
+        batch_[NumPW - 1].add(graph1, graph2, sources1, sources2, sinks1, sinks2);
+        if (!have_params_[NumPW - 1]) {
+            have_params_[NumPW - 1] = true;
+            params_[NumPW - 1].match = params.match;
+            params_[NumPW - 1].mismatch = params.mismatch;
+            for (int k = 0; k < NumPW; ++k) {
+                params_[NumPW - 1].gap_open[k] = params.gap_open[k];
+                params_[NumPW - 1].gap_extend[k] = params.gap_extend[k];
+            }
+        }
+        AlignmentT marker;
+        marker.push_back(Pair(uint64_t(-1), uint64_t(-1)));
+        return marker;
+    }
+
+    // the redirected translate call: true if `aln` is the marker of the window recorded last
+    bool note_translation(const AlignmentT& aln, const std::vector<uint64_t>& back_translation1,
+                          const std::vector<uint64_t>& back_translation2) {
+        if (!active_ || !is_marker(aln) || translations_.size() >= windows_.size()) return false;
+        translations_.push_back(std::make_pair(back_translation1, back_translation2));
+        return true;
+    }
+
+    // run the batches and splice the results over the markers
+    AlignmentT finish(AlignmentT&& stitched) {
+        active_ = false;
+        if (windows_.empty()) return std::move(stitched);
+        std::vector<AlignmentT> out[CLB_MAX_PW];
+        if (batch_[0].size()) batch_[0].template align<1, GenericParams, AlignmentT>(params_[0], out[0]);
+        if (batch_[1].size()) batch_[1].template align<2, GenericParams, AlignmentT>(params_[1], out[1]);
+        if (batch_[2].size()) batch_[2].template align<3, GenericParams, AlignmentT>(params_[2], out[2]);
+        AlignmentT result;
+        result.reserve(stitched.size());
+        size_t w = 0;
+        for (const Pair& p : stitched) {
+            if (p.node_id1 == uint64_t(-1) && p.node_id2 == uint64_t(-1)) {
+                const AlignmentT& sub = out[windows_[w].first - 1][windows_[w].second];
+                const std::vector<uint64_t>& bt1 = translations_[w].first;
+                const std::vector<uint64_t>& bt2 = translations_[w].second;
+                for (const Pair& q : sub)  // same mapping as translate(), src/alignment.cpp:26-39
+                    result.push_back(Pair(q.node_id1 == uint64_t(-1) ? q.node_id1 : bt1[q.node_id1],
+                                          q.node_id2 == uint64_t(-1) ? q.node_id2 : bt2[q.node_id2]));
+                ++w;
+            } else {
+                result.push_back(p);
+            }
+        }
+        return result;
+    }
+
+private:
+    struct GenericParams {
+        uint32_t match, mismatch, gap_open[CLB_MAX_PW], gap_extend[CLB_MAX_PW];
+    };
+    static bool is_marker(const AlignmentT& aln) {
+        return aln.size() == 1 && aln[0].node_id1 == uint64_t(-1) && aln[0].node_id2 == uint64_t(-1);
+    }
+
+    bool active_ = false;
+    PoPoaBatch batch_[CLB_MAX_PW];
+    GenericParams params_[CLB_MAX_PW];
+    bool have_params_[CLB_MAX_PW] = {false, false, false};
+    std::vector<std::pair<int, size_t>> windows_;  // (NumPW, index in that batch), in call order
+    std::vector<std::pair<std::vector<uint64_t>, std::vector<uint64_t>>> translations_;
+};
+
+}  // namespace centrolign_b200
+
+#endif

@@ -1,18 +1,32 @@
 // integration/shadow/centrolign/stitcher.hpp -- zero-edit drop-in of the B200 gap fill into the reference.
 //
-// Put `integration/shadow` BEFORE the reference's include directory on the compiler's include path.
-// Every `#include "centrolign/stitcher.hpp"` then lands here first; this file pulls in the untouched
-// reference header with #include_next, but while that header is being read the identifier `po_poa`
-// is redirected to `po_poa_b200` below.  The only use of `po_poa` in that header is the gap-fill call
-// in Stitcher::do_alignment (reference: include/centrolign/stitcher.hpp:297-299), so that one call --
-// and nothing else in the reference -- goes to the GPU.  alignment.hpp is included beforehand, so the
-// reference's own po_poa definition is not renamed.
+// Put `integration/shadow` BEFORE the reference's include directory on the include path of the four
+// translation units that see stitcher.hpp (stitcher.cpp, core.cpp, parameters.cpp, main.cpp).  Every
+// `#include "centrolign/stitcher.hpp"` then lands here first.  This file reads the untouched reference
+// header with #include_next, with two identifiers redirected while it is being read:
+//   * `Stitcher` -> `StitcherReference`: the reference class, whole and unchanged, under another name;
+//   * `po_poa`   -> `po_poa_b200`: the one use of po_poa in that header is the gap-fill call in
+//     Stitcher::do_alignment (reference: include/centrolign/stitcher.hpp:297-299).
+// `centrolign::Stitcher` is then a thin subclass whose stitch() / internal_stitch() run the reference's
+// own loop in recording mode and finish with one batched GPU call (centrolign_b200/hostcpp/
+// stitch_recorder.hpp).  In stitcher.cpp itself (compiled with -DCLB_SHADOW_STITCHER_TU) the member
+// definitions must land on the reference class and its translate() call is hooked, so this header ends by
+// redirecting `Stitcher` and `translate` for the rest of that one translation unit.
 #ifndef CENTROLIGN_B200_SHADOW_STITCHER_HPP
 #define CENTROLIGN_B200_SHADOW_STITCHER_HPP
 
+// everything the reference's stitcher.hpp includes, read first so the redirections cannot touch it
+#include "centrolign/chain_merge.hpp"
 #include "centrolign/alignment.hpp"
 #include "centrolign/graph.hpp"
-#include "po_poa_b200.hpp"
+#include "centrolign/topological_order.hpp"
+#include "centrolign/step_index.hpp"
+#include "centrolign/anchorer.hpp"
+#include "centrolign/subgraph_extraction.hpp"
+#include "centrolign/logging.hpp"
+#include "centrolign/partition_client.hpp"
+
+#include "stitch_recorder.hpp"
 
 namespace centrolign {
 
@@ -22,23 +36,60 @@ Alignment po_poa_b200(const Graph& graph1, const Graph& graph2, const std::vecto
                       const std::vector<uint64_t>& sources2, const std::vector<uint64_t>& sinks1,
                       const std::vector<uint64_t>& sinks2, const AlignmentParameters<NumPW>& params,
                       int64_t* score_out = nullptr) {
+    auto& rec = centrolign_b200::StitchRecorder<Alignment>::instance();
+    if (rec.active() && !score_out)
+        return rec.record<NumPW>(graph1, graph2, sources1, sources2, sinks1, sinks2, params);
     return centrolign_b200::po_poa<NumPW, Graph, AlignmentParameters<NumPW>, Alignment>(
         graph1, graph2, sources1, sources2, sinks1, sinks2, params, score_out);
 }
 
+// hook for the translate() call in Stitcher::subalign (src/stitcher.cpp:66)
+inline void translate_b200(Alignment& alignment, const std::vector<uint64_t>& back_translation1,
+                           const std::vector<uint64_t>& back_translation2) {
+    if (centrolign_b200::StitchRecorder<Alignment>::instance().note_translation(alignment, back_translation1, back_translation2))
+        return;  // a marker: translated when the batch result is spliced in
+    translate(alignment, back_translation1, back_translation2);
+}
+
 }  // namespace centrolign
 
-// headers the reference's stitcher.hpp includes, read now so the redirection below cannot touch them
-#include "centrolign/chain_merge.hpp"
-#include "centrolign/topological_order.hpp"
-#include "centrolign/step_index.hpp"
-#include "centrolign/anchorer.hpp"
-#include "centrolign/subgraph_extraction.hpp"
-#include "centrolign/logging.hpp"
-#include "centrolign/partition_client.hpp"
-
+#define Stitcher StitcherReference
 #define po_poa po_poa_b200
 #include_next "centrolign/stitcher.hpp"
 #undef po_poa
+#undef Stitcher
+
+namespace centrolign {
+
+class Stitcher : public StitcherReference {
+public:
+    // reference signature, include/centrolign/stitcher.hpp:34-38
+    template <class BGraph1, class BGraph2, class XMerge1, class XMerge2>
+    Alignment stitch(const std::vector<std::vector<anchor_t>>& anchor_segments, const BGraph1& graph1,
+                     const BGraph2& graph2, const SentinelTableau& tableau1, const SentinelTableau& tableau2,
+                     XMerge1& chain_merge1, XMerge2& chain_merge2) const {
+        auto& rec = centrolign_b200::StitchRecorder<Alignment>::instance();
+        rec.begin();
+        Alignment with_markers = StitcherReference::stitch(anchor_segments, graph1, graph2, tableau1, tableau2,
+                                                           chain_merge1, chain_merge2);
+        return rec.finish(std::move(with_markers));
+    }
+    // reference signature, include/centrolign/stitcher.hpp:41-43
+    template <class BGraph, class XMerge>
+    Alignment internal_stitch(const std::vector<anchor_t>& anchors, const BGraph& graph, const XMerge& xmerge) const {
+        auto& rec = centrolign_b200::StitchRecorder<Alignment>::instance();
+        rec.begin();
+        Alignment with_markers = StitcherReference::internal_stitch(anchors, graph, xmerge);
+        return rec.finish(std::move(with_markers));
+    }
+};
+
+}  // namespace centrolign
+
+#ifdef CLB_SHADOW_STITCHER_TU
+// the rest of this translation unit is src/stitcher.cpp: its member definitions belong to the reference class
+#define Stitcher StitcherReference
+#define translate translate_b200
+#endif
 
 #endif

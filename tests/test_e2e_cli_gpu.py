@@ -31,4 +31,8 @@ def test_cli_output_is_byte_identical(name, tmp_path):
     assert len(res.stdout) == case["output_bytes"]
     assert hashlib.md5(res.stdout).hexdigest() == case["output_md5"], "CIGAR/GFA differs from the unmodified reference"
     calls = [l for l in res.stderr.decode().splitlines() if l.startswith("[clb] calls")]
-    assert calls and int(calls[-1].split()[2]) > 0, "the GPU gap fill was never called"
+    assert calls, "the GPU gap fill was never called"
+    n_calls, n_windows = int(calls[-1].split()[2]), int(calls[-1].split()[4])
+    print(f"{name}: {n_windows} gap-fill windows in {n_calls} batched GPU calls")
+    # batched: one call per stitch() and NumPW, not one per window (stitch_recorder.hpp)
+    assert n_calls > 0 and n_windows >= 20 * n_calls
