@@ -195,6 +195,22 @@ def main():
     lib = load_library()
     params = AlignmentParameters()
 
+    # host-memory guard: ~0.8 MB of host RAM per window (raw arrays, pinned staging, outputs) and rank
+    try:
+        import psutil
+
+        avail = psutil.virtual_memory().available / max(1, world)
+        fit = int(avail * 0.6 / 0.8e6)
+        if fit < args.windows:
+            if rank == 0:
+                print(f"[bench] host RAM allows {fit} windows per rank, not {args.windows}: reducing", file=sys.stderr)
+            args.windows = max(1000, fit)
+    except ImportError:
+        pass
+    if use_dist:
+        t = torch.tensor([args.windows], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        args.windows = int(t.item())
     t_gen = time.perf_counter()
     batch = synth_windows(args.windows, first_index=rank * args.windows, seed=SEED, len_min=args.len_min, len_max=args.len_max,
                           snp_rate=args.snp_rate, alt_period=args.alt_period)
