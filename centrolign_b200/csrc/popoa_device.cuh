@@ -68,6 +68,7 @@ struct LaunchArgs {
     Params prm;
     int debug_flags;        // bit0: skip the traceback walk (profiling the fill alone; results are then invalid)
     int start_lag;          // rows a strip stays behind its left neighbour when it starts
+    int slot_by_smid;       // 1: workspace slot pair chosen by %smid (kernels of several chunks share one workspace)
 };
 
 // Workspace of one window: rowbuf {M,I_k} + colbuf {M,D_k} + boundary row + boundary column (16 B per

@@ -28,6 +28,7 @@ namespace clb {
 cudaError_t launch_popoa(int num_pw, const LaunchArgs& args, int grid, cudaStream_t stream);
 int popoa_smem_bytes();
 double int32_probe(int use_dpx, int sm_count);
+int popoa_nsmid();
 }  // namespace clb
 
 namespace {
@@ -184,6 +185,9 @@ struct clb_batch {
     bool uploaded = false, ran = false;
     clb_batch_stats stats{};
     std::vector<int64_t> out_off;  // pair offset per window in the device output
+    std::vector<int32_t> sel;      // caller window id of batch window k (empty = identity)
+    bool shared_workspace = false; // workspace owned by the caller of the chunked one-shot path; slots by SM id
+    int64_t max_ws_bytes = 0;      // largest single-window workspace of this batch
 };
 
 namespace {
@@ -331,15 +335,16 @@ void clb_batch_destroy(clb_batch* b) {
     for (auto& s : b->s) s.release();
     b->meta.release(); b->order.release(); b->score.release(); b->aln.release(); b->aln_len.release();
     if (b->d_queue) g_cache.dev_release(b->device, b->d_queue, 4096);
-    if (b->d_workspace) g_cache.dev_release(b->device, b->d_workspace, b->workspace_cap);
+    if (b->d_workspace && !b->shared_workspace) g_cache.dev_release(b->device, b->d_workspace, b->workspace_cap);
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
     if (b->stream) cudaStreamDestroy(b->stream);
     delete b;
 }
 
-int clb_batch_create(int device, int32_t n_windows, const clb_graph_batch* g1, const clb_graph_batch* g2,
-                     const clb_params* params, clb_batch** out) {
+// Build a batch from all `n_windows` windows (sel == nullptr) or from the `n_sel` windows listed in `sel`.
+static int create_internal(int device, int32_t n_windows, const clb_graph_batch* g1, const clb_graph_batch* g2,
+                           const clb_params* params, const int32_t* sel, int32_t n_sel, clb_batch** out) {
     if (!out) return fail(CLB_EINVAL, "out is null");
     *out = nullptr;
     if (n_windows < 0 || !params || params->num_pw < 1 || params->num_pw > CLB_MAX_PW)
@@ -353,16 +358,25 @@ int clb_batch_create(int device, int32_t n_windows, const clb_graph_batch* g1, c
 
     clb_batch* b = new clb_batch();
     b->device = device;
-    b->nw = n_windows;
+    b->nw = sel ? n_sel : n_windows;
     b->params = *params;
-    const int64_t nw = n_windows;
+    if (sel) b->sel.assign(sel, sel + n_sel);
+    const int64_t nw = b->nw;
+    auto src = [&](int64_t k) -> int64_t { return sel ? sel[k] : k; };
     const clb_graph_batch* gs[2] = {g1, g2};
     int rc = b->meta.alloc_host(nw) | b->order.alloc_host(nw) | b->score.alloc_host(nw) | b->aln_len.alloc_host(nw);
     int64_t tot_pairs = 0;
     b->out_off.assign(nw + 1, 0);
     for (int sd = 0; sd < 2 && rc == CLB_OK; ++sd) {
-        const int64_t N = nw ? gs[sd]->node_off[nw] : 0, E = nw ? gs[sd]->edge_off[nw] : 0;
-        const int64_t S = nw ? gs[sd]->src_off[nw] : 0, K = nw ? gs[sd]->snk_off[nw] : 0;
+        int64_t N = 0, E = 0, S = 0, K = 0;
+        for (int64_t k = 0; k < nw; ++k) {
+            const int64_t w = src(k);
+            if (w < 0 || w >= n_windows) { rc = CLB_EINVAL; break; }
+            N += gs[sd]->node_off[w + 1] - gs[sd]->node_off[w];
+            E += gs[sd]->edge_off[w + 1] - gs[sd]->edge_off[w];
+            S += gs[sd]->src_off[w + 1] - gs[sd]->src_off[w];
+            K += gs[sd]->snk_off[w + 1] - gs[sd]->snk_off[w];
+        }
         if (N < 0 || E < 0 || S < 0 || K < 0) rc = CLB_EINVAL;
         SideStage& st = b->s[sd];
         rc |= st.info.alloc_host(N + nw + 1) | st.slot.alloc_host(N + nw) | st.depth.alloc_host(N + nw) |  // info: +1 pad, read one past
@@ -373,23 +387,32 @@ int clb_batch_create(int device, int32_t n_windows, const clb_graph_batch* g1, c
         clb_batch_destroy(b);
         return fail(rc == CLB_EINVAL ? CLB_EINVAL : CLB_ENOMEM, "staging allocation failed");
     }
-    for (int64_t w = 0; w < nw; ++w) {
-        clb::WindowMeta& m = b->meta.h[w];
-        memset(&m, 0, sizeof(m));
-        m.node1 = g1->node_off[w] + w; m.node2 = g2->node_off[w] + w;
-        m.poff1 = g1->node_off[w] + 2 * w; m.poff2 = g2->node_off[w] + 2 * w;
-        m.pidx1 = g1->edge_off[w] + g1->src_off[w]; m.pidx2 = g2->edge_off[w] + g2->src_off[w];
-        m.snk1 = g1->snk_off[w]; m.snk2 = g2->snk_off[w];
-        const int64_t n1 = g1->node_off[w + 1] - g1->node_off[w], n2 = g2->node_off[w + 1] - g2->node_off[w];
-        if (n1 < 0 || n2 < 0 || n1 > 0x3fffffff || n2 > 0x3fffffff) {
-            clb_batch_destroy(b);
-            return fail(CLB_EINVAL, "window size out of range");
+    {
+        int64_t nb[2] = {0, 0}, eb[2] = {0, 0}, kb[2] = {0, 0};  // running node / pidx / sink bases per side
+        for (int64_t k = 0; k < nw; ++k) {
+            const int64_t w = src(k);
+            clb::WindowMeta& m = b->meta.h[k];
+            memset(&m, 0, sizeof(m));
+            m.node1 = nb[0] + k; m.node2 = nb[1] + k;
+            m.poff1 = nb[0] + 2 * k; m.poff2 = nb[1] + 2 * k;
+            m.pidx1 = eb[0]; m.pidx2 = eb[1];
+            m.snk1 = kb[0]; m.snk2 = kb[1];
+            const int64_t n1 = g1->node_off[w + 1] - g1->node_off[w], n2 = g2->node_off[w + 1] - g2->node_off[w];
+            if (n1 < 0 || n2 < 0 || n1 > 0x3fffffff || n2 > 0x3fffffff) {
+                clb_batch_destroy(b);
+                return fail(CLB_EINVAL, "window size out of range");
+            }
+            nb[0] += n1; nb[1] += n2;
+            eb[0] += (g1->edge_off[w + 1] - g1->edge_off[w]) + (g1->src_off[w + 1] - g1->src_off[w]);
+            eb[1] += (g2->edge_off[w + 1] - g2->edge_off[w]) + (g2->src_off[w + 1] - g2->src_off[w]);
+            kb[0] += g1->snk_off[w + 1] - g1->snk_off[w];
+            kb[1] += g2->snk_off[w + 1] - g2->snk_off[w];
+            m.out = tot_pairs;
+            b->out_off[k] = tot_pairs;
+            tot_pairs += n1 + n2;
         }
-        m.out = tot_pairs;
-        b->out_off[w] = tot_pairs;
-        tot_pairs += n1 + n2;
+        b->out_off[nw] = tot_pairs;
     }
-    b->out_off[nw] = tot_pairs;
 
     // multi-threaded flatten
     const double t_alloc_done = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -409,11 +432,11 @@ int clb_batch_create(int device, int32_t n_windows, const clb_graph_batch* g1, c
             for (int64_t w = w0; w < std::min<int64_t>(nw, w0 + 16); ++w) {
                 clb::WindowMeta& m = b->meta.h[w];
                 int64_t deg1 = 0, deg2 = 0;
-                int r = flatten_side(*g1, w, 0, b->s[0], m, sc, deg1);
-                if (r == CLB_OK) r = flatten_side(*g2, w, 1, b->s[1], m, sc, deg2);
+                int r = flatten_side(*g1, src(w), 0, b->s[0], m, sc, deg1);
+                if (r == CLB_OK) r = flatten_side(*g2, src(w), 1, b->s[1], m, sc, deg2);
                 if (r != CLB_OK) {
                     status.store(r);
-                    bad_window.store(w);
+                    bad_window.store(src(w));
                     return;
                 }
                 // per cell a*b + 1 + 4P(a+b) + 2P add/max; summed over the window this factorises:
@@ -464,6 +487,7 @@ int clb_batch_create(int device, int32_t n_windows, const clb_graph_batch* g1, c
         b->slot_bytes = std::max(b->slot_bytes, ws);
         b->stats.persist_bytes += ws;
     }
+    b->max_ws_bytes = b->slot_bytes;
     b->slot_bytes = (b->slot_bytes + 255) & ~int64_t(255);
     if (b->aln.alloc_host(2 * tot_pairs) != CLB_OK) {
         clb_batch_destroy(b);
@@ -473,7 +497,17 @@ int clb_batch_create(int device, int32_t n_windows, const clb_graph_batch* g1, c
     return CLB_OK;
 }
 
-int clb_batch_upload(clb_batch* b) {
+int clb_batch_create(int device, int32_t n_windows, const clb_graph_batch* g1, const clb_graph_batch* g2,
+                     const clb_params* params, clb_batch** out) {
+    return create_internal(device, n_windows, g1, g2, params, nullptr, 0, out);
+}
+
+static int upload_internal(clb_batch* b, char* shared_ws, int64_t shared_slot_bytes);
+
+int clb_batch_upload(clb_batch* b) { return upload_internal(b, nullptr, 0); }
+
+// shared_ws != nullptr: the workspace belongs to the caller (chunked one-shot path), slot pairs are picked by SM id
+static int upload_internal(clb_batch* b, char* shared_ws, int64_t shared_slot_bytes) {
     if (!b) return fail(CLB_EINVAL, "null batch");
     if (b->uploaded) return fail(CLB_ESTATE, "batch already uploaded");
     CUDA_TRY(cudaSetDevice(b->device));
@@ -501,6 +535,17 @@ int clb_batch_upload(clb_batch* b) {
     size_t qcap = 0;
     b->d_queue = (int32_t*)g_cache.dev_alloc(b->device, sizeof(int32_t), &qcap, false);
     if (!b->d_queue) return fail(CLB_ENOMEM, "device allocation failed (queue)");
+    if (shared_ws) {
+        b->shared_workspace = true;
+        b->d_workspace = shared_ws;
+        b->slot_bytes = shared_slot_bytes;
+        b->grid = std::max(1, std::min<int>(b->nw, prop.multiProcessorCount));
+        CUDA_TRY(cudaStreamSynchronize(b->stream));
+        b->stats.h2d_bytes = h2d;
+        b->stats.workspace_bytes = 0;
+        b->uploaded = true;
+        return CLB_OK;
+    }
     // one workspace slot per persistent CTA; shrink the grid if memory is short
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
@@ -521,7 +566,15 @@ int clb_batch_upload(clb_batch* b) {
     return CLB_OK;
 }
 
+static int launch_internal(clb_batch* b);
+static int wait_internal(clb_batch* b);
+
 int clb_batch_run(clb_batch* b) {
+    const int rc = launch_internal(b);
+    return rc == CLB_OK ? wait_internal(b) : rc;
+}
+
+static int launch_internal(clb_batch* b) {
     if (!b) return fail(CLB_EINVAL, "null batch");
     if (!b->uploaded) return fail(CLB_ESTATE, "upload the batch before running it");
     CUDA_TRY(cudaSetDevice(b->device));
@@ -546,10 +599,16 @@ int clb_batch_run(clb_batch* b) {
         }
         a.debug_flags = getenv("CLB_DEBUG_FLAGS") ? atoi(getenv("CLB_DEBUG_FLAGS")) : 0;
         a.start_lag = getenv("CLB_START_LAG") ? atoi(getenv("CLB_START_LAG")) : 64;
+        a.slot_by_smid = b->shared_workspace ? 1 : 0;
         CUDA_TRY(clb::launch_popoa(b->params.num_pw, a, b->grid, b->stream));
         b->stats.kernel_launches = 1;
     }
     CUDA_TRY(cudaEventRecord(b->ev1, b->stream));
+    return CLB_OK;
+}
+
+static int wait_internal(clb_batch* b) {
+    CUDA_TRY(cudaSetDevice(b->device));
     CUDA_TRY(cudaStreamSynchronize(b->stream));
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
@@ -565,9 +624,10 @@ int clb_batch_download(clb_batch* b, int64_t* score_out, const int64_t* aln_off,
     if (b->nw > 0 && (!score_out || !aln_off || !aln_pairs || !aln_len)) return fail(CLB_EINVAL, "null output arrays");
     CUDA_TRY(cudaSetDevice(b->device));
     const int64_t nw = b->nw;
+    auto dst_w = [&](int64_t k) -> int64_t { return b->sel.empty() ? k : b->sel[k]; };
     for (int64_t w = 0; w < nw; ++w)
-        if (aln_off[w + 1] - aln_off[w] < b->out_off[w + 1] - b->out_off[w])
-            return fail(CLB_EINVAL, "alignment capacity of window " + std::to_string(w) + " is below n1+n2");
+        if (aln_off[dst_w(w) + 1] - aln_off[dst_w(w)] < b->out_off[w + 1] - b->out_off[w])
+            return fail(CLB_EINVAL, "alignment capacity of window " + std::to_string(dst_w(w)) + " is below n1+n2");
     if (nw) {
         CUDA_TRY(cudaMemcpyAsync(b->score.h, b->score.d, b->score.bytes(), cudaMemcpyDeviceToHost, b->stream));
         CUDA_TRY(cudaMemcpyAsync(b->aln_len.h, b->aln_len.d, b->aln_len.bytes(), cudaMemcpyDeviceToHost, b->stream));
@@ -582,7 +642,7 @@ int clb_batch_download(clb_batch* b, int64_t* score_out, const int64_t* aln_off,
         const uint32_t len = b->aln_len.h[w];
         const int64_t cap = b->out_off[w + 1] - b->out_off[w];
         const int32_t* src = b->aln.h + 2 * (b->out_off[w] + cap - len);
-        int32_t* dst = aln_pairs + 2 * aln_off[w];
+        int32_t* dst = aln_pairs + 2 * aln_off[dst_w(w)];
         const uint32_t* o1 = b->s[0].orig.data() + m.node1;
         const uint32_t* o2 = b->s[1].orig.data() + m.node2;
         for (uint32_t k = 0; k < len; ++k) {
@@ -590,8 +650,8 @@ int clb_batch_download(clb_batch* b, int64_t* score_out, const int64_t* aln_off,
             dst[2 * k] = a < 0 ? CLB_GAP : (int32_t)o1[a + 1];
             dst[2 * k + 1] = c < 0 ? CLB_GAP : (int32_t)o2[c + 1];
         }
-        aln_len[w] = len;
-        score_out[w] = b->score.h[w];
+        aln_len[dst_w(w)] = len;
+        score_out[dst_w(w)] = b->score.h[w];
     };
     unsigned nthreads = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
     if (nw < 64) nthreads = 1;
@@ -634,19 +694,96 @@ int clb_popoa_batch(int device, int32_t n_windows, const clb_graph_batch* g1, co
     }
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t0 = now(), t1 = t0, t2 = t0, t3 = t0, t4 = t0;
-    clb_batch* b = nullptr;
-    int rc = clb_batch_create(device, n_windows, g1, g2, params, &b);
-    t1 = now();
-    if (rc == CLB_OK) rc = clb_batch_upload(b);
+    // Large batches go through in chunks (largest windows first, geometrically growing host work), each with its
+    // own stream: while the GPU works on chunk c the host flattens and uploads chunk c+1, and results of finished
+    // chunks are copied back while later chunks still run.  All chunks share one workspace (slot pair = SM id).
+    int64_t tot_nodes = 0;
+    if (n_windows > 0 && g1 && g2 && g1->node_off && g2->node_off) tot_nodes = g1->node_off[n_windows] + g2->node_off[n_windows];
+    // CLB_CHUNK_MIN_NODES lowers the node threshold (tests exercise the chunked path on small batches)
+    const int64_t chunk_min_nodes = getenv("CLB_CHUNK_MIN_NODES") ? atoll(getenv("CLB_CHUNK_MIN_NODES")) : (int64_t(1) << 24);
+    const bool chunked = n_windows >= 1024 && tot_nodes >= chunk_min_nodes && !getenv("CLB_NO_CHUNKS");
+    if (!chunked) {
+        clb_batch* b = nullptr;
+        int rc = clb_batch_create(device, n_windows, g1, g2, params, &b);
+        t1 = now();
+        if (rc == CLB_OK) rc = clb_batch_upload(b);
+        t2 = now();
+        if (rc == CLB_OK) rc = clb_batch_run(b);
+        t3 = now();
+        if (rc == CLB_OK) rc = clb_batch_download(b, score_out, aln_off, aln_pairs, aln_len);
+        t4 = now();
+        clb_batch_destroy(b);
+        if (timing)
+            fprintf(stderr, "[clb] create %.3f s, upload %.3f s, run %.3f s, download %.3f s, destroy %.3f s\n", t1 - t0,
+                    t2 - t1, t3 - t2, t4 - t3, now() - t4);
+        return rc;
+    }
+    if (check_side(g1) || check_side(g2) || !params) return fail(CLB_EINVAL, "null graph arrays");
+    // windows by matrix size, largest first
+    std::vector<int32_t> ord(n_windows);
+    for (int32_t w = 0; w < n_windows; ++w) ord[w] = w;
+    auto cells_of = [&](int32_t w) {
+        return (g1->node_off[w + 1] - g1->node_off[w] + 1) * (g2->node_off[w + 1] - g2->node_off[w] + 1);
+    };
+    std::stable_sort(ord.begin(), ord.end(), [&](int32_t a, int32_t c) { return cells_of(a) > cells_of(c); });
+    static const double kCut[] = {0.03, 0.09, 0.20, 0.40, 0.70, 1.0};
+    std::vector<std::pair<int32_t, int32_t>> ranges;  // [begin, end) in ord
+    {
+        int64_t acc = 0;
+        int32_t begin = 0;
+        size_t cut = 0;
+        for (int32_t i = 0; i < n_windows; ++i) {
+            const int32_t w = ord[i];
+            acc += (g1->node_off[w + 1] - g1->node_off[w]) + (g2->node_off[w + 1] - g2->node_off[w]);
+            if (acc >= kCut[cut] * (double)tot_nodes || i == n_windows - 1) {
+                ranges.emplace_back(begin, i + 1);
+                begin = i + 1;
+                while (cut + 1 < sizeof(kCut) / sizeof(kCut[0]) && acc >= kCut[cut] * (double)tot_nodes) ++cut;
+            }
+        }
+    }
+    std::vector<clb_batch*> chunks(ranges.size(), nullptr);
+    char* shared_ws = nullptr;
+    size_t shared_cap = 0;
+    int64_t shared_slot = 0;
+    int rc = CLB_OK;
+    double t_create = 0, t_upload = 0;
+    for (size_t c = 0; c < ranges.size() && rc == CLB_OK; ++c) {
+        const double ta = now();
+        rc = create_internal(device, n_windows, g1, g2, params, ord.data() + ranges[c].first,
+                             ranges[c].second - ranges[c].first, &chunks[c]);
+        const double tb = now();
+        t_create += tb - ta;
+        if (rc != CLB_OK) break;
+        if (c == 0) {  // chunk 0 holds the largest windows: its slot size serves every chunk
+            const int nsm = clb::popoa_nsmid();
+            if (nsm <= 0) { rc = fail(CLB_ECUDA, "could not query the SM id space"); break; }
+            shared_slot = chunks[0]->max_ws_bytes;
+            shared_ws = (char*)g_cache.dev_alloc(device, (size_t)nsm * 2 * shared_slot, &shared_cap, true);
+            if (!shared_ws) { rc = fail(CLB_ENOMEM, "device allocation failed (shared workspace)"); break; }
+        }
+        rc = upload_internal(chunks[c], shared_ws, shared_slot);
+        if (rc == CLB_OK) rc = launch_internal(chunks[c]);
+        t_upload += now() - tb;
+    }
     t2 = now();
-    if (rc == CLB_OK) rc = clb_batch_run(b);
+    double t_down = 0, kernel_ms = 0;
+    for (size_t c = 0; c < chunks.size() && rc == CLB_OK; ++c) {
+        rc = wait_internal(chunks[c]);
+        const double ta = now();
+        if (rc == CLB_OK) rc = clb_batch_download(chunks[c], score_out, aln_off, aln_pairs, aln_len);
+        t_down += now() - ta;
+        kernel_ms += chunks[c]->stats.kernel_ms;
+    }
     t3 = now();
-    if (rc == CLB_OK) rc = clb_batch_download(b, score_out, aln_off, aln_pairs, aln_len);
-    t4 = now();
-    clb_batch_destroy(b);
+    if (rc != CLB_OK) cudaDeviceSynchronize();  // no kernel may outlive the shared workspace
+    for (clb_batch* b : chunks) clb_batch_destroy(b);
+    if (shared_ws) g_cache.dev_release(device, shared_ws, shared_cap);
     if (timing)
-        fprintf(stderr, "[clb] create %.3f s, upload %.3f s, run %.3f s, download %.3f s, destroy %.3f s\n", t1 - t0, t2 - t1,
-                t3 - t2, t4 - t3, now() - t4);
+        fprintf(stderr, "[clb] %zu chunks: create %.3f s, upload+launch %.3f s (issue phase %.3f s), wait+download %.3f s "
+                        "(download %.3f s), sum of kernel times %.1f ms, total %.3f s\n",
+                chunks.size(), t_create, t_upload, t2 - t0, t3 - t2, t_down, kernel_ms, now() - t0);
+    (void)t1; (void)t4;
     return rc;
 }
 

@@ -1078,6 +1078,16 @@ struct CtaState {
     int strips_done[2];  // per workspace slot
 };
 
+__device__ __forceinline__ unsigned smid() {
+    unsigned v;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(v));
+    return v;
+}
+__global__ void nsmid_kernel(unsigned* out) {
+    unsigned v;
+    asm volatile("mov.u32 %0, %%nsmid;" : "=r"(v));
+    *out = v;
+}
 __device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 
 template <int P>
@@ -1134,7 +1144,9 @@ __global__ void __launch_bounds__(kThreads, 1) popoa_kernel(const LaunchArgs A) 
                     W.poff1 = A.s1.poff + m.poff1; W.poff2 = A.s2.poff + m.poff2;
                     W.pidx1 = A.s1.pidx + m.pidx1; W.pidx2 = A.s2.pidx + m.pidx2;
                     W.snk1 = A.s1.sinks + m.snk1; W.snk2 = A.s2.sinks + m.snk2;
-                    int4* ws = reinterpret_cast<int4*>(A.workspace + ((int64_t)blockIdx.x * 2 + (k & 1)) * A.slot_bytes);
+                    // one CTA per SM at a time (217 KB of shared memory each), so the SM id names a free slot pair
+                    const int64_t pair = A.slot_by_smid ? (int64_t)smid() : (int64_t)blockIdx.x;
+                    int4* ws = reinterpret_cast<int4*>(A.workspace + (pair * 2 + (k & 1)) * A.slot_bytes);
                     W.rowbuf = ws;
                     W.colbuf = W.rowbuf + (int64_t)m.nrslot * (m.n2 + 1);
                     W.brow = W.colbuf + (int64_t)m.ncslot * (m.n1 + 1);
@@ -1173,6 +1185,15 @@ __global__ void __launch_bounds__(kThreads, 1) popoa_kernel(const LaunchArgs A) 
     }
 }
 
+int popoa_nsmid() {  // size of the %smid id space (>= number of SMs)
+    unsigned* d = nullptr;
+    unsigned h = 0;
+    if (cudaMalloc(&d, 4) != cudaSuccess) return -1;
+    nsmid_kernel<<<1, 1>>>(d);
+    const cudaError_t e = cudaMemcpy(&h, d, 4, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    return e == cudaSuccess ? (int)h : -1;
+}
 int popoa_smem_bytes() { return (kTileInt4 + kFillWarps * (int)(sizeof(FillSmemAny) / sizeof(int4))) * (int)sizeof(int4); }
 int popoa_threads() { return kThreads; }
 

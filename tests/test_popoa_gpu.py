@@ -195,3 +195,24 @@ def test_repeated_runs_are_identical_and_valid():
         assert all(np.array_equal(x, y) for x, y in zip(a, ref_a))
     for w in range(0, batch.n_windows, 17):
         assert_valid_and_rescore(batch, w, PROD, int(ref_s[w]), ref_a[w])
+
+
+def test_chunked_one_shot_matches_single_batch(monkeypatch):
+    """Large one-shot calls are split into chunks that overlap host flattening, H2D, kernels and D2H
+    (shared workspace, slot pair by SM id).  Same bytes as the single-batch path are required."""
+    batch = concat_batches([
+        synth_windows(1100, first_index=9000, seed=12, len_min=100, len_max=900),
+        synth_windows(30, first_index=9500, seed=12, len_min=1500, len_max=2500),
+    ])
+    monkeypatch.setenv("CLB_NO_CHUNKS", "1")
+    ref_s, ref_a = po_poa_batch(batch, PROD)
+    ref_s = ref_s.copy()
+    ref_a = [a.copy() for a in ref_a]
+    monkeypatch.delenv("CLB_NO_CHUNKS")
+    monkeypatch.setenv("CLB_CHUNK_MIN_NODES", "1")
+    for _ in range(2):
+        s, a = po_poa_batch(batch, PROD)
+        assert np.array_equal(s, ref_s)
+        assert all(np.array_equal(x, y) for x, y in zip(a, ref_a))
+    for w in range(0, batch.n_windows, 97):
+        assert_valid_and_rescore(batch, w, PROD, int(ref_s[w]), ref_a[w])
