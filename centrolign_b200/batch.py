@@ -199,6 +199,36 @@ def select_windows(batch: WindowBatch, idx: Sequence[int]) -> WindowBatch:
     return WindowBatch(sel(batch.g1), sel(batch.g2))
 
 
+def successor_form(batch: WindowBatch, rng: np.random.Generator = None) -> WindowBatch:
+    """The same windows with each side's CSR holding SUCCESSOR lists in ``next()`` order (what the
+    wavefront variant ``pwfa_po_poa`` enumerates, include/centrolign/alignment.hpp:1788-1826) in the
+    ``pred_off`` / ``pred`` fields.  ``BaseGraph::add_edge(a, b)`` appends ``b`` to ``next(a)`` and ``a`` to
+    ``previous(b)``; replaying the predecessor lists head by head (as oracle/ref_shim.cpp does) therefore
+    gives ``next(a)`` = heads in ascending id order.  With ``rng`` the order inside every successor list is
+    shuffled instead, to exercise the order dependence."""
+
+    def conv(side: GraphSide) -> GraphSide:
+        offs, succs = [], []
+        for w in range(len(side.node_off) - 1):
+            lab, po, pr, _, _ = side.window(w)
+            n = len(lab)
+            heads = np.repeat(np.arange(n, dtype=np.uint32), np.diff(po.astype(np.int64)))
+            tails = pr.astype(np.int64)
+            if rng is not None and len(tails):
+                perm = rng.permutation(len(tails))
+                heads, tails = heads[perm], tails[perm]
+            order = np.argsort(tails, kind="stable")
+            no = np.zeros(n + 1, np.uint32)
+            np.cumsum(np.bincount(tails, minlength=n), out=no[1:])
+            offs.append(no)
+            succs.append(heads[order].astype(np.uint32))
+        cat = lambda xs: np.ascontiguousarray(np.concatenate(xs)) if xs else np.zeros(0, np.uint32)  # noqa: E731
+        return GraphSide(side.node_off, side.label, side.edge_off, cat(offs).astype(np.uint32), cat(succs).astype(np.uint32),
+                         side.src_off, side.src, side.snk_off, side.snk)
+
+    return WindowBatch(conv(batch.g1), conv(batch.g2))
+
+
 # ----------------------------------------------------------------------------------------
 # synthetic HOR-like windows (csrc/synth.c)
 # ----------------------------------------------------------------------------------------
@@ -303,11 +333,11 @@ _u8p = ctypes.POINTER(ctypes.c_uint8)
 _SIDE_ARGS = [ctypes.c_uint32, _u8p, _u32p, _u32p, ctypes.c_uint32, _u32p, ctypes.c_uint32, _u32p]
 
 
-def _bind_checker(lib, name, extra=()):
+def _bind_checker(lib, name, extra=(), tail=()):
     fn = getattr(lib, name)
     fn.restype = ctypes.c_int
     fn.argtypes = [ctypes.c_int, _u32p, *extra, *_SIDE_ARGS, *_SIDE_ARGS, ctypes.POINTER(ctypes.c_int64),
-                   ctypes.POINTER(ctypes.c_int32), _u32p]
+                   ctypes.POINTER(ctypes.c_int32), _u32p, *tail]
     return fn
 
 
@@ -328,6 +358,8 @@ class CpuChecker:
         self.lib = ctypes.CDLL(path)
         self._po_poa = _bind_checker(self.lib, sym)
         self._pwfa = _bind_checker(self.lib, "clref_pwfa_po_poa", (ctypes.c_int64,)) if kind == "reference" else None
+        self._pwfa_succ = _bind_checker(self.lib, "clo_pwfa_po_poa" if kind == "port" else "clref_pwfa_po_poa_succ",
+                                        (ctypes.c_int64,), (ctypes.POINTER(ctypes.c_int64),))
 
     @staticmethod
     def available(kind: str) -> bool:
@@ -359,4 +391,23 @@ class CpuChecker:
                 aln.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), ctypes.byref(ln))
         if rc != 0:
             raise RuntimeError(f"{self.kind} checker failed with code {rc}")
+        return int(score.value), aln[: ln.value].copy()
+
+    def pwfa_po_poa(self, succ_batch: WindowBatch, w: int, params: AlignmentParameters, prune_limit: int, stats=None):
+        """``pwfa_po_poa`` (alignment.hpp:2299-2338) on window ``w`` of a batch in ``successor_form``.
+        Returns (score, alignment); ``stats`` (int64[3], port only) receives settled states, dequeued
+        entries and the final WFA score."""
+        k1, a1 = self._side(succ_batch.g1, w)
+        k2, a2 = self._side(succ_batch.g2, w)
+        pk = params.packed()
+        score = ctypes.c_int64(0)
+        cap = max(1, succ_batch.g1.n(w) + succ_batch.g2.n(w))
+        aln = np.empty((cap, 2), np.int32)
+        ln = ctypes.c_uint32(0)
+        st = stats if stats is not None else np.zeros(3, np.int64)
+        rc = self._pwfa_succ(params.num_pw, pk.ctypes.data_as(_u32p), ctypes.c_int64(prune_limit), *a1, *a2,
+                             ctypes.byref(score), aln.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), ctypes.byref(ln),
+                             st.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)))
+        if rc != 0:
+            raise RuntimeError(f"{self.kind} pwfa checker failed with code {rc}")
         return int(score.value), aln[: ln.value].copy()

@@ -319,6 +319,10 @@ int check_side(const clb_graph_batch* g) {
 
 }  // namespace
 
+namespace clb {
+int host_fail(int code, const std::string& msg) { return fail(code, msg); }  // for the other host files of the library
+}  // namespace clb
+
 extern "C" {
 
 const char* clb_last_error(void) { return g_err.c_str(); }

@@ -21,7 +21,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "li
 
 EXPORTS = ["clb_popoa_batch", "clb_batch_create", "clb_batch_upload", "clb_batch_run", "clb_batch_download",
            "clb_batch_destroy", "clb_batch_get_stats", "clb_int32_peak_tops", "clb_last_error", "clb_device_count",
-           "clb_release_cached_memory"]
+           "clb_release_cached_memory", "clb_pwfa_batch"]
 ERROR_NAMES = {0: "CLB_OK", 1: "CLB_EINVAL", 2: "CLB_ECYCLE", 3: "CLB_ECUDA", 4: "CLB_ENOMEM", 5: "CLB_ESTATE"}
 
 
@@ -46,6 +46,12 @@ class BatchStats(ctypes.Structure):
     _fields_ = [("cells", ctypes.c_double), ("kernel_ms", ctypes.c_double), ("fill_ms", ctypes.c_double),
                 ("kernel_launches", ctypes.c_int64), ("h2d_bytes", ctypes.c_int64), ("d2h_bytes", ctypes.c_int64),
                 ("workspace_bytes", ctypes.c_int64), ("int_ops", ctypes.c_int64), ("persist_bytes", ctypes.c_int64)]
+
+
+class PwfaStats(ctypes.Structure):
+    _fields_ = [("kernel_ms", ctypes.c_double), ("kernel_launches", ctypes.c_int64), ("retries", ctypes.c_int64),
+                ("states", ctypes.c_int64), ("dequeued", ctypes.c_int64), ("steps", ctypes.c_int64),
+                ("h2d_bytes", ctypes.c_int64), ("d2h_bytes", ctypes.c_int64), ("workspace_bytes", ctypes.c_int64)]
 
 
 _lib = None
@@ -80,6 +86,8 @@ def load_library() -> ctypes.CDLL:
     lib.clb_last_error.restype = ctypes.c_char_p
     lib.clb_device_count.restype = ctypes.c_int
     lib.clb_release_cached_memory.restype = None
+    lib.clb_pwfa_batch.restype = ctypes.c_int
+    lib.clb_pwfa_batch.argtypes = [ctypes.c_int, i32, gp, gp, pp, ctypes.c_int64, vp, vp, vp, vp, ctypes.POINTER(PwfaStats)]
     _lib = lib
     return lib
 
@@ -197,3 +205,25 @@ def po_poa(graph1, graph2, params: AlignmentParameters, device: int = 0):
 
     score, alns = po_poa_batch(batch_from_graph_pairs([(graph1, graph2)]), params, device)
     return alns[0], int(score[0])
+
+
+def pwfa_po_poa_batch(succ_batch: WindowBatch, params: AlignmentParameters, prune_limit: int, device: int = 0,
+                      stats: Optional[PwfaStats] = None):
+    """Batched ``pwfa_po_poa`` (include/centrolign/alignment.hpp:117-125, body :2299-2338) through
+    ``clb_pwfa_batch``.  ``succ_batch`` holds SUCCESSOR lists in ``next()`` order (``batch.successor_form``).
+    Returns (scores, [alignment per window])."""
+    lib = load_library()
+    p = _c_params(params)
+    g1, k1 = _c_side(succ_batch.g1)
+    g2, k2 = _c_side(succ_batch.g2)
+    nw = succ_batch.n_windows
+    aln_off = np.zeros(nw + 1, np.int64)
+    np.cumsum(succ_batch.aln_capacity(), out=aln_off[1:])
+    score = np.zeros(nw, np.int64)
+    aln_len = np.zeros(nw, np.uint32)
+    pairs = np.empty((max(1, int(aln_off[-1])), 2), np.int32)
+    _check(lib.clb_pwfa_batch(device, nw, ctypes.byref(g1), ctypes.byref(g2), ctypes.byref(p), int(prune_limit),
+                              score.ctypes.data, aln_off.ctypes.data, pairs.ctypes.data, aln_len.ctypes.data,
+                              ctypes.byref(stats) if stats is not None else None))
+    del k1, k2
+    return score, [pairs[int(aln_off[w]): int(aln_off[w]) + int(aln_len[w])] for w in range(nw)]

@@ -118,6 +118,41 @@ typedef struct clb_batch_stats {
 } clb_batch_stats;
 int clb_batch_get_stats(const clb_batch* b, clb_batch_stats* out);
 
+/*
+ * Wavefront variant of the gap fill.  Replaces n_windows calls of
+ *
+ *     Alignment pwfa_po_poa<NumPW, Graph>(graph1, graph2, sources1, sources2, sinks1, sinks2,
+ *                                         const AlignmentParameters<NumPW>&, int64_t prune_limit, int64_t* score_out)
+ *         -- reference: include/centrolign/alignment.hpp:117-125 (body :2299-2338, search :1959-2033, :1712-1827),
+ *            called from Stitcher::do_alignment (include/centrolign/stitcher.hpp:336-339) with
+ *            prune_limit = 2 * wfa_pruning_dist.
+ *
+ * This algorithm walks the graphs FORWARD, so the two sides are given as SUCCESSOR lists: same struct
+ * layout as clb_graph_batch, but pred_off / pred hold, per node, its successors in the graph's next()
+ * order (include/centrolign/graph.hpp next()); that order and the caller's order of the source lists
+ * decide ties (alignment.hpp:1788-1826) and are reproduced exactly: identical alignment, identical score.
+ * Outputs as for clb_popoa_batch.  Preconditions are the reference's: acyclic graphs, some source reaches
+ * some sink on both sides (else CLB_EINVAL where the reference would dereference an empty queue),
+ * non-zero gap_open (the reference's gcd divides by it), prune_limit >= 0.
+ */
+typedef clb_graph_batch clb_succ_graph_batch;
+
+typedef struct clb_pwfa_stats {
+    double kernel_ms;        /* CUDA-event time of the search+traceback kernel(s) */
+    int64_t kernel_launches; /* 1 + re-runs of windows whose tables had to be enlarged */
+    int64_t retries;         /* enlargement rounds */
+    int64_t states;          /* search states settled (first dequeues), all windows */
+    int64_t dequeued;        /* queue entries dequeued */
+    int64_t steps;           /* warp steps (each resolves up to 32 queue entries in order) */
+    int64_t h2d_bytes;
+    int64_t d2h_bytes;
+    int64_t workspace_bytes; /* back-pointer tables + FIFOs held during the run */
+} clb_pwfa_stats;
+
+int clb_pwfa_batch(int device, int32_t n_windows, const clb_succ_graph_batch* g1, const clb_succ_graph_batch* g2,
+                   const clb_params* params, int64_t prune_limit, int64_t* score_out, const int64_t* aln_off,
+                   int32_t* aln_pairs, uint32_t* aln_len, clb_pwfa_stats* stats /* may be NULL */);
+
 /* Measured INT32 issue-rate probe (a dependent-free add/max loop on every SM):
  * returns achieved 10^12 INT32 lane-ops per second on `device`, <0 on error. */
 double clb_int32_peak_tops(int device, int use_dpx);

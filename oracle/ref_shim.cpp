@@ -99,3 +99,32 @@ extern "C" int clref_pwfa_po_poa(int P, const uint32_t* params, int64_t prune_li
     emit(aln, aln_out, aln_len);
     return 0;
 }
+
+// Same call with SUCCESSOR lists in next() order: edges are added grouped by tail node, in list order, which
+// reproduces exactly that next() order (pwfa's enumeration order, alignment.hpp:1788-1826, depends on it).
+extern "C" int clref_pwfa_po_poa_succ(int P, const uint32_t* params, int64_t prune_limit,
+                                      uint32_t n1, const uint8_t* label1, const uint32_t* next_off1, const uint32_t* next1,
+                                      uint32_t nsrc1, const uint32_t* src1, uint32_t nsnk1, const uint32_t* snk1,
+                                      uint32_t n2, const uint8_t* label2, const uint32_t* next_off2, const uint32_t* next2,
+                                      uint32_t nsrc2, const uint32_t* src2, uint32_t nsnk2, const uint32_t* snk2,
+                                      int64_t* score_out, int32_t* aln_out, uint32_t* aln_len, int64_t* /*stats_out*/) {
+    BaseGraph g1, g2;
+    for (uint32_t v = 0; v < n1; ++v) g1.add_node((char)label1[v]);
+    for (uint32_t v = 0; v < n2; ++v) g2.add_node((char)label2[v]);
+    for (uint32_t v = 0; v < n1; ++v)
+        for (uint32_t k = next_off1[v]; k < next_off1[v + 1]; ++k) g1.add_edge(v, next1[k]);
+    for (uint32_t v = 0; v < n2; ++v)
+        for (uint32_t k = next_off2[v]; k < next_off2[v + 1]; ++k) g2.add_edge(v, next2[k]);
+    auto s1 = widen(nsrc1, src1), s2 = widen(nsrc2, src2), k1 = widen(nsnk1, snk1), k2 = widen(nsnk2, snk2);
+    Alignment aln;
+    int64_t score = 0;
+    switch (P) {
+        case 1: aln = pwfa_po_poa(g1, g2, s1, s2, k1, k2, unpack<1>(params), prune_limit, &score); break;
+        case 2: aln = pwfa_po_poa(g1, g2, s1, s2, k1, k2, unpack<2>(params), prune_limit, &score); break;
+        case 3: aln = pwfa_po_poa(g1, g2, s1, s2, k1, k2, unpack<3>(params), prune_limit, &score); break;
+        default: return -3;
+    }
+    if (score_out) *score_out = score;
+    emit(aln, aln_out, aln_len);
+    return 0;
+}

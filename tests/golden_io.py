@@ -8,6 +8,27 @@ from centrolign_b200.batch import AlignmentParameters, GraphSide, WindowBatch
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "popoa_golden.npz")
 
 
+PWFA_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pwfa_golden.npz")
+
+
+def load_pwfa_golden():
+    """tests/golden/pwfa_golden.npz (tests/golden/make_pwfa_golden.py): outputs of the unmodified reference's
+    pwfa_po_poa.  Returns ([batch_v0, batch_v1] in successor form, params, cases[(variant, window, param, prune_limit)],
+    scores, alignments)."""
+    z = np.load(PWFA_GOLDEN)
+    batches = []
+    for v in ("v0", "v1"):
+        sides = [GraphSide(*[z[f"{v}_{name}_{f}"] for f in
+                             ("node_off", "label", "edge_off", "pred_off", "pred", "src_off", "src", "snk_off", "snk")])
+                 for name in ("g1", "g2")]
+        batches.append(WindowBatch(*sides))
+    params = [AlignmentParameters(int(row[0]), int(row[1]), tuple(int(x) for x in row[2:2 + p]),
+                                  tuple(int(x) for x in row[5:5 + p]))
+              for row, p in zip(z["param_sets"], z["param_num_pw"])]
+    alns = [z["aln"][z["aln_off"][k]:z["aln_off"][k + 1]] for k in range(len(z["score"]))]
+    return batches, params, z["cases"], z["score"], alns
+
+
 def load_golden():
     z = np.load(GOLDEN)
     sides = []

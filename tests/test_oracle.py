@@ -9,8 +9,8 @@ import numpy as np
 import pytest
 
 from centrolign_b200.batch import (AlignmentParameters, CpuChecker, batch_from_graph_pairs, graph_from_edges,
-                                   synth_windows)
-from golden_io import REFERENCE_UNIT_GOLDENS, TIEBREAK_PROBES, load_golden
+                                   successor_form, synth_windows)
+from golden_io import REFERENCE_UNIT_GOLDENS, TIEBREAK_PROBES, load_golden, load_pwfa_golden
 
 
 @pytest.fixture(scope="module")
@@ -78,3 +78,34 @@ def test_live_against_reference(oracle):
         so, ao = oracle.po_poa(eb, w, AlignmentParameters())
         sr, ar = ref.po_poa(eb, w, AlignmentParameters())
         assert so == sr and np.array_equal(ao, ar)
+
+
+# ---- wavefront variant (oracle/pwfa_oracle.c) ------------------------------------------------------------
+def test_pwfa_reference_unit_goldens(oracle):
+    """src/test/test_alignment.cpp:717-771: pwfa_po_poa(..., prune_limit 4) gives the same golden pairs."""
+    batch = successor_form(_unit_batch(REFERENCE_UNIT_GOLDENS))
+    p = AlignmentParameters(1, 1, (1,), (1,))
+    for w, case in enumerate(REFERENCE_UNIT_GOLDENS):
+        _, aln = oracle.pwfa_po_poa(batch, w, p, 4)
+        assert [tuple(x) for x in aln.tolist()] == case[8]
+
+
+def test_pwfa_golden_fixture(oracle):
+    batches, params, cases, scores, alns = load_pwfa_golden()
+    assert len(cases) >= 1500
+    for k, (variant, w, pi, lim) in enumerate(cases.tolist()):
+        s, a = oracle.pwfa_po_poa(batches[variant], w, params[pi], lim)
+        assert s == scores[k], f"case {k}: score"
+        assert np.array_equal(a, alns[k]), f"case {k}: alignment"
+
+
+@pytest.mark.skipif(not CpuChecker.available("reference"), reason="oracle/_ref/libclref.so not built")
+def test_pwfa_live_against_reference(oracle):
+    ref = CpuChecker("reference")
+    batch = synth_windows(10, first_index=500, seed=5, len_min=200, len_max=3000, alt_len=41, alt_period=300)
+    for sb in (successor_form(batch), successor_form(batch, np.random.default_rng(1))):
+        for w in range(batch.n_windows):
+            for p, lim in ((AlignmentParameters(), 50), (AlignmentParameters().truncated(1), 8)):
+                so, ao = oracle.pwfa_po_poa(sb, w, p, lim)
+                sr, ar = ref.pwfa_po_poa(sb, w, p, lim)
+                assert so == sr and np.array_equal(ao, ar), f"window {w} P={p.num_pw}"
