@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <thread>
@@ -171,6 +172,15 @@ extern "C" int clb_pwfa_batch(int device, int32_t n_windows, const clb_succ_grap
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return host_fail(CLB_ECUDA, "no CUDA device available (there is no CPU fallback)");
     if (device < 0 || device >= ndev) return host_fail(CLB_EINVAL, "device index out of range");
+    if (getenv("CLB_COUNT_CALLS")) {  // evidence for integration tests that the GPU path really ran
+        static std::atomic<int64_t> calls(0), windows(0);
+        static std::once_flag once;
+        std::call_once(once, [] {
+            atexit([] { fprintf(stderr, "[clb] pwfa calls %lld windows %lld\n", (long long)calls.load(), (long long)windows.load()); });
+        });
+        calls += 1;
+        windows += n_windows;
+    }
     if (n_windows == 0) return CLB_OK;
     const int64_t nw = n_windows;
     const int P = params->num_pw;

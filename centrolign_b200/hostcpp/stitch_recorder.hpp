@@ -7,8 +7,9 @@
 // marker (gap, gap) -- a pair the reference never produces -- and the redirected translate() call notes
 // the window's back-translation tables.  When the loop is done, all recorded windows go to the GPU in
 // one clb_popoa_batch per NumPW, and every marker is replaced, in order, by the translated alignment of
-// its window.  Routing, gap-piece truncation, anchor copies and every non-po_poa route are the
-// reference's own code, executed as is.
+// its window.  The wavefront route (pwfa_po_poa, stitcher.hpp:336-339) is recorded the same way and goes
+// out as one clb_pwfa_batch per NumPW.  Routing, gap-piece truncation, anchor copies and every other
+// route are the reference's own code, executed as is.
 #ifndef CENTROLIGN_B200_STITCH_RECORDER_HPP
 #define CENTROLIGN_B200_STITCH_RECORDER_HPP
 
@@ -36,6 +37,7 @@ public:
         active_ = true;
         for (int k = 0; k < CLB_MAX_PW; ++k) {
             batch_[k] = PoPoaBatch();
+            wbatch_[k] = PwfaBatch();
             have_params_[k] = false;
         }
         windows_.clear();
@@ -49,6 +51,30 @@ public:
                       const std::vector<uint64_t>& sinks2, const Params& params) {
         windows_.push_back(std::make_pair(NumPW, batch_[NumPW - 1].size()));
         batch_[NumPW - 1].add(graph1, graph2, sources1, sources2, sinks1, sinks2);
+        keep_params<NumPW>(params);
+        return marker();
+    }
+
+    // the redirected pwfa_po_poa call
+    template <int NumPW, class Graph, class Params>
+    AlignmentT record_pwfa(const Graph& graph1, const Graph& graph2, const std::vector<uint64_t>& sources1,
+                           const std::vector<uint64_t>& sources2, const std::vector<uint64_t>& sinks1,
+                           const std::vector<uint64_t>& sinks2, const Params& params, int64_t prune_limit) {
+        windows_.push_back(std::make_pair(-NumPW, wbatch_[NumPW - 1].size()));  // negative = wavefront route
+        wbatch_[NumPW - 1].add(graph1, graph2, sources1, sources2, sinks1, sinks2);
+        prune_limit_ = prune_limit;  // one value per Stitcher (2 * wfa_pruning_dist, stitcher.hpp:339)
+        keep_params<NumPW>(params);
+        return marker();
+    }
+
+private:
+    static AlignmentT marker() {
+        AlignmentT m;
+        m.push_back(Pair(uint64_t(-1), uint64_t(-1)));
+        return m;
+    }
+    template <int NumPW, class Params>
+    void keep_params(const Params& params) {
         if (!have_params_[NumPW - 1]) {
             have_params_[NumPW - 1] = true;
             params_[NumPW - 1].match = params.match;
@@ -58,10 +84,9 @@ public:
                 params_[NumPW - 1].gap_extend[k] = params.gap_extend[k];
             }
         }
-        AlignmentT marker;
-        marker.push_back(Pair(uint64_t(-1), uint64_t(-1)));
-        return marker;
     }
+
+public:
 
     // the redirected translate call: true if `aln` is the marker of the window recorded last
     bool note_translation(const AlignmentT& aln, const std::vector<uint64_t>& back_translation1,
@@ -75,16 +100,20 @@ public:
     AlignmentT finish(AlignmentT&& stitched) {
         active_ = false;
         if (windows_.empty()) return std::move(stitched);
-        std::vector<AlignmentT> out[CLB_MAX_PW];
+        std::vector<AlignmentT> out[CLB_MAX_PW], wout[CLB_MAX_PW];
         if (batch_[0].size()) batch_[0].template align<1, GenericParams, AlignmentT>(params_[0], out[0]);
         if (batch_[1].size()) batch_[1].template align<2, GenericParams, AlignmentT>(params_[1], out[1]);
         if (batch_[2].size()) batch_[2].template align<3, GenericParams, AlignmentT>(params_[2], out[2]);
+        if (wbatch_[0].size()) wbatch_[0].template align<1, GenericParams, AlignmentT>(params_[0], prune_limit_, wout[0]);
+        if (wbatch_[1].size()) wbatch_[1].template align<2, GenericParams, AlignmentT>(params_[1], prune_limit_, wout[1]);
+        if (wbatch_[2].size()) wbatch_[2].template align<3, GenericParams, AlignmentT>(params_[2], prune_limit_, wout[2]);
         AlignmentT result;
         result.reserve(stitched.size());
         size_t w = 0;
         for (const Pair& p : stitched) {
             if (p.node_id1 == uint64_t(-1) && p.node_id2 == uint64_t(-1)) {
-                const AlignmentT& sub = out[windows_[w].first - 1][windows_[w].second];
+                const int pw = windows_[w].first;
+                const AlignmentT& sub = pw > 0 ? out[pw - 1][windows_[w].second] : wout[-pw - 1][windows_[w].second];
                 const std::vector<uint64_t>& bt1 = translations_[w].first;
                 const std::vector<uint64_t>& bt2 = translations_[w].second;
                 for (const Pair& q : sub)  // same mapping as translate(), src/alignment.cpp:26-39
@@ -108,9 +137,11 @@ private:
 
     bool active_ = false;
     PoPoaBatch batch_[CLB_MAX_PW];
+    PwfaBatch wbatch_[CLB_MAX_PW];
+    int64_t prune_limit_ = 0;
     GenericParams params_[CLB_MAX_PW];
     bool have_params_[CLB_MAX_PW] = {false, false, false};
-    std::vector<std::pair<int, size_t>> windows_;  // (NumPW, index in that batch), in call order
+    std::vector<std::pair<int, size_t>> windows_;  // (+NumPW po_poa / -NumPW pwfa, index in that batch), in call order
     std::vector<std::pair<std::vector<uint64_t>, std::vector<uint64_t>>> translations_;
 };
 

@@ -17,7 +17,27 @@ CASES = [
     ("pair20k", [2, 20000, 7, 0], ["-a", "60000"]),
     ("pair60k_hor_indels", [2, 60000, 3, 2], ["-a", "100000"]),
     ("msa3_40k", [3, 40000, 9, 1], ["-a", "100000"]),
+    # the wavefront route: min_wfa_size lowered through a config file so that every window above 100 cells with
+    # similar side lengths goes to pwfa_po_poa (stitcher.hpp:327-339); the output differs from the default route's
+    ("pair60k_wfa_route", [2, 60000, 3, 2], ["-a", "100000"], {"min_wfa_size": 100}),
+    ("msa3_40k_wfa_route", [3, 40000, 9, 1], ["-a", "100000"], {"min_wfa_size": 100}),
 ]
+
+
+def run_cli(cli, opts, fa, overrides, tmp, env=None):
+    """Run the CLI; with config overrides, go through --generate-config / --config (src/main.cpp:137-193)."""
+    if not overrides:
+        return subprocess.run([cli, "-v", "0"] + opts + [fa], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
+    cfg = subprocess.run([cli] + opts + ["-G", fa], stdout=subprocess.PIPE, check=True).stdout.decode().splitlines()
+    overrides = dict(overrides, logging_level=0)
+    out = []
+    for line in cfg:
+        key = line.strip().split(":")[0]
+        out.append(f" {key}: {overrides[key]}" if key in overrides and not line.strip().startswith("#") else line)
+    path = os.path.join(tmp, "config.yaml")
+    with open(path, "w") as f:
+        f.write("\n".join(out) + "\n")
+    return subprocess.run([cli, "-C", path], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
 
 
 def make_fasta(path, args):
@@ -32,12 +52,16 @@ def main():
     ref = os.path.join(ROOT, "oracle", "_ref", "centrolign_ref")
     out = {}
     with tempfile.TemporaryDirectory() as tmp:
-        for name, fa_args, opts in CASES:
+        for case in CASES:
+            name, fa_args, opts = case[:3]
+            overrides = case[3] if len(case) > 3 else {}
             fa = os.path.join(tmp, name + ".fa")
             make_fasta(fa, fa_args)
             t0 = time.time()
-            res = subprocess.run([ref, "-v", "0"] + opts + [fa], stdout=subprocess.PIPE, check=True)
-            out[name] = {"fasta_args": fa_args, "options": opts, "fasta_md5": md5(open(fa, "rb").read()),
+            res = run_cli(ref, opts, fa, overrides, tmp)
+            assert res.returncode == 0, res.stderr.decode()[-2000:]
+            out[name] = {"fasta_args": fa_args, "options": opts, "config_overrides": overrides,
+                         "fasta_md5": md5(open(fa, "rb").read()),
                          "output_md5": md5(res.stdout), "output_bytes": len(res.stdout),
                          "reference_seconds": round(time.time() - t0, 1), "head": res.stdout[:120].decode()}
             print(name, out[name]["output_md5"], out[name]["output_bytes"], out[name]["reference_seconds"])

@@ -6,7 +6,8 @@
 // header with #include_next, with two identifiers redirected while it is being read:
 //   * `Stitcher` -> `StitcherReference`: the reference class, whole and unchanged, under another name;
 //   * `po_poa`   -> `po_poa_b200`: the one use of po_poa in that header is the gap-fill call in
-//     Stitcher::do_alignment (reference: include/centrolign/stitcher.hpp:297-299).
+//     Stitcher::do_alignment (reference: include/centrolign/stitcher.hpp:297-299);
+//   * `pwfa_po_poa` -> `pwfa_po_poa_b200`: likewise the wavefront route (stitcher.hpp:336-339).
 // `centrolign::Stitcher` is then a thin subclass whose stitch() / internal_stitch() run the reference's
 // own loop in recording mode and finish with one batched GPU call (centrolign_b200/hostcpp/
 // stitch_recorder.hpp).  In stitcher.cpp itself (compiled with -DCLB_SHADOW_STITCHER_TU) the member
@@ -43,6 +44,19 @@ Alignment po_poa_b200(const Graph& graph1, const Graph& graph2, const std::vecto
         graph1, graph2, sources1, sources2, sinks1, sinks2, params, score_out);
 }
 
+// same argument list as centrolign::pwfa_po_poa (include/centrolign/alignment.hpp:117-125)
+template <int NumPW, class Graph>
+Alignment pwfa_po_poa_b200(const Graph& graph1, const Graph& graph2, const std::vector<uint64_t>& sources1,
+                           const std::vector<uint64_t>& sources2, const std::vector<uint64_t>& sinks1,
+                           const std::vector<uint64_t>& sinks2, const AlignmentParameters<NumPW>& params,
+                           int64_t prune_limit, int64_t* score_out = nullptr) {
+    auto& rec = centrolign_b200::StitchRecorder<Alignment>::instance();
+    if (rec.active() && !score_out)
+        return rec.record_pwfa<NumPW>(graph1, graph2, sources1, sources2, sinks1, sinks2, params, prune_limit);
+    return centrolign_b200::pwfa_po_poa<NumPW, Graph, AlignmentParameters<NumPW>, Alignment>(
+        graph1, graph2, sources1, sources2, sinks1, sinks2, params, prune_limit, score_out);
+}
+
 // hook for the translate() call in Stitcher::subalign (src/stitcher.cpp:66)
 inline void translate_b200(Alignment& alignment, const std::vector<uint64_t>& back_translation1,
                            const std::vector<uint64_t>& back_translation2) {
@@ -55,7 +69,9 @@ inline void translate_b200(Alignment& alignment, const std::vector<uint64_t>& ba
 
 #define Stitcher StitcherReference
 #define po_poa po_poa_b200
+#define pwfa_po_poa pwfa_po_poa_b200
 #include_next "centrolign/stitcher.hpp"
+#undef pwfa_po_poa
 #undef po_poa
 #undef Stitcher
 

@@ -51,6 +51,23 @@ static int trial(std::mt19937& gen, const AlignmentParameters<P>& params, int le
     return 0;
 }
 
+// the wavefront variant: centrolign_b200::pwfa_po_poa against centrolign::pwfa_po_poa (alignment.hpp:117-125)
+template <int P>
+static int trial_pwfa(std::mt19937& gen, const AlignmentParameters<P>& params, int len1, int len2, int64_t prune_limit) {
+    std::vector<uint64_t> s1, k1, s2, k2;
+    BaseGraph g1 = random_bubbly(gen, len1, s1, k1), g2 = random_bubbly(gen, len2, s2, k2);
+    int64_t sr = 0, sg = 0;
+    Alignment ref = pwfa_po_poa(g1, g2, s1, s2, k1, k2, params, prune_limit, &sr);
+    Alignment got = centrolign_b200::pwfa_po_poa<P, BaseGraph, AlignmentParameters<P>, Alignment>(g1, g2, s1, s2, k1, k2, params,
+                                                                                                 prune_limit, &sg);
+    if (sr != sg || !(ref == got)) {
+        std::fprintf(stderr, "PWFA MISMATCH P=%d len %d x %d prune %lld: score %lld vs %lld, %zu vs %zu pairs\n", P, len1, len2,
+                     (long long)prune_limit, (long long)sr, (long long)sg, ref.size(), got.size());
+        return 1;
+    }
+    return 0;
+}
+
 int main() {
     std::mt19937 gen(20261017);
     AlignmentParameters<3> prod;  // src/stitcher.cpp:13-22
@@ -63,6 +80,12 @@ int main() {
         bad += trial<3>(gen, prod, len(gen), len(gen));
         bad += trial<2>(gen, truncate_parameters<3, 2>(prod), len(gen) % 90 + 1, len(gen) % 90 + 1);
         bad += trial<1>(gen, truncate_parameters<3, 1>(prod), len(gen) % 40 + 1, len(gen) % 40 + 1);
+    }
+    for (int t = 0; t < 40; ++t) {
+        const int l = len(gen);
+        bad += trial_pwfa<3>(gen, prod, l, l + t % 7, 50);  // Stitcher: 2 * wfa_pruning_dist (stitcher.hpp:339)
+        bad += trial_pwfa<2>(gen, truncate_parameters<3, 2>(prod), l % 90 + 1, l % 90 + 2, 6);
+        bad += trial_pwfa<1>(gen, truncate_parameters<3, 1>(prod), l % 40 + 1, l % 40 + 1, 1000000);
     }
     if (!bad) std::printf("passed all tests!\n");
     return bad ? 1 : 0;

@@ -26,10 +26,18 @@ def test_cli_output_is_byte_identical(name, tmp_path):
                    check=True)
     assert hashlib.md5(open(fa, "rb").read()).hexdigest() == case["fasta_md5"], "input generator drifted"
     env = dict(os.environ, CLB_COUNT_CALLS="1")
-    res = subprocess.run([CLI, "-v", "0"] + case["options"] + [fa], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
+    sys.path.insert(0, os.path.join(ROOT, "integration"))
+    from make_e2e_golden import run_cli
+    res = run_cli(CLI, case["options"], fa, case.get("config_overrides") or {}, str(tmp_path), env=env)
     assert res.returncode == 0, res.stderr.decode()[-2000:]
     assert len(res.stdout) == case["output_bytes"]
     assert hashlib.md5(res.stdout).hexdigest() == case["output_md5"], "CIGAR/GFA differs from the unmodified reference"
+    if case.get("config_overrides", {}).get("min_wfa_size"):  # the wavefront route must have run on the GPU, batched
+        wcalls = [l for l in res.stderr.decode().splitlines() if l.startswith("[clb] pwfa calls")]
+        assert wcalls, "the GPU wavefront gap fill was never called"
+        n_wcalls, n_wwin = int(wcalls[-1].split()[3]), int(wcalls[-1].split()[5])
+        print(f"{name}: {n_wwin} wavefront windows in {n_wcalls} batched GPU calls")
+        assert n_wcalls > 0 and n_wwin > n_wcalls  # one call per stitch() and NumPW, not one per window
     calls = [l for l in res.stderr.decode().splitlines() if l.startswith("[clb] calls")]
     assert calls, "the GPU gap fill was never called"
     n_calls, n_windows = int(calls[-1].split()[2]), int(calls[-1].split()[4])

@@ -1,0 +1,66 @@
+"""Throughput of the wavefront-variant kernel (clb_pwfa_batch) on windows of the size the Stitcher routes to
+pwfa_po_poa (4e7 < cells < 7.5e7, i.e. ~6.3-8.7 k nodes per side, stitcher.hpp:327-339), next to the
+reference's CPU pwfa_po_poa on a sample of the same windows (each compared: score + alignment).
+    python tools/bench_pwfa.py [--windows 2000] [--cpu-sample 8]
+Prints one JSON line."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from centrolign_b200.batch import AlignmentParameters, CpuChecker, select_windows, successor_form, synth_windows  # noqa: E402
+from centrolign_b200.popoa import PwfaStats, pwfa_po_poa_batch  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--windows", type=int, default=2000)
+    ap.add_argument("--cpu-sample", type=int, default=8)
+    ap.add_argument("--len-min", type=float, default=5600.0)
+    ap.add_argument("--len-max", type=float, default=7600.0)
+    ap.add_argument("--prune", type=int, default=50)
+    ap.add_argument("--reps", type=int, default=2)
+    a = ap.parse_args()
+    p = AlignmentParameters()
+    batch = synth_windows(a.windows, first_index=0, seed=20261017, len_min=a.len_min, len_max=a.len_max)
+    t0 = time.time()
+    sb = successor_form(batch)
+    t_succ = time.time() - t0
+    best = None
+    for _ in range(a.reps + 1):  # first call warms the context
+        st = PwfaStats()
+        t0 = time.perf_counter()
+        scores, alns = pwfa_po_poa_batch(sb, p, a.prune, stats=st)
+        wall = time.perf_counter() - t0
+        if best is None or wall < best[0]:
+            best = (wall, st.kernel_ms, st)
+    wall, kms, st = best
+    kind = "reference" if CpuChecker.available("reference") else "port"
+    chk = CpuChecker(kind)
+    idx = np.linspace(0, a.windows - 1, a.cpu_sample).astype(int)
+    sub = select_windows(sb, idx)
+    t0 = time.perf_counter()
+    ok = True
+    for k, w in enumerate(idx):
+        s, al = chk.pwfa_po_poa(sub, k, p, a.prune)
+        ok &= bool(s == scores[w] and np.array_equal(al, alns[w]))
+    cpu_s = (time.perf_counter() - t0) / len(idx)
+    n1, n2 = batch.sizes()
+    print(json.dumps({
+        "path": "pwfa_po_poa", "windows": a.windows, "nodes_per_side": [int(n1.min()), int(n1.max())],
+        "cells_equiv": float(batch.cells().sum()), "prune_limit": a.prune,
+        "gpu_kernel_ms": kms, "gpu_wall_ms": wall * 1e3, "windows_per_s_kernel": a.windows / (kms / 1e3),
+        "windows_per_s_e2e": a.windows / wall, "states": st.states, "dequeued": st.dequeued, "steps": st.steps,
+        "entries_per_step": st.dequeued / max(1, st.steps), "states_per_s": st.states / (kms / 1e3),
+        "retries": st.retries, "workspace_bytes": st.workspace_bytes,
+        "cpu": {"kind": kind, "ms_per_window": cpu_s * 1e3, "windows_per_s_1core": 1 / cpu_s, "sample": int(len(idx)),
+                "all_equal_to_gpu": ok},
+        "successor_form_s": t_succ}))
+
+
+if __name__ == "__main__":
+    main()
