@@ -1,0 +1,404 @@
+// chain_host.cu -- host side of clb_chain_dp (include/centrolign_b200.h): lays out the reference's search
+// structures for the device (shapes only -- see chain_device.cuh), runs the DP kernel, and performs the
+// reference's traceback (Anchorer::traceback_sparse_dp, include/centrolign/anchorer.hpp:2473-2547).
+//
+// Shapes reproduced here:
+//   * MaxSearchTree: implicit binary heap 0..n-1 filled with the sorted keys by an in-order walk
+//     (max_search_tree.hpp:108-150); one per (p1, p2, shift) for the gap-free trees, keys (offset, match)
+//     (anchorer.hpp:2143-2215);
+//   * OrthogonalMaxSearchTree: the same heap over keys ((shift, match), offset), and for every node outside
+//     the two outer spines a cross structure over the node's subtree ordered by offset, ties in the outer
+//     key order (stable sort on key 2 only, orthogonal_max_search_tree.hpp:175-239, max_search_tree.hpp:100-106).
+// There is no CPU fallback: without a CUDA device the call fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <numeric>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "centrolign_b200.h"
+#include "chain_device.cuh"
+
+namespace clb {
+cudaError_t launch_chain(const ChainArgs& args, int grid, cudaStream_t stream);
+int chain_max_grid(int device);
+int host_fail(int code, const std::string& msg);
+}  // namespace clb
+
+namespace {
+
+using clb::host_fail;
+
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// heap index of every in-order position of an n-node implicit heap (max_search_tree.hpp:119-150)
+void inorder_layout(uint32_t n, std::vector<uint32_t>& heap_of_pos, std::vector<uint32_t>& stack) {
+    heap_of_pos.resize(n);
+    stack.clear();
+    uint32_t pos = 0;
+    uint64_t cur = 0;
+    while (cur < n || !stack.empty()) {
+        while (cur < n) {
+            stack.push_back((uint32_t)cur);
+            cur = 2 * cur + 1;
+        }
+        const uint32_t x = stack.back();
+        stack.pop_back();
+        heap_of_pos[pos++] = x;
+        cur = 2 * (uint64_t)x + 2;
+    }
+}
+
+struct DeviceBuffers {
+    std::vector<void*> ptrs;
+    int64_t bytes = 0;
+    template <class T>
+    cudaError_t upload(const std::vector<T>& h, T** d, cudaStream_t st, size_t min_count = 1) {
+        const size_t n = std::max(h.size(), min_count);
+        cudaError_t e = cudaMalloc((void**)d, n * sizeof(T));
+        if (e != cudaSuccess) return e;
+        ptrs.push_back(*d);
+        bytes += (int64_t)(n * sizeof(T));
+        if (!h.empty()) e = cudaMemcpyAsync(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st);
+        return e;
+    }
+    template <class T>
+    cudaError_t zeros(size_t n, T** d, cudaStream_t st) {
+        n = std::max<size_t>(n, 1);
+        cudaError_t e = cudaMalloc((void**)d, n * sizeof(T));
+        if (e != cudaSuccess) return e;
+        ptrs.push_back(*d);
+        bytes += (int64_t)(n * sizeof(T));
+        return cudaMemsetAsync(*d, 0, n * sizeof(T), st);
+    }
+    ~DeviceBuffers() {
+        for (void* p : ptrs) cudaFree(p);
+    }
+};
+
+}  // namespace
+
+extern "C" int clb_chain_dp(int device, const clb_chain_problem* p, float* dp_out, int64_t* backptr_out, int64_t* chain_out,
+                            int64_t* chain_len, float* opt_score, clb_chain_stats* stats) {
+    const double t_start = now_ms();
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (!p || !chain_out || !chain_len) return host_fail(CLB_EINVAL, "null problem or output");
+    if (p->num_pw < 0 || p->num_pw > CLB_MAX_PW) return host_fail(CLB_EINVAL, "num_pw outside 0..3");
+    if (p->n_match < 0 || p->n_step < 0 || p->n_chain1 < 1 || p->n_chain2 < 1)
+        return host_fail(CLB_EINVAL, "negative sizes or no chains");
+    if (p->n_match >= (int64_t(1) << 31)) return host_fail(CLB_EINVAL, "more than 2^31 matches");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return host_fail(CLB_ECUDA, "no CUDA device available (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) return host_fail(CLB_EINVAL, "device index out of range");
+    *chain_len = 0;
+    const float kLowest = std::numeric_limits<float>::lowest();
+    if (opt_score) *opt_score = kLowest;
+    const int64_t M = p->n_match, S = p->n_step;
+    if (M == 0) return CLB_OK;
+    if (!p->weight || !p->dp_init || !p->final_term || !p->end_off || !p->qry_off || !p->ins_off || !p->qa1 || !p->qa2 || !p->qoff)
+        return host_fail(CLB_EINVAL, "null problem arrays");
+    const int C1 = p->n_chain1, C2 = p->n_chain2, P = p->num_pw, T = 2 * P;
+    const int64_t npair = (int64_t)C1 * C2;
+    const int64_t E = p->ins_off[M];  // tree entries
+    if (E < 0 || E >= (int64_t(1) << 32) - 1) return host_fail(CLB_EINVAL, "entry count out of range");
+    const int64_t n_end = p->end_off[S], n_qry = p->qry_off[S];
+    for (int64_t k = 0; k < n_end; ++k)
+        if (p->end_match[k] >= (uint64_t)M) return host_fail(CLB_EINVAL, "end_match out of range");
+    for (int64_t k = 0; k < n_qry; ++k)
+        if (p->qry_match[k] >= (uint64_t)M || p->qry_chain1[k] >= (uint32_t)C1) return host_fail(CLB_EINVAL, "query out of range");
+    for (int64_t e = 0; e < E; ++e)
+        if (p->ins_p1[e] >= (uint32_t)C1 || p->ins_p2[e] >= (uint32_t)C2) return host_fail(CLB_EINVAL, "insert path out of range");
+
+    // ------------------------------------------------------------------ layout ------------------------------------------------------------------
+    std::vector<uint32_t> ent_match(E), ent_pair(E);
+    for (int64_t m = 0; m < M; ++m)
+        for (int64_t e = p->ins_off[m]; e < p->ins_off[m + 1]; ++e) {
+            ent_match[e] = (uint32_t)m;
+            ent_pair[e] = p->ins_p1[e] * (uint32_t)C2 + p->ins_p2[e];
+        }
+    // step -> entries, in the reference's order (anchorer.hpp:2301-2310); positions double as sequence numbers
+    std::vector<int64_t> sins_off(S + 1, 0);
+    std::vector<uint32_t> sins_entry;
+    sins_entry.reserve(E);
+    int64_t max_q = 0;
+    for (int64_t s = 0; s < S; ++s) {
+        for (int64_t k = p->end_off[s]; k < p->end_off[s + 1]; ++k) {
+            const uint32_t m = p->end_match[k];
+            for (int64_t e = p->ins_off[m]; e < p->ins_off[m + 1]; ++e)
+                if (!p->ins_active || p->ins_active[e]) sins_entry.push_back((uint32_t)e);
+        }
+        sins_off[s + 1] = (int64_t)sins_entry.size();
+        max_q = std::max(max_q, p->qry_off[s + 1] - p->qry_off[s]);
+    }
+    if ((int64_t)sins_entry.size() >= (int64_t(1) << 32) - 1) return host_fail(CLB_EINVAL, "more than 2^32 insertions");
+    if (max_q * C2 >= (int64_t(1) << 32) - 1) return host_fail(CLB_EINVAL, "too many queries in one step");
+
+    std::vector<uint32_t> order(E);
+    std::iota(order.begin(), order.end(), 0u);
+    std::vector<uint32_t> heap_of_pos, stack;
+
+    // gap-free trees: one per (pair, shift), keys (offset, match)
+    std::vector<int64_t> pair_grp_off(npair + 1, 0), grp_base;
+    std::vector<int32_t> grp_shift;
+    std::vector<uint32_t> grp_n, gf_key(E), gf_match(E), ent_gf_grp(E), ent_gf_node(E);
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+        if (ent_pair[a] != ent_pair[b]) return ent_pair[a] < ent_pair[b];
+        if (p->ins_shift[a] != p->ins_shift[b]) return p->ins_shift[a] < p->ins_shift[b];
+        if (p->ins_offset[a] != p->ins_offset[b]) return p->ins_offset[a] < p->ins_offset[b];
+        return ent_match[a] < ent_match[b];
+    });
+    for (int64_t i = 0; i < E;) {
+        int64_t j = i;
+        while (j < E && ent_pair[order[j]] == ent_pair[order[i]] && p->ins_shift[order[j]] == p->ins_shift[order[i]]) ++j;
+        const uint32_t g = (uint32_t)grp_base.size(), n = (uint32_t)(j - i);
+        grp_base.push_back(i);
+        grp_shift.push_back(p->ins_shift[order[i]]);
+        grp_n.push_back(n);
+        pair_grp_off[ent_pair[order[i]] + 1] += 1;
+        inorder_layout(n, heap_of_pos, stack);
+        for (uint32_t k = 0; k < n; ++k) {
+            const uint32_t e = order[i + k], h = heap_of_pos[k];
+            gf_key[i + h] = p->ins_offset[e];
+            gf_match[i + h] = ent_match[e];
+            ent_gf_grp[e] = g;
+            ent_gf_node[e] = h;
+        }
+        i = j;
+    }
+    for (int64_t pr = 0; pr < npair; ++pr) pair_grp_off[pr + 1] += pair_grp_off[pr];
+
+    // orthogonal trees: one shape per pair, keys ((shift, match), offset)
+    std::vector<int64_t> pair_base(npair + 1, 0), in_base, ent_rank_off;
+    std::vector<int32_t> or_shift;
+    std::vector<uint32_t> or_off, or_match, in_n, in_off, ent_or_node, ent_rank;
+    int64_t n_inner = 0;
+    if (P > 0) {
+        or_shift.resize(E); or_off.resize(E); or_match.resize(E); in_n.assign(E, 0); in_base.assign(E, -1);
+        ent_or_node.resize(E); ent_rank_off.assign(E + 1, 0);
+        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+            if (ent_pair[a] != ent_pair[b]) return ent_pair[a] < ent_pair[b];
+            if (p->ins_shift[a] != p->ins_shift[b]) return p->ins_shift[a] < p->ins_shift[b];
+            return ent_match[a] < ent_match[b];
+        });
+        for (int64_t e = 0; e < E; ++e) pair_base[ent_pair[e] + 1] += 1;
+        for (int64_t pr = 0; pr < npair; ++pr) pair_base[pr + 1] += pair_base[pr];
+        std::vector<uint32_t> pos_of_heap, sub_lo, sub_n, nanc;
+        std::vector<uint8_t> spine;
+        std::vector<std::vector<uint32_t>> lists;  // per heap node: sorted positions of its subtree ordered by (offset, position)
+        // pass 1: shapes, inner-list sizes and bases
+        for (int64_t pr = 0; pr < npair; ++pr) {
+            const int64_t ob = pair_base[pr];
+            const uint32_t n = (uint32_t)(pair_base[pr + 1] - ob);
+            if (!n) continue;
+            inorder_layout(n, heap_of_pos, stack);
+            for (uint32_t k = 0; k < n; ++k) {
+                const uint32_t e = order[ob + k], h = heap_of_pos[k];
+                or_shift[ob + h] = p->ins_shift[e];
+                or_off[ob + h] = p->ins_offset[e];
+                or_match[ob + h] = ent_match[e];
+                ent_or_node[e] = h;
+            }
+            spine.assign(n, 0);  // orthogonal_max_search_tree.hpp:175-182: the two outer spines carry no cross tree
+            for (uint64_t c = 0; c < n; c = 2 * c + 1) spine[c] = 1;
+            for (uint64_t c = 2; c < n; c = 2 * c + 2) spine[c] = 1;
+            sub_n.assign(n, 1);
+            for (uint32_t h = n; h-- > 1;) sub_n[(h - 1) / 2] += sub_n[h];
+            nanc.assign(n, 0);
+            for (uint32_t h = 0; h < n; ++h) {
+                nanc[h] = (h ? nanc[(h - 1) / 2] : 0) + (spine[h] ? 0 : 1);
+                if (!spine[h]) {
+                    in_base[ob + h] = n_inner;
+                    in_n[ob + h] = sub_n[h];
+                    n_inner += sub_n[h];
+                }
+            }
+            for (uint32_t k = 0; k < n; ++k) ent_rank_off[order[ob + k] + 1] = nanc[heap_of_pos[k]];
+        }
+        for (int64_t e = 0; e < E; ++e) ent_rank_off[e + 1] += ent_rank_off[e];
+        if (ent_rank_off[E] != n_inner) return host_fail(CLB_ECUDA, "internal: inner list accounting mismatch");
+        in_off.resize(n_inner);
+        ent_rank.resize(n_inner);
+        // pass 2: inner lists by merging children lists bottom-up; ranks of every element in every list it is part of
+        for (int64_t pr = 0; pr < npair; ++pr) {
+            const int64_t ob = pair_base[pr];
+            const uint32_t n = (uint32_t)(pair_base[pr + 1] - ob);
+            if (!n) continue;
+            inorder_layout(n, heap_of_pos, stack);
+            pos_of_heap.resize(n);
+            for (uint32_t k = 0; k < n; ++k) pos_of_heap[heap_of_pos[k]] = k;
+            lists.assign(n, std::vector<uint32_t>());
+            auto depth_of = [](uint32_t h) { return 31 - __builtin_clz(h + 1); };  // heap index -> depth
+            for (uint32_t h = n; h-- > 0;) {
+                if (in_base[ob + h] < 0) continue;  // spine: never queried, never built
+                const uint32_t l = 2 * h + 1, r = 2 * h + 2;
+                std::vector<uint32_t>& out = lists[h];
+                out.reserve(in_n[ob + h]);
+                const uint32_t self = pos_of_heap[h];
+                auto less = [&](uint32_t a, uint32_t b) {  // (offset, outer key order)
+                    const uint32_t oa = or_off[ob + heap_of_pos[a]], obb = or_off[ob + heap_of_pos[b]];
+                    return oa != obb ? oa < obb : a < b;
+                };
+                static const std::vector<uint32_t> kEmpty;
+                const std::vector<uint32_t>& L = l < n ? lists[l] : kEmpty;
+                const std::vector<uint32_t>& R = r < n ? lists[r] : kEmpty;
+                size_t a = 0, b = 0;
+                bool self_done = false;
+                while (a < L.size() || b < R.size() || !self_done) {
+                    // three-way merge; all positions are distinct
+                    int pick = -1;
+                    uint32_t best = 0;
+                    if (a < L.size()) { pick = 0; best = L[a]; }
+                    if (!self_done && (pick < 0 || less(self, best))) { pick = 1; best = self; }
+                    if (b < R.size() && (pick < 0 || less(R[b], best))) { pick = 2; best = R[b]; }
+                    out.push_back(best);
+                    if (pick == 0) ++a;
+                    else if (pick == 1) self_done = true;
+                    else ++b;
+                }
+                const int dh = depth_of(h);
+                const int64_t ib = in_base[ob + h];
+                for (uint32_t k = 0; k < out.size(); ++k) {
+                    const uint32_t eh = heap_of_pos[out[k]];
+                    in_off[ib + k] = or_off[ob + eh];
+                    const uint32_t e = order[ob + out[k]];
+                    ent_rank[ent_rank_off[e] + (depth_of(eh) - dh)] = k;  // climbing order: the element's own node first
+                }
+                if (l < n) std::vector<uint32_t>().swap(lists[l]);
+                if (r < n) std::vector<uint32_t>().swap(lists[r]);
+            }
+        }
+    }
+    const double t_built = now_ms();
+
+    // ------------------------------------------------------------------ device ------------------------------------------------------------------
+    int rc = CLB_OK;
+    DeviceBuffers dev;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    clb::ChainArgs a{};
+    std::vector<float> h_dp(M);
+    std::vector<uint32_t> h_bp(M);
+    std::vector<int32_t> ent_shift(p->ins_shift, p->ins_shift + E);
+    unsigned long long h_counter = 0;
+    int grid = 1;
+#define CHAIN_TRY(expr)                                                                                               \
+    do {                                                                                                              \
+        cudaError_t _e = (expr);                                                                                      \
+        if (_e != cudaSuccess) {                                                                                      \
+            rc = host_fail(_e == cudaErrorMemoryAllocation ? CLB_ENOMEM : CLB_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+            goto cleanup;                                                                                             \
+        }                                                                                                             \
+    } while (0)
+#define UP(vec, field) CHAIN_TRY(dev.upload(vec, const_cast<typename std::remove_const<typename std::remove_pointer<decltype(a.field)>::type>::type**>(&a.field), stream))
+    CHAIN_TRY(cudaSetDevice(device));
+    CHAIN_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CHAIN_TRY(cudaEventCreate(&ev0));
+    CHAIN_TRY(cudaEventCreate(&ev1));
+    a.num_pw = P; a.n_chain1 = C1; a.n_chain2 = C2; a.scale = p->scale;
+    for (int k = 0; k < 3; ++k) {
+        a.gap_open[k] = p->gap_open[k];
+        a.gap_extend[k] = p->gap_extend[k];
+        a.scale_ext[k] = p->scale * p->gap_extend[k];  // anchorer.hpp:2330: local_scale * gap_extend[pw / 2] (* shift on the device)
+    }
+    a.n_match = M; a.n_step = S; a.n_entry = E; a.n_inner = n_inner;
+    {
+        std::vector<float> w(p->weight, p->weight + M), d0(p->dp_init, p->dp_init + M);
+        std::vector<uint32_t> bp0(M, 0xffffffffu), qm(p->qry_match, p->qry_match + n_qry), qc(p->qry_chain1, p->qry_chain1 + n_qry);
+        std::vector<int64_t> qo(p->qry_off, p->qry_off + S + 1);
+        std::vector<int32_t> qa1(p->qa1, p->qa1 + M * C1), qa2(p->qa2, p->qa2 + M * C2);
+        std::vector<uint32_t> qoff(p->qoff, p->qoff + M * C2);
+        UP(w, weight); UP(d0, dp); UP(bp0, backptr); UP(sins_off, sins_off); UP(sins_entry, sins_entry); UP(ent_match, ent_match);
+        UP(qo, qry_off); UP(qm, qry_match); UP(qc, qry_chain1); UP(qa1, qa1); UP(qa2, qa2); UP(qoff, qoff);
+        UP(pair_grp_off, pair_grp_off); UP(grp_shift, grp_shift); UP(grp_base, grp_base); UP(grp_n, grp_n);
+        UP(gf_key, gf_key); UP(gf_match, gf_match); UP(ent_gf_grp, ent_gf_grp); UP(ent_gf_node, ent_gf_node);
+        std::vector<float> lowest(E, kLowest);
+        UP(lowest, gf_val);
+        CHAIN_TRY(dev.zeros((size_t)E, &a.gf_best, stream));
+        UP(pair_base, pair_base); UP(ent_pair, ent_pair);
+        if (P > 0) {
+            UP(or_shift, or_shift); UP(or_off, or_off); UP(or_match, or_match); UP(in_base, in_base); UP(in_n, in_n); UP(in_off, in_off);
+            UP(ent_or_node, ent_or_node); UP(ent_shift, ent_shift); UP(ent_rank_off, ent_rank_off); UP(ent_rank, ent_rank);
+            std::vector<float> lowest_t((size_t)T * E, kLowest);
+            UP(lowest_t, or_val);
+            CHAIN_TRY(dev.zeros((size_t)T * n_inner, &a.bit, stream));
+        }
+        CHAIN_TRY(dev.zeros((size_t)M, &a.cand_best, stream));
+        CHAIN_TRY(dev.zeros((size_t)(max_q * C2), &a.cand_bp, stream));
+        CHAIN_TRY(dev.zeros(1, &a.counters, stream));
+        CHAIN_TRY(cudaStreamSynchronize(stream));  // the staging vectors above go out of scope
+    }
+    {
+        // grid: one CTA unless a step has enough independent warps of work to pay for grid-wide barriers
+        const double warps_per_step = S ? ((double)sins_entry.size() + (double)n_qry * C2) / (double)S : 0.0;
+        const int max_grid = clb::chain_max_grid(device);
+        grid = getenv("CLB_CHAIN_GRID") ? std::max(1, std::min(max_grid, atoi(getenv("CLB_CHAIN_GRID"))))
+                                         : (warps_per_step > 64.0 ? std::min<int>(max_grid, (int)(warps_per_step / 16.0) + 1) : 1);
+    }
+    CHAIN_TRY(cudaEventRecord(ev0, stream));
+    CHAIN_TRY(clb::launch_chain(a, grid, stream));
+    CHAIN_TRY(cudaEventRecord(ev1, stream));
+    CHAIN_TRY(cudaMemcpyAsync(h_dp.data(), a.dp, M * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    CHAIN_TRY(cudaMemcpyAsync(h_bp.data(), a.backptr, M * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    CHAIN_TRY(cudaMemcpyAsync(&h_counter, a.counters, sizeof(h_counter), cudaMemcpyDeviceToHost, stream));
+    CHAIN_TRY(cudaStreamSynchronize(stream));
+    {
+        float ms = 0.f;
+        CHAIN_TRY(cudaEventElapsedTime(&ms, ev0, ev1));
+        if (stats) {
+            stats->build_ms = t_built - t_start;
+            stats->kernel_ms = ms;
+            stats->steps = S;
+            stats->inserts = (int64_t)sins_entry.size();
+            stats->queries = n_qry * C2;
+            stats->tree_bytes = dev.bytes;
+            stats->h2d_bytes = dev.bytes;
+            stats->d2h_bytes = M * 8;
+            stats->kernel_launches = 1;
+        }
+    }
+    // ---- traceback_sparse_dp (anchorer.hpp:2483-2534) ----
+    {
+        float opt_value = kLowest;
+        int64_t opt = -1;
+        for (int64_t m = 0; m < M; ++m) {
+            float dp_val = h_dp[m];
+            const float fin = p->final_term[m];
+            if (fin == kLowest) dp_val = fin;
+            else dp_val += fin;
+            if (dp_val > opt_value && dp_val > p->min_score) {
+                opt_value = dp_val;
+                opt = m;
+            }
+        }
+        int64_t len = 0;
+        for (int64_t here = opt; here >= 0; here = h_bp[here] == 0xffffffffu ? -1 : (int64_t)h_bp[here]) {
+            if (len >= M) {
+                rc = host_fail(CLB_ECUDA, "internal: back-pointer cycle");
+                goto cleanup;
+            }
+            chain_out[len++] = here;
+        }
+        std::reverse(chain_out, chain_out + len);
+        *chain_len = len;
+        if (opt_score) *opt_score = opt_value;
+        if (dp_out) memcpy(dp_out, h_dp.data(), M * sizeof(float));
+        if (backptr_out)
+            for (int64_t m = 0; m < M; ++m) backptr_out[m] = h_bp[m] == 0xffffffffu ? -1 : (int64_t)h_bp[m];
+    }
+    if (stats) stats->total_ms = now_ms() - t_start;
+cleanup:
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (stream) cudaStreamDestroy(stream);
+    return rc;
+#undef UP
+#undef CHAIN_TRY
+}

@@ -153,6 +153,83 @@ int clb_pwfa_batch(int device, int32_t n_windows, const clb_succ_graph_batch* g1
                    const clb_params* params, int64_t prune_limit, int64_t* score_out, const int64_t* aln_off,
                    int32_t* aln_pairs, uint32_t* aln_len, clb_pwfa_stats* stats /* may be NULL */);
 
+/*
+ * Sparse anchor-chaining DP.  Replaces the main loops of
+ *
+ *     Anchorer::sparse_affine_chain_dp<...>   reference: include/centrolign/anchorer.hpp:1812-2471 (loop :2290-2417)
+ *     Anchorer::sparse_chain_dp<...>          reference: include/centrolign/anchorer.hpp:1511-1750 (loop :1640-1728)
+ *     Anchorer::traceback_sparse_dp           reference: include/centrolign/anchorer.hpp:2473-2547 (arg-max + back-pointer walk)
+ *
+ * called through the _gen_sparse_affine / _gen_sparse macros of Anchorer::anchor_chain (anchorer.hpp:1213-1307).
+ * The C++ wrapper that keeps those signatures and produces this flat problem from the reference's own
+ * MatchBank / ForwardEdges / PathMerge / PostSwitchDistances objects is centrolign_b200/hostcpp/chain_b200.hpp.
+ *
+ * A match is identified by its RANK in MatchBank iteration order (set, walk1 index, walk2 index ascending,
+ * masked matches skipped; match_bank.hpp:251-267) -- order-isomorphic to the reference's match_id_t tuple, which
+ * matters because match ids are the low-order part of every search-tree key.
+ *
+ * "Steps" are the nodes of graph 1 in the reference's topological order (only nodes with events need to be
+ * listed).  At a step the reference first enters the DP value of every match ENDING on the node into its
+ * search trees (anchorer.hpp:2301-2345), then, for every forward edge leaving the node and every match
+ * STARTING on the edge's head, queries the trees and keeps the first strictly greater candidate
+ * (:2352-2416).  The result depends on that order, on the order of equal keys inside the trees and on the
+ * trees' own traversal order; all three are reproduced (see centrolign_b200/csrc/chain_host.cu).
+ * Scores are IEEE float (the reference's ScoreFloat) with the gap terms evaluated in double, as there.
+ */
+typedef struct clb_chain_problem {
+    int32_t num_pw;        /* 0: gap-free sparse_chain_dp; 1..3: sparse_affine_chain_dp with that many gap pieces */
+    double gap_open[CLB_MAX_PW];
+    double gap_extend[CLB_MAX_PW];
+    double scale;          /* local_scale (anchorer.hpp:1821) */
+    int32_t n_chain1;      /* xmerge1.chain_size() */
+    int32_t n_chain2;      /* xmerge2.chain_size() */
+    int64_t n_match;
+    const float* weight;     /* [n_match] anchor_weight of the match's set, as ScoreFloat (anchorer.hpp:2367-2368) */
+    const float* dp_init;    /* [n_match] single-anchor chain value incl. lead gap, or lowest() (anchorer.hpp:2023-2041) */
+    const float* final_term; /* [n_match] final indel score, or lowest() = cannot reach a sink (anchorer.hpp:2431-2438) */
+    float min_score;         /* the chain must beat the empty chain (anchorer.hpp:2419-2424) */
+    int64_t n_step;
+    const int64_t* end_off;     /* [n_step+1] into end_match */
+    const uint32_t* end_match;  /* matches ending on the step's node, ends_on() order */
+    const int64_t* qry_off;     /* [n_step+1] into qry_match / qry_chain1 */
+    const uint32_t* qry_match;  /* matches starting on the head of a forward edge: edge order, then starts_on() order */
+    const uint32_t* qry_chain1; /* the edge's chain on graph 1 */
+    const int64_t* ins_off;     /* [n_match+1] into ins_*: one entry per (p1,p2) in chains_on(end1) x chains_on(end2), loop order */
+    const uint32_t* ins_p1;
+    const uint32_t* ins_p2;
+    const int32_t* ins_shift;   /* index_on(end1,p1) - index_on(end2,p2)      (anchorer.hpp:1875-1880) */
+    const uint32_t* ins_offset; /* index_on(end2,p2)                          (anchorer.hpp:1894-1896) */
+    const uint8_t* ins_active;  /* NULL = all 1.  0 marks a key that shapes its search tree but is never entered: the gap-free
+                                   sparse_chain_dp builds, for EVERY chain of graph 1, a tree over all matches ending on a chain
+                                   of graph 2 (anchorer.hpp:1546-1552, 1595-1603) and enters a match only into the tree of its own
+                                   graph-1 chain (:1661-1666); the idle keys still decide the tree's traversal order */
+    const int32_t* qa1;  /* [n_match*n_chain1] predecessor_index(start1,c1) + D1(start1,c1), low 32 bits */
+    const int32_t* qa2;  /* [n_match*n_chain2] predecessor_index(start2,c2) + D2(start2,c2), low 32 bits;
+                            query shift = qa1 - qa2 in wrapping 32-bit arithmetic (anchorer.hpp:1886-1892) */
+    const uint32_t* qoff; /* [n_match*n_chain2] predecessor_index(start2,c2) + 1, 0 = nothing reachable (anchorer.hpp:1898-1901) */
+} clb_chain_problem;
+
+typedef struct clb_chain_stats {
+    double build_ms;   /* host: search-structure layout */
+    double kernel_ms;  /* CUDA-event time of the DP kernel */
+    double total_ms;   /* whole call */
+    int64_t steps, inserts, queries; /* events processed; queries = (match, edge, chain2) triples */
+    int64_t tree_bytes;              /* device bytes of the search structures */
+    int64_t h2d_bytes, d2h_bytes;
+    int64_t kernel_launches;
+} clb_chain_stats;
+
+/*
+ * Runs the DP on `device` and the reference's traceback.
+ *   dp_out      [n_match] final DP values (may be NULL)
+ *   backptr_out [n_match] back-pointer match rank, -1 = none (may be NULL)
+ *   chain_out   [n_match] capacity; the optimal chain as match ranks in forward order
+ *   chain_len   number of matches in the chain (0 = nothing beats min_score)
+ *   opt_score   value of the optimum (lowest() if the chain is empty); may be NULL
+ */
+int clb_chain_dp(int device, const clb_chain_problem* problem, float* dp_out, int64_t* backptr_out, int64_t* chain_out,
+                 int64_t* chain_len, float* opt_score, clb_chain_stats* stats /* may be NULL */);
+
 /* Measured INT32 issue-rate probe (a dependent-free add/max loop on every SM):
  * returns achieved 10^12 INT32 lane-ops per second on `device`, <0 on error. */
 double clb_int32_peak_tops(int device, int use_dpx);

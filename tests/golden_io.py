@@ -67,3 +67,16 @@ TIEBREAK_PROBES = [
     # mismatch vs insert+delete tie: gap close beats diagonal, I tested before D
     ("AG", [(0, 1)], [0], [1], "AC", [(0, 1)], [0], [1], (2, 2, (0,), (1,)), [(0, 0), (G, 1), (1, G)]),
 ]
+
+
+CHAIN_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "chain_golden.npz")
+
+
+def load_chain_golden():
+    """tests/golden/chain_golden.npz (tests/golden/make_chain_golden.py): chaining problems in the flat
+    clb_chain_problem layout with the chains the unmodified reference found.  Returns {case: {kind: ChainProblem}}."""
+    from centrolign_b200.chain import problems_from_arrays
+
+    z = np.load(CHAIN_GOLDEN)
+    cases = sorted({k.split("/")[0] for k in z.files})
+    return {c: problems_from_arrays(z, prefix=c + "/") for c in cases}
