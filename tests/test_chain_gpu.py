@@ -5,7 +5,7 @@ between equal-scoring chains included, which is where the reference's search-tre
 import numpy as np
 import pytest
 
-from centrolign_b200.chain import ChainStats, chain_dp
+from centrolign_b200.chain import ChainStats, chain_dp, chain_oracle
 from golden_io import load_chain_golden
 
 pytestmark = pytest.mark.gpu
@@ -50,3 +50,15 @@ def test_multi_cta_gives_the_same_values(grid, monkeypatch):
     chain, dp, bp, opt = chain_dp(prob)
     assert np.array_equal(chain, ref_chain) and np.array_equal(bp, ref_bp)
     assert np.array_equal(dp.view(np.uint32), ref_dp.view(np.uint32)) and opt == ref_opt
+
+
+@pytest.mark.parametrize("case,kind", CASES)
+def test_every_dp_value_and_backpointer_equals_the_oracle(case, kind):
+    """Stronger than chain identity: all DP values bit for bit and all back-pointers, against the literal C
+    restatement of the reference's search trees (oracle/chain_oracle.c)."""
+    prob = GOLD[case][kind]
+    chain, dp, bp, opt = chain_dp(prob)
+    ochain, odp, obp, oopt = chain_oracle(prob)
+    assert np.array_equal(chain, ochain) and opt == oopt
+    assert np.array_equal(dp.view(np.uint32), odp.view(np.uint32))
+    assert np.array_equal(bp, obp)

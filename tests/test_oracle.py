@@ -10,7 +10,7 @@ import pytest
 
 from centrolign_b200.batch import (AlignmentParameters, CpuChecker, batch_from_graph_pairs, graph_from_edges,
                                    successor_form, synth_windows)
-from golden_io import REFERENCE_UNIT_GOLDENS, TIEBREAK_PROBES, load_golden, load_pwfa_golden
+from golden_io import REFERENCE_UNIT_GOLDENS, TIEBREAK_PROBES, load_chain_golden, load_golden, load_pwfa_golden
 
 
 @pytest.fixture(scope="module")
@@ -109,3 +109,19 @@ def test_pwfa_live_against_reference(oracle):
                 so, ao = oracle.pwfa_po_poa(sb, w, p, lim)
                 sr, ar = ref.pwfa_po_poa(sb, w, p, lim)
                 assert so == sr and np.array_equal(ao, ar), f"window {w} P={p.num_pw}"
+
+
+# ---- sparse anchor-chaining DP (oracle/chain_oracle.c) ---------------------------------------------------
+def test_chain_oracle_reproduces_reference_chains():
+    """tests/golden/chain_golden.npz: flat problems + the chains Anchorer::sparse_chain_dp /
+    sparse_affine_chain_dp of the unmodified reference returned (anchorer.hpp:1511-1750, 1812-2471)."""
+    from centrolign_b200.chain import chain_oracle
+
+    gold = load_chain_golden()
+    assert len(gold) >= 4
+    for case in sorted(gold):
+        for kind in ("gapfree", "affine", "local"):
+            prob = gold[case][kind]
+            chain, dp, bp, opt = chain_oracle(prob)
+            assert np.array_equal(chain, prob.expect_chain), f"{case}/{kind}"
+            assert len(chain) > 50
