@@ -13,6 +13,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -89,10 +91,19 @@ extern "C" int clb_chain_dp(int device, const clb_chain_problem* p, float* dp_ou
                             int64_t* chain_len, float* opt_score, clb_chain_stats* stats) {
     const double t_start = now_ms();
     if (stats) memset(stats, 0, sizeof(*stats));
+    if (getenv("CLB_COUNT_CALLS") && p) {  // evidence for integration tests that the GPU path really ran
+        static std::atomic<int64_t> calls(0), matches(0);
+        static std::once_flag once;
+        std::call_once(once, [] {
+            atexit([] { fprintf(stderr, "[clb] chain calls %lld matches %lld\n", (long long)calls.load(), (long long)matches.load()); });
+        });
+        calls += 1;
+        matches += p->n_match;
+    }
     if (!p || !chain_out || !chain_len) return host_fail(CLB_EINVAL, "null problem or output");
     if (p->num_pw < 0 || p->num_pw > CLB_MAX_PW) return host_fail(CLB_EINVAL, "num_pw outside 0..3");
-    if (p->n_match < 0 || p->n_step < 0 || p->n_chain1 < 1 || p->n_chain2 < 1)
-        return host_fail(CLB_EINVAL, "negative sizes or no chains");
+    if (p->n_match < 0 || p->n_step < 0 || p->n_chain1 < 0 || p->n_chain2 < 0) return host_fail(CLB_EINVAL, "negative sizes");
+    if (p->n_match > 0 && (p->n_chain1 < 1 || p->n_chain2 < 1)) return host_fail(CLB_EINVAL, "matches but no chains");
     if (p->n_match >= (int64_t(1) << 31)) return host_fail(CLB_EINVAL, "more than 2^31 matches");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
@@ -139,7 +150,7 @@ extern "C" int clb_chain_dp(int device, const clb_chain_problem* p, float* dp_ou
         max_q = std::max(max_q, p->qry_off[s + 1] - p->qry_off[s]);
     }
     if ((int64_t)sins_entry.size() >= (int64_t(1) << 32) - 1) return host_fail(CLB_EINVAL, "more than 2^32 insertions");
-    if (max_q * C2 >= (int64_t(1) << 32) - 1) return host_fail(CLB_EINVAL, "too many queries in one step");
+    if (max_q * C2 * (T + 1) >= (int64_t(1) << 32) - 1) return host_fail(CLB_EINVAL, "too many queries in one step");
 
     std::vector<uint32_t> order(E);
     std::iota(order.begin(), order.end(), 0u);
@@ -331,13 +342,13 @@ extern "C" int clb_chain_dp(int device, const clb_chain_problem* p, float* dp_ou
             CHAIN_TRY(dev.zeros((size_t)T * n_inner, &a.bit, stream));
         }
         CHAIN_TRY(dev.zeros((size_t)M, &a.cand_best, stream));
-        CHAIN_TRY(dev.zeros((size_t)(max_q * C2), &a.cand_bp, stream));
+        CHAIN_TRY(dev.zeros((size_t)(max_q * C2 * (T + 1)), &a.cand_bp, stream));
         CHAIN_TRY(dev.zeros(1, &a.counters, stream));
         CHAIN_TRY(cudaStreamSynchronize(stream));  // the staging vectors above go out of scope
     }
     {
         // grid: one CTA unless a step has enough independent warps of work to pay for grid-wide barriers
-        const double warps_per_step = S ? ((double)sins_entry.size() + (double)n_qry * C2) / (double)S : 0.0;
+        const double warps_per_step = S ? ((double)sins_entry.size() + (double)n_qry * C2 * (P > 0 ? 3 : 1)) / (double)S : 0.0;
         const int max_grid = clb::chain_max_grid(device);
         grid = getenv("CLB_CHAIN_GRID") ? std::max(1, std::min(max_grid, atoi(getenv("CLB_CHAIN_GRID"))))
                                          : (warps_per_step > 64.0 ? std::min<int>(max_grid, (int)(warps_per_step / 16.0) + 1) : 1);

@@ -48,81 +48,55 @@ __device__ __forceinline__ unsigned long long pack(float v, uint32_t low) {
 }
 
 struct WalkEntry {
-    uint32_t node;  // outer heap index
-    uint32_t kind;  // 0: the node itself, 1: the whole subtree of `node` (its inner list)
+    uint32_t node;  // heap index
+    uint32_t kind;  // 0: the node itself, 1: the whole subtree of `node`
 };
 
 struct WarpScratch {
     WalkEntry blk[kMaxBlocks];
 };
 
-// MaxSearchTree::range_max(lo = (0, min), hi = (offset, min)) on one gap-free tree (max_search_tree.hpp:361-444).
-// Keys (offset, match) < hi  <=>  offset key < offset; nothing is below lo.  Executed uniformly by the warp.
-__device__ bool gapfree_range_max(const ChainArgs& A, int64_t base, uint32_t n, uint32_t offset, float& val_out, uint32_t& match_out) {
-    uint32_t cursor = 0;
-    while (cursor < n && __ldg(&A.gf_key[base + cursor]) >= offset) cursor = 2 * cursor + 1;
-    if (cursor >= n) return false;
-    float best = __ldcg(&A.gf_val[base + cursor]);
-    uint32_t best_match = __ldg(&A.gf_match[base + cursor]);
-    uint32_t lc = 2 * cursor + 1, rc = 2 * cursor + 2;
-    while (lc < n) {  // every key on this side is >= lo: take the node and its whole right subtree
-        const float v = __ldcg(&A.gf_val[base + lc]);
-        if (v > best) {
-            best = v;
-            best_match = __ldg(&A.gf_match[base + lc]);
+// The walk shared by MaxSearchTree::range_max (max_search_tree.hpp:361-444) and the outer level of
+// OrthogonalMaxSearchTree::range_max (orthogonal_max_search_tree.hpp:340-470), for one-sided key ranges:
+//   prefix: in_range(x) <=> key[x] <  bound  (nothing lies below the range: its left walk takes every node)
+//   suffix: in_range(x) <=> key[x] >  bound  (nothing lies above the range: its right walk takes every node)
+// Records the blocks -- a node itself, or the whole subtree hanging off the walk -- in the order the reference
+// tests them.  The walk is uniform over the warp; to avoid one memory round trip per tree level, the range
+// flags of a node and of its descendants four levels down (31 nodes) are fetched by the 31 lanes at once and
+// the next moves are resolved from the resulting bit mask.
+template <class InRange>
+__device__ int tree_walk(uint32_t n, bool prefix, const InRange& in_range, WalkEntry* blk, int lane) {
+    uint32_t wbase = 0xffffffffu;
+    unsigned wbits = 0;
+    auto flag = [&](uint32_t y) -> bool {
+        const uint32_t rel = y + 1;
+        int d = -1;
+        if (wbase != 0xffffffffu) {
+            const uint32_t b = wbase + 1;
+            d = (31 - __clz(rel)) - (31 - __clz(b));
+            if (d < 0 || d > 4 || (rel >> d) != b) d = -1;
         }
-        const uint32_t r = 2 * lc + 2;
-        if (r < n) {
-            const unsigned long long pk = __ldcg(&A.gf_best[base + r]);
-            if (pk) {
-                const float sv = funord((uint32_t)(pk >> 32));
-                if (sv > best) {
-                    best = sv;
-                    best_match = __ldg(&A.ent_match[__ldg(&A.sins_entry[~(uint32_t)pk])]);
+        if (d < 0) {  // fetch the window rooted at y
+            wbase = y;
+            bool f = false;
+            if (lane < 31) {
+                uint32_t idx = y;
+                if (lane < 30) {
+                    const int dj = 31 - __clz(lane + 2);
+                    idx = (rel << dj) - 1 + (uint32_t)(lane + 2 - (1 << dj));
+                    if ((rel << dj) < rel) idx = 0xffffffffu;  // overflow: no such node
                 }
+                if (idx < n) f = in_range(idx);
             }
+            wbits = __ballot_sync(kFull, f);
+            d = 0;
         }
-        lc = 2 * lc + 1;
-    }
-    while (rc < n) {
-        if (__ldg(&A.gf_key[base + rc]) < offset) {
-            const float v = __ldcg(&A.gf_val[base + rc]);
-            if (v > best) {
-                best = v;
-                best_match = __ldg(&A.gf_match[base + rc]);
-            }
-            const uint32_t l = 2 * rc + 1;
-            if (l < n) {
-                const unsigned long long pk = __ldcg(&A.gf_best[base + l]);
-                if (pk) {
-                    const float sv = funord((uint32_t)(pk >> 32));
-                    if (sv > best) {
-                        best = sv;
-                        best_match = __ldg(&A.ent_match[__ldg(&A.sins_entry[~(uint32_t)pk])]);
-                    }
-                }
-            }
-            rc = 2 * rc + 2;
-        } else {
-            rc = 2 * rc + 1;
-        }
-    }
-    val_out = best;
-    match_out = best_match;
-    return true;
-}
-
-// The outer walk of OrthogonalMaxSearchTree::range_max (orthogonal_max_search_tree.hpp:340-470) for
-//   prefix: key1 in [(-inf, min), (q, min))  <=> shift <  q   (odd pieces,  anchorer.hpp:2396-2398)
-//   suffix: key1 in [(q+1, min), (+inf, max)) <=> shift >  q   (even pieces, anchorer.hpp:2405-2407)
-// Records the blocks in the order the reference tests them.  Uniform over the warp; lane 0 writes.
-__device__ int ortho_walk(const ChainArgs& A, int64_t ob, uint32_t n, int q, bool prefix, WalkEntry* blk, int lane) {
-    auto in_range = [&](uint32_t x) {
-        const int s = __ldg(&A.or_shift[ob + x]);
-        return prefix ? (s < q) : (s > q);
+        if (d == 0) return (wbits >> 30) & 1u;
+        const uint32_t k = rel - ((wbase + 1) << d);
+        return (wbits >> ((1u << d) - 2 + k)) & 1u;
     };
     uint32_t cursor = 0;
-    while (cursor < n && !in_range(cursor)) cursor = prefix ? 2 * cursor + 1 : 2 * cursor + 2;
+    while (cursor < n && !flag(cursor)) cursor = prefix ? 2 * cursor + 1 : 2 * cursor + 2;
     if (cursor >= n) return 0;
     int nb = 0;
     auto push = [&](uint32_t node, uint32_t kind) {
@@ -131,8 +105,8 @@ __device__ int ortho_walk(const ChainArgs& A, int64_t ob, uint32_t n, int q, boo
     };
     push(cursor, 0);
     uint32_t lc = 2 * cursor + 1, rc = 2 * cursor + 2;
-    while (lc < n) {  // leftward: right subtrees hang entirely inside the key-1 range
-        if (prefix || in_range(lc)) {
+    while (lc < n) {  // leftward: right subtrees hang entirely inside the range
+        if (prefix || flag(lc)) {
             push(lc, 0);
             if (2 * lc + 2 < n) push(2 * lc + 2, 1);
             lc = 2 * lc + 1;
@@ -141,7 +115,7 @@ __device__ int ortho_walk(const ChainArgs& A, int64_t ob, uint32_t n, int q, boo
         }
     }
     while (rc < n) {  // rightward: left subtrees hang entirely inside
-        if (!prefix || in_range(rc)) {
+        if (!prefix || flag(rc)) {
             push(rc, 0);
             if (2 * rc + 1 < n) push(2 * rc + 1, 1);
             rc = 2 * rc + 2;
@@ -150,6 +124,46 @@ __device__ int ortho_walk(const ChainArgs& A, int64_t ob, uint32_t n, int q, boo
         }
     }
     return nb;
+}
+
+// first index in [lo, hi) whose value is >= q, by 32-ary search over the warp (uniform result)
+__device__ int64_t warp_lower_bound(const int32_t* arr, int64_t lo, int64_t hi, int q, int lane) {
+    while (hi - lo > 32) {
+        const int64_t step = (hi - lo + 31) / 32;
+        const int64_t at = lo + (int64_t)lane * step;
+        const bool less = at < hi && __ldg(&arr[at]) < q;
+        const int cnt = __popc(__ballot_sync(kFull, less));  // pivots below q form a prefix
+        if (cnt == 0) return lo;
+        const int64_t nlo = lo + (int64_t)(cnt - 1) * step + 1;
+        hi = min(hi, lo + (int64_t)cnt * step);
+        lo = nlo;
+    }
+    const bool less = lo + lane < hi && __ldg(&arr[lo + lane]) < q;
+    return lo + __popc(__ballot_sync(kFull, less));
+}
+
+// number of entries of the ascending list `a[0, n)` that are < key, 8-ary search with independent probes
+__device__ __forceinline__ uint32_t count_less(const uint32_t* a, uint32_t n, uint32_t key) {
+    uint32_t lo = 0, hi = n;  // answer in [lo, hi]
+    while (hi - lo > 7) {
+        const uint32_t step = (hi - lo) >> 3;
+        uint32_t v[7];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) v[i] = __ldg(&a[lo + (i + 1) * step - 1]);
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) c += v[i] < key;
+        const uint32_t nlo = lo + c * step;
+        hi = c == 7 ? hi : lo + (c + 1) * step - 1;
+        lo = nlo;
+    }
+    uint32_t v[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) v[i] = lo + i < hi ? __ldg(&a[lo + i]) : 0xffffffffu;
+    uint32_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) c += (lo + i < hi) && v[i] < key;
+    return lo + c;
 }
 
 }  // namespace
@@ -162,12 +176,19 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainArgs A) {
     const int64_t gwarp = (int64_t)blockIdx.x * kWarps + wib, nwarp = (int64_t)gridDim.x * kWarps;
     const int64_t gthread = (int64_t)blockIdx.x * kThreads + threadIdx.x, nthread = (int64_t)gridDim.x * kThreads;
     const int C1 = A.n_chain1, C2 = A.n_chain2, P = A.num_pw, T = 2 * A.num_pw;
+    const int n_type = P > 0 ? 3 : 1;        // work items per (query, chain2): gap-free tree, even pieces, odd pieces
+    const uint32_t slots = (uint32_t)(T + 1);  // candidate slots per (query, chain2), in the reference's order
     WalkEntry* blk = scratch[wib].blk;
     unsigned long long n_tree_queries = 0;
 
     auto barrier = [&]() {
         if (multi) grid.sync();
         else __syncthreads();
+    };
+    auto post = [&](uint32_t m, int64_t qc, uint32_t slot, float cand, uint32_t bp) {  // lane 0 only
+        const uint32_t order = (uint32_t)qc * slots + slot;
+        A.cand_bp[order] = bp;
+        atomicMax(&A.cand_best[m], pack(cand, ~order));
     };
 
     for (int64_t s = 0; s < A.n_step; ++s) {
@@ -191,6 +212,14 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainArgs A) {
                 const int shift = A.ent_shift[e];
                 const int64_t r0 = A.ent_rank_off[e];
                 const int nr = (int)(A.ent_rank_off[e + 1] - r0);
+                int64_t ib = 0;
+                uint32_t cn = 0, rank = 0;
+                if (lane < nr) {  // lane = level: the node itself and its ancestors below the outer spines
+                    const uint32_t a = ((oh + 1) >> lane) - 1;
+                    ib = A.in_base[ob + a];
+                    cn = A.in_n[ob + a];
+                    rank = A.ent_rank[r0 + lane];
+                }
                 for (int t = 0; t < T; ++t) {
                     // anchorer.hpp:2328-2335: odd pieces add, even pieces subtract local_scale * gap_extend * shift
                     const double gap = __dmul_rn(A.scale_ext[t >> 1], (double)shift);
@@ -198,12 +227,9 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainArgs A) {
                     if (!(v > mininf())) continue;  // anchorer.hpp:2338
                     if (lane == 0) A.or_val[(int64_t)t * A.n_entry + ob + oh] = v;
                     if (lane < nr) {
-                        const uint32_t a = ((oh + 1) >> lane) - 1;
-                        const int64_t ib = A.in_base[ob + a];
-                        const uint32_t n = A.in_n[ob + a];
                         const unsigned long long pk = pack(v, oh);
                         unsigned long long* bit = A.bit + (int64_t)t * A.n_inner + ib;
-                        for (uint32_t k = A.ent_rank[r0 + lane]; k < n; k |= k + 1) atomicMax(&bit[k], pk);
+                        for (uint32_t k = rank; k < cn; k |= k + 1) atomicMax(&bit[k], pk);
                     }
                 }
             }
@@ -216,10 +242,12 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainArgs A) {
         if (i0 != i1) barrier();
 
         // ------------------------------ B: queries (anchorer.hpp:2352-2416) ------------------------------
-        const int64_t n_items = (q1 - q0) * C2;
+        const int64_t n_items = (q1 - q0) * C2 * n_type;
         for (int64_t item = gwarp; item < n_items; item += nwarp) {
-            const int64_t qi = item / C2;
-            const int c2 = (int)(item - qi * C2);
+            const int64_t qc = item / n_type;  // (query, chain2) pair
+            const int type = (int)(item - qc * n_type);
+            const int64_t qi = qc / C2;
+            const int c2 = (int)(qc - qi * C2);
             const uint32_t m = A.qry_match[q0 + qi];
             const uint32_t c1 = A.qry_chain1[q0 + qi];
             const uint32_t offset = A.qoff[(int64_t)m * C2 + c2];
@@ -227,114 +255,112 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainArgs A) {
             const int q = (int)((uint32_t)A.qa1[(int64_t)m * C1 + c1] - (uint32_t)A.qa2[(int64_t)m * C2 + c2]);
             const int64_t pair = (int64_t)c1 * C2 + c2;
             const float w = A.weight[m];
-            float best = mininf();
-            uint32_t best_bp = 0xffffffffu;
-            {   // same diagonal (anchorer.hpp:2379-2389): binary search the pair's diagonals for shift == q
-                int64_t lo = A.pair_grp_off[pair], hi = A.pair_grp_off[pair + 1];
-                while (lo < hi) {
-                    const int64_t mid = (lo + hi) >> 1;
-                    if (__ldg(&A.grp_shift[mid]) < q) lo = mid + 1;
-                    else hi = mid;
-                }
-                if (lo < A.pair_grp_off[pair + 1] && __ldg(&A.grp_shift[lo]) == q) {
-                    float v;
-                    uint32_t bm;
-                    ++n_tree_queries;
-                    if (gapfree_range_max(A, A.grp_base[lo], A.grp_n[lo], offset, v, bm) && v > mininf()) {
-                        const float cand = __fadd_rn(v, w);
-                        if (cand > best) {
-                            best = cand;
-                            best_bp = bm;
+            ++n_tree_queries;
+            __syncwarp();
+            if (type == 0) {
+                // same diagonal (anchorer.hpp:2379-2389): MaxSearchTree::range_max((0, min), (offset, min))
+                const int64_t g1 = A.pair_grp_off[pair + 1];
+                const int64_t g = warp_lower_bound(A.grp_shift, A.pair_grp_off[pair], g1, q, lane);
+                if (g >= g1 || __ldg(&A.grp_shift[g]) != q) continue;
+                const int64_t base = A.grp_base[g];
+                const uint32_t n = A.grp_n[g];
+                const uint32_t* key = A.gf_key + base;
+                const int nb = tree_walk(n, true, [&](uint32_t x) { return __ldg(&key[x]) < offset; }, blk, lane);
+                __syncwarp();
+                unsigned long long lbest = 0;  // pack(value, ~block index)
+                uint32_t lmatch = 0;
+                for (int b = lane; b < nb && b < kMaxBlocks; b += 32) {
+                    const WalkEntry we = blk[b];
+                    float v = mininf();
+                    uint32_t bm = 0;
+                    if (we.kind == 0) {
+                        v = __ldcg(&A.gf_val[base + we.node]);
+                        bm = __ldg(&A.gf_match[base + we.node]);
+                    } else {
+                        const unsigned long long pk = __ldcg(&A.gf_best[base + we.node]);
+                        if (pk) {
+                            v = funord((uint32_t)(pk >> 32));
+                            bm = __ldg(&A.ent_match[__ldg(&A.sins_entry[~(uint32_t)pk])]);
                         }
                     }
-                }
-            }
-            if (P > 0) {
-                const int64_t ob = A.pair_base[pair];
-                const uint32_t n = (uint32_t)(A.pair_base[pair + 1] - ob);
-                float tv[kChainMaxTrees];
-                uint32_t tn[kChainMaxTrees];
-                for (int t = 0; t < kChainMaxTrees; ++t) {
-                    tv[t] = mininf();
-                    tn[t] = 0;
-                }
-                for (int par = 0; par < 2 && n > 0; ++par) {  // par 0: even pieces (suffix), par 1: odd pieces (prefix)
-                    __syncwarp();
-                    const int nb = ortho_walk(A, ob, n, q, par == 1, blk, lane);
-                    __syncwarp();
-                    unsigned long long lbest[3] = {0, 0, 0};  // per piece: pack(value, ~block index) of this lane's best block
-                    uint32_t lnode[3] = {0, 0, 0};
-                    for (int b = lane; b < nb && b < kMaxBlocks; b += 32) {
-                        const WalkEntry we = blk[b];
-                        if (we.kind == 0) {
-                            if (__ldg(&A.or_off[ob + we.node]) < offset) {
-                                for (int k = 0; k < P; ++k) {
-                                    const float v = __ldcg(&A.or_val[(int64_t)(2 * k + par) * A.n_entry + ob + we.node]);
-                                    const unsigned long long pk = pack(v, ~(uint32_t)b);
-                                    if (v > mininf() && (pk >> 32) > (lbest[k] >> 32)) {
-                                        lbest[k] = pk;
-                                        lnode[k] = we.node;
-                                    }
-                                }
-                            }
-                        } else {
-                            const int64_t ib = A.in_base[ob + we.node];
-                            const uint32_t cn = A.in_n[ob + we.node];
-                            uint32_t lo = 0, hi = cn;  // elements of the subtree with offset < `offset`
-                            while (lo < hi) {
-                                const uint32_t mid = (lo + hi) >> 1;
-                                if (__ldg(&A.in_off[ib + mid]) < offset) lo = mid + 1;
-                                else hi = mid;
-                            }
-                            if (lo) {
-                                for (int k = 0; k < P; ++k) {
-                                    const unsigned long long* bit = A.bit + (int64_t)(2 * k + par) * A.n_inner + ib;
-                                    unsigned long long r = 0;
-                                    for (uint32_t c = lo; c > 0; c &= c - 1) {
-                                        const unsigned long long x = __ldcg(&bit[c - 1]);
-                                        r = x > r ? x : r;
-                                    }
-                                    if (r && (r >> 32) > (lbest[k] >> 32)) {
-                                        lbest[k] = (r & 0xffffffff00000000ull) | (~(uint32_t)b);
-                                        lnode[k] = (uint32_t)r;
-                                    }
-                                }
-                            }
-                        }
+                    const unsigned long long pk = pack(v, ~(uint32_t)b);
+                    if (v > mininf() && (pk >> 32) > (lbest >> 32)) {
+                        lbest = pk;
+                        lmatch = bm;
                     }
-                    n_tree_queries += P;
-                    for (int k = 0; k < P; ++k) {  // first block, in walk order, that attains the maximum value
-                        unsigned long long r = lbest[k];
+                }
+                unsigned long long r = lbest;
 #pragma unroll
-                        for (int d = 16; d; d >>= 1) {
-                            const unsigned long long o = __shfl_xor_sync(kFull, r, d);
-                            r = o > r ? o : r;
-                        }
-                        if (r) {
-                            const unsigned src = __ffs(__ballot_sync(kFull, lbest[k] == r)) - 1;
-                            tv[2 * k + par] = funord((uint32_t)(r >> 32));
-                            tn[2 * k + par] = __shfl_sync(kFull, lnode[k], src);
-                        } else {
-                            __ballot_sync(kFull, false);
+                for (int d = 16; d; d >>= 1) {
+                    const unsigned long long o = __shfl_xor_sync(kFull, r, d);
+                    r = o > r ? o : r;
+                }
+                if (!r) continue;
+                const unsigned src = __ffs(__ballot_sync(kFull, lbest == r)) - 1;
+                const uint32_t bm = __shfl_sync(kFull, lmatch, src);
+                if (lane == 0) post(m, qc, 0, __fadd_rn(funord((uint32_t)(r >> 32)), w), bm);
+                continue;
+            }
+            // orthogonal trees of one parity (anchorer.hpp:2390-2413): par 0 = even pieces (shift > q), par 1 = odd (shift < q)
+            const int par = type - 1;
+            const int64_t ob = A.pair_base[pair];
+            const uint32_t n = (uint32_t)(A.pair_base[pair + 1] - ob);
+            if (n == 0) continue;
+            const int32_t* shift = A.or_shift + ob;
+            const int nb = par ? tree_walk(n, true, [&](uint32_t x) { return __ldg(&shift[x]) < q; }, blk, lane)
+                               : tree_walk(n, false, [&](uint32_t x) { return __ldg(&shift[x]) > q; }, blk, lane);
+            __syncwarp();
+            unsigned long long lbest[3] = {0, 0, 0};  // per piece: pack(value, ~block index) of this lane's best block
+            uint32_t lnode[3] = {0, 0, 0};
+            for (int b = lane; b < nb && b < kMaxBlocks; b += 32) {
+                const WalkEntry we = blk[b];
+                if (we.kind == 0) {
+                    if (__ldg(&A.or_off[ob + we.node]) < offset) {
+                        float v[3];
+                        for (int k = 0; k < P; ++k) v[k] = __ldcg(&A.or_val[(int64_t)(2 * k + par) * A.n_entry + ob + we.node]);
+                        for (int k = 0; k < P; ++k) {
+                            const unsigned long long pk = pack(v[k], ~(uint32_t)b);
+                            if (v[k] > mininf() && (pk >> 32) > (lbest[k] >> 32)) {
+                                lbest[k] = pk;
+                                lnode[k] = we.node;
+                            }
                         }
                     }
-                }
-                for (int t = 0; t < T; ++t) {  // pieces in the reference's order (anchorer.hpp:2390-2413)
-                    if (!(tv[t] > mininf())) continue;
-                    const int k = t >> 1;
-                    const double eq = __dmul_rn(A.gap_extend[k], (double)q);
-                    const double pen = __dmul_rn(A.scale, (t & 1) ? __dadd_rn(A.gap_open[k], eq) : __dsub_rn(A.gap_open[k], eq));
-                    const float cand = __double2float_rn(__dsub_rn((double)__fadd_rn(tv[t], w), pen));
-                    if (cand > best) {
-                        best = cand;
-                        best_bp = __ldg(&A.or_match[ob + tn[t]]);
+                } else {
+                    const int64_t ib = A.in_base[ob + we.node];
+                    const uint32_t cnt = count_less(A.in_off + ib, A.in_n[ob + we.node], offset);
+                    if (cnt) {  // Fenwick prefix maximum over the first cnt entries; the probes are independent
+                        unsigned long long r[3] = {0, 0, 0};
+                        for (uint32_t c = cnt; c > 0; c &= c - 1) {
+                            unsigned long long x[3];
+                            for (int k = 0; k < P; ++k) x[k] = __ldcg(&A.bit[(int64_t)(2 * k + par) * A.n_inner + ib + c - 1]);
+                            for (int k = 0; k < P; ++k) r[k] = x[k] > r[k] ? x[k] : r[k];
+                        }
+                        for (int k = 0; k < P; ++k)
+                            if (r[k] && (r[k] >> 32) > (lbest[k] >> 32)) {
+                                lbest[k] = (r[k] & 0xffffffff00000000ull) | (~(uint32_t)b);
+                                lnode[k] = (uint32_t)r[k];
+                            }
                     }
                 }
             }
-            if (lane == 0 && best_bp != 0xffffffffu) {
-                const uint32_t order = (uint32_t)(qi * C2 + c2);
-                A.cand_bp[order] = best_bp;
-                atomicMax(&A.cand_best[m], pack(best, ~order));
+            for (int k = 0; k < P; ++k) {  // first block, in walk order, that attains the maximum value
+                unsigned long long r = lbest[k];
+#pragma unroll
+                for (int d = 16; d; d >>= 1) {
+                    const unsigned long long o = __shfl_xor_sync(kFull, r, d);
+                    r = o > r ? o : r;
+                }
+                if (!r) continue;
+                const unsigned src = __ffs(__ballot_sync(kFull, lbest[k] == r)) - 1;
+                const uint32_t node = __shfl_sync(kFull, lnode[k], src);
+                if (lane == 0) {
+                    const int t = 2 * k + par;
+                    const double eq = __dmul_rn(A.gap_extend[k], (double)q);
+                    const double pen = __dmul_rn(A.scale, par ? __dadd_rn(A.gap_open[k], eq) : __dsub_rn(A.gap_open[k], eq));
+                    const float cand = __double2float_rn(__dsub_rn((double)__fadd_rn(funord((uint32_t)(r >> 32)), w), pen));
+                    post(m, qc, (uint32_t)(1 + t), cand, __ldg(&A.or_match[ob + node]));
+                }
             }
         }
         barrier();
@@ -345,7 +371,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainArgs A) {
             const unsigned long long pk = __ldcg(&A.cand_best[m]);
             if (!pk) continue;
             const uint32_t order = ~(uint32_t)pk;
-            if ((int64_t)(order / (uint32_t)C2) != qi) continue;  // the winner is posted by another query of this match
+            if ((int64_t)(order / ((uint32_t)C2 * slots)) != qi) continue;  // the winner was posted by another query of this match
             const float v = funord((uint32_t)(pk >> 32));
             if (v > __ldcg(&A.dp[m])) {
                 A.dp[m] = v;

@@ -1,6 +1,7 @@
 """End-to-end drop-in: the reference CLI, compiled from its own unmodified sources with only the include
-path changed so that Stitcher::do_alignment's po_poa call lands in libcentrolign_b200.so
-(integration/shadow/centrolign/stitcher.hpp), must print byte-identical CIGAR / GFA.  Expected md5s come
+path changed so that Stitcher::do_alignment's po_poa / pwfa_po_poa calls (integration/shadow/centrolign/stitcher.hpp)
+and the Anchorer's chaining DP (integration/shadow/centrolign/anchorer.hpp) land in libcentrolign_b200.so,
+must print byte-identical CIGAR / GFA.  Expected md5s come
 from the unmodified CLI (tests/golden/e2e.json, written by integration/make_e2e_golden.py)."""
 import hashlib
 import json
@@ -38,6 +39,11 @@ def test_cli_output_is_byte_identical(name, tmp_path):
         n_wcalls, n_wwin = int(wcalls[-1].split()[3]), int(wcalls[-1].split()[5])
         print(f"{name}: {n_wwin} wavefront windows in {n_wcalls} batched GPU calls")
         assert n_wcalls > 0 and n_wwin > n_wcalls  # one call per stitch() and NumPW, not one per window
+    ccalls = [l for l in res.stderr.decode().splitlines() if l.startswith("[clb] chain calls")]
+    assert ccalls, "the GPU chaining DP was never called"
+    n_ccalls, n_cmatches = int(ccalls[-1].split()[3]), int(ccalls[-1].split()[5])
+    print(f"{name}: {n_cmatches} matches chained in {n_ccalls} GPU chaining calls")
+    assert n_ccalls >= 2 and n_cmatches > 1000  # at least the calibration chain (gap-free) and the main chain (affine)
     calls = [l for l in res.stderr.decode().splitlines() if l.startswith("[clb] calls")]
     assert calls, "the GPU gap fill was never called"
     n_calls, n_windows = int(calls[-1].split()[2]), int(calls[-1].split()[4])
