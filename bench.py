@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--snp-rate", type=float, default=0.05)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-other-paths", action="store_true", help="skip the short pwfa / chaining measurements")
     return ap.parse_args()
 
 
@@ -170,6 +171,77 @@ def run_reference_arm(args, rank, world):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample_desc},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def other_paths(device):
+    """Short measurements of the two other hot-path kernels (outside the timed region of the headline metric),
+    each next to the reference's CPU code on the same inputs and parity-checked: the wavefront variant
+    pwfa_po_poa (clb_pwfa_batch) and the sparse anchor-chaining DP (clb_chain_dp)."""
+    import tempfile
+
+    from centrolign_b200.batch import AlignmentParameters, CpuChecker, select_windows, successor_form, synth_windows
+    from centrolign_b200.chain import ChainStats, chain_dp, chain_oracle, read_chain_bin
+    from centrolign_b200.popoa import PwfaStats, pwfa_po_poa_batch
+
+    out = {}
+    # ---- pwfa: windows of the size the Stitcher routes to it (4e7 < cells < 7.5e7, stitcher.hpp:327-339) ----
+    params = AlignmentParameters()
+    nw = 512
+    sb = successor_form(synth_windows(nw, first_index=0, seed=SEED, len_min=5600.0, len_max=7600.0))
+    pwfa_po_poa_batch(sb, params, 50, device=device)  # warm-up
+    st = PwfaStats()
+    t0 = time.perf_counter()
+    scores, alns = pwfa_po_poa_batch(sb, params, 50, device=device, stats=st)
+    wall = time.perf_counter() - t0
+    kind = "reference" if CpuChecker.available("reference") else "port"
+    chk = CpuChecker(kind)
+    idx = np.linspace(0, nw - 1, 6).astype(int)
+    sub = select_windows(sb, idx)
+    t0 = time.perf_counter()
+    for k, w in enumerate(idx):
+        s, a = chk.pwfa_po_poa(sub, k, params, 50)
+        assert s == scores[w] and np.array_equal(a, alns[w]), f"pwfa: GPU result differs from the CPU {kind} on window {w}"
+    cpu_s = (time.perf_counter() - t0) / len(idx)
+    out["pwfa_po_poa"] = {"windows": nw, "nodes_per_side": "6.3-8.7 k", "prune_limit": 50, "kernel_ms": st.kernel_ms,
+                          "windows_per_s": nw / (st.kernel_ms * 1e-3), "e2e_windows_per_s": nw / wall,
+                          "search_states_per_s": st.states / (st.kernel_ms * 1e-3), "entries_per_warp_step": st.dequeued / max(1, st.steps),
+                          "gpu_launches": int(st.kernel_launches),
+                          "cpu_baseline": {"kind": kind, "cores": 1, "windows_per_s": 1.0 / cpu_s,
+                                           "sample": f"{len(idx)} windows, each equal to the GPU result (score + alignment)"}}
+    # ---- chaining: a pairwise HOR problem made by the reference's own match finder where its objects travelled ----
+    shim = os.path.join(ROOT, "oracle", "_ref", "chain_fixture")
+    probs, src = None, None
+    if os.path.exists(shim):
+        with tempfile.TemporaryDirectory() as tmp:
+            fa, binp = os.path.join(tmp, "x.fa"), os.path.join(tmp, "x.bin")
+            subprocess.run([sys.executable, os.path.join(ROOT, "integration", "make_hor_fasta.py"), fa, "2", "20000", "7", "0"], check=True)
+            r = subprocess.run([shim, fa, binp, "pair", "100000", "1.0"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL)
+            if r.returncode == 0:
+                probs, src = read_chain_bin(binp), "two 20 kbp HOR arrays, 100 k match pairs, reference timed in this run (1 thread)"
+    if probs is None:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from golden_io import load_chain_golden
+
+        probs, src = load_chain_golden()["pair8k_indels"], "tests/golden fixture pair8k_indels (reference time recorded where the fixture was made)"
+    chain_out = {"problem": src}
+    for kind_name in ("gapfree", "affine"):
+        prob = probs[kind_name]
+        chain_dp(prob, device=device)
+        cst = ChainStats()
+        t0 = time.perf_counter()
+        chain, dp, bp, opt = chain_dp(prob, device=device, stats=cst)
+        wall = (time.perf_counter() - t0) * 1e3
+        assert np.array_equal(chain, prob.expect_chain), f"chaining ({kind_name}): GPU chain differs from the reference's"
+        t0 = time.perf_counter()
+        ochain = chain_oracle(prob)[0]
+        oracle_ms = (time.perf_counter() - t0) * 1e3
+        assert np.array_equal(chain, ochain)
+        chain_out[kind_name] = {"matches": prob.n_match, "steps": prob.n_step, "kernel_ms": cst.kernel_ms, "build_ms": cst.build_ms,
+                                "e2e_ms": wall, "matches_per_s": prob.n_match / (cst.kernel_ms * 1e-3), "reference_cpu_ms": prob.ref_ms,
+                                "oracle_cpu_ms": oracle_ms, "chain_len": int(len(chain)), "equal_to_reference": True,
+                                "gpu_launches": int(cst.kernel_launches)}
+    out["chain_dp"] = chain_out
+    return out
 
 
 def main():
@@ -332,6 +404,11 @@ def main():
                 "gpu_launches": launches_per_step * args.steps,
                 "wall_ms_per_step": wall_ms / args.steps, "cells_per_step": total_cells, "windows_gen_s": t_gen,
                 "workspace_bytes": int(st.workspace_bytes)}
+        if world == 1 and not args.no_other_paths:
+            try:
+                line["other_paths"] = other_paths(local)
+            except Exception as exc:  # the headline metric stands on its own
+                line["other_paths"] = {"error": str(exc)[:300]}
         print(json.dumps(line), flush=True)
     if use_dist:
         dist.barrier()
