@@ -4,7 +4,7 @@ REP=$1
 echo "# ncu summary of $(basename $REP)"
 echo
 echo '```'
-ncu -i $REP --page details 2>/dev/null | grep -E "popoa_kernel|Duration|SM Frequency|Elapsed Cycles|Executed Ipc|Issue Slots Busy|Issued Warp|No Eligible|Eligible Warps|Warp Cycles Per Issued|Avg. Active Threads|Avg. Not Predicated|Registers Per Thread|Dynamic Shared|Theoretical Occupancy|Achieved Occupancy|DRAM Throughput|Mem Busy|L1/TEX Hit|L2 Hit|Grid Size|Block Size|highest-utilized"
+ncu -i $REP --page details 2>/dev/null | grep -E "popoa_kernel|pwfa_kernel|chain_kernel|Duration|SM Frequency|Elapsed Cycles|Executed Ipc|Issue Slots Busy|Issued Warp|No Eligible|Eligible Warps|Warp Cycles Per Issued|Avg. Active Threads|Avg. Not Predicated|Registers Per Thread|Dynamic Shared|Theoretical Occupancy|Achieved Occupancy|DRAM Throughput|Mem Busy|L1/TEX Hit|L2 Hit|Grid Size|Block Size|highest-utilized"
 echo '```'
 echo
 echo "## raw metrics"
@@ -24,5 +24,5 @@ echo '```'
 echo
 echo "## hottest source lines (share of warp instructions, avg active threads, share of stall samples)"
 echo '```'
-python3 $(dirname $0)/ncu_lines.py $REP popoa_kernelILi3 25
+python3 $(dirname $0)/ncu_lines.py $REP ${2:-popoa_kernelILi3} 25
 echo '```'
