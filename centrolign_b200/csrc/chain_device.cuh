@@ -20,65 +20,93 @@
 // The queries walk the outer trees exactly as the reference's range_max does and take the FIRST block, in
 // that walk's order, that attains the maximum (strict '>' replaces, max_search_tree.hpp:361-444,
 // orthogonal_max_search_tree.hpp:340-470).
+//
+// Values are stored as order-preserving 32-bit images of the reference's floats ("ord", 0 = never entered), so
+// that zero-filled memory is the initial state and comparisons are integer comparisons.  Everything about a query
+// that does not depend on DP values -- its diagonal's tree, the shape of its three tree walks -- is computed for
+// all queries at once by a preparation kernel (QueryRec), so that a DP step only has to look at values.
 #pragma once
 #include <stdint.h>
 
 namespace clb {
 
-constexpr int kChainMaxTrees = 6;  // 2 * NumPW orthogonal value sets
+constexpr int kChainMaxTrees = 6;            // 2 * NumPW orthogonal value sets
+constexpr uint32_t kChainNone = 0xffffffffu;
+
+// One tree insertion (a match end on one path pair), in the reference's insertion order; the index of the
+// record is the insertion sequence number that breaks ties inside the gap-free trees.
+struct InsRec {
+    uint32_t match;
+    uint32_t gf_base;   // first node of the gap-free tree of its diagonal
+    uint32_t gf_node;   // its heap index in that tree
+    uint32_t or_base;   // first outer node of the path pair's orthogonal trees
+    uint32_t or_node;   // its outer heap index
+    int32_t shift;
+    uint32_t rank_off;  // ranks in the inner lists of its non-spine ancestors, self first
+    uint32_t n_rank;
+};
+
+// One (query, path of graph 2) pair.  A tree walk is stored as its split node S and the in-range decisions along
+// the one conditional side of the walk (the other side takes every node), LSB first.
+struct QueryRec {
+    uint32_t match;
+    float weight;
+    uint32_t offset;    // 0 = nothing on this path reaches the match: no candidates
+    int32_t q;          // query shift
+    uint32_t gf_base, gf_n;   // gap-free tree of diagonal q, gf_n == 0 if there is none
+    uint32_t gf_S, gf_bits;   // prefix walk over keys < offset
+    uint32_t or_base, or_n;
+    uint32_t ev_S, ev_bits;   // even pieces: shift > q (suffix walk)
+    uint32_t od_S, od_bits;   // odd pieces:  shift < q (prefix walk)
+    uint32_t pad[2];
+};
 
 struct ChainArgs {
-    // ---- problem (see clb_chain_problem) ----
     int num_pw;
     int n_chain1, n_chain2;
     double scale_ext[3];   // local_scale * gap_extend[k]
     double gap_open[3], gap_extend[3], scale;
     int64_t n_match;
-    const float* weight;
     float* dp;             // [n_match] starts as dp_init
-    uint32_t* backptr;     // [n_match] 0xffffffff = none
+    uint32_t* backptr;     // [n_match] kChainNone = none
     int64_t n_step;
-    const int64_t* sins_off;      // [n_step+1] insert entries of the step, reference order (= sequence numbers)
-    const uint32_t* sins_entry;   // entry id
-    const uint32_t* ent_match;    // [n_entry]
-    const int64_t* qry_off;       // [n_step+1]
+    const int64_t* sins_off;   // [n_step+1] insertions of the step
+    const InsRec* ins;
+    const int64_t* qry_off;    // [n_step+1]
     const uint32_t* qry_match;
+    QueryRec* qrec;            // [n_qry * n_chain2]
+    int64_t n_qry;
+    // raw query data, read by the preparation kernel only
+    const float* weight;
     const uint32_t* qry_chain1;
     const int32_t* qa1;
     const int32_t* qa2;
     const uint32_t* qoff;
-    // ---- gap-free trees ----
-    const int64_t* pair_grp_off;  // [n_chain1*n_chain2+1] groups (diagonals) of the pair, ascending shift
-    const int32_t* grp_shift;     // [n_grp]
-    const int64_t* grp_base;      // [n_grp] first node of the group's tree
-    const uint32_t* grp_n;        // [n_grp]
-    const uint32_t* gf_key;       // [n_entry] offset key, heap layout per group
+    const int64_t* pair_grp_off;  // [npair+1] diagonals of the pair, ascending shift
+    const int32_t* grp_shift;
+    const uint32_t* grp_base;
+    const uint32_t* grp_n;
+    const uint32_t* pair_base;    // [npair+1] first outer node of the pair
+    // gap-free trees
+    const uint32_t* gf_key;       // [n_entry] offset key, heap layout per tree
     const uint32_t* gf_match;     // [n_entry]
-    float* gf_val;                // [n_entry]
-    unsigned long long* gf_best;  // [n_entry]
-    const uint32_t* ent_gf_grp;   // [n_entry] group of the entry
-    const uint32_t* ent_gf_node;  // [n_entry] heap index inside the group
-    // ---- orthogonal trees ----
-    const int64_t* pair_base;     // [npair+1] first outer node of the pair
+    uint32_t* gf_ord;             // [n_entry] value of the node
+    unsigned long long* gf_best;  // [n_entry] subtree maximum
+    // orthogonal trees
     const int32_t* or_shift;      // [n_entry] heap layout per pair
-    const uint32_t* or_off;       // [n_entry]
-    const uint32_t* or_match;     // [n_entry]
-    float* or_val;                // [2*num_pw][n_entry]
-    const int64_t* in_base;       // [n_entry] per outer node: first slot of its inner list, -1 = none (outer spine)
-    const uint32_t* in_n;         // [n_entry]
-    const uint32_t* in_off;       // [n_inner] offsets of the inner list, ascending
+    const uint32_t* or_off;
+    const uint32_t* or_match;
+    uint32_t* or_ord;             // [2*num_pw][n_entry]
+    const uint32_t* in_base;      // [n_entry] per outer node: first slot of its inner list, kChainNone on the outer spines
+    const uint32_t* in_n;
+    const uint32_t* in_off;       // [n_inner] offsets of the inner lists, ascending
     unsigned long long* bit;      // [2*num_pw][n_inner] Fenwick trees over max
+    const uint32_t* ent_rank;     // [n_inner]
     int64_t n_inner;
     int64_t n_entry;
-    const uint32_t* ent_pair;     // [n_entry]
-    const uint32_t* ent_or_node;  // [n_entry] outer heap index inside the pair
-    const int32_t* ent_shift;     // [n_entry]
-    const int64_t* ent_rank_off;  // [n_entry+1] ranks of the entry in the inner lists of its non-spine ancestors, self first
-    const uint32_t* ent_rank;
-    // ---- per-step candidate exchange ----
-    unsigned long long* cand_best;  // [n_match] pack(value, ~(query index in step * n_chain2 + chain2)), 0 = none
-    uint32_t* cand_bp;              // [max queries per step * n_chain2]
-    // ---- stats ----
+    // per-step candidate exchange
+    unsigned long long* cand_best;  // [n_match] pack(value, ~order), 0 = none
+    uint32_t* cand_bp;              // [max queries per step * n_chain2 * (2*num_pw+1)]
     unsigned long long* counters;   // [0] tree queries answered
 };
 

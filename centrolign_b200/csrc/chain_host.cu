@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <map>
 #include <numeric>
 #include <string>
 #include <type_traits>
@@ -29,7 +30,7 @@
 #include "chain_device.cuh"
 
 namespace clb {
-cudaError_t launch_chain(const ChainArgs& args, int grid, cudaStream_t stream);
+cudaError_t launch_chain(const ChainArgs& args, int grid, int prepare_grid, cudaStream_t stream);
 int chain_max_grid(int device);
 int host_fail(int code, const std::string& msg);
 }  // namespace clb
@@ -58,30 +59,41 @@ void inorder_layout(uint32_t n, std::vector<uint32_t>& heap_of_pos, std::vector<
     }
 }
 
-struct DeviceBuffers {
-    std::vector<void*> ptrs;
-    int64_t bytes = 0;
+// All device data of one call lives in one arena: [copied segments][zero-filled segments].  The arena, its pinned
+// staging twin, the stream and the events are kept per device across calls (the Anchorer's fill-in pass makes
+// thousands of small chaining calls per alignment), up to kArenaKeep bytes.
+struct DeviceArena {
+    char* d = nullptr;
+    size_t cap = 0;
+    char* h = nullptr;  // pinned
+    size_t hcap = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+constexpr size_t kArenaKeep = size_t(1) << 30;
+std::mutex g_arena_mu;
+std::map<int, DeviceArena> g_arenas;
+
+struct ArenaPlan {
+    struct Seg {
+        size_t off, bytes;
+        const void* src;
+    };
+    std::vector<Seg> segs;
+    size_t copy_bytes = 0, zero_bytes = 0;
+    static size_t align(size_t x) { return (x + 255) & ~size_t(255); }
     template <class T>
-    cudaError_t upload(const std::vector<T>& h, T** d, cudaStream_t st, size_t min_count = 1) {
-        const size_t n = std::max(h.size(), min_count);
-        cudaError_t e = cudaMalloc((void**)d, n * sizeof(T));
-        if (e != cudaSuccess) return e;
-        ptrs.push_back(*d);
-        bytes += (int64_t)(n * sizeof(T));
-        if (!h.empty()) e = cudaMemcpyAsync(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st);
-        return e;
+    size_t copy(const std::vector<T>& v) { return copy(v.data(), v.size() * sizeof(T)); }
+    size_t copy(const void* src, size_t bytes) {
+        const size_t off = copy_bytes;
+        segs.push_back(Seg{off, bytes, src});
+        copy_bytes = align(copy_bytes + std::max<size_t>(bytes, 1));
+        return off;
     }
-    template <class T>
-    cudaError_t zeros(size_t n, T** d, cudaStream_t st) {
-        n = std::max<size_t>(n, 1);
-        cudaError_t e = cudaMalloc((void**)d, n * sizeof(T));
-        if (e != cudaSuccess) return e;
-        ptrs.push_back(*d);
-        bytes += (int64_t)(n * sizeof(T));
-        return cudaMemsetAsync(*d, 0, n * sizeof(T), st);
-    }
-    ~DeviceBuffers() {
-        for (void* p : ptrs) cudaFree(p);
+    size_t zero(size_t bytes) {  // offset relative to the start of the zero region
+        const size_t off = zero_bytes;
+        zero_bytes = align(zero_bytes + std::max<size_t>(bytes, 1));
+        return off;
     }
 };
 
@@ -287,19 +299,36 @@ extern "C" int clb_chain_dp(int device, const clb_chain_problem* p, float* dp_ou
             }
         }
     }
+    // insertion records in the reference's order, and the remaining per-entry tables in 32-bit form
+    if (n_inner >= (int64_t(1) << 32) - 1) return host_fail(CLB_EINVAL, "search structures exceed 2^32 inner slots");
+    if ((int64_t)sins_entry.size() >= (int64_t(1) << 31)) return host_fail(CLB_EINVAL, "more than 2^31 insertions");
+    std::vector<clb::InsRec> ins(sins_entry.size());
+    for (size_t i = 0; i < sins_entry.size(); ++i) {
+        const uint32_t e = sins_entry[i];
+        clb::InsRec& r = ins[i];
+        r.match = ent_match[e];
+        r.gf_base = (uint32_t)grp_base[ent_gf_grp[e]];
+        r.gf_node = ent_gf_node[e];
+        r.or_base = P > 0 ? (uint32_t)pair_base[ent_pair[e]] : 0;
+        r.or_node = P > 0 ? ent_or_node[e] : 0;
+        r.shift = p->ins_shift[e];
+        r.rank_off = P > 0 ? (uint32_t)ent_rank_off[e] : 0;
+        r.n_rank = P > 0 ? (uint32_t)(ent_rank_off[e + 1] - ent_rank_off[e]) : 0;
+    }
+    std::vector<uint32_t> grp_base32(grp_base.begin(), grp_base.end()), pair_base32(pair_base.begin(), pair_base.end());
+    std::vector<uint32_t> in_base32(in_base.size());
+    for (size_t k = 0; k < in_base.size(); ++k) in_base32[k] = in_base[k] < 0 ? clb::kChainNone : (uint32_t)in_base[k];
     const double t_built = now_ms();
 
     // ------------------------------------------------------------------ device ------------------------------------------------------------------
     int rc = CLB_OK;
-    DeviceBuffers dev;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     clb::ChainArgs a{};
     std::vector<float> h_dp(M);
     std::vector<uint32_t> h_bp(M);
-    std::vector<int32_t> ent_shift(p->ins_shift, p->ins_shift + E);
-    unsigned long long h_counter = 0;
     int grid = 1;
+    std::lock_guard<std::mutex> arena_lock(g_arena_mu);
+    DeviceArena& ar = g_arenas[device];
+    bool keep = true;
 #define CHAIN_TRY(expr)                                                                                               \
     do {                                                                                                              \
         cudaError_t _e = (expr);                                                                                      \
@@ -308,71 +337,98 @@ extern "C" int clb_chain_dp(int device, const clb_chain_problem* p, float* dp_ou
             goto cleanup;                                                                                             \
         }                                                                                                             \
     } while (0)
-#define UP(vec, field) CHAIN_TRY(dev.upload(vec, const_cast<typename std::remove_const<typename std::remove_pointer<decltype(a.field)>::type>::type**>(&a.field), stream))
-    CHAIN_TRY(cudaSetDevice(device));
-    CHAIN_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    CHAIN_TRY(cudaEventCreate(&ev0));
-    CHAIN_TRY(cudaEventCreate(&ev1));
-    a.num_pw = P; a.n_chain1 = C1; a.n_chain2 = C2; a.scale = p->scale;
-    for (int k = 0; k < 3; ++k) {
-        a.gap_open[k] = p->gap_open[k];
-        a.gap_extend[k] = p->gap_extend[k];
-        a.scale_ext[k] = p->scale * p->gap_extend[k];  // anchorer.hpp:2330: local_scale * gap_extend[pw / 2] (* shift on the device)
-    }
-    a.n_match = M; a.n_step = S; a.n_entry = E; a.n_inner = n_inner;
     {
-        std::vector<float> w(p->weight, p->weight + M), d0(p->dp_init, p->dp_init + M);
-        std::vector<uint32_t> bp0(M, 0xffffffffu), qm(p->qry_match, p->qry_match + n_qry), qc(p->qry_chain1, p->qry_chain1 + n_qry);
-        std::vector<int64_t> qo(p->qry_off, p->qry_off + S + 1);
-        std::vector<int32_t> qa1(p->qa1, p->qa1 + M * C1), qa2(p->qa2, p->qa2 + M * C2);
-        std::vector<uint32_t> qoff(p->qoff, p->qoff + M * C2);
-        UP(w, weight); UP(d0, dp); UP(bp0, backptr); UP(sins_off, sins_off); UP(sins_entry, sins_entry); UP(ent_match, ent_match);
-        UP(qo, qry_off); UP(qm, qry_match); UP(qc, qry_chain1); UP(qa1, qa1); UP(qa2, qa2); UP(qoff, qoff);
-        UP(pair_grp_off, pair_grp_off); UP(grp_shift, grp_shift); UP(grp_base, grp_base); UP(grp_n, grp_n);
-        UP(gf_key, gf_key); UP(gf_match, gf_match); UP(ent_gf_grp, ent_gf_grp); UP(ent_gf_node, ent_gf_node);
-        std::vector<float> lowest(E, kLowest);
-        UP(lowest, gf_val);
-        CHAIN_TRY(dev.zeros((size_t)E, &a.gf_best, stream));
-        UP(pair_base, pair_base); UP(ent_pair, ent_pair);
-        if (P > 0) {
-            UP(or_shift, or_shift); UP(or_off, or_off); UP(or_match, or_match); UP(in_base, in_base); UP(in_n, in_n); UP(in_off, in_off);
-            UP(ent_or_node, ent_or_node); UP(ent_shift, ent_shift); UP(ent_rank_off, ent_rank_off); UP(ent_rank, ent_rank);
-            std::vector<float> lowest_t((size_t)T * E, kLowest);
-            UP(lowest_t, or_val);
-            CHAIN_TRY(dev.zeros((size_t)T * n_inner, &a.bit, stream));
+        ArenaPlan plan;
+        std::vector<uint32_t> bp0(M, clb::kChainNone);
+        const size_t o_dp = plan.copy(p->dp_init, M * sizeof(float)), o_bp = plan.copy(bp0);
+        const size_t o_sins = plan.copy(sins_off), o_ins = plan.copy(ins);
+        const size_t o_qoff = plan.copy(p->qry_off, (S + 1) * sizeof(int64_t)), o_qm = plan.copy(p->qry_match, n_qry * sizeof(uint32_t));
+        const size_t o_w = plan.copy(p->weight, M * sizeof(float)), o_qc1 = plan.copy(p->qry_chain1, n_qry * sizeof(uint32_t));
+        const size_t o_qa1 = plan.copy(p->qa1, (size_t)M * C1 * sizeof(int32_t)), o_qa2 = plan.copy(p->qa2, (size_t)M * C2 * sizeof(int32_t));
+        const size_t o_qo = plan.copy(p->qoff, (size_t)M * C2 * sizeof(uint32_t));
+        const size_t o_pg = plan.copy(pair_grp_off), o_gs = plan.copy(grp_shift), o_gb = plan.copy(grp_base32), o_gn = plan.copy(grp_n);
+        const size_t o_pb = plan.copy(pair_base32), o_gk = plan.copy(gf_key), o_gm = plan.copy(gf_match);
+        const size_t o_os = plan.copy(or_shift), o_oo = plan.copy(or_off), o_om = plan.copy(or_match);
+        const size_t o_ib = plan.copy(in_base32), o_in = plan.copy(in_n), o_io = plan.copy(in_off), o_er = plan.copy(ent_rank);
+        const size_t z_qrec = plan.zero((size_t)n_qry * C2 * sizeof(clb::QueryRec));
+        const size_t z_gford = plan.zero((size_t)E * 4), z_gfbest = plan.zero((size_t)E * 8);
+        const size_t z_orord = plan.zero((size_t)T * E * 4), z_bit = plan.zero((size_t)T * n_inner * 8);
+        const size_t z_cbest = plan.zero((size_t)M * 8), z_cbp = plan.zero((size_t)(max_q * C2 * (T + 1)) * 4), z_cnt = plan.zero(8);
+        const size_t total = plan.copy_bytes + plan.zero_bytes;
+        keep = total <= kArenaKeep;
+        CHAIN_TRY(cudaSetDevice(device));
+        if (!ar.stream) {
+            CHAIN_TRY(cudaStreamCreateWithFlags(&ar.stream, cudaStreamNonBlocking));
+            CHAIN_TRY(cudaEventCreate(&ar.ev0));
+            CHAIN_TRY(cudaEventCreate(&ar.ev1));
         }
-        CHAIN_TRY(dev.zeros((size_t)M, &a.cand_best, stream));
-        CHAIN_TRY(dev.zeros((size_t)(max_q * C2 * (T + 1)), &a.cand_bp, stream));
-        CHAIN_TRY(dev.zeros(1, &a.counters, stream));
-        CHAIN_TRY(cudaStreamSynchronize(stream));  // the staging vectors above go out of scope
-    }
-    {
+        if (ar.cap < total) {
+            if (ar.d) cudaFree(ar.d);
+            ar.d = nullptr;
+            ar.cap = 0;
+            const size_t want = keep ? std::max(total, std::min(kArenaKeep, 2 * total)) : total;
+            CHAIN_TRY(cudaMalloc((void**)&ar.d, want));
+            ar.cap = want;
+        }
+        if (ar.hcap < plan.copy_bytes) {
+            if (ar.h) cudaFreeHost(ar.h);
+            ar.h = nullptr;
+            ar.hcap = 0;
+            const size_t want = keep ? std::max(plan.copy_bytes, std::min(kArenaKeep, 2 * plan.copy_bytes)) : plan.copy_bytes;
+            CHAIN_TRY(cudaHostAlloc((void**)&ar.h, want, cudaHostAllocDefault));
+            ar.hcap = want;
+        }
+        for (const auto& sg : plan.segs)
+            if (sg.bytes) memcpy(ar.h + sg.off, sg.src, sg.bytes);
+        CHAIN_TRY(cudaMemcpyAsync(ar.d, ar.h, plan.copy_bytes, cudaMemcpyHostToDevice, ar.stream));
+        char* zr = ar.d + plan.copy_bytes;
+        CHAIN_TRY(cudaMemsetAsync(zr, 0, plan.zero_bytes, ar.stream));
+        a.num_pw = P; a.n_chain1 = C1; a.n_chain2 = C2; a.scale = p->scale;
+        for (int k = 0; k < 3; ++k) {
+            a.gap_open[k] = p->gap_open[k];
+            a.gap_extend[k] = p->gap_extend[k];
+            a.scale_ext[k] = p->scale * p->gap_extend[k];  // anchorer.hpp:2330: local_scale * gap_extend[pw / 2] (* shift on the device)
+        }
+        a.n_match = M; a.n_step = S; a.n_entry = E; a.n_inner = n_inner; a.n_qry = n_qry;
+        a.dp = (float*)(ar.d + o_dp); a.backptr = (uint32_t*)(ar.d + o_bp);
+        a.sins_off = (const int64_t*)(ar.d + o_sins); a.ins = (const clb::InsRec*)(ar.d + o_ins);
+        a.qry_off = (const int64_t*)(ar.d + o_qoff); a.qry_match = (const uint32_t*)(ar.d + o_qm);
+        a.weight = (const float*)(ar.d + o_w); a.qry_chain1 = (const uint32_t*)(ar.d + o_qc1);
+        a.qa1 = (const int32_t*)(ar.d + o_qa1); a.qa2 = (const int32_t*)(ar.d + o_qa2); a.qoff = (const uint32_t*)(ar.d + o_qo);
+        a.pair_grp_off = (const int64_t*)(ar.d + o_pg); a.grp_shift = (const int32_t*)(ar.d + o_gs);
+        a.grp_base = (const uint32_t*)(ar.d + o_gb); a.grp_n = (const uint32_t*)(ar.d + o_gn); a.pair_base = (const uint32_t*)(ar.d + o_pb);
+        a.gf_key = (const uint32_t*)(ar.d + o_gk); a.gf_match = (const uint32_t*)(ar.d + o_gm);
+        a.or_shift = (const int32_t*)(ar.d + o_os); a.or_off = (const uint32_t*)(ar.d + o_oo); a.or_match = (const uint32_t*)(ar.d + o_om);
+        a.in_base = (const uint32_t*)(ar.d + o_ib); a.in_n = (const uint32_t*)(ar.d + o_in); a.in_off = (const uint32_t*)(ar.d + o_io);
+        a.ent_rank = (const uint32_t*)(ar.d + o_er);
+        a.qrec = (clb::QueryRec*)(zr + z_qrec);
+        a.gf_ord = (uint32_t*)(zr + z_gford); a.gf_best = (unsigned long long*)(zr + z_gfbest);
+        a.or_ord = (uint32_t*)(zr + z_orord); a.bit = (unsigned long long*)(zr + z_bit);
+        a.cand_best = (unsigned long long*)(zr + z_cbest); a.cand_bp = (uint32_t*)(zr + z_cbp); a.counters = (unsigned long long*)(zr + z_cnt);
         // grid: one CTA unless a step has enough independent warps of work to pay for grid-wide barriers
-        const double warps_per_step = S ? ((double)sins_entry.size() + (double)n_qry * C2 * (P > 0 ? 3 : 1)) / (double)S : 0.0;
+        const double warps_per_step = S ? ((double)ins.size() + (double)n_qry * C2 * (P > 0 ? 3 : 1)) / (double)S : 0.0;
         const int max_grid = clb::chain_max_grid(device);
         grid = getenv("CLB_CHAIN_GRID") ? std::max(1, std::min(max_grid, atoi(getenv("CLB_CHAIN_GRID"))))
                                          : (warps_per_step > 64.0 ? std::min<int>(max_grid, (int)(warps_per_step / 16.0) + 1) : 1);
-    }
-    CHAIN_TRY(cudaEventRecord(ev0, stream));
-    CHAIN_TRY(clb::launch_chain(a, grid, stream));
-    CHAIN_TRY(cudaEventRecord(ev1, stream));
-    CHAIN_TRY(cudaMemcpyAsync(h_dp.data(), a.dp, M * sizeof(float), cudaMemcpyDeviceToHost, stream));
-    CHAIN_TRY(cudaMemcpyAsync(h_bp.data(), a.backptr, M * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-    CHAIN_TRY(cudaMemcpyAsync(&h_counter, a.counters, sizeof(h_counter), cudaMemcpyDeviceToHost, stream));
-    CHAIN_TRY(cudaStreamSynchronize(stream));
-    {
+        const int prepare_grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_qry * C2 + 7) / 8, 8 * (int64_t)max_grid));
+        CHAIN_TRY(cudaEventRecord(ar.ev0, ar.stream));
+        CHAIN_TRY(clb::launch_chain(a, grid, prepare_grid, ar.stream));
+        CHAIN_TRY(cudaEventRecord(ar.ev1, ar.stream));
+        CHAIN_TRY(cudaMemcpyAsync(h_dp.data(), a.dp, M * sizeof(float), cudaMemcpyDeviceToHost, ar.stream));
+        CHAIN_TRY(cudaMemcpyAsync(h_bp.data(), a.backptr, M * sizeof(uint32_t), cudaMemcpyDeviceToHost, ar.stream));
+        CHAIN_TRY(cudaStreamSynchronize(ar.stream));
         float ms = 0.f;
-        CHAIN_TRY(cudaEventElapsedTime(&ms, ev0, ev1));
+        CHAIN_TRY(cudaEventElapsedTime(&ms, ar.ev0, ar.ev1));
         if (stats) {
             stats->build_ms = t_built - t_start;
             stats->kernel_ms = ms;
             stats->steps = S;
-            stats->inserts = (int64_t)sins_entry.size();
+            stats->inserts = (int64_t)ins.size();
             stats->queries = n_qry * C2;
-            stats->tree_bytes = dev.bytes;
-            stats->h2d_bytes = dev.bytes;
+            stats->tree_bytes = (int64_t)total;
+            stats->h2d_bytes = (int64_t)plan.copy_bytes;
             stats->d2h_bytes = M * 8;
-            stats->kernel_launches = 1;
+            stats->kernel_launches = n_qry > 0 ? 2 : 1;
         }
     }
     // ---- traceback_sparse_dp (anchorer.hpp:2483-2534) ----
@@ -406,10 +462,27 @@ extern "C" int clb_chain_dp(int device, const clb_chain_problem* p, float* dp_ou
     }
     if (stats) stats->total_ms = now_ms() - t_start;
 cleanup:
-    if (ev0) cudaEventDestroy(ev0);
-    if (ev1) cudaEventDestroy(ev1);
-    if (stream) cudaStreamDestroy(stream);
+    if (!keep || rc != CLB_OK) {  // large arenas are not kept: other calls of the library size themselves by free memory
+        if (ar.d) cudaFree(ar.d);
+        if (ar.h) cudaFreeHost(ar.h);
+        ar.d = ar.h = nullptr;
+        ar.cap = ar.hcap = 0;
+    }
     return rc;
-#undef UP
 #undef CHAIN_TRY
 }
+
+namespace clb {
+void chain_release_cache() {
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    for (auto& kv : g_arenas) {
+        cudaSetDevice(kv.first);
+        if (kv.second.d) cudaFree(kv.second.d);
+        if (kv.second.h) cudaFreeHost(kv.second.h);
+        if (kv.second.ev0) cudaEventDestroy(kv.second.ev0);
+        if (kv.second.ev1) cudaEventDestroy(kv.second.ev1);
+        if (kv.second.stream) cudaStreamDestroy(kv.second.stream);
+    }
+    g_arenas.clear();
+}
+}  // namespace clb

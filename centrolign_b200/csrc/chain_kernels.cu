@@ -4,7 +4,9 @@
 // Anchorer::sparse_chain_dp main loop (:1640-1728); search structures max_search_tree.hpp:312-444 and
 // orthogonal_max_search_tree.hpp:293-470.  Data layout and the equivalence argument: chain_device.cuh.
 //
-// One persistent cooperative kernel walks the graph-1 nodes ("steps") in topological order.  Per step:
+// A preparation kernel first computes, for all (query, path of graph 2) pairs at once, everything that does not
+// depend on DP values: the gap-free tree of the query's diagonal and the shape of its three tree walks.
+// Then one persistent cooperative kernel walks the graph-1 nodes ("steps") in topological order.  Per step:
 //   A  every match ending here enters its DP value into the gap-free tree of its diagonal and into the
 //      2*NumPW orthogonal value sets, for every path pair of its end point -- all entries of the step in
 //      parallel, one warp per entry, lanes over the ancestors of the entry's node (atomicMax on packed words);
@@ -46,6 +48,7 @@ __device__ __forceinline__ float funord(uint32_t u) {
 __device__ __forceinline__ unsigned long long pack(float v, uint32_t low) {
     return ((unsigned long long)ford(v) << 32) | low;
 }
+constexpr uint32_t kOrdLowest = 0x00800000u;  // ford(lowest()); 0 = never entered; both fail "ord > kOrdLowest"
 
 struct WalkEntry {
     uint32_t node;  // heap index
@@ -60,18 +63,18 @@ struct WarpScratch {
 // OrthogonalMaxSearchTree::range_max (orthogonal_max_search_tree.hpp:340-470), for one-sided key ranges:
 //   prefix: in_range(x) <=> key[x] <  bound  (nothing lies below the range: its left walk takes every node)
 //   suffix: in_range(x) <=> key[x] >  bound  (nothing lies above the range: its right walk takes every node)
-// Records the blocks -- a node itself, or the whole subtree hanging off the walk -- in the order the reference
-// tests them.  The walk is uniform over the warp; to avoid one memory round trip per tree level, the range
-// flags of a node and of its descendants four levels down (31 nodes) are fetched by the 31 lanes at once and
-// the next moves are resolved from the resulting bit mask.
+// walk_shape finds the split node S and the in-range decisions along the conditional side (LSB first).  The walk
+// is uniform over the warp; to avoid one memory round trip per tree level, the range flags of a node and of its
+// descendants four levels down (31 nodes) are fetched by the 31 lanes at once and the next moves are resolved
+// from the resulting bit mask.
 template <class InRange>
-__device__ int tree_walk(uint32_t n, bool prefix, const InRange& in_range, WalkEntry* blk, int lane) {
-    uint32_t wbase = 0xffffffffu;
+__device__ void walk_shape(uint32_t n, bool prefix, const InRange& in_range, int lane, uint32_t& S_out, uint32_t& bits_out) {
+    uint32_t wbase = kChainNone;
     unsigned wbits = 0;
     auto flag = [&](uint32_t y) -> bool {
         const uint32_t rel = y + 1;
         int d = -1;
-        if (wbase != 0xffffffffu) {
+        if (wbase != kChainNone) {
             const uint32_t b = wbase + 1;
             d = (31 - __clz(rel)) - (31 - __clz(b));
             if (d < 0 || d > 4 || (rel >> d) != b) d = -1;
@@ -84,7 +87,7 @@ __device__ int tree_walk(uint32_t n, bool prefix, const InRange& in_range, WalkE
                 if (lane < 30) {
                     const int dj = 31 - __clz(lane + 2);
                     idx = (rel << dj) - 1 + (uint32_t)(lane + 2 - (1 << dj));
-                    if ((rel << dj) < rel) idx = 0xffffffffu;  // overflow: no such node
+                    if ((rel << dj) < rel) idx = kChainNone;  // overflow: no such node
                 }
                 if (idx < n) f = in_range(idx);
             }
@@ -97,16 +100,34 @@ __device__ int tree_walk(uint32_t n, bool prefix, const InRange& in_range, WalkE
     };
     uint32_t cursor = 0;
     while (cursor < n && !flag(cursor)) cursor = prefix ? 2 * cursor + 1 : 2 * cursor + 2;
-    if (cursor >= n) return 0;
+    S_out = cursor < n ? cursor : kChainNone;
+    uint32_t bits = 0;
+    if (cursor < n) {
+        int nbit = 0;
+        uint32_t c = prefix ? 2 * cursor + 2 : 2 * cursor + 1;  // the conditional side: right walk of a prefix, left walk of a suffix
+        while (c < n) {
+            const bool f = flag(c);
+            bits |= (uint32_t)f << nbit;
+            ++nbit;
+            c = (f == prefix) ? 2 * c + 2 : 2 * c + 1;  // prefix: in range -> right, else left; suffix: in range -> left, else right
+        }
+    }
+    bits_out = bits;
+}
+
+// Expands a stored walk into the blocks the reference tests, in its order: S, the left walk, the right walk
+// (each taken node followed by the subtree hanging off the walk).  Pure arithmetic; uniform, lane 0 writes.
+__device__ int walk_blocks(uint32_t n, bool prefix, uint32_t S, uint32_t bits, WalkEntry* blk, int lane) {
     int nb = 0;
     auto push = [&](uint32_t node, uint32_t kind) {
         if (lane == 0 && nb < kMaxBlocks) blk[nb] = WalkEntry{node, kind};
         ++nb;
     };
-    push(cursor, 0);
-    uint32_t lc = 2 * cursor + 1, rc = 2 * cursor + 2;
+    push(S, 0);
+    uint32_t lc = 2 * S + 1, rc = 2 * S + 2;
+    int i = 0;
     while (lc < n) {  // leftward: right subtrees hang entirely inside the range
-        if (prefix || flag(lc)) {
+        if (prefix || ((bits >> i++) & 1u)) {
             push(lc, 0);
             if (2 * lc + 2 < n) push(2 * lc + 2, 1);
             lc = 2 * lc + 1;
@@ -115,7 +136,7 @@ __device__ int tree_walk(uint32_t n, bool prefix, const InRange& in_range, WalkE
         }
     }
     while (rc < n) {  // rightward: left subtrees hang entirely inside
-        if (!prefix || flag(rc)) {
+        if (!prefix || ((bits >> i++) & 1u)) {
             push(rc, 0);
             if (2 * rc + 1 < n) push(2 * rc + 1, 1);
             rc = 2 * rc + 2;
@@ -159,7 +180,7 @@ __device__ __forceinline__ uint32_t count_less(const uint32_t* a, uint32_t n, ui
     }
     uint32_t v[7];
 #pragma unroll
-    for (int i = 0; i < 7; ++i) v[i] = lo + i < hi ? __ldg(&a[lo + i]) : 0xffffffffu;
+    for (int i = 0; i < 7; ++i) v[i] = lo + i < hi ? __ldg(&a[lo + i]) : kChainNone;
     uint32_t c = 0;
 #pragma unroll
     for (int i = 0; i < 7; ++i) c += (lo + i < hi) && v[i] < key;
@@ -168,6 +189,50 @@ __device__ __forceinline__ uint32_t count_less(const uint32_t* a, uint32_t n, ui
 
 }  // namespace
 
+// Everything about a (query, path of graph 2) pair that does not depend on DP values (anchorer.hpp:2374-2381).
+__global__ void __launch_bounds__(256) chain_prepare_kernel(const ChainArgs A) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int C1 = A.n_chain1, C2 = A.n_chain2;
+    for (int64_t qc = gwarp; qc < A.n_qry * C2; qc += nwarp) {
+        const int64_t k = qc / C2;
+        const int c2 = (int)(qc - k * C2);
+        const uint32_t m = A.qry_match[k], c1 = A.qry_chain1[k];
+        QueryRec r;
+        r.match = m;
+        r.weight = A.weight[m];
+        r.offset = A.qoff[(int64_t)m * C2 + c2];
+        r.q = (int)((uint32_t)A.qa1[(int64_t)m * C1 + c1] - (uint32_t)A.qa2[(int64_t)m * C2 + c2]);
+        r.gf_base = r.gf_n = r.or_base = r.or_n = 0;
+        r.gf_S = r.ev_S = r.od_S = kChainNone;
+        r.gf_bits = r.ev_bits = r.od_bits = 0;
+        r.pad[0] = r.pad[1] = 0;
+        if (r.offset != 0) {
+            const int64_t pair = (int64_t)c1 * C2 + c2;
+            const int64_t g1 = A.pair_grp_off[pair + 1];
+            const int64_t g = warp_lower_bound(A.grp_shift, A.pair_grp_off[pair], g1, r.q, lane);
+            if (g < g1 && __ldg(&A.grp_shift[g]) == r.q) {  // the diagonal exists (anchorer.hpp:2379-2382)
+                r.gf_base = A.grp_base[g];
+                r.gf_n = A.grp_n[g];
+                const uint32_t* key = A.gf_key + r.gf_base;
+                const uint32_t offset = r.offset;
+                walk_shape(r.gf_n, true, [&](uint32_t x) { return __ldg(&key[x]) < offset; }, lane, r.gf_S, r.gf_bits);
+            }
+            if (A.num_pw > 0) {
+                r.or_base = A.pair_base[pair];
+                r.or_n = A.pair_base[pair + 1] - r.or_base;
+                const int32_t* shift = A.or_shift + r.or_base;
+                const int q = r.q;
+                if (r.or_n) {
+                    walk_shape(r.or_n, false, [&](uint32_t x) { return __ldg(&shift[x]) > q; }, lane, r.ev_S, r.ev_bits);
+                    walk_shape(r.or_n, true, [&](uint32_t x) { return __ldg(&shift[x]) < q; }, lane, r.od_S, r.od_bits);
+                }
+            }
+        }
+        if (lane == 0) A.qrec[qc] = r;
+    }
+}
+
 __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainArgs A) {
     __shared__ WarpScratch scratch[kWarps];
     cg::grid_group grid = cg::this_grid();
@@ -175,7 +240,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainArgs A) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t gwarp = (int64_t)blockIdx.x * kWarps + wib, nwarp = (int64_t)gridDim.x * kWarps;
     const int64_t gthread = (int64_t)blockIdx.x * kThreads + threadIdx.x, nthread = (int64_t)gridDim.x * kThreads;
-    const int C1 = A.n_chain1, C2 = A.n_chain2, P = A.num_pw, T = 2 * A.num_pw;
+    const int C2 = A.n_chain2, P = A.num_pw, T = 2 * A.num_pw;
     const int n_type = P > 0 ? 3 : 1;        // work items per (query, chain2): gap-free tree, even pieces, odd pieces
     const uint32_t slots = (uint32_t)(T + 1);  // candidate slots per (query, chain2), in the reference's order
     WalkEntry* blk = scratch[wib].blk;
@@ -195,42 +260,35 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainArgs A) {
         // ------------------------------ A: inserts (anchorer.hpp:2301-2345) ------------------------------
         const int64_t i0 = A.sins_off[s], i1 = A.sins_off[s + 1];
         for (int64_t i = i0 + gwarp; i < i1; i += nwarp) {
-            const uint32_t e = A.sins_entry[i];
-            const uint32_t m = A.ent_match[e];
+            const uint4 ra = __ldg(reinterpret_cast<const uint4*>(&A.ins[i]));
+            const uint4 rb = __ldg(reinterpret_cast<const uint4*>(&A.ins[i]) + 1);
+            const uint32_t m = ra.x, gf_base = ra.y, gf_node = ra.z, or_base = ra.w, or_node = rb.x, rank_off = rb.z;
+            const int shift = (int)rb.y, nr = (int)rb.w;
+            int64_t ib = 0;
+            uint32_t cn = 0, rank = 0;
+            if (P > 0 && lane < nr) {  // lane = level: the node itself and its ancestors below the outer spines
+                const uint32_t a = ((or_node + 1) >> lane) - 1;
+                ib = __ldg(&A.in_base[or_base + a]);
+                cn = __ldg(&A.in_n[or_base + a]);
+                rank = __ldg(&A.ent_rank[rank_off + lane]);
+            }
             const float dpv = __ldcg(&A.dp[m]);
             if (!(dpv > mininf())) continue;  // entering lowest() changes nothing in the reference's trees
             {   // gap-free tree of the entry's diagonal: lanes = the node and its ancestors
-                const uint32_t g = A.ent_gf_grp[e], x = A.ent_gf_node[e];
-                const int64_t base = A.grp_base[g];
-                if (lane == 0) A.gf_val[base + x] = dpv;
-                const uint32_t anc = (x + 1) >> lane;
-                if (anc) atomicMax(&A.gf_best[base + anc - 1], pack(dpv, ~(uint32_t)i));
+                if (lane == 0) A.gf_ord[gf_base + gf_node] = ford(dpv);
+                const uint32_t anc = (gf_node + 1) >> lane;
+                if (anc) atomicMax(&A.gf_best[gf_base + anc - 1], pack(dpv, ~(uint32_t)i));
             }
-            if (P > 0) {
-                const uint32_t pr = A.ent_pair[e], oh = A.ent_or_node[e];
-                const int64_t ob = A.pair_base[pr];
-                const int shift = A.ent_shift[e];
-                const int64_t r0 = A.ent_rank_off[e];
-                const int nr = (int)(A.ent_rank_off[e + 1] - r0);
-                int64_t ib = 0;
-                uint32_t cn = 0, rank = 0;
-                if (lane < nr) {  // lane = level: the node itself and its ancestors below the outer spines
-                    const uint32_t a = ((oh + 1) >> lane) - 1;
-                    ib = A.in_base[ob + a];
-                    cn = A.in_n[ob + a];
-                    rank = A.ent_rank[r0 + lane];
-                }
-                for (int t = 0; t < T; ++t) {
-                    // anchorer.hpp:2328-2335: odd pieces add, even pieces subtract local_scale * gap_extend * shift
-                    const double gap = __dmul_rn(A.scale_ext[t >> 1], (double)shift);
-                    const float v = __double2float_rn((t & 1) ? __dadd_rn((double)dpv, gap) : __dsub_rn((double)dpv, gap));
-                    if (!(v > mininf())) continue;  // anchorer.hpp:2338
-                    if (lane == 0) A.or_val[(int64_t)t * A.n_entry + ob + oh] = v;
-                    if (lane < nr) {
-                        const unsigned long long pk = pack(v, oh);
-                        unsigned long long* bit = A.bit + (int64_t)t * A.n_inner + ib;
-                        for (uint32_t k = rank; k < cn; k |= k + 1) atomicMax(&bit[k], pk);
-                    }
+            for (int t = 0; t < T; ++t) {
+                // anchorer.hpp:2328-2335: odd pieces add, even pieces subtract local_scale * gap_extend * shift
+                const double gap = __dmul_rn(A.scale_ext[t >> 1], (double)shift);
+                const float v = __double2float_rn((t & 1) ? __dadd_rn((double)dpv, gap) : __dsub_rn((double)dpv, gap));
+                if (!(v > mininf())) continue;  // anchorer.hpp:2338
+                if (lane == 0) A.or_ord[(int64_t)t * A.n_entry + or_base + or_node] = ford(v);
+                if (lane < nr) {
+                    const unsigned long long pk = pack(v, or_node);
+                    unsigned long long* bit = A.bit + (int64_t)t * A.n_inner + ib;
+                    for (uint32_t k = rank; k < cn; k |= k + 1) atomicMax(&bit[k], pk);
                 }
             }
         }
@@ -244,49 +302,40 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainArgs A) {
         // ------------------------------ B: queries (anchorer.hpp:2352-2416) ------------------------------
         const int64_t n_items = (q1 - q0) * C2 * n_type;
         for (int64_t item = gwarp; item < n_items; item += nwarp) {
-            const int64_t qc = item / n_type;  // (query, chain2) pair
+            const int64_t qc = item / n_type;  // (query, chain2) pair inside the step
             const int type = (int)(item - qc * n_type);
-            const int64_t qi = qc / C2;
-            const int c2 = (int)(qc - qi * C2);
-            const uint32_t m = A.qry_match[q0 + qi];
-            const uint32_t c1 = A.qry_chain1[q0 + qi];
-            const uint32_t offset = A.qoff[(int64_t)m * C2 + c2];
+            const uint4* rp = reinterpret_cast<const uint4*>(&A.qrec[q0 * C2 + qc]);
+            const uint4 r0 = __ldg(rp);  // match, weight, offset, q
+            const uint32_t offset = r0.z;
             if (offset == 0) continue;  // nothing on this path reaches the match: every range [0, 0) is empty
-            const int q = (int)((uint32_t)A.qa1[(int64_t)m * C1 + c1] - (uint32_t)A.qa2[(int64_t)m * C2 + c2]);
-            const int64_t pair = (int64_t)c1 * C2 + c2;
-            const float w = A.weight[m];
-            ++n_tree_queries;
+            const uint32_t m = r0.x;
+            const float w = __uint_as_float(r0.y);
+            const int q = (int)r0.w;
             __syncwarp();
             if (type == 0) {
                 // same diagonal (anchorer.hpp:2379-2389): MaxSearchTree::range_max((0, min), (offset, min))
-                const int64_t g1 = A.pair_grp_off[pair + 1];
-                const int64_t g = warp_lower_bound(A.grp_shift, A.pair_grp_off[pair], g1, q, lane);
-                if (g >= g1 || __ldg(&A.grp_shift[g]) != q) continue;
-                const int64_t base = A.grp_base[g];
-                const uint32_t n = A.grp_n[g];
-                const uint32_t* key = A.gf_key + base;
-                const int nb = tree_walk(n, true, [&](uint32_t x) { return __ldg(&key[x]) < offset; }, blk, lane);
+                const uint4 r1 = __ldg(rp + 1);  // gf_base, gf_n, gf_S, gf_bits
+                if (r1.y == 0 || r1.z == kChainNone) continue;
+                ++n_tree_queries;
+                const uint32_t base = r1.x;
+                const int nb = walk_blocks(r1.y, true, r1.z, r1.w, blk, lane);
                 __syncwarp();
-                unsigned long long lbest = 0;  // pack(value, ~block index)
-                uint32_t lmatch = 0;
+                unsigned long long lbest = 0;  // pack(ord, ~block index)
+                uint32_t lsel = 0;             // kind << 31 | node, resolved to a match for the winner only
                 for (int b = lane; b < nb && b < kMaxBlocks; b += 32) {
                     const WalkEntry we = blk[b];
-                    float v = mininf();
-                    uint32_t bm = 0;
+                    uint32_t ord, sel;
                     if (we.kind == 0) {
-                        v = __ldcg(&A.gf_val[base + we.node]);
-                        bm = __ldg(&A.gf_match[base + we.node]);
+                        ord = __ldcg(&A.gf_ord[base + we.node]);
+                        sel = we.node;
                     } else {
                         const unsigned long long pk = __ldcg(&A.gf_best[base + we.node]);
-                        if (pk) {
-                            v = funord((uint32_t)(pk >> 32));
-                            bm = __ldg(&A.ent_match[__ldg(&A.sins_entry[~(uint32_t)pk])]);
-                        }
+                        ord = (uint32_t)(pk >> 32);
+                        sel = 0x80000000u | (~(uint32_t)pk & 0x7fffffffu);  // the insertion sequence number (< 2^31)
                     }
-                    const unsigned long long pk = pack(v, ~(uint32_t)b);
-                    if (v > mininf() && (pk >> 32) > (lbest >> 32)) {
-                        lbest = pk;
-                        lmatch = bm;
+                    if (ord > kOrdLowest && ord > (uint32_t)(lbest >> 32)) {
+                        lbest = ((unsigned long long)ord << 32) | (~(uint32_t)b);
+                        lsel = sel;
                     }
                 }
                 unsigned long long r = lbest;
@@ -297,44 +346,65 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainArgs A) {
                 }
                 if (!r) continue;
                 const unsigned src = __ffs(__ballot_sync(kFull, lbest == r)) - 1;
-                const uint32_t bm = __shfl_sync(kFull, lmatch, src);
-                if (lane == 0) post(m, qc, 0, __fadd_rn(funord((uint32_t)(r >> 32)), w), bm);
+                const uint32_t sel = __shfl_sync(kFull, lsel, src);
+                if (lane == 0) {
+                    const uint32_t bm = (sel & 0x80000000u) ? __ldg(&A.ins[sel & 0x7fffffffu].match) : __ldg(&A.gf_match[base + sel]);
+                    post(m, qc, 0, __fadd_rn(funord((uint32_t)(r >> 32)), w), bm);
+                }
                 continue;
             }
             // orthogonal trees of one parity (anchorer.hpp:2390-2413): par 0 = even pieces (shift > q), par 1 = odd (shift < q)
             const int par = type - 1;
-            const int64_t ob = A.pair_base[pair];
-            const uint32_t n = (uint32_t)(A.pair_base[pair + 1] - ob);
-            if (n == 0) continue;
-            const int32_t* shift = A.or_shift + ob;
-            const int nb = par ? tree_walk(n, true, [&](uint32_t x) { return __ldg(&shift[x]) < q; }, blk, lane)
-                               : tree_walk(n, false, [&](uint32_t x) { return __ldg(&shift[x]) > q; }, blk, lane);
+            const uint4 r2 = __ldg(rp + 2);  // or_base, or_n, ev_S, ev_bits
+            const uint32_t ob = r2.x, n = r2.y;
+            uint32_t S = r2.z, bits = r2.w;
+            if (par) {
+                const uint4 r3 = __ldg(rp + 3);  // od_S, od_bits
+                S = r3.x;
+                bits = r3.y;
+            }
+            if (n == 0 || S == kChainNone) continue;
+            n_tree_queries += P;
+            const int nb = walk_blocks(n, par == 1, S, bits, blk, lane);
             __syncwarp();
-            unsigned long long lbest[3] = {0, 0, 0};  // per piece: pack(value, ~block index) of this lane's best block
+            unsigned long long lbest[3] = {0, 0, 0};  // per piece: pack(ord, ~block index) of this lane's best block
             uint32_t lnode[3] = {0, 0, 0};
             for (int b = lane; b < nb && b < kMaxBlocks; b += 32) {
                 const WalkEntry we = blk[b];
                 if (we.kind == 0) {
-                    if (__ldg(&A.or_off[ob + we.node]) < offset) {
-                        float v[3];
-                        for (int k = 0; k < P; ++k) v[k] = __ldcg(&A.or_val[(int64_t)(2 * k + par) * A.n_entry + ob + we.node]);
-                        for (int k = 0; k < P; ++k) {
-                            const unsigned long long pk = pack(v[k], ~(uint32_t)b);
-                            if (v[k] > mininf() && (pk >> 32) > (lbest[k] >> 32)) {
-                                lbest[k] = pk;
+                    const uint32_t off = __ldg(&A.or_off[ob + we.node]);
+                    uint32_t v[3];
+                    for (int k = 0; k < P; ++k) v[k] = __ldcg(&A.or_ord[(int64_t)(2 * k + par) * A.n_entry + ob + we.node]);
+                    if (off < offset) {
+                        for (int k = 0; k < P; ++k)
+                            if (v[k] > kOrdLowest && v[k] > (uint32_t)(lbest[k] >> 32)) {
+                                lbest[k] = ((unsigned long long)v[k] << 32) | (~(uint32_t)b);
                                 lnode[k] = we.node;
                             }
-                        }
                     }
                 } else {
-                    const int64_t ib = A.in_base[ob + we.node];
-                    const uint32_t cnt = count_less(A.in_off + ib, A.in_n[ob + we.node], offset);
-                    if (cnt) {  // Fenwick prefix maximum over the first cnt entries; the probes are independent
+                    const uint32_t ib = __ldg(&A.in_base[ob + we.node]);
+                    const uint32_t cnt = count_less(A.in_off + ib, __ldg(&A.in_n[ob + we.node]), offset);
+                    if (cnt) {  // Fenwick prefix maximum over the first cnt entries
                         unsigned long long r[3] = {0, 0, 0};
-                        for (uint32_t c = cnt; c > 0; c &= c - 1) {
-                            unsigned long long x[3];
-                            for (int k = 0; k < P; ++k) x[k] = __ldcg(&A.bit[(int64_t)(2 * k + par) * A.n_inner + ib + c - 1]);
-                            for (int k = 0; k < P; ++k) r[k] = x[k] > r[k] ? x[k] : r[k];
+                        uint32_t c = cnt;
+                        while (c) {  // the probe addresses only depend on cnt: issue six levels of probes before using any
+                            uint32_t at[6];
+#pragma unroll
+                            for (int j = 0; j < 6; ++j) {
+                                at[j] = c ? c - 1 : kChainNone;
+                                c &= c - 1;  // 0 stays 0
+                            }
+                            unsigned long long x[6][3];
+#pragma unroll
+                            for (int j = 0; j < 6; ++j)
+#pragma unroll
+                                for (int k = 0; k < 3; ++k)
+                                    x[j][k] = (k < P && at[j] != kChainNone) ? __ldcg(&A.bit[(int64_t)(2 * k + par) * A.n_inner + ib + at[j]]) : 0ull;
+#pragma unroll
+                            for (int j = 0; j < 6; ++j)
+#pragma unroll
+                                for (int k = 0; k < 3; ++k) r[k] = x[j][k] > r[k] ? x[j][k] : r[k];
                         }
                         for (int k = 0; k < P; ++k)
                             if (r[k] && (r[k] >> 32) > (lbest[k] >> 32)) {
@@ -384,7 +454,10 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainArgs A) {
     if (lane == 0 && n_tree_queries) atomicAdd(A.counters, n_tree_queries);
 }
 
-cudaError_t launch_chain(const ChainArgs& args, int grid, cudaStream_t stream) {
+cudaError_t launch_chain(const ChainArgs& args, int grid, int prepare_grid, cudaStream_t stream) {
+    if (args.n_qry > 0) chain_prepare_kernel<<<prepare_grid, 256, 0, stream>>>(args);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
     void* params[] = {(void*)&args};
     if (grid > 1)
         return cudaLaunchCooperativeKernel((const void*)chain_kernel, dim3(grid), dim3(kThreads), params, 0, stream);

@@ -29,6 +29,7 @@ cudaError_t launch_popoa(int num_pw, const LaunchArgs& args, int grid, cudaStrea
 int popoa_smem_bytes();
 double int32_probe(int use_dpx, int sm_count);
 int popoa_nsmid();
+void chain_release_cache();  // chain_host.cu
 }  // namespace clb
 
 namespace {
@@ -791,7 +792,10 @@ int clb_popoa_batch(int device, int32_t n_windows, const clb_graph_batch* g1, co
     return rc;
 }
 
-void clb_release_cached_memory(void) { g_cache.trim(); }
+void clb_release_cached_memory(void) {
+    g_cache.trim();
+    clb::chain_release_cache();
+}
 
 double clb_int32_peak_tops(int device, int use_dpx) {
     int ndev = 0;

@@ -35,7 +35,7 @@ def test_chain_equals_reference(case, kind):
     prob = GOLD[case][kind]
     st = ChainStats()
     chain, dp, bp, opt = chain_dp(prob, stats=st)
-    assert st.kernel_launches == 1 and st.steps == prob.n_step
+    assert st.kernel_launches == 2 and st.steps == prob.n_step  # preparation kernel + the persistent DP kernel
     assert len(chain) == len(prob.expect_chain), f"{case}/{kind}: chain length {len(chain)} != {len(prob.expect_chain)}"
     assert np.array_equal(chain, prob.expect_chain), f"{case}/{kind}: chain differs from the reference's"
     _check_chain_consistency(prob, chain, dp, bp)
