@@ -105,9 +105,14 @@ struct ChainArgs {
     int64_t n_inner;
     int64_t n_entry;
     // per-step candidate exchange
-    unsigned long long* cand_best;  // [n_match] pack(value, ~order), 0 = none
+    unsigned long long* cand_best;  // [2][n_match] by step parity: pack(value, ~order), 0 = none
     uint32_t* cand_bp;              // [max queries per step * n_chain2 * (2*num_pw+1)]
     unsigned long long* counters;   // [0] tree queries answered
+    // ranks of the subtree blocks of every orthogonal walk, computed by the preparation kernel: per (query, chain2,
+    // parity) rank_stride words, one per subtree block in walk order; nullptr = computed on the fly
+    uint32_t* rank_pool;
+    int rank_stride;
+    int split_phases;  // debug: separate barrier between update_dp and the next step's insertions
 };
 
 }  // namespace clb

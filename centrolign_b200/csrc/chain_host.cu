@@ -30,7 +30,7 @@
 #include "chain_device.cuh"
 
 namespace clb {
-cudaError_t launch_chain(const ChainArgs& args, int grid, int prepare_grid, cudaStream_t stream);
+cudaError_t launch_chain(const ChainArgs& args, int grid, int prepare_grid, cudaStream_t stream, cudaEvent_t after_prepare);
 int chain_max_grid(int device);
 int host_fail(int code, const std::string& msg);
 }  // namespace clb
@@ -68,7 +68,7 @@ struct DeviceArena {
     char* h = nullptr;  // pinned
     size_t hcap = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp = nullptr;
 };
 constexpr size_t kArenaKeep = size_t(1) << 30;
 std::mutex g_arena_mu;
@@ -353,7 +353,20 @@ extern "C" int clb_chain_dp(int device, const clb_chain_problem* p, float* dp_ou
         const size_t z_qrec = plan.zero((size_t)n_qry * C2 * sizeof(clb::QueryRec));
         const size_t z_gford = plan.zero((size_t)E * 4), z_gfbest = plan.zero((size_t)E * 8);
         const size_t z_orord = plan.zero((size_t)T * E * 4), z_bit = plan.zero((size_t)T * n_inner * 8);
-        const size_t z_cbest = plan.zero((size_t)M * 8), z_cbp = plan.zero((size_t)(max_q * C2 * (T + 1)) * 4), z_cnt = plan.zero(8);
+        const size_t z_cbest = plan.zero((size_t)M * 16), z_cbp = plan.zero((size_t)(max_q * C2 * (T + 1)) * 4), z_cnt = plan.zero(8);
+        // subtree-block ranks of every orthogonal walk (2 * (depth + 1) blocks at most), if memory allows
+        int rank_stride = 0;
+        size_t z_ranks = 0;
+        if (P > 0 && n_qry > 0 && !getenv("CLB_CHAIN_NO_RANKS")) {
+            uint32_t max_n = 1;
+            for (int64_t pr = 0; pr < npair; ++pr) max_n = std::max<uint32_t>(max_n, (uint32_t)(pair_base[pr + 1] - pair_base[pr]));
+            rank_stride = 2 * (32 - __builtin_clz(max_n));
+            const size_t bytes = (size_t)n_qry * C2 * 2 * rank_stride * 4;
+            size_t free_b = 0, total_b = 0;
+            cudaSetDevice(device);
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && bytes < free_b / 4 + (ar.cap > 0 ? ar.cap / 4 : 0)) z_ranks = plan.zero(bytes);
+            else rank_stride = 0;
+        }
         const size_t total = plan.copy_bytes + plan.zero_bytes;
         keep = total <= kArenaKeep;
         CHAIN_TRY(cudaSetDevice(device));
@@ -361,6 +374,7 @@ extern "C" int clb_chain_dp(int device, const clb_chain_problem* p, float* dp_ou
             CHAIN_TRY(cudaStreamCreateWithFlags(&ar.stream, cudaStreamNonBlocking));
             CHAIN_TRY(cudaEventCreate(&ar.ev0));
             CHAIN_TRY(cudaEventCreate(&ar.ev1));
+            CHAIN_TRY(cudaEventCreate(&ar.evp));
         }
         if (ar.cap < total) {
             if (ar.d) cudaFree(ar.d);
@@ -404,6 +418,9 @@ extern "C" int clb_chain_dp(int device, const clb_chain_problem* p, float* dp_ou
         a.qrec = (clb::QueryRec*)(zr + z_qrec);
         a.gf_ord = (uint32_t*)(zr + z_gford); a.gf_best = (unsigned long long*)(zr + z_gfbest);
         a.or_ord = (uint32_t*)(zr + z_orord); a.bit = (unsigned long long*)(zr + z_bit);
+        a.rank_pool = rank_stride ? (uint32_t*)(zr + z_ranks) : nullptr;
+        a.rank_stride = rank_stride;
+        a.split_phases = getenv("CLB_CHAIN_SPLIT_PHASES") ? 1 : 0;
         a.cand_best = (unsigned long long*)(zr + z_cbest); a.cand_bp = (uint32_t*)(zr + z_cbp); a.counters = (unsigned long long*)(zr + z_cnt);
         // grid: one CTA unless a step has enough independent warps of work to pay for grid-wide barriers
         const double warps_per_step = S ? ((double)ins.size() + (double)n_qry * C2 * (P > 0 ? 3 : 1)) / (double)S : 0.0;
@@ -412,13 +429,19 @@ extern "C" int clb_chain_dp(int device, const clb_chain_problem* p, float* dp_ou
                                          : (warps_per_step > 64.0 ? std::min<int>(max_grid, (int)(warps_per_step / 16.0) + 1) : 1);
         const int prepare_grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_qry * C2 + 7) / 8, 8 * (int64_t)max_grid));
         CHAIN_TRY(cudaEventRecord(ar.ev0, ar.stream));
-        CHAIN_TRY(clb::launch_chain(a, grid, prepare_grid, ar.stream));
+        CHAIN_TRY(clb::launch_chain(a, grid, prepare_grid, ar.stream, ar.evp));
         CHAIN_TRY(cudaEventRecord(ar.ev1, ar.stream));
         CHAIN_TRY(cudaMemcpyAsync(h_dp.data(), a.dp, M * sizeof(float), cudaMemcpyDeviceToHost, ar.stream));
         CHAIN_TRY(cudaMemcpyAsync(h_bp.data(), a.backptr, M * sizeof(uint32_t), cudaMemcpyDeviceToHost, ar.stream));
         CHAIN_TRY(cudaStreamSynchronize(ar.stream));
         float ms = 0.f;
         CHAIN_TRY(cudaEventElapsedTime(&ms, ar.ev0, ar.ev1));
+        if (getenv("CLB_TIMING")) {
+            float pms = 0.f;
+            cudaEventElapsedTime(&pms, ar.ev0, ar.evp);
+            fprintf(stderr, "[clb] chain: build %.1f ms, prepare kernel %.2f ms, DP kernel %.2f ms (grid %d, %lld steps, rank pool %s)\n",
+                    t_built - t_start, pms, ms - pms, grid, (long long)S, rank_stride ? "on" : "off");
+        }
         if (stats) {
             stats->build_ms = t_built - t_start;
             stats->kernel_ms = ms;
@@ -481,6 +504,7 @@ void chain_release_cache() {
         if (kv.second.h) cudaFreeHost(kv.second.h);
         if (kv.second.ev0) cudaEventDestroy(kv.second.ev0);
         if (kv.second.ev1) cudaEventDestroy(kv.second.ev1);
+        if (kv.second.evp) cudaEventDestroy(kv.second.evp);
         if (kv.second.stream) cudaStreamDestroy(kv.second.stream);
     }
     g_arenas.clear();

@@ -191,6 +191,8 @@ __device__ __forceinline__ uint32_t count_less(const uint32_t* a, uint32_t n, ui
 
 // Everything about a (query, path of graph 2) pair that does not depend on DP values (anchorer.hpp:2374-2381).
 __global__ void __launch_bounds__(256) chain_prepare_kernel(const ChainArgs A) {
+    __shared__ WarpScratch prep_scratch[8];
+    WalkEntry* blk = prep_scratch[threadIdx.x >> 5].blk;
     const int lane = threadIdx.x & 31;
     const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int C1 = A.n_chain1, C2 = A.n_chain2;
@@ -226,6 +228,29 @@ __global__ void __launch_bounds__(256) chain_prepare_kernel(const ChainArgs A) {
                 if (r.or_n) {
                     walk_shape(r.or_n, false, [&](uint32_t x) { return __ldg(&shift[x]) > q; }, lane, r.ev_S, r.ev_bits);
                     walk_shape(r.or_n, true, [&](uint32_t x) { return __ldg(&shift[x]) < q; }, lane, r.od_S, r.od_bits);
+                    if (A.rank_pool) {  // how many elements of every subtree block lie below the query offset
+                        for (int par = 0; par < 2; ++par) {
+                            const uint32_t S = par ? r.od_S : r.ev_S;
+                            if (S == kChainNone) continue;
+                            __syncwarp();
+                            const int nb = walk_blocks(r.or_n, par == 1, S, par ? r.od_bits : r.ev_bits, blk, lane);
+                            __syncwarp();
+                            uint32_t* pool = A.rank_pool + ((int64_t)qc * 2 + par) * A.rank_stride;
+                            int seen = 0;  // subtree blocks before this group of 32
+                            for (int b0 = 0; b0 < nb && b0 < kMaxBlocks; b0 += 32) {
+                                const int b = b0 + lane;
+                                const bool sub = b < nb && b < kMaxBlocks && blk[b].kind == 1;
+                                const unsigned subm = __ballot_sync(kFull, sub);
+                                if (sub) {
+                                    const int j = seen + __popc(subm & ((1u << lane) - 1));
+                                    const uint32_t node = blk[b].node;
+                                    if (j < A.rank_stride)
+                                        pool[j] = count_less(A.in_off + __ldg(&A.in_base[r.or_base + node]), __ldg(&A.in_n[r.or_base + node]), r.offset);
+                                }
+                                seen += __popc(subm);
+                            }
+                        }
+                    }
                 }
             }
         }
@@ -250,15 +275,52 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainArgs A) {
         if (multi) grid.sync();
         else __syncthreads();
     };
+    unsigned long long* post_to = A.cand_best;
     auto post = [&](uint32_t m, int64_t qc, uint32_t slot, float cand, uint32_t bp) {  // lane 0 only
         const uint32_t order = (uint32_t)qc * slots + slot;
         A.cand_bp[order] = bp;
-        atomicMax(&A.cand_best[m], pack(cand, ~order));
+        atomicMax(&post_to[m], pack(cand, ~order));
     };
 
+    // update_dp of the winners of one step (match_bank.hpp:171-184).  Runs in the same phase as the insertions of
+    // the next step; a match may be queried in one step and end in the next, so an insertion takes the maximum of
+    // the stored value and the pending winner (effective_dp).  The candidate words are double-buffered by step
+    // parity and cleared one phase later, so nothing a concurrent reader looks at is ever reset under it.
+    auto apply_winners = [&](int64_t q0, int64_t q1, const unsigned long long* cand) {
+        for (int64_t qi = gthread; qi < q1 - q0; qi += nthread) {
+            const uint32_t m = A.qry_match[q0 + qi];
+            const unsigned long long pk = __ldcg(&cand[m]);
+            if (!pk) continue;
+            const uint32_t order = ~(uint32_t)pk;
+            if ((int64_t)(order / ((uint32_t)C2 * slots)) != qi) continue;  // the winner was posted by another query of this match
+            const float v = funord((uint32_t)(pk >> 32));
+            if (v > __ldcg(&A.dp[m])) {
+                A.dp[m] = v;
+                A.backptr[m] = __ldcg(&A.cand_bp[order]);
+            }
+        }
+    };
+    auto effective_dp = [&](uint32_t m, const unsigned long long* cand) -> float {
+        const unsigned long long pk = __ldcg(&cand[m]);
+        float dpv = __ldcg(&A.dp[m]);
+        if (pk) {
+            const float v = funord((uint32_t)(pk >> 32));
+            if (v > dpv) dpv = v;
+        }
+        return dpv;
+    };
+
+    int64_t pq0 = 0, pq1 = 0;  // queries of the previous step, whose winners are still to be applied
     for (int64_t s = 0; s < A.n_step; ++s) {
-        // ------------------------------ A: inserts (anchorer.hpp:2301-2345) ------------------------------
+        // ---------------- update_dp of the previous step + A: inserts (anchorer.hpp:2301-2345) ----------------
         const int64_t i0 = A.sins_off[s], i1 = A.sins_off[s + 1];
+        const int64_t q0 = A.qry_off[s], q1 = A.qry_off[s + 1];
+        unsigned long long* cand_prev = A.cand_best + ((s + 1) & 1) * A.n_match;  // posted in step s-1
+        unsigned long long* cand_cur = A.cand_best + (s & 1) * A.n_match;         // posted in this step
+        if (pq0 != pq1) {
+            apply_winners(pq0, pq1, cand_prev);
+            if (A.split_phases) barrier();
+        }
         for (int64_t i = i0 + gwarp; i < i1; i += nwarp) {
             const uint4 ra = __ldg(reinterpret_cast<const uint4*>(&A.ins[i]));
             const uint4 rb = __ldg(reinterpret_cast<const uint4*>(&A.ins[i]) + 1);
@@ -272,7 +334,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainArgs A) {
                 cn = __ldg(&A.in_n[or_base + a]);
                 rank = __ldg(&A.ent_rank[rank_off + lane]);
             }
-            const float dpv = __ldcg(&A.dp[m]);
+            const float dpv = effective_dp(m, cand_prev);
             if (!(dpv > mininf())) continue;  // entering lowest() changes nothing in the reference's trees
             {   // gap-free tree of the entry's diagonal: lanes = the node and its ancestors
                 if (lane == 0) A.gf_ord[gf_base + gf_node] = ford(dpv);
@@ -292,14 +354,19 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainArgs A) {
                 }
             }
         }
-        const int64_t q0 = A.qry_off[s], q1 = A.qry_off[s + 1];
+        if (i0 != i1 || pq0 != pq1) barrier();
+        // the previous step's candidate words are spent now: clear them while this step's queries run
+        const bool cleared = pq0 != pq1;
+        for (int64_t qi = gthread; qi < pq1 - pq0; qi += nthread) cand_prev[A.qry_match[pq0 + qi]] = 0;
+        pq0 = q0;
+        pq1 = q1;
         if (q0 == q1) {
-            if (i0 != i1) barrier();
+            if (cleared) barrier();  // the clears must land before that buffer is posted to again
             continue;
         }
-        if (i0 != i1) barrier();
 
         // ------------------------------ B: queries (anchorer.hpp:2352-2416) ------------------------------
+        post_to = cand_cur;
         const int64_t n_items = (q1 - q0) * C2 * n_type;
         for (int64_t item = gwarp; item < n_items; item += nwarp) {
             const int64_t qc = item / n_type;  // (query, chain2) pair inside the step
@@ -367,10 +434,18 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainArgs A) {
             n_tree_queries += P;
             const int nb = walk_blocks(n, par == 1, S, bits, blk, lane);
             __syncwarp();
+            const uint32_t* ranks = A.rank_pool ? A.rank_pool + ((q0 * C2 + qc) * 2 + par) * A.rank_stride : nullptr;
             unsigned long long lbest[3] = {0, 0, 0};  // per piece: pack(ord, ~block index) of this lane's best block
             uint32_t lnode[3] = {0, 0, 0};
-            for (int b = lane; b < nb && b < kMaxBlocks; b += 32) {
-                const WalkEntry we = blk[b];
+            int seen = 0;  // subtree blocks before the current group of 32
+            for (int b0 = 0; b0 < nb && b0 < kMaxBlocks; b0 += 32) {
+                const int b = b0 + lane;
+                const bool mine = b < nb && b < kMaxBlocks;
+                const WalkEntry we = mine ? blk[b] : WalkEntry{0, 0};
+                const unsigned subm = __ballot_sync(kFull, mine && we.kind == 1);
+                const int j = seen + __popc(subm & ((1u << lane) - 1));
+                seen += __popc(subm);
+                if (!mine) continue;
                 if (we.kind == 0) {
                     const uint32_t off = __ldg(&A.or_off[ob + we.node]);
                     uint32_t v[3];
@@ -384,27 +459,28 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainArgs A) {
                     }
                 } else {
                     const uint32_t ib = __ldg(&A.in_base[ob + we.node]);
-                    const uint32_t cnt = count_less(A.in_off + ib, __ldg(&A.in_n[ob + we.node]), offset);
+                    const uint32_t cnt = (ranks && j < A.rank_stride) ? __ldg(&ranks[j])
+                                                                     : count_less(A.in_off + ib, __ldg(&A.in_n[ob + we.node]), offset);
                     if (cnt) {  // Fenwick prefix maximum over the first cnt entries
                         unsigned long long r[3] = {0, 0, 0};
                         uint32_t c = cnt;
                         while (c) {  // the probe addresses only depend on cnt: issue six levels of probes before using any
                             uint32_t at[6];
 #pragma unroll
-                            for (int j = 0; j < 6; ++j) {
-                                at[j] = c ? c - 1 : kChainNone;
+                            for (int jj = 0; jj < 6; ++jj) {
+                                at[jj] = c ? c - 1 : kChainNone;
                                 c &= c - 1;  // 0 stays 0
                             }
                             unsigned long long x[6][3];
 #pragma unroll
-                            for (int j = 0; j < 6; ++j)
+                            for (int jj = 0; jj < 6; ++jj)
 #pragma unroll
                                 for (int k = 0; k < 3; ++k)
-                                    x[j][k] = (k < P && at[j] != kChainNone) ? __ldcg(&A.bit[(int64_t)(2 * k + par) * A.n_inner + ib + at[j]]) : 0ull;
+                                    x[jj][k] = (k < P && at[jj] != kChainNone) ? __ldcg(&A.bit[(int64_t)(2 * k + par) * A.n_inner + ib + at[jj]]) : 0ull;
 #pragma unroll
-                            for (int j = 0; j < 6; ++j)
+                            for (int jj = 0; jj < 6; ++jj)
 #pragma unroll
-                                for (int k = 0; k < 3; ++k) r[k] = x[j][k] > r[k] ? x[j][k] : r[k];
+                                for (int k = 0; k < 3; ++k) r[k] = x[jj][k] > r[k] ? x[jj][k] : r[k];
                         }
                         for (int k = 0; k < P; ++k)
                             if (r[k] && (r[k] >> 32) > (lbest[k] >> 32)) {
@@ -434,30 +510,16 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainArgs A) {
             }
         }
         barrier();
-
-        // ------------------------------ C: update_dp (match_bank.hpp:171-184) ------------------------------
-        for (int64_t qi = gthread; qi < q1 - q0; qi += nthread) {
-            const uint32_t m = A.qry_match[q0 + qi];
-            const unsigned long long pk = __ldcg(&A.cand_best[m]);
-            if (!pk) continue;
-            const uint32_t order = ~(uint32_t)pk;
-            if ((int64_t)(order / ((uint32_t)C2 * slots)) != qi) continue;  // the winner was posted by another query of this match
-            const float v = funord((uint32_t)(pk >> 32));
-            if (v > __ldcg(&A.dp[m])) {
-                A.dp[m] = v;
-                A.backptr[m] = __ldcg(&A.cand_bp[order]);
-            }
-            A.cand_best[m] = 0;
-        }
-        barrier();
     }
+    if (pq0 != pq1) apply_winners(pq0, pq1, A.cand_best + ((A.n_step + 1) & 1) * A.n_match);  // the last step's winners
     if (lane == 0 && n_tree_queries) atomicAdd(A.counters, n_tree_queries);
 }
 
-cudaError_t launch_chain(const ChainArgs& args, int grid, int prepare_grid, cudaStream_t stream) {
+cudaError_t launch_chain(const ChainArgs& args, int grid, int prepare_grid, cudaStream_t stream, cudaEvent_t after_prepare) {
     if (args.n_qry > 0) chain_prepare_kernel<<<prepare_grid, 256, 0, stream>>>(args);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    if (after_prepare) cudaEventRecord(after_prepare, stream);
     void* params[] = {(void*)&args};
     if (grid > 1)
         return cudaLaunchCooperativeKernel((const void*)chain_kernel, dim3(grid), dim3(kThreads), params, 0, stream);
