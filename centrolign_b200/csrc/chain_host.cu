@@ -23,6 +23,7 @@
 #include <map>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -74,6 +75,52 @@ constexpr size_t kArenaKeep = size_t(1) << 30;
 std::mutex g_arena_mu;
 std::map<int, DeviceArena> g_arenas;
 
+// fn(begin, end) over [0, n) on up to 16 host threads (the layout of a million-match problem is tens of millions of
+// small steps; the Anchorer calls us from one thread)
+template <class Fn>
+void parallel_for(int64_t n, int64_t min_per_thread, const Fn& fn) {
+    const int64_t hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    const int64_t nt = std::max<int64_t>(1, std::min<int64_t>(hw, n / std::max<int64_t>(1, min_per_thread)));
+    if (nt <= 1) {
+        fn((int64_t)0, n);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (int64_t t = 1; t < nt; ++t) th.emplace_back([&, t] { fn(n * t / nt, n * (t + 1) / nt); });
+    fn((int64_t)0, n / nt);
+    for (auto& x : th) x.join();
+}
+
+struct SortKey {
+    uint64_t hi, lo;
+    uint32_t e;
+    bool operator<(const SortKey& o) const { return hi != o.hi ? hi < o.hi : lo < o.lo; }
+};
+// sorts `keys` on the host threads: sorted chunks, then pairwise merges
+void parallel_sort(std::vector<SortKey>& keys) {
+    const int64_t n = (int64_t)keys.size();
+    const int64_t hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    int64_t nt = 1;
+    while (nt * 2 <= hw && n / (nt * 2) >= 65536) nt *= 2;
+    if (nt == 1) {
+        std::sort(keys.begin(), keys.end());
+        return;
+    }
+    parallel_for(nt, 1, [&](int64_t a, int64_t b) {
+        for (int64_t t = a; t < b; ++t) std::sort(keys.begin() + n * t / nt, keys.begin() + n * (t + 1) / nt);
+    });
+    std::vector<SortKey> tmp(keys.size());
+    for (int64_t w = 1; w < nt; w *= 2) {
+        parallel_for(nt / (2 * w), 1, [&](int64_t a, int64_t b) {
+            for (int64_t g = a; g < b; ++g) {
+                const int64_t lo = n * (g * 2 * w) / nt, mid = n * (g * 2 * w + w) / nt, hi = n * (g * 2 * w + 2 * w) / nt;
+                std::merge(keys.begin() + lo, keys.begin() + mid, keys.begin() + mid, keys.begin() + hi, tmp.begin() + lo);
+            }
+        });
+        keys.swap(tmp);
+    }
+}
+
 struct ArenaPlan {
     struct Seg {
         size_t off, bytes;
@@ -103,11 +150,20 @@ extern "C" int clb_chain_dp(int device, const clb_chain_problem* p, float* dp_ou
                             int64_t* chain_len, float* opt_score, clb_chain_stats* stats) {
     const double t_start = now_ms();
     if (stats) memset(stats, 0, sizeof(*stats));
-    if (getenv("CLB_COUNT_CALLS") && p) {  // evidence for integration tests that the GPU path really ran
+    struct CallTimer {  // evidence for integration tests that the GPU path really ran, and what it cost
+        static std::atomic<int64_t>& us() { static std::atomic<int64_t> v(0); return v; }
+        double t0;
+        bool on;
+        ~CallTimer() { if (on) us() += (int64_t)((now_ms() - t0) * 1e3); }
+    } call_timer{t_start, getenv("CLB_COUNT_CALLS") != nullptr};
+    if (call_timer.on && p) {
         static std::atomic<int64_t> calls(0), matches(0);
         static std::once_flag once;
         std::call_once(once, [] {
-            atexit([] { fprintf(stderr, "[clb] chain calls %lld matches %lld\n", (long long)calls.load(), (long long)matches.load()); });
+            atexit([] {
+                fprintf(stderr, "[clb] chain calls %lld matches %lld seconds %.3f\n", (long long)calls.load(), (long long)matches.load(),
+                        CallTimer::us().load() * 1e-6);
+            });
         });
         calls += 1;
         matches += p->n_match;
@@ -172,12 +228,14 @@ extern "C" int clb_chain_dp(int device, const clb_chain_problem* p, float* dp_ou
     std::vector<int64_t> pair_grp_off(npair + 1, 0), grp_base;
     std::vector<int32_t> grp_shift;
     std::vector<uint32_t> grp_n, gf_key(E), gf_match(E), ent_gf_grp(E), ent_gf_node(E);
-    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-        if (ent_pair[a] != ent_pair[b]) return ent_pair[a] < ent_pair[b];
-        if (p->ins_shift[a] != p->ins_shift[b]) return p->ins_shift[a] < p->ins_shift[b];
-        if (p->ins_offset[a] != p->ins_offset[b]) return p->ins_offset[a] < p->ins_offset[b];
-        return ent_match[a] < ent_match[b];
+    std::vector<SortKey> keys(E);
+    parallel_for(E, 1 << 16, [&](int64_t a, int64_t b) {  // (pair, shift, offset, match)
+        for (int64_t e = a; e < b; ++e)
+            keys[e] = SortKey{((uint64_t)ent_pair[e] << 32) | ((uint32_t)p->ins_shift[e] ^ 0x80000000u),
+                              ((uint64_t)p->ins_offset[e] << 32) | ent_match[e], (uint32_t)e};
     });
+    parallel_sort(keys);
+    for (int64_t i = 0; i < E; ++i) order[i] = keys[i].e;
     for (int64_t i = 0; i < E;) {
         int64_t j = i;
         while (j < E && ent_pair[order[j]] == ent_pair[order[i]] && p->ins_shift[order[j]] == p->ins_shift[order[i]]) ++j;
@@ -206,16 +264,16 @@ extern "C" int clb_chain_dp(int device, const clb_chain_problem* p, float* dp_ou
     if (P > 0) {
         or_shift.resize(E); or_off.resize(E); or_match.resize(E); in_n.assign(E, 0); in_base.assign(E, -1);
         ent_or_node.resize(E); ent_rank_off.assign(E + 1, 0);
-        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-            if (ent_pair[a] != ent_pair[b]) return ent_pair[a] < ent_pair[b];
-            if (p->ins_shift[a] != p->ins_shift[b]) return p->ins_shift[a] < p->ins_shift[b];
-            return ent_match[a] < ent_match[b];
+        parallel_for(E, 1 << 16, [&](int64_t a, int64_t b) {  // (pair, shift, match)
+            for (int64_t e = a; e < b; ++e)
+                keys[e] = SortKey{((uint64_t)ent_pair[e] << 32) | ((uint32_t)p->ins_shift[e] ^ 0x80000000u), (uint64_t)ent_match[e], (uint32_t)e};
         });
+        parallel_sort(keys);
+        for (int64_t i = 0; i < E; ++i) order[i] = keys[i].e;
         for (int64_t e = 0; e < E; ++e) pair_base[ent_pair[e] + 1] += 1;
         for (int64_t pr = 0; pr < npair; ++pr) pair_base[pr + 1] += pair_base[pr];
         std::vector<uint32_t> pos_of_heap, sub_lo, sub_n, nanc;
         std::vector<uint8_t> spine;
-        std::vector<std::vector<uint32_t>> lists;  // per heap node: sorted positions of its subtree ordered by (offset, position)
         // pass 1: shapes, inner-list sizes and bases
         for (int64_t pr = 0; pr < npair; ++pr) {
             const int64_t ob = pair_base[pr];
@@ -249,7 +307,9 @@ extern "C" int clb_chain_dp(int device, const clb_chain_problem* p, float* dp_ou
         if (ent_rank_off[E] != n_inner) return host_fail(CLB_ECUDA, "internal: inner list accounting mismatch");
         in_off.resize(n_inner);
         ent_rank.resize(n_inner);
-        // pass 2: inner lists by merging children lists bottom-up; ranks of every element in every list it is part of
+        // pass 2: inner lists by merging children lists, one tree level at a time from the leaves up (the nodes of a
+        // level are independent); a list holds outer key-order positions and is stored where the device will read it
+        std::vector<uint32_t> in_pos(n_inner);
         for (int64_t pr = 0; pr < npair; ++pr) {
             const int64_t ob = pair_base[pr];
             const uint32_t n = (uint32_t)(pair_base[pr + 1] - ob);
@@ -257,45 +317,46 @@ extern "C" int clb_chain_dp(int device, const clb_chain_problem* p, float* dp_ou
             inorder_layout(n, heap_of_pos, stack);
             pos_of_heap.resize(n);
             for (uint32_t k = 0; k < n; ++k) pos_of_heap[heap_of_pos[k]] = k;
-            lists.assign(n, std::vector<uint32_t>());
             auto depth_of = [](uint32_t h) { return 31 - __builtin_clz(h + 1); };  // heap index -> depth
-            for (uint32_t h = n; h-- > 0;) {
-                if (in_base[ob + h] < 0) continue;  // spine: never queried, never built
-                const uint32_t l = 2 * h + 1, r = 2 * h + 2;
-                std::vector<uint32_t>& out = lists[h];
-                out.reserve(in_n[ob + h]);
-                const uint32_t self = pos_of_heap[h];
-                auto less = [&](uint32_t a, uint32_t b) {  // (offset, outer key order)
-                    const uint32_t oa = or_off[ob + heap_of_pos[a]], obb = or_off[ob + heap_of_pos[b]];
-                    return oa != obb ? oa < obb : a < b;
-                };
-                static const std::vector<uint32_t> kEmpty;
-                const std::vector<uint32_t>& L = l < n ? lists[l] : kEmpty;
-                const std::vector<uint32_t>& R = r < n ? lists[r] : kEmpty;
-                size_t a = 0, b = 0;
-                bool self_done = false;
-                while (a < L.size() || b < R.size() || !self_done) {
-                    // three-way merge; all positions are distinct
-                    int pick = -1;
-                    uint32_t best = 0;
-                    if (a < L.size()) { pick = 0; best = L[a]; }
-                    if (!self_done && (pick < 0 || less(self, best))) { pick = 1; best = self; }
-                    if (b < R.size() && (pick < 0 || less(R[b], best))) { pick = 2; best = R[b]; }
-                    out.push_back(best);
-                    if (pick == 0) ++a;
-                    else if (pick == 1) self_done = true;
-                    else ++b;
-                }
-                const int dh = depth_of(h);
-                const int64_t ib = in_base[ob + h];
-                for (uint32_t k = 0; k < out.size(); ++k) {
-                    const uint32_t eh = heap_of_pos[out[k]];
-                    in_off[ib + k] = or_off[ob + eh];
-                    const uint32_t e = order[ob + out[k]];
-                    ent_rank[ent_rank_off[e] + (depth_of(eh) - dh)] = k;  // climbing order: the element's own node first
-                }
-                if (l < n) std::vector<uint32_t>().swap(lists[l]);
-                if (r < n) std::vector<uint32_t>().swap(lists[r]);
+            for (int d = depth_of(n - 1); d >= 0; --d) {
+                const int64_t first = (int64_t(1) << d) - 1, last = std::min<int64_t>(n, (int64_t(2) << d) - 1);
+                parallel_for(last - first, std::max<int64_t>(1, 65536 / std::max<int64_t>(1, n >> d)), [&](int64_t a0, int64_t b0) {
+                    for (int64_t hh = first + a0; hh < first + b0; ++hh) {
+                        const uint32_t h = (uint32_t)hh;
+                        if (in_base[ob + h] < 0) continue;  // spine: never queried, never built
+                        const uint32_t l = 2 * h + 1, r = 2 * h + 2;
+                        uint32_t* out = in_pos.data() + in_base[ob + h];
+                        const uint32_t* L = l < n ? in_pos.data() + in_base[ob + l] : nullptr;
+                        const uint32_t* R = r < n ? in_pos.data() + in_base[ob + r] : nullptr;
+                        const uint32_t nl = l < n ? in_n[ob + l] : 0, nr = r < n ? in_n[ob + r] : 0;
+                        const uint32_t self = pos_of_heap[h];
+                        auto off_of = [&](uint32_t pos) { return or_off[ob + heap_of_pos[pos]]; };
+                        // positions of the left subtree < self < positions of the right subtree: ties in offset resolve by side
+                        const uint32_t so = off_of(self);
+                        uint32_t a = 0, b = 0, k = 0;
+                        bool self_done = false;
+                        while (a < nl || b < nr || !self_done) {
+                            // candidates in position order: L[a] < self < R[b]; pick the smallest (offset, position)
+                            int pick = -1;
+                            uint32_t bo = 0;
+                            if (a < nl) { pick = 0; bo = off_of(L[a]); }
+                            if (!self_done && (pick < 0 || so < bo)) { pick = 1; bo = so; }
+                            if (b < nr) {
+                                const uint32_t ro = off_of(R[b]);
+                                if (pick < 0 || ro < bo) pick = 2;
+                            }
+                            out[k++] = pick == 0 ? L[a++] : (pick == 1 ? self : R[b++]);
+                            if (pick == 1) self_done = true;
+                        }
+                        // offsets of the list entries and the rank of every element in this list
+                        const int64_t ib = in_base[ob + h];
+                        for (uint32_t kk = 0; kk < k; ++kk) {
+                            const uint32_t pos = out[kk], eh = heap_of_pos[pos];
+                            in_off[ib + kk] = or_off[ob + eh];
+                            ent_rank[ent_rank_off[order[ob + pos]] + (depth_of(eh) - d)] = kk;  // climbing order: the element's own node first
+                        }
+                    }
+                });
             }
         }
     }
@@ -426,7 +487,7 @@ extern "C" int clb_chain_dp(int device, const clb_chain_problem* p, float* dp_ou
         const double warps_per_step = S ? ((double)ins.size() + (double)n_qry * C2 * (P > 0 ? 3 : 1)) / (double)S : 0.0;
         const int max_grid = clb::chain_max_grid(device);
         grid = getenv("CLB_CHAIN_GRID") ? std::max(1, std::min(max_grid, atoi(getenv("CLB_CHAIN_GRID"))))
-                                         : (warps_per_step > 64.0 ? std::min<int>(max_grid, (int)(warps_per_step / 16.0) + 1) : 1);
+                                         : (warps_per_step > 64.0 ? std::min<int>(max_grid, (int)(warps_per_step / 12.0) + 1) : 1);
         const int prepare_grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_qry * C2 + 7) / 8, 8 * (int64_t)max_grid));
         CHAIN_TRY(cudaEventRecord(ar.ev0, ar.stream));
         CHAIN_TRY(clb::launch_chain(a, grid, prepare_grid, ar.stream, ar.evp));

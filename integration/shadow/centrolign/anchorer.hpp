@@ -18,6 +18,7 @@
 
 #include_next "centrolign/anchorer.hpp"
 
+#include "centrolign/chain_merge.hpp"
 #include "centrolign/forward_edges.hpp"
 #include "centrolign/match_bank.hpp"
 #include "centrolign/path_merge.hpp"
@@ -26,8 +27,14 @@
 
 #include "chain_b200.hpp"
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
 namespace centrolign {
 namespace b200_chain {
+
+inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 typedef PathMerge<uint32_t, uint8_t> XMerge;
 typedef MatchBank<uint32_t, uint16_t, float> Bank;
@@ -71,6 +78,7 @@ Anchorer::sparse_affine_chain_dp<uint32_t, uint16_t, uint32_t, int32_t, uint32_t
     const std::vector<uint64_t>* sources1, const std::vector<uint64_t>* sources2, const std::vector<uint64_t>* sinks1,
     const std::vector<uint64_t>* sinks2, const std::unordered_set<std::tuple<size_t, size_t, size_t>>* masked_matches) const {
     using namespace b200_chain;
+    const double t0 = now_s();
     Bank match_bank(graph1, match_sets, num_match_sets, true, masked_matches);                 // anchorer.hpp:1861
     PostSwitchDistances<std::vector<uint32_t>> switch_dists1(graph1, xmerge1), switch_dists2(graph2, xmerge2);  // :1871-1872
     std::vector<bool> mask_to, mask_from;
@@ -80,11 +88,16 @@ Anchorer::sparse_affine_chain_dp<uint32_t, uint16_t, uint32_t, int32_t, uint32_t
     auto weight_of = [&](const match_set_t& ms) -> float {
         return score_function->anchor_weight(ms.count1, ms.count2, ms.walks1.front().size(), ms.full_length);
     };
+    const double t1 = now_s();
     auto P = centrolign_b200::build_affine_chain_problem<int32_t>(match_bank, forward_edges, switch_dists1, switch_dists2, graph1,
                                                                   order1, xmerge1, xmerge2, match_sets, num_match_sets, gap_open,
                                                                   gap_extend, local_scale, sources1, sources2, sinks1, sinks2, weight_of);
+    const double t2 = now_s();
     float opt_value = 0.0f;
     auto traceback = anchors_of(P.solve(0, &opt_value), P, match_sets);
+    if (getenv("CLB_TIMING") && P.n_match() > 10000)
+        fprintf(stderr, "[clb] affine chaining of %zu matches: reference-side tables %.3f s, flat problem %.3f s, clb_chain_dp %.3f s\n",
+                P.n_match(), t1 - t0, t2 - t1, now_s() - t2);
     annotate_scores(traceback);  // :2536
     // gap length and score between the anchors (:2443-2468)
     centrolign_b200::GapMeasure<int32_t, float, XMerge, PostSwitchDistances<std::vector<uint32_t>>, 3> gaps{
@@ -120,31 +133,38 @@ Anchorer::sparse_affine_chain_dp<uint32_t, uint16_t, uint32_t, int32_t, uint32_t
     return traceback;
 }
 
-// ---- sparse_chain_dp, production instantiation (anchorer.hpp:1291) ----
-template <>
-inline std::vector<anchor_t>
-Anchorer::sparse_chain_dp<uint32_t, uint32_t, uint16_t, uint32_t, float, b200_chain::DistMatchVector, std::vector<uint32_t>,
-                          b200_chain::Bank, b200_chain::FwdEdges, BaseGraph, b200_chain::XMerge>(
-    const std::vector<match_set_t>& match_sets, const BaseGraph& graph1, const b200_chain::XMerge& chain_merge1,
-    const b200_chain::XMerge& chain_merge2, size_t num_match_sets, bool suppress_verbose_logging,
-    const std::vector<uint64_t>* sources1, const std::vector<uint64_t>* sources2, const std::vector<uint64_t>* sinks1,
-    const std::vector<uint64_t>* sinks2, const std::unordered_set<std::tuple<size_t, size_t, size_t>>* masked_matches) const {
-    using namespace b200_chain;
-    Bank match_bank(graph1, match_sets, num_match_sets, true, masked_matches);  // anchorer.hpp:1531
-    std::vector<bool> mask_to, mask_from;
-    std::tie(mask_to, mask_from) = generate_forward_edge_masks(graph1, match_sets, num_match_sets);  // :1620-1622
-    FwdEdges forward_edges(chain_merge1, &mask_to, &mask_from);
-    const auto order1 = topological_order(graph1);  // :1640
-    auto weight_of = [&](const match_set_t& ms) -> float {
-        return score_function->anchor_weight(ms.count1, ms.count2, ms.walks1.front().size(), ms.full_length);
-    };
-    auto P = centrolign_b200::build_gapfree_chain_problem(match_bank, forward_edges, graph1, order1, chain_merge1, chain_merge2,
-                                                          match_sets, num_match_sets, sources1, sources2, sinks1, sinks2, weight_of);
-    auto traceback = anchors_of(P.solve(0), P, match_sets);
-    annotate_scores(traceback);  // :2536
-    (void)suppress_verbose_logging;
-    return traceback;
-}
+// ---- sparse_chain_dp, production instantiation (anchorer.hpp:1291), for the two reachability structures Core uses with
+// it: PathMerge<uint32_t, uint8_t> in the alignment subproblems (core.hpp:336-338) and ChainMerge in the per-sequence
+// scale calibration (src/core.cpp:150-157) ----
+#define CLB_GAPFREE_CHAIN_SPECIALIZATION(XM)                                                                                       \
+    template <>                                                                                                                    \
+    inline std::vector<anchor_t>                                                                                                   \
+    Anchorer::sparse_chain_dp<uint32_t, uint32_t, uint16_t, uint32_t, float, b200_chain::DistMatchVector, std::vector<uint32_t>,  \
+                              b200_chain::Bank, ForwardEdges<XM::node_id_t, XM::chain_id_t>, BaseGraph, XM>(                      \
+        const std::vector<match_set_t>& match_sets, const BaseGraph& graph1, const XM& chain_merge1, const XM& chain_merge2,       \
+        size_t num_match_sets, bool suppress_verbose_logging, const std::vector<uint64_t>* sources1,                               \
+        const std::vector<uint64_t>* sources2, const std::vector<uint64_t>* sinks1, const std::vector<uint64_t>* sinks2,           \
+        const std::unordered_set<std::tuple<size_t, size_t, size_t>>* masked_matches) const {                                      \
+        using namespace b200_chain;                                                                                                \
+        Bank match_bank(graph1, match_sets, num_match_sets, true, masked_matches); /* anchorer.hpp:1531 */                         \
+        std::vector<bool> mask_to, mask_from;                                                                                      \
+        std::tie(mask_to, mask_from) = generate_forward_edge_masks(graph1, match_sets, num_match_sets); /* :1620-1622 */           \
+        ForwardEdges<XM::node_id_t, XM::chain_id_t> forward_edges(chain_merge1, &mask_to, &mask_from);                             \
+        const auto order1 = topological_order(graph1); /* :1640 */                                                                 \
+        auto weight_of = [&](const match_set_t& ms) -> float {                                                                     \
+            return score_function->anchor_weight(ms.count1, ms.count2, ms.walks1.front().size(), ms.full_length);                  \
+        };                                                                                                                         \
+        auto P = centrolign_b200::build_gapfree_chain_problem(match_bank, forward_edges, graph1, order1, chain_merge1,             \
+                                                              chain_merge2, match_sets, num_match_sets, sources1, sources2,        \
+                                                              sinks1, sinks2, weight_of);                                          \
+        auto traceback = anchors_of(P.solve(0), P, match_sets);                                                                    \
+        annotate_scores(traceback); /* :2536 */                                                                                    \
+        (void)suppress_verbose_logging;                                                                                            \
+        return traceback;                                                                                                          \
+    }
+CLB_GAPFREE_CHAIN_SPECIALIZATION(b200_chain::XMerge)
+CLB_GAPFREE_CHAIN_SPECIALIZATION(ChainMerge)
+#undef CLB_GAPFREE_CHAIN_SPECIALIZATION
 
 }  // namespace centrolign
 
