@@ -32,6 +32,7 @@ namespace clb {
 
 constexpr int kChainMaxTrees = 6;            // 2 * NumPW orthogonal value sets
 constexpr uint32_t kChainNone = 0xffffffffu;
+constexpr int kChainSmallArena = 200 * 1024;   // problems whose whole arena fits run from shared memory
 
 // One tree insertion (a match end on one path pair), in the reference's insertion order; the index of the
 // record is the insertion sequence number that breaks ties inside the gap-free trees.
@@ -112,6 +113,8 @@ struct ChainArgs {
     // parity) rank_stride words, one per subtree block in walk order; nullptr = computed on the fly
     uint32_t* rank_pool;
     int rank_stride;
+    const char* arena_base;  // the arena all pointers above point into, and its size
+    int64_t arena_bytes;
     int split_phases;  // debug: separate barrier between update_dp and the next step's insertions
 };
 

@@ -488,6 +488,9 @@ extern "C" int clb_chain_dp(int device, const clb_chain_problem* p, float* dp_ou
         const int max_grid = clb::chain_max_grid(device);
         grid = getenv("CLB_CHAIN_GRID") ? std::max(1, std::min(max_grid, atoi(getenv("CLB_CHAIN_GRID"))))
                                          : (warps_per_step > 64.0 ? std::min<int>(max_grid, (int)(warps_per_step / 12.0) + 1) : 1);
+        a.arena_base = ar.d;
+        a.arena_bytes = (int64_t)total;
+        if (total <= (size_t)clb::kChainSmallArena && !getenv("CLB_CHAIN_NO_SMALL") && !getenv("CLB_CHAIN_GRID")) grid = 0;
         const int prepare_grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_qry * C2 + 7) / 8, 8 * (int64_t)max_grid));
         CHAIN_TRY(cudaEventRecord(ar.ev0, ar.stream));
         CHAIN_TRY(clb::launch_chain(a, grid, prepare_grid, ar.stream, ar.evp));
@@ -512,7 +515,7 @@ extern "C" int clb_chain_dp(int device, const clb_chain_problem* p, float* dp_ou
             stats->tree_bytes = (int64_t)total;
             stats->h2d_bytes = (int64_t)plan.copy_bytes;
             stats->d2h_bytes = M * 8;
-            stats->kernel_launches = n_qry > 0 ? 2 : 1;
+            stats->kernel_launches = (grid == 0 || n_qry == 0) ? 1 : 2;
         }
     }
     // ---- traceback_sparse_dp (anchorer.hpp:2483-2534) ----

@@ -50,6 +50,24 @@ __device__ __forceinline__ unsigned long long pack(float v, uint32_t low) {
 }
 constexpr uint32_t kOrdLowest = 0x00800000u;  // ford(lowest()); 0 = never entered; both fail "ord > kOrdLowest"
 
+// Loads.  SM = the whole problem was copied into shared memory (small problems: the Anchorer's fill-in pass makes
+// thousands of chaining calls with a few dozen matches each, where a step is nothing but memory latency).
+template <bool SM, class T>
+__device__ __forceinline__ T ld_const(const T* p) {  // never written while a kernel runs
+    if (SM) return *p;
+    return __ldg(p);
+}
+template <bool SM, class T>
+__device__ __forceinline__ T ld_live(const T* p) {  // written by other warps between barriers
+    if (SM) return *reinterpret_cast<const volatile T*>(p);
+    return __ldcg(p);
+}
+template <bool SM>
+__device__ __forceinline__ uint4 ld_const4(const uint4* p) {
+    if (SM) return *p;
+    return __ldg(p);
+}
+
 struct WalkEntry {
     uint32_t node;  // heap index
     uint32_t kind;  // 0: the node itself, 1: the whole subtree of `node`
@@ -148,29 +166,31 @@ __device__ int walk_blocks(uint32_t n, bool prefix, uint32_t S, uint32_t bits, W
 }
 
 // first index in [lo, hi) whose value is >= q, by 32-ary search over the warp (uniform result)
+template <bool SM>
 __device__ int64_t warp_lower_bound(const int32_t* arr, int64_t lo, int64_t hi, int q, int lane) {
     while (hi - lo > 32) {
         const int64_t step = (hi - lo + 31) / 32;
         const int64_t at = lo + (int64_t)lane * step;
-        const bool less = at < hi && __ldg(&arr[at]) < q;
+        const bool less = at < hi && ld_const<SM>(&arr[at]) < q;
         const int cnt = __popc(__ballot_sync(kFull, less));  // pivots below q form a prefix
         if (cnt == 0) return lo;
         const int64_t nlo = lo + (int64_t)(cnt - 1) * step + 1;
         hi = min(hi, lo + (int64_t)cnt * step);
         lo = nlo;
     }
-    const bool less = lo + lane < hi && __ldg(&arr[lo + lane]) < q;
+    const bool less = lo + lane < hi && ld_const<SM>(&arr[lo + lane]) < q;
     return lo + __popc(__ballot_sync(kFull, less));
 }
 
 // number of entries of the ascending list `a[0, n)` that are < key, 8-ary search with independent probes
+template <bool SM>
 __device__ __forceinline__ uint32_t count_less(const uint32_t* a, uint32_t n, uint32_t key) {
     uint32_t lo = 0, hi = n;  // answer in [lo, hi]
     while (hi - lo > 7) {
         const uint32_t step = (hi - lo) >> 3;
         uint32_t v[7];
 #pragma unroll
-        for (int i = 0; i < 7; ++i) v[i] = __ldg(&a[lo + (i + 1) * step - 1]);
+        for (int i = 0; i < 7; ++i) v[i] = ld_const<SM>(&a[lo + (i + 1) * step - 1]);
         int c = 0;
 #pragma unroll
         for (int i = 0; i < 7; ++i) c += v[i] < key;
@@ -180,7 +200,7 @@ __device__ __forceinline__ uint32_t count_less(const uint32_t* a, uint32_t n, ui
     }
     uint32_t v[7];
 #pragma unroll
-    for (int i = 0; i < 7; ++i) v[i] = lo + i < hi ? __ldg(&a[lo + i]) : kChainNone;
+    for (int i = 0; i < 7; ++i) v[i] = lo + i < hi ? ld_const<SM>(&a[lo + i]) : kChainNone;
     uint32_t c = 0;
 #pragma unroll
     for (int i = 0; i < 7; ++i) c += (lo + i < hi) && v[i] < key;
@@ -190,11 +210,8 @@ __device__ __forceinline__ uint32_t count_less(const uint32_t* a, uint32_t n, ui
 }  // namespace
 
 // Everything about a (query, path of graph 2) pair that does not depend on DP values (anchorer.hpp:2374-2381).
-__global__ void __launch_bounds__(256) chain_prepare_kernel(const ChainArgs A) {
-    __shared__ WarpScratch prep_scratch[8];
-    WalkEntry* blk = prep_scratch[threadIdx.x >> 5].blk;
-    const int lane = threadIdx.x & 31;
-    const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+template <bool SM>
+__device__ void prepare_queries(const ChainArgs& A, WalkEntry* blk, int lane, int64_t gwarp, int64_t nwarp) {
     const int C1 = A.n_chain1, C2 = A.n_chain2;
     for (int64_t qc = gwarp; qc < A.n_qry * C2; qc += nwarp) {
         const int64_t k = qc / C2;
@@ -212,13 +229,13 @@ __global__ void __launch_bounds__(256) chain_prepare_kernel(const ChainArgs A) {
         if (r.offset != 0) {
             const int64_t pair = (int64_t)c1 * C2 + c2;
             const int64_t g1 = A.pair_grp_off[pair + 1];
-            const int64_t g = warp_lower_bound(A.grp_shift, A.pair_grp_off[pair], g1, r.q, lane);
-            if (g < g1 && __ldg(&A.grp_shift[g]) == r.q) {  // the diagonal exists (anchorer.hpp:2379-2382)
+            const int64_t g = warp_lower_bound<SM>(A.grp_shift, A.pair_grp_off[pair], g1, r.q, lane);
+            if (g < g1 && ld_const<SM>(&A.grp_shift[g]) == r.q) {  // the diagonal exists (anchorer.hpp:2379-2382)
                 r.gf_base = A.grp_base[g];
                 r.gf_n = A.grp_n[g];
                 const uint32_t* key = A.gf_key + r.gf_base;
                 const uint32_t offset = r.offset;
-                walk_shape(r.gf_n, true, [&](uint32_t x) { return __ldg(&key[x]) < offset; }, lane, r.gf_S, r.gf_bits);
+                walk_shape(r.gf_n, true, [&](uint32_t x) { return ld_const<SM>(&key[x]) < offset; }, lane, r.gf_S, r.gf_bits);
             }
             if (A.num_pw > 0) {
                 r.or_base = A.pair_base[pair];
@@ -226,8 +243,8 @@ __global__ void __launch_bounds__(256) chain_prepare_kernel(const ChainArgs A) {
                 const int32_t* shift = A.or_shift + r.or_base;
                 const int q = r.q;
                 if (r.or_n) {
-                    walk_shape(r.or_n, false, [&](uint32_t x) { return __ldg(&shift[x]) > q; }, lane, r.ev_S, r.ev_bits);
-                    walk_shape(r.or_n, true, [&](uint32_t x) { return __ldg(&shift[x]) < q; }, lane, r.od_S, r.od_bits);
+                    walk_shape(r.or_n, false, [&](uint32_t x) { return ld_const<SM>(&shift[x]) > q; }, lane, r.ev_S, r.ev_bits);
+                    walk_shape(r.or_n, true, [&](uint32_t x) { return ld_const<SM>(&shift[x]) < q; }, lane, r.od_S, r.od_bits);
                     if (A.rank_pool) {  // how many elements of every subtree block lie below the query offset
                         for (int par = 0; par < 2; ++par) {
                             const uint32_t S = par ? r.od_S : r.ev_S;
@@ -245,7 +262,7 @@ __global__ void __launch_bounds__(256) chain_prepare_kernel(const ChainArgs A) {
                                     const int j = seen + __popc(subm & ((1u << lane) - 1));
                                     const uint32_t node = blk[b].node;
                                     if (j < A.rank_stride)
-                                        pool[j] = count_less(A.in_off + __ldg(&A.in_base[r.or_base + node]), __ldg(&A.in_n[r.or_base + node]), r.offset);
+                                        pool[j] = count_less<SM>(A.in_off + ld_const<SM>(&A.in_base[r.or_base + node]), ld_const<SM>(&A.in_n[r.or_base + node]), r.offset);
                                 }
                                 seen += __popc(subm);
                             }
@@ -258,10 +275,16 @@ __global__ void __launch_bounds__(256) chain_prepare_kernel(const ChainArgs A) {
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainArgs A) {
-    __shared__ WarpScratch scratch[kWarps];
+__global__ void __launch_bounds__(256) chain_prepare_kernel(const ChainArgs A) {
+    __shared__ WarpScratch prep_scratch[8];
+    prepare_queries<false>(A, prep_scratch[threadIdx.x >> 5].blk, threadIdx.x & 31,
+                           ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, ((int64_t)gridDim.x * blockDim.x) >> 5);
+}
+
+template <bool SM>
+__device__ __forceinline__ void chain_steps(const ChainArgs& A, WarpScratch* scratch) {
     cg::grid_group grid = cg::this_grid();
-    const bool multi = gridDim.x > 1;
+    const bool multi = !SM && gridDim.x > 1;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t gwarp = (int64_t)blockIdx.x * kWarps + wib, nwarp = (int64_t)gridDim.x * kWarps;
     const int64_t gthread = (int64_t)blockIdx.x * kThreads + threadIdx.x, nthread = (int64_t)gridDim.x * kThreads;
@@ -289,20 +312,20 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainArgs A) {
     auto apply_winners = [&](int64_t q0, int64_t q1, const unsigned long long* cand) {
         for (int64_t qi = gthread; qi < q1 - q0; qi += nthread) {
             const uint32_t m = A.qry_match[q0 + qi];
-            const unsigned long long pk = __ldcg(&cand[m]);
+            const unsigned long long pk = ld_live<SM>(&cand[m]);
             if (!pk) continue;
             const uint32_t order = ~(uint32_t)pk;
             if ((int64_t)(order / ((uint32_t)C2 * slots)) != qi) continue;  // the winner was posted by another query of this match
             const float v = funord((uint32_t)(pk >> 32));
-            if (v > __ldcg(&A.dp[m])) {
+            if (v > ld_live<SM>(&A.dp[m])) {
                 A.dp[m] = v;
-                A.backptr[m] = __ldcg(&A.cand_bp[order]);
+                A.backptr[m] = ld_live<SM>(&A.cand_bp[order]);
             }
         }
     };
     auto effective_dp = [&](uint32_t m, const unsigned long long* cand) -> float {
-        const unsigned long long pk = __ldcg(&cand[m]);
-        float dpv = __ldcg(&A.dp[m]);
+        const unsigned long long pk = ld_live<SM>(&cand[m]);
+        float dpv = ld_live<SM>(&A.dp[m]);
         if (pk) {
             const float v = funord((uint32_t)(pk >> 32));
             if (v > dpv) dpv = v;
@@ -322,17 +345,17 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainArgs A) {
             if (A.split_phases) barrier();
         }
         for (int64_t i = i0 + gwarp; i < i1; i += nwarp) {
-            const uint4 ra = __ldg(reinterpret_cast<const uint4*>(&A.ins[i]));
-            const uint4 rb = __ldg(reinterpret_cast<const uint4*>(&A.ins[i]) + 1);
+            const uint4 ra = ld_const4<SM>(reinterpret_cast<const uint4*>(&A.ins[i]));
+            const uint4 rb = ld_const4<SM>(reinterpret_cast<const uint4*>(&A.ins[i]) + 1);
             const uint32_t m = ra.x, gf_base = ra.y, gf_node = ra.z, or_base = ra.w, or_node = rb.x, rank_off = rb.z;
             const int shift = (int)rb.y, nr = (int)rb.w;
             int64_t ib = 0;
             uint32_t cn = 0, rank = 0;
             if (P > 0 && lane < nr) {  // lane = level: the node itself and its ancestors below the outer spines
                 const uint32_t a = ((or_node + 1) >> lane) - 1;
-                ib = __ldg(&A.in_base[or_base + a]);
-                cn = __ldg(&A.in_n[or_base + a]);
-                rank = __ldg(&A.ent_rank[rank_off + lane]);
+                ib = ld_const<SM>(&A.in_base[or_base + a]);
+                cn = ld_const<SM>(&A.in_n[or_base + a]);
+                rank = ld_const<SM>(&A.ent_rank[rank_off + lane]);
             }
             const float dpv = effective_dp(m, cand_prev);
             if (!(dpv > mininf())) continue;  // entering lowest() changes nothing in the reference's trees
@@ -372,7 +395,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainArgs A) {
             const int64_t qc = item / n_type;  // (query, chain2) pair inside the step
             const int type = (int)(item - qc * n_type);
             const uint4* rp = reinterpret_cast<const uint4*>(&A.qrec[q0 * C2 + qc]);
-            const uint4 r0 = __ldg(rp);  // match, weight, offset, q
+            const uint4 r0 = ld_const4<SM>(rp);  // match, weight, offset, q
             const uint32_t offset = r0.z;
             if (offset == 0) continue;  // nothing on this path reaches the match: every range [0, 0) is empty
             const uint32_t m = r0.x;
@@ -381,7 +404,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainArgs A) {
             __syncwarp();
             if (type == 0) {
                 // same diagonal (anchorer.hpp:2379-2389): MaxSearchTree::range_max((0, min), (offset, min))
-                const uint4 r1 = __ldg(rp + 1);  // gf_base, gf_n, gf_S, gf_bits
+                const uint4 r1 = ld_const4<SM>(rp + 1);  // gf_base, gf_n, gf_S, gf_bits
                 if (r1.y == 0 || r1.z == kChainNone) continue;
                 ++n_tree_queries;
                 const uint32_t base = r1.x;
@@ -393,10 +416,10 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainArgs A) {
                     const WalkEntry we = blk[b];
                     uint32_t ord, sel;
                     if (we.kind == 0) {
-                        ord = __ldcg(&A.gf_ord[base + we.node]);
+                        ord = ld_live<SM>(&A.gf_ord[base + we.node]);
                         sel = we.node;
                     } else {
-                        const unsigned long long pk = __ldcg(&A.gf_best[base + we.node]);
+                        const unsigned long long pk = ld_live<SM>(&A.gf_best[base + we.node]);
                         ord = (uint32_t)(pk >> 32);
                         sel = 0x80000000u | (~(uint32_t)pk & 0x7fffffffu);  // the insertion sequence number (< 2^31)
                     }
@@ -415,18 +438,18 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainArgs A) {
                 const unsigned src = __ffs(__ballot_sync(kFull, lbest == r)) - 1;
                 const uint32_t sel = __shfl_sync(kFull, lsel, src);
                 if (lane == 0) {
-                    const uint32_t bm = (sel & 0x80000000u) ? __ldg(&A.ins[sel & 0x7fffffffu].match) : __ldg(&A.gf_match[base + sel]);
+                    const uint32_t bm = (sel & 0x80000000u) ? ld_const<SM>(&A.ins[sel & 0x7fffffffu].match) : ld_const<SM>(&A.gf_match[base + sel]);
                     post(m, qc, 0, __fadd_rn(funord((uint32_t)(r >> 32)), w), bm);
                 }
                 continue;
             }
             // orthogonal trees of one parity (anchorer.hpp:2390-2413): par 0 = even pieces (shift > q), par 1 = odd (shift < q)
             const int par = type - 1;
-            const uint4 r2 = __ldg(rp + 2);  // or_base, or_n, ev_S, ev_bits
+            const uint4 r2 = ld_const4<SM>(rp + 2);  // or_base, or_n, ev_S, ev_bits
             const uint32_t ob = r2.x, n = r2.y;
             uint32_t S = r2.z, bits = r2.w;
             if (par) {
-                const uint4 r3 = __ldg(rp + 3);  // od_S, od_bits
+                const uint4 r3 = ld_const4<SM>(rp + 3);  // od_S, od_bits
                 S = r3.x;
                 bits = r3.y;
             }
@@ -447,9 +470,9 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainArgs A) {
                 seen += __popc(subm);
                 if (!mine) continue;
                 if (we.kind == 0) {
-                    const uint32_t off = __ldg(&A.or_off[ob + we.node]);
+                    const uint32_t off = ld_const<SM>(&A.or_off[ob + we.node]);
                     uint32_t v[3];
-                    for (int k = 0; k < P; ++k) v[k] = __ldcg(&A.or_ord[(int64_t)(2 * k + par) * A.n_entry + ob + we.node]);
+                    for (int k = 0; k < P; ++k) v[k] = ld_live<SM>(&A.or_ord[(int64_t)(2 * k + par) * A.n_entry + ob + we.node]);
                     if (off < offset) {
                         for (int k = 0; k < P; ++k)
                             if (v[k] > kOrdLowest && v[k] > (uint32_t)(lbest[k] >> 32)) {
@@ -458,9 +481,9 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainArgs A) {
                             }
                     }
                 } else {
-                    const uint32_t ib = __ldg(&A.in_base[ob + we.node]);
-                    const uint32_t cnt = (ranks && j < A.rank_stride) ? __ldg(&ranks[j])
-                                                                     : count_less(A.in_off + ib, __ldg(&A.in_n[ob + we.node]), offset);
+                    const uint32_t ib = ld_const<SM>(&A.in_base[ob + we.node]);
+                    const uint32_t cnt = (ranks && j < A.rank_stride) ? ld_const<SM>(&ranks[j])
+                                                                     : count_less<SM>(A.in_off + ib, ld_const<SM>(&A.in_n[ob + we.node]), offset);
                     if (cnt) {  // Fenwick prefix maximum over the first cnt entries
                         unsigned long long r[3] = {0, 0, 0};
                         uint32_t c = cnt;
@@ -476,7 +499,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainArgs A) {
                             for (int jj = 0; jj < 6; ++jj)
 #pragma unroll
                                 for (int k = 0; k < 3; ++k)
-                                    x[jj][k] = (k < P && at[jj] != kChainNone) ? __ldcg(&A.bit[(int64_t)(2 * k + par) * A.n_inner + ib + at[jj]]) : 0ull;
+                                    x[jj][k] = (k < P && at[jj] != kChainNone) ? ld_live<SM>(&A.bit[(int64_t)(2 * k + par) * A.n_inner + ib + at[jj]]) : 0ull;
 #pragma unroll
                             for (int jj = 0; jj < 6; ++jj)
 #pragma unroll
@@ -505,7 +528,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainArgs A) {
                     const double eq = __dmul_rn(A.gap_extend[k], (double)q);
                     const double pen = __dmul_rn(A.scale, par ? __dadd_rn(A.gap_open[k], eq) : __dsub_rn(A.gap_open[k], eq));
                     const float cand = __double2float_rn(__dsub_rn((double)__fadd_rn(funord((uint32_t)(r >> 32)), w), pen));
-                    post(m, qc, (uint32_t)(1 + t), cand, __ldg(&A.or_match[ob + node]));
+                    post(m, qc, (uint32_t)(1 + t), cand, ld_const<SM>(&A.or_match[ob + node]));
                 }
             }
         }
@@ -515,7 +538,53 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainArgs A) {
     if (lane == 0 && n_tree_queries) atomicAdd(A.counters, n_tree_queries);
 }
 
+__global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainArgs A) {
+    __shared__ WarpScratch scratch[kWarps];
+    chain_steps<false>(A, scratch);
+}
+
+// Small problems: one CTA copies the whole arena into shared memory, rebases the pointers, prepares the queries,
+// runs the same step loop on shared memory and copies the DP values and back-pointers out again.
+__global__ void __launch_bounds__(kThreads, 1) chain_small_kernel(const ChainArgs G) {
+    __shared__ WarpScratch scratch[kWarps];
+    extern __shared__ uint4 arena_smem[];
+    const char* gbase = G.arena_base;
+    for (int64_t i = threadIdx.x; i < (G.arena_bytes + 15) / 16; i += kThreads)
+        arena_smem[i] = __ldg(reinterpret_cast<const uint4*>(gbase) + i);
+    ChainArgs A = G;
+    char* sbase = reinterpret_cast<char*>(arena_smem);
+#define CLB_REBASE(f) A.f = reinterpret_cast<decltype(A.f)>(sbase + (reinterpret_cast<const char*>(G.f) - gbase))
+    CLB_REBASE(dp); CLB_REBASE(backptr); CLB_REBASE(sins_off); CLB_REBASE(ins); CLB_REBASE(qry_off); CLB_REBASE(qry_match);
+    CLB_REBASE(qrec); CLB_REBASE(weight); CLB_REBASE(qry_chain1); CLB_REBASE(qa1); CLB_REBASE(qa2); CLB_REBASE(qoff);
+    CLB_REBASE(pair_grp_off); CLB_REBASE(grp_shift); CLB_REBASE(grp_base); CLB_REBASE(grp_n); CLB_REBASE(pair_base);
+    CLB_REBASE(gf_key); CLB_REBASE(gf_match); CLB_REBASE(gf_ord); CLB_REBASE(gf_best); CLB_REBASE(or_shift); CLB_REBASE(or_off);
+    CLB_REBASE(or_match); CLB_REBASE(or_ord); CLB_REBASE(in_base); CLB_REBASE(in_n); CLB_REBASE(in_off); CLB_REBASE(bit);
+    CLB_REBASE(ent_rank); CLB_REBASE(cand_best); CLB_REBASE(cand_bp); CLB_REBASE(counters);
+    if (G.rank_pool) CLB_REBASE(rank_pool);
+#undef CLB_REBASE
+    __syncthreads();
+    prepare_queries<true>(A, scratch[threadIdx.x >> 5].blk, threadIdx.x & 31, threadIdx.x >> 5, kWarps);
+    __syncthreads();
+    chain_steps<true>(A, scratch);
+    __syncthreads();
+    for (int64_t m = threadIdx.x; m < G.n_match; m += kThreads) {
+        G.dp[m] = A.dp[m];
+        G.backptr[m] = A.backptr[m];
+    }
+}
+
 cudaError_t launch_chain(const ChainArgs& args, int grid, int prepare_grid, cudaStream_t stream, cudaEvent_t after_prepare) {
+    if (grid == 0) {  // the whole problem fits into shared memory
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e0 = cudaFuncSetAttribute(chain_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmallArena);
+            if (e0 != cudaSuccess) return e0;
+            attr_set = true;
+        }
+        if (after_prepare) cudaEventRecord(after_prepare, stream);
+        chain_small_kernel<<<1, kThreads, (size_t)((args.arena_bytes + 15) / 16 * 16), stream>>>(args);
+        return cudaGetLastError();
+    }
     if (args.n_qry > 0) chain_prepare_kernel<<<prepare_grid, 256, 0, stream>>>(args);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
