@@ -152,6 +152,7 @@ extern "C" int clb_chain_dp(int device, const clb_chain_problem* p, float* dp_ou
     if (stats) memset(stats, 0, sizeof(*stats));
     struct CallTimer {  // evidence for integration tests that the GPU path really ran, and what it cost
         static std::atomic<int64_t>& us() { static std::atomic<int64_t> v(0); return v; }
+        static std::atomic<int64_t>* phase() { static std::atomic<int64_t> v[4]; return v; }  // layout, staging, gpu, traceback
         double t0;
         bool on;
         ~CallTimer() { if (on) us() += (int64_t)((now_ms() - t0) * 1e3); }
@@ -161,8 +162,10 @@ extern "C" int clb_chain_dp(int device, const clb_chain_problem* p, float* dp_ou
         static std::once_flag once;
         std::call_once(once, [] {
             atexit([] {
-                fprintf(stderr, "[clb] chain calls %lld matches %lld seconds %.3f\n", (long long)calls.load(), (long long)matches.load(),
-                        CallTimer::us().load() * 1e-6);
+                fprintf(stderr, "[clb] chain calls %lld matches %lld seconds %.3f (layout %.3f, staging %.3f, gpu %.3f, traceback %.3f)\n",
+                        (long long)calls.load(), (long long)matches.load(), CallTimer::us().load() * 1e-6,
+                        CallTimer::phase()[0].load() * 1e-6, CallTimer::phase()[1].load() * 1e-6, CallTimer::phase()[2].load() * 1e-6,
+                        CallTimer::phase()[3].load() * 1e-6);
             });
         });
         calls += 1;
@@ -455,6 +458,7 @@ extern "C" int clb_chain_dp(int device, const clb_chain_problem* p, float* dp_ou
         }
         for (const auto& sg : plan.segs)
             if (sg.bytes) memcpy(ar.h + sg.off, sg.src, sg.bytes);
+        const double t_staged = now_ms();
         CHAIN_TRY(cudaMemcpyAsync(ar.d, ar.h, plan.copy_bytes, cudaMemcpyHostToDevice, ar.stream));
         char* zr = ar.d + plan.copy_bytes;
         CHAIN_TRY(cudaMemsetAsync(zr, 0, plan.zero_bytes, ar.stream));
@@ -498,6 +502,11 @@ extern "C" int clb_chain_dp(int device, const clb_chain_problem* p, float* dp_ou
         CHAIN_TRY(cudaMemcpyAsync(h_dp.data(), a.dp, M * sizeof(float), cudaMemcpyDeviceToHost, ar.stream));
         CHAIN_TRY(cudaMemcpyAsync(h_bp.data(), a.backptr, M * sizeof(uint32_t), cudaMemcpyDeviceToHost, ar.stream));
         CHAIN_TRY(cudaStreamSynchronize(ar.stream));
+        if (call_timer.on) {
+            CallTimer::phase()[0] += (int64_t)((t_built - t_start) * 1e3);
+            CallTimer::phase()[1] += (int64_t)((t_staged - t_built) * 1e3);
+            CallTimer::phase()[2] += (int64_t)((now_ms() - t_staged) * 1e3);
+        }
         float ms = 0.f;
         CHAIN_TRY(cudaEventElapsedTime(&ms, ar.ev0, ar.ev1));
         if (getenv("CLB_TIMING")) {
