@@ -322,6 +322,11 @@ int check_side(const clb_graph_batch* g) {
 
 namespace clb {
 int host_fail(int code, const std::string& msg) { return fail(code, msg); }  // for the other host files of the library
+// the process-wide cache of pinned-host and device blocks, for the other host files
+void* cache_host_alloc(size_t bytes, size_t* cap) { return g_cache.host_alloc(bytes, cap); }
+void cache_host_release(void* p, size_t cap) { g_cache.host_release(p, cap); }
+void* cache_dev_alloc(int device, size_t bytes, size_t* cap, bool any_larger) { return g_cache.dev_alloc(device, bytes, cap, any_larger); }
+void cache_dev_release(int device, void* p, size_t cap) { g_cache.dev_release(device, p, cap); }
 }  // namespace clb
 
 extern "C" {

@@ -28,6 +28,12 @@
 namespace clb {
 cudaError_t launch_pwfa(const PwfaArgs& args, int grid, cudaStream_t stream);
 int host_fail(int code, const std::string& msg);  // popoa_host.cu: sets clb_last_error()
+// popoa_host.cu: process-wide cache of pinned-host and device blocks (cudaHostAlloc / cudaMalloc of the staging and
+// workspace buffers cost more than the search itself on small batches)
+void* cache_host_alloc(size_t bytes, size_t* cap);
+void cache_host_release(void* p, size_t cap);
+void* cache_dev_alloc(int device, size_t bytes, size_t* cap, bool any_larger);
+void cache_dev_release(int device, void* p, size_t cap);
 }  // namespace clb
 
 namespace {
@@ -59,10 +65,36 @@ int ceil_log2(uint64_t v) {
     return l;
 }
 
+// pinned host block + device twin, both drawn from the library's cache
+template <class T>
+struct Staged {
+    T* h = nullptr;
+    T* d = nullptr;
+    size_t n = 0, cap_h = 0, cap_d = 0;
+    int dev = 0;
+    bool alloc(int device, size_t count, bool host, bool any_larger = false) {
+        dev = device;
+        n = std::max<size_t>(count, 1);
+        if (host) {
+            h = (T*)clb::cache_host_alloc(n * sizeof(T), &cap_h);
+            if (!h) return false;
+        }
+        d = (T*)clb::cache_dev_alloc(device, n * sizeof(T), &cap_d, any_larger);
+        return d != nullptr;
+    }
+    size_t bytes() const { return n * sizeof(T); }
+    void release() {
+        if (h) clb::cache_host_release(h, cap_h);
+        if (d) clb::cache_dev_release(dev, d, cap_d);
+        h = d = nullptr;
+    }
+    ~Staged() { release(); }
+};
+
 struct SideOut {
-    std::vector<int4> info;
-    std::vector<uint32_t> next;
-    std::vector<uint8_t> nlab;
+    Staged<int4> info;
+    Staged<uint32_t> next;
+    Staged<uint8_t> nlab;
 };
 
 struct Scratch {
@@ -260,12 +292,12 @@ extern "C" int clb_pwfa_batch(int device, int32_t n_windows, const clb_succ_grap
     }
     out_off[nw] = tot_pairs;
 
+    if (cudaSetDevice(device) != cudaSuccess) return host_fail(CLB_ECUDA, "cudaSetDevice failed");
     SideOut so[2];
-    for (int sd = 0; sd < 2; ++sd) {
-        so[sd].info.resize(tot_info[sd]);
-        so[sd].next.resize(std::max<int64_t>(tot_next[sd], 1));
-        so[sd].nlab.resize(std::max<int64_t>(tot_next[sd], 1));
-    }
+    for (int sd = 0; sd < 2; ++sd)
+        if (!so[sd].info.alloc(device, tot_info[sd], true) || !so[sd].next.alloc(device, tot_next[sd], true) ||
+            !so[sd].nlab.alloc(device, tot_next[sd], true))
+            return host_fail(CLB_ENOMEM, "pwfa: staging allocation failed");
     {
         std::atomic<int64_t> next_w{0};
         std::atomic<int> st{CLB_OK};
@@ -277,11 +309,11 @@ extern "C" int clb_pwfa_batch(int device, int32_t n_windows, const clb_succ_grap
             for (;;) {
                 const int64_t w = next_w.fetch_add(1);
                 if (w >= nw || st.load() != CLB_OK) return;
-                int r = flatten_side(*g1, w, so[0].info.data() + win[w].info1, so[0].next.data() + win[w].next1,
-                                     so[0].nlab.data() + win[w].next1, sc);
+                int r = flatten_side(*g1, w, so[0].info.h + win[w].info1, so[0].next.h + win[w].next1,
+                                     so[0].nlab.h + win[w].next1, sc);
                 if (r == CLB_OK)
-                    r = flatten_side(*g2, w, so[1].info.data() + win[w].info2, so[1].next.data() + win[w].next2,
-                                     so[1].nlab.data() + win[w].next2, sc);
+                    r = flatten_side(*g2, w, so[1].info.h + win[w].info2, so[1].next.h + win[w].next2,
+                                     so[1].nlab.h + win[w].next2, sc);
                 if (r != CLB_OK) {
                     st.store(r);
                     bad.store(w);
@@ -299,45 +331,33 @@ extern "C" int clb_pwfa_batch(int device, int32_t n_windows, const clb_succ_grap
     }
 
     int rc = CLB_OK;
-    int4 *d_info[2] = {nullptr, nullptr};
-    uint32_t *d_next[2] = {nullptr, nullptr};
-    uint8_t *d_nlab[2] = {nullptr, nullptr};
-    clb::PwfaWindow* d_win = nullptr;
-    int32_t *d_order = nullptr, *d_queue = nullptr, *d_status = nullptr, *d_aln = nullptr;
-    int64_t *d_score = nullptr, *d_wstats = nullptr;
-    uint32_t* d_len = nullptr;
-    char* d_ws = nullptr;
+    Staged<clb::PwfaWindow> s_win;
+    Staged<int32_t> s_order, s_queue, s_status, s_aln;
+    Staged<int64_t> s_score, s_wstats;
+    Staged<uint32_t> s_len;
+    Staged<char> s_ws;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    std::vector<int32_t> h_status(nw, -1), h_aln;
-    std::vector<int64_t> h_score(nw), h_wstats(4 * nw);
-    std::vector<uint32_t> h_len(nw);
     std::vector<int32_t> pending(nw);
     int64_t h2d = 0;
     cudaDeviceProp prop;
 
-    PWFA_CUDA_TRY(cudaSetDevice(device));
     PWFA_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     PWFA_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     PWFA_CUDA_TRY(cudaEventCreate(&ev0));
     PWFA_CUDA_TRY(cudaEventCreate(&ev1));
     for (int sd = 0; sd < 2; ++sd) {
-        PWFA_CUDA_TRY(cudaMalloc(&d_info[sd], so[sd].info.size() * sizeof(int4)));
-        PWFA_CUDA_TRY(cudaMalloc(&d_next[sd], so[sd].next.size() * sizeof(uint32_t)));
-        PWFA_CUDA_TRY(cudaMalloc(&d_nlab[sd], so[sd].nlab.size()));
-        PWFA_CUDA_TRY(cudaMemcpyAsync(d_info[sd], so[sd].info.data(), so[sd].info.size() * sizeof(int4), cudaMemcpyHostToDevice, stream));
-        PWFA_CUDA_TRY(cudaMemcpyAsync(d_next[sd], so[sd].next.data(), so[sd].next.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
-        PWFA_CUDA_TRY(cudaMemcpyAsync(d_nlab[sd], so[sd].nlab.data(), so[sd].nlab.size(), cudaMemcpyHostToDevice, stream));
-        h2d += so[sd].info.size() * sizeof(int4) + so[sd].next.size() * 5;
+        PWFA_CUDA_TRY(cudaMemcpyAsync(so[sd].info.d, so[sd].info.h, (size_t)tot_info[sd] * sizeof(int4), cudaMemcpyHostToDevice, stream));
+        PWFA_CUDA_TRY(cudaMemcpyAsync(so[sd].next.d, so[sd].next.h, (size_t)tot_next[sd] * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+        PWFA_CUDA_TRY(cudaMemcpyAsync(so[sd].nlab.d, so[sd].nlab.h, (size_t)tot_next[sd], cudaMemcpyHostToDevice, stream));
+        h2d += tot_info[sd] * (int64_t)sizeof(int4) + tot_next[sd] * 5;
     }
-    PWFA_CUDA_TRY(cudaMalloc(&d_win, nw * sizeof(clb::PwfaWindow)));
-    PWFA_CUDA_TRY(cudaMalloc(&d_order, nw * sizeof(int32_t)));
-    PWFA_CUDA_TRY(cudaMalloc(&d_queue, sizeof(int32_t)));
-    PWFA_CUDA_TRY(cudaMalloc(&d_status, nw * sizeof(int32_t)));
-    PWFA_CUDA_TRY(cudaMalloc(&d_score, nw * sizeof(int64_t)));
-    PWFA_CUDA_TRY(cudaMalloc(&d_wstats, 4 * nw * sizeof(int64_t)));
-    PWFA_CUDA_TRY(cudaMalloc(&d_len, nw * sizeof(uint32_t)));
-    PWFA_CUDA_TRY(cudaMalloc(&d_aln, std::max<int64_t>(1, 2 * tot_pairs) * sizeof(int32_t)));
+    if (!s_win.alloc(device, nw, true) || !s_order.alloc(device, nw, true) || !s_queue.alloc(device, 1, false) ||
+        !s_status.alloc(device, nw, true) || !s_score.alloc(device, nw, true) || !s_wstats.alloc(device, 4 * nw, true) ||
+        !s_len.alloc(device, nw, true) || !s_aln.alloc(device, 2 * tot_pairs, true)) {
+        rc = host_fail(CLB_ENOMEM, "pwfa: result buffer allocation failed");
+        goto cleanup;
+    }
     h2d += nw * (sizeof(clb::PwfaWindow) + sizeof(int32_t));
 
     std::iota(pending.begin(), pending.end(), 0);
@@ -362,28 +382,32 @@ extern "C" int clb_pwfa_batch(int device, int32_t n_windows, const clb_succ_grap
             rc = host_fail(CLB_ENOMEM, "pwfa: the tables of one window (" + std::to_string(slot_bytes) + " B) do not fit in device memory");
             goto cleanup;
         }
-        PWFA_CUDA_TRY(cudaMalloc(&d_ws, (size_t)grid * slot_bytes));
-        PWFA_CUDA_TRY(cudaMemcpyAsync(d_win, win.data(), nw * sizeof(clb::PwfaWindow), cudaMemcpyHostToDevice, stream));
-        PWFA_CUDA_TRY(cudaMemcpyAsync(d_order, pending.data(), pending.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
-        PWFA_CUDA_TRY(cudaMemsetAsync(d_queue, 0, sizeof(int32_t), stream));
+        s_ws.release();
+        if (!s_ws.alloc(device, (size_t)grid * slot_bytes, false, true)) {
+            rc = host_fail(CLB_ENOMEM, "pwfa: workspace allocation failed");
+            goto cleanup;
+        }
+        memcpy(s_win.h, win.data(), nw * sizeof(clb::PwfaWindow));
+        memcpy(s_order.h, pending.data(), pending.size() * sizeof(int32_t));
+        PWFA_CUDA_TRY(cudaMemcpyAsync(s_win.d, s_win.h, nw * sizeof(clb::PwfaWindow), cudaMemcpyHostToDevice, stream));
+        PWFA_CUDA_TRY(cudaMemcpyAsync(s_order.d, s_order.h, pending.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+        PWFA_CUDA_TRY(cudaMemsetAsync(s_queue.d, 0, sizeof(int32_t), stream));
         clb::PwfaArgs a{};
-        a.info1 = d_info[0]; a.info2 = d_info[1];
-        a.next1 = d_next[0]; a.next2 = d_next[1];
-        a.nlab1 = d_nlab[0]; a.nlab2 = d_nlab[1];
-        a.win = d_win; a.order = d_order; a.n_run = (int32_t)pending.size(); a.queue = d_queue;
-        a.workspace = d_ws; a.slot_bytes = slot_bytes;
-        a.score = d_score; a.status = d_status; a.aln_len = d_len; a.aln = d_aln; a.wstats = d_wstats;
+        a.info1 = so[0].info.d; a.info2 = so[1].info.d;
+        a.next1 = so[0].next.d; a.next2 = so[1].next.d;
+        a.nlab1 = so[0].nlab.d; a.nlab2 = so[1].nlab.d;
+        a.win = s_win.d; a.order = s_order.d; a.n_run = (int32_t)pending.size(); a.queue = s_queue.d;
+        a.workspace = s_ws.d; a.slot_bytes = slot_bytes;
+        a.score = s_score.d; a.status = s_status.d; a.aln_len = s_len.d; a.aln = s_aln.d; a.wstats = s_wstats.d;
         a.prm = prm;
         PWFA_CUDA_TRY(cudaEventRecord(ev0, stream));
         PWFA_CUDA_TRY(clb::launch_pwfa(a, grid, stream));
         PWFA_CUDA_TRY(cudaEventRecord(ev1, stream));
-        PWFA_CUDA_TRY(cudaMemcpyAsync(h_status.data(), d_status, nw * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
-        PWFA_CUDA_TRY(cudaMemcpyAsync(h_wstats.data(), d_wstats, 4 * nw * sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+        PWFA_CUDA_TRY(cudaMemcpyAsync(s_status.h, s_status.d, nw * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+        PWFA_CUDA_TRY(cudaMemcpyAsync(s_wstats.h, s_wstats.d, 4 * nw * sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
         PWFA_CUDA_TRY(cudaStreamSynchronize(stream));
         float ms = 0.f;
         PWFA_CUDA_TRY(cudaEventElapsedTime(&ms, ev0, ev1));
-        PWFA_CUDA_TRY(cudaFree(d_ws));
-        d_ws = nullptr;
         if (stats) {
             stats->kernel_ms += ms;
             stats->kernel_launches += 1;
@@ -392,12 +416,12 @@ extern "C" int clb_pwfa_batch(int device, int32_t n_windows, const clb_succ_grap
         }
         std::vector<int32_t> again;
         for (int32_t w : pending) {
-            const int s = h_status[w];
+            const int s = s_status.h[w];
             if (s == clb::kPwfaOk) {
                 if (stats) {
-                    stats->states += h_wstats[4 * w];
-                    stats->dequeued += h_wstats[4 * w + 1];
-                    stats->steps += h_wstats[4 * w + 3];
+                    stats->states += s_wstats.h[4 * w];
+                    stats->dequeued += s_wstats.h[4 * w + 1];
+                    stats->steps += s_wstats.h[4 * w + 3];
                 }
             } else if (s == clb::kPwfaHashFull || s == clb::kPwfaFifoFull) {
                 // the two grow together (queue entries per settled state are bounded by the out-degrees)
@@ -415,17 +439,16 @@ extern "C" int clb_pwfa_batch(int device, int32_t n_windows, const clb_succ_grap
         }
         pending.swap(again);
     }
-    h_aln.resize(std::max<int64_t>(1, 2 * tot_pairs));
-    PWFA_CUDA_TRY(cudaMemcpyAsync(h_score.data(), d_score, nw * sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
-    PWFA_CUDA_TRY(cudaMemcpyAsync(h_len.data(), d_len, nw * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-    PWFA_CUDA_TRY(cudaMemcpyAsync(h_aln.data(), d_aln, 2 * tot_pairs * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    PWFA_CUDA_TRY(cudaMemcpyAsync(s_score.h, s_score.d, nw * sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+    PWFA_CUDA_TRY(cudaMemcpyAsync(s_len.h, s_len.d, nw * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    PWFA_CUDA_TRY(cudaMemcpyAsync(s_aln.h, s_aln.d, 2 * tot_pairs * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
     PWFA_CUDA_TRY(cudaStreamSynchronize(stream));
     for (int64_t w = 0; w < nw; ++w) {
-        const uint32_t len = h_len[w];
+        const uint32_t len = s_len.h[w];
         const int64_t cap = out_off[w + 1] - out_off[w];
-        memcpy(aln_pairs + 2 * aln_off[w], h_aln.data() + 2 * (out_off[w] + cap - len), 2 * (size_t)len * sizeof(int32_t));
+        memcpy(aln_pairs + 2 * aln_off[w], s_aln.h + 2 * (out_off[w] + cap - len), 2 * (size_t)len * sizeof(int32_t));
         aln_len[w] = len;
-        score_out[w] = h_score[w];
+        score_out[w] = s_score.h[w];
     }
     if (stats) {
         stats->h2d_bytes = h2d;
@@ -433,13 +456,7 @@ extern "C" int clb_pwfa_batch(int device, int32_t n_windows, const clb_succ_grap
     }
 
 cleanup:
-    for (int sd = 0; sd < 2; ++sd) {
-        cudaFree(d_info[sd]);
-        cudaFree(d_next[sd]);
-        cudaFree(d_nlab[sd]);
-    }
-    cudaFree(d_win); cudaFree(d_order); cudaFree(d_queue); cudaFree(d_status); cudaFree(d_score);
-    cudaFree(d_wstats); cudaFree(d_len); cudaFree(d_aln); cudaFree(d_ws);
+    if (rc != CLB_OK) cudaDeviceSynchronize();  // nothing may still run on buffers that go back to the cache
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
