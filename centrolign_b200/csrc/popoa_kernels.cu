@@ -657,9 +657,9 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
 #pragma unroll 1
         for (int q8 = s0; q8 < s1; q8 += 8) {
             const int e8 = min(q8 + 8, s1);
-            if (inner) {
-#pragma unroll 1
-                for (int s = q8; s < e8; ++s) step(s, std::false_type{});
+            if (inner) {  // exactly 8 steps: unrolled in pairs so that the row registers ping-pong instead of being copied
+#pragma unroll 2
+                for (int s = q8; s < q8 + 8; ++s) step(s, std::false_type{});
             } else {
 #pragma unroll 1
                 for (int s = q8; s < e8; ++s) step(s, std::true_type{});

@@ -62,10 +62,11 @@ def load_library() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_LIB_PATH):
+    path = os.environ.get("CLB_LIBRARY", _LIB_PATH)  # A/B runs of kernel variants load another build of the same library
+    if not os.path.exists(path):
         raise ClbError(3, f"{_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`; "
                           "there is no CPU fallback for the gap-fill path")
-    lib = ctypes.CDLL(_LIB_PATH)
+    lib = ctypes.CDLL(path)
     vp, i32 = ctypes.c_void_p, ctypes.c_int32
     gp, pp = ctypes.POINTER(_GraphBatch), ctypes.POINTER(_Params)
     lib.clb_popoa_batch.restype = ctypes.c_int
