@@ -21,6 +21,9 @@ CASES = [
     # similar side lengths goes to pwfa_po_poa (stitcher.hpp:327-339); the output differs from the default route's
     ("pair60k_wfa_route", [2, 60000, 3, 2], ["-a", "100000"], {"min_wfa_size": 100}),
     ("msa3_40k_wfa_route", [3, 40000, 9, 1], ["-a", "100000"], {"min_wfa_size": 100}),
+    # cyclizing mode (-c, configs[4]): tandem-duplication detection with min_cyclizing_length lowered so that the
+    # HOR indels of the small input qualify; exercises Stitcher::internal_stitch and the bond alignment path
+    ("msa3_40k_cyclic", [3, 40000, 9, 3], ["-c", "-a", "100000"], {"min_cyclizing_length": 1000}),
 ]
 
 
