@@ -7,7 +7,7 @@ import numpy as np
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from centrolign_b200.batch import AlignmentParameters, CpuChecker, synth_windows
+from centrolign_b200.batch import AlignmentParameters, CpuChecker, successor_form, synth_windows
 from centrolign_b200.sharding import balanced_partition, run_sharded, stream_shard
 
 
@@ -35,16 +35,24 @@ def _oracle_runner(batch, params):
     return np.asarray([r[0] for r in res], np.int64), [r[1] for r in res]
 
 
+def _pwfa_oracle_runner(batch, params):
+    """The wavefront variant shards the same way (windows in successor form; prune limit of the Stitcher)."""
+    chk = CpuChecker("port")
+    res = [chk.pwfa_po_poa(batch, w, params, 50) for w in range(batch.n_windows)]
+    return np.asarray([r[0] for r in res], np.int64), [r[1] for r in res]
+
+
 def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     batch = synth_windows(9, first_index=40, seed=13, len_min=20, len_max=200, alt_len=21, alt_period=100)
     out = run_sharded(batch, AlignmentParameters(), runner=_oracle_runner)
+    wout = run_sharded(successor_form(batch), AlignmentParameters(), runner=_pwfa_oracle_runner)
     if rank == 0:
-        q.put((out[0].tolist(), [a.tolist() for a in out[1]]))
+        q.put((out[0].tolist(), [a.tolist() for a in out[1]], wout[0].tolist(), [a.tolist() for a in wout[1]]))
     else:
-        assert out is None
+        assert out is None and wout is None
     dist.barrier()
     dist.destroy_process_group()
 
@@ -58,7 +66,7 @@ def test_world_size_2_gloo_matches_single_process():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    scores, alns = q.get(timeout=120)
+    scores, alns, wscores, walns = q.get(timeout=120)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
@@ -66,3 +74,6 @@ def test_world_size_2_gloo_matches_single_process():
     want_s, want_a = _oracle_runner(batch, AlignmentParameters())
     assert scores == want_s.tolist()
     assert alns == [a.tolist() for a in want_a]
+    want_ws, want_wa = _pwfa_oracle_runner(successor_form(batch), AlignmentParameters())
+    assert wscores == want_ws.tolist()
+    assert walns == [a.tolist() for a in want_wa]
