@@ -23,6 +23,9 @@ CASES = [
     ("pair8k_indels", [2, 8000, 11, 2], "pair", 12000, 0.7),
     ("msa3_4k", [3, 4000, 9, 1], "msa", 6000, 1.0),
     ("msa4_3k", [4, 3000, 13, 1], "msa", 5000, 1.3),
+    # long enough for the reference to really merge the two pairs (shorter arrays come out of its partitioner unaligned, i.e.
+    # as two disjoint paths): nodes on several paths, ~4 tree entries per match
+    ("msa4_24k_merged", [4, 24000, 7, 0], "msa", 12000, 1.0),
     # tiny problems, the size of the Anchorer's fill-in calls: they run from shared memory (chain_small_kernel)
     ("pair600", [2, 600, 3, 0], "pair", 300, 1.0),
     ("msa3_500", [3, 500, 4, 0], "msa", 250, 0.9),
