@@ -5,7 +5,7 @@ between equal-scoring chains included, which is where the reference's search-tre
 import numpy as np
 import pytest
 
-from centrolign_b200.chain import ChainStats, chain_dp, chain_oracle
+from centrolign_b200.chain import ChainProblem, ChainStats, chain_dp, chain_oracle
 from golden_io import load_chain_golden
 
 pytestmark = pytest.mark.gpu
@@ -65,3 +65,31 @@ def test_every_dp_value_and_backpointer_equals_the_oracle(case, kind):
     assert np.array_equal(chain, ochain) and opt == oopt
     assert np.array_equal(dp.view(np.uint32), odp.view(np.uint32))
     assert np.array_equal(bp, obp)
+
+
+def _handmade(num_pw, with_query=True, n=2):
+    """Two matches on one path pair; the second starts behind the first (offset 3 < query offset 5)."""
+    a = dict(weight=np.array([1.5, 2.0], np.float32)[:n], dp_init=np.array([1.5, 2.0], np.float32)[:n],
+             final_term=np.zeros(n, np.float32), end_off=np.array([0, 1, 2], np.int64)[:n + 1], end_match=np.arange(n, dtype=np.uint32),
+             qry_off=np.array([0, 0, 1 if with_query else 0], np.int64)[:n + 1],
+             qry_match=np.array([1] if with_query and n == 2 else [], np.uint32),
+             qry_chain1=np.array([0] if with_query and n == 2 else [], np.uint32), ins_off=np.array([0, 1, 2], np.int64)[:n + 1],
+             ins_p1=np.zeros(n, np.uint32), ins_p2=np.zeros(n, np.uint32), ins_shift=np.zeros(n, np.int32),
+             ins_offset=np.array([3, 9], np.uint32)[:n], ins_active=np.ones(n, np.uint8), qa1=np.zeros(n, np.int32),
+             qa2=np.zeros(n, np.int32), qoff=np.array([0, 5], np.uint32)[:n])
+    k = max(1, num_pw)
+    return ChainProblem(num_pw, (1.0, 2.0, 3.0)[:k], (0.5, 0.2, 0.1)[:k], 1.0, 1, 1, 0.0, a)
+
+
+@pytest.mark.parametrize("num_pw", [0, 1, 3])
+def test_handmade_edge_cases(num_pw):
+    for prob in (_handmade(num_pw), _handmade(num_pw, with_query=False), _handmade(num_pw, n=1)):
+        chain, dp, bp, opt = chain_dp(prob)
+        ochain, odp, obp, oopt = chain_oracle(prob)
+        assert np.array_equal(chain, ochain) and np.array_equal(dp, odp) and np.array_equal(bp, obp) and opt == oopt
+    chain, dp, bp, opt = chain_dp(_handmade(num_pw))
+    assert chain.tolist() == [0, 1] and dp.tolist() == [1.5, 3.5] and bp.tolist() == [-1, 0]
+    empty = _handmade(num_pw, n=1)
+    empty.arrays = {k: v[:0] if k not in ("end_off", "qry_off", "ins_off") else v[:1] for k, v in empty.arrays.items()}
+    chain, dp, bp, opt = chain_dp(empty)  # no matches at all: the empty chain
+    assert len(chain) == 0
