@@ -426,9 +426,13 @@ extern "C" int clb_chain_dp(int device, const clb_chain_problem* p, float* dp_ou
             for (int64_t pr = 0; pr < npair; ++pr) max_n = std::max<uint32_t>(max_n, (uint32_t)(pair_base[pr + 1] - pair_base[pr]));
             rank_stride = 2 * (32 - __builtin_clz(max_n));
             const size_t bytes = (size_t)n_qry * C2 * 2 * rank_stride * 4;
-            size_t free_b = 0, total_b = 0;
-            cudaSetDevice(device);
-            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && bytes < free_b / 4 + (ar.cap > 0 ? ar.cap / 4 : 0)) z_ranks = plan.zero(bytes);
+            bool fits = bytes <= (size_t(64) << 20);  // small pools always fit; cudaMemGetInfo costs more than a small problem
+            if (!fits) {
+                size_t free_b = 0, total_b = 0;
+                cudaSetDevice(device);
+                fits = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && bytes < free_b / 4 + (ar.cap > 0 ? ar.cap / 4 : 0);
+            }
+            if (fits) z_ranks = plan.zero(bytes);
             else rank_stride = 0;
         }
         const size_t total = plan.copy_bytes + plan.zero_bytes;
