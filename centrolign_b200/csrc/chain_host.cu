@@ -176,10 +176,13 @@ extern "C" int clb_chain_dp(int device, const clb_chain_problem* p, float* dp_ou
     if (p->n_match < 0 || p->n_step < 0 || p->n_chain1 < 0 || p->n_chain2 < 0) return host_fail(CLB_EINVAL, "negative sizes");
     if (p->n_match > 0 && (p->n_chain1 < 1 || p->n_chain2 < 1)) return host_fail(CLB_EINVAL, "matches but no chains");
     if (p->n_match >= (int64_t(1) << 31)) return host_fail(CLB_EINVAL, "more than 2^31 matches");
+    const bool layout_only = getenv("CLB_CHAIN_LAYOUT_ONLY") != nullptr;  // host-layout timing without a device (no results)
     int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
-        return host_fail(CLB_ECUDA, "no CUDA device available (there is no CPU fallback)");
-    if (device < 0 || device >= ndev) return host_fail(CLB_EINVAL, "device index out of range");
+    if (!layout_only) {
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+            return host_fail(CLB_ECUDA, "no CUDA device available (there is no CPU fallback)");
+        if (device < 0 || device >= ndev) return host_fail(CLB_EINVAL, "device index out of range");
+    }
     *chain_len = 0;
     const float kLowest = std::numeric_limits<float>::lowest();
     if (opt_score) *opt_score = kLowest;
@@ -383,6 +386,11 @@ extern "C" int clb_chain_dp(int device, const clb_chain_problem* p, float* dp_ou
     std::vector<uint32_t> in_base32(in_base.size());
     for (size_t k = 0; k < in_base.size(); ++k) in_base32[k] = in_base[k] < 0 ? clb::kChainNone : (uint32_t)in_base[k];
     const double t_built = now_ms();
+    if (layout_only) {
+        fprintf(stderr, "[clb] chain layout only: %lld matches, %lld entries, %lld inner slots, %.1f ms\n", (long long)M, (long long)E,
+                (long long)n_inner, t_built - t_start);
+        return host_fail(CLB_ECUDA, "CLB_CHAIN_LAYOUT_ONLY: layout timed, nothing computed");
+    }
 
     // ------------------------------------------------------------------ device ------------------------------------------------------------------
     int rc = CLB_OK;
