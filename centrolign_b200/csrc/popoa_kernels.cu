@@ -488,14 +488,48 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
         crare[c] = (cinfo[c] & ((4u << kInfoNearShift) | kInfoFar)) != 0;
     }
 
-    // warp-uniform: does any column of this strip have a distance-3 or far predecessor / a persisted column 0..2?
-    bool lane_rare = false, lane_pers012 = false;
+    // Far predecessor columns (long bubbles, the boundary column of a source).  The common shape -- one such
+    // column in the lane, with ONE far predecessor that lies in an earlier strip or at least two lanes back --
+    // takes a fast path: the predecessor's persisted entry {M, D_k} / diagonal input for row r+1 is requested
+    // while row r is being computed (it was written a step earlier at the latest), so the next step folds it in
+    // without a list walk and without a load on the column chain.  Anything else keeps the generic walk.
+    int farc = -1;
+    const int4* farv = colbuf;
+    const int* fare = coleff;
+    bool slowfar[C], cx[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-        lane_rare |= crare[c];
-        if (c < C - 1) lane_pers012 |= coff[c] != 0xffffffffu;
+        slowfar[c] = false;
+        if (cinfo[c] & kInfoFar) {  // never set for a column beyond n2
+            const int j = j0 + c;
+            int nf = 0, qsel = 0;
+            const uint32_t b1 = Wsh.poff2[j + 1];
+#pragma unroll 1
+            for (uint32_t b = Wsh.poff2[j]; b < b1; ++b) {
+                const int q = (int)Wsh.pidx2[b];
+                if (q >= 1 && j - q <= kNear) continue;
+                ++nf;
+                qsel = q;
+            }
+            if (nf == 1 && farc < 0 && slot2[qsel] >= 0 && (qsel < C0 || (qsel - C0) / C <= lane - 2)) {
+                farc = c;
+                farv = colbuf + (size_t)((uint32_t)slot2[qsel] * cstride);
+                fare = coleff + (size_t)((uint32_t)slot2[qsel] * cstride);
+            } else {
+                slowfar[c] = true;
+            }
+        }
+        crare[c] = (cinfo[c] & (4u << kInfoNearShift)) != 0 || slowfar[c];
     }
-    const bool strip_rare = __any_sync(kFull, lane_rare);
+#pragma unroll
+    for (int c = 0; c < C; ++c) cx[c] = crare[c] || farc == c;
+    int4 Fv = make_int4(kMinInf, kMinInf, kMinInf, kMinInf);
+    int Fe = kMinInf;
+
+    // warp-uniform: does any lane of this strip persist one of its first three columns?
+    bool lane_pers012 = false;
+#pragma unroll
+    for (int c = 0; c < C - 1; ++c) lane_pers012 |= coff[c] != 0xffffffffu;
     const bool strip_pers012 = __any_sync(kFull, lane_pers012);
 
     auto shfl_col = [&](const ColState& v) {
@@ -546,10 +580,20 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
             if (!(rinfo & kInfoRegular)) {
                 const bool rb1 = (rinfo & (1u << kInfoNearShift)) != 0;
                 const uint32_t rs2 = saA + (uint32_t)((r - 2) & (H - 1)) * (C * 32 * 16);  // row r-2
+                if (rinfo & (2u << kInfoNearShift)) {
+                    if (!rb1) {  // second allele of a SNP bubble: row r-2 replaces row r-1
 #pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    if (!rb1) { upM[c] = kMinInf; upI[c][0] = upI[c][1] = upI[c][2] = kMinInf; }
-                    if (rinfo & (2u << kInfoNearShift)) max4(upM[c], upI[c], lds_128(rs2 + c * (32 * 16)));
+                        for (int c = 0; c < C; ++c) {
+                            const int4 t = lds_128(rs2 + c * (32 * 16));
+                            upM[c] = t.x; upI[c][0] = t.y; upI[c][1] = t.z; upI[c][2] = t.w;
+                        }
+                    } else {     // node after the bubble: both
+#pragma unroll
+                        for (int c = 0; c < C; ++c) max4(upM[c], upI[c], lds_128(rs2 + c * (32 * 16)));
+                    }
+                } else if (!rb1) {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) { upM[c] = kMinInf; upI[c][0] = upI[c][1] = upI[c][2] = kMinInf; }
                 }
                 if (rinfo & ((4u << kInfoNearShift) | kInfoFar)) {
                     if (rinfo & (4u << kInfoNearShift)) {
@@ -583,13 +627,21 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
                 for (int k = 0; k < 3; ++k) L.D[k] = (k < P && cb1[c]) ? d1.D[k] : kMinInf;
                 L.E = cb1[c] ? d1.E : kMinInf;
                 if (cb2[c]) fold(L, d2);
-                if (strip_rare && crare[c]) {
+                if (cx[c]) {
+                  if (farc == c) {  // fast far column
+                    if (r == 1) { Fv = farv[1]; Fe = fare[1]; }
+                    L.M = imax(L.M, Fv.x); L.D[0] = imax(L.D[0], Fv.y); L.D[1] = imax(L.D[1], Fv.z); L.D[2] = imax(L.D[2], Fv.w);
+                    L.E = imax(L.E, Fe);
+                    const int rn = min(r + 1, n1);
+                    Fv = farv[rn]; Fe = fare[rn];
+                  }
+                  if (crare[c]) {
                     const uint32_t ci = cinfo[c];
                     if (ci & (4u << kInfoNearShift)) {
                         const ColState& d3 = (c >= 3) ? cur[0] : (c == 2 ? S0 : (c == 1 ? S1 : S2));
                         fold(L, d3);
                     }
-                    if (ci & kInfoFar) {
+                    if (slowfar[c]) {
                         const int j = j0 + c;
                         const uint32_t b1 = Wsh.poff2[j + 1];
 #pragma unroll 1
@@ -602,6 +654,7 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
                             L.E = imax(L.E, coleff[o]);
                         }
                     }
+                  }
                 }
                 // ---- the cell ----
                 const int sub = (rlabel == (int)(cinfo[c] & kInfoLabelMask)) ? prm.match : -prm.mismatch;
@@ -619,19 +672,27 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
                 cur[c].E = eM;
                 const int4 cellA = make_int4(M, I[0], I[1], I[2]);
                 sts_128(rsA + c * (32 * 16), cellA);
-                if ((c == C - 1 || strip_pers012) && coff[c] != 0xffffffffu) {
+                if (c == C - 1 && coff[c] != 0xffffffffu) {  // the regular persisted columns (every 32nd) are a lane's last
                     colbuf[coff[c] + (uint32_t)r] = make_int4(M, cur[c].D[0], cur[c].D[1], cur[c].D[2]);
                     coleff[coff[c] + (uint32_t)r] = eM;
                 }
                 upM[c] = M; upI[c][0] = I[0]; upI[c][1] = I[1]; upI[c][2] = I[2];
             }
+            if (strip_pers012) {  // warp-uniform and rare: a column with a far successor among a lane's first three
+#pragma unroll
+                for (int c = 0; c < C - 1; ++c)
+                    if (coff[c] != 0xffffffffu) {
+                        colbuf[coff[c] + (uint32_t)r] = make_int4(cur[c].M, cur[c].D[0], cur[c].D[1], cur[c].D[2]);
+                        coleff[coff[c] + (uint32_t)r] = cur[c].E;
+                    }
+            }
             if (rinfo & kInfoPersist) {  // persisted row: the new row is in the up registers
                 uint32_t rslot = rinfo >> kInfoSlotShift;
                 if (rslot == kInfoSlotEscape) rslot = (uint32_t)Wsh.slot1[r];
-                rslot = rslot * rstride + (uint32_t)j0;
+                int4* const rp = rowbuf + (size_t)(rslot * rstride + (uint32_t)j0);  // one address, immediate offsets
 #pragma unroll
                 for (int c = 0; c < C; ++c)
-                    if (c < (int)nvalid) rowbuf[rslot + c] = make_int4(upM[c], upI[c][0], upI[c][1], upI[c][2]);
+                    if (c < (int)nvalid) rp[c] = make_int4(upM[c], upI[c][0], upI[c][1], upI[c][2]);
             }
 #pragma unroll
             for (int c = 0; c < C; ++c) out[c] = cur[c];
