@@ -117,6 +117,51 @@ def test_skewed_shapes_vs_oracle():
     _compare(batch, PROD, scores, alns, oracle, "skewed")
 
 
+def _irregular_chain(rng, length):
+    """Backbone with SNP bubbles, short skip edges (distance 2..7: near, distance-3 and previous-lane far
+    predecessors), long skip edges (far predecessors in earlier lanes / strips, several into one node) and
+    extra source nodes joining the chain late (a boundary predecessor far from column 1)."""
+    labels, edges = random_bubble_chain(rng, length, snp_rate=0.08, del_rate=0.04)
+    labels = list(labels)
+    edges = set(edges)
+    for _ in range(max(2, length // 60)):  # short skips incl. distances 4..7
+        p = int(rng.integers(0, length - 9))
+        edges.add((p, p + 2 + int(rng.integers(0, 6))))
+    for _ in range(max(2, length // 120)):  # long skips, sometimes two into the same node
+        q = int(rng.integers(10, length))
+        for _ in range(1 + int(rng.integers(0, 2))):
+            p = int(rng.integers(max(0, q - 400), q - 8))
+            edges.add((p, q))
+    for _ in range(2):  # late sources
+        a = len(labels)
+        labels.append("ACGT"[int(rng.integers(0, 4))])
+        edges.add((a, int(rng.integers(1, length))))
+    edges = [(int(a), int(b)) for a, b in edges]
+    rng.shuffle(edges)
+    return "".join(labels), edges
+
+
+@pytest.mark.parametrize("num_pw", [1, 3])
+def test_wide_strips_irregular_graphs_vs_oracle(num_pw):
+    """The 128-column strip path (windows of at least 384 columns) on graphs that are not the benchmark's:
+    every predecessor shape the fill distinguishes (near 1..3, far through the fast and the generic path,
+    persisted columns anywhere in a lane) on both sides, checked cell-exactly through score + alignment."""
+    oracle = CpuChecker("port")
+    rng = np.random.default_rng(4242 + num_pw)
+    pairs = []
+    for t in range(24):
+        sides = []
+        for _ in range(2):
+            labels, edges = _irregular_chain(rng, int(rng.integers(400, 1300)))
+            src, snk = sources_and_sinks(len(labels), edges)
+            sides.append(graph_from_edges(labels, edges, src, snk))
+        pairs.append(tuple(sides))
+    batch = batch_from_graph_pairs(pairs)
+    p = PROD.truncated(num_pw)
+    scores, alns = po_poa_batch(batch, p)
+    _compare(batch, p, scores, alns, oracle, f"wide irregular P={num_pw}")
+
+
 @pytest.mark.skipif(not CpuChecker.available("reference"), reason="oracle/_ref/libclref.so did not travel")
 def test_live_against_unmodified_reference():
     ref = CpuChecker("reference")
