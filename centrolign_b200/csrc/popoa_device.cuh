@@ -16,6 +16,7 @@ constexpr int kStrip = 32;              // columns per strip = lanes per warp
 constexpr int kRowBlock = 64;           // rows per traceback tile
 constexpr int kNear = 3;                // predecessors at most this far back are served from the shared-memory ring
 constexpr int kRingRows = 8;            // fill-kernel ring depth (>= 2*kNear+2)
+constexpr int kPanelRows = 1024;        // default panel height of tiled windows (multiple of kRowBlock; CLB_PANEL_ROWS overrides, 0 = off)
 
 // per-node info word
 constexpr uint32_t kInfoLabelMask = 0xffu;
@@ -69,6 +70,7 @@ struct LaunchArgs {
     int debug_flags;        // bit0: skip the traceback walk (profiling the fill alone; results are then invalid)
     int start_lag;          // rows a strip stays behind its left neighbour when it starts
     int slot_by_smid;       // 1: workspace slot pair chosen by %smid (kernels of several chunks share one workspace)
+    int panel_rows;         // > 0: wide windows with more rows are filled as (panel, strip) tiles; rows p*panel_rows-2..p*panel_rows are persisted
 };
 
 // Workspace of one window: rowbuf {M,I_k} + colbuf {M,D_k} + boundary row + boundary column (16 B per

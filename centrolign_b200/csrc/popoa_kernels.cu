@@ -93,6 +93,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // per-fill-warp shared memory
 // (the start lag between neighbouring strips is a launch parameter, LaunchArgs::start_lag; 64 rows measured best)
+constexpr int kProgMask = 511;  // progress words per CTA (one per strip in flight; a tiled window keeps all its strips live)
 constexpr int kFillRing = 4;    // ring rows: a row is read at most kNear steps after it was written
 struct __align__(16) FillSmem {
     int4 ringA[kFillRing * 32];  // {M, I_k} of the last rows, own column
@@ -186,7 +187,7 @@ __device__ __forceinline__ void fill_strip(const Win& Wsh, const Params& prm, co
     auto wait_rows = [&](int want) {
         if (avail < want) {
             for (;;) {
-                const unsigned long long v = progress[(g - 1) & 63];
+                const unsigned long long v = progress[(g - 1) & kProgMask];
                 avail = ((int)(v >> 32) == g) ? (int)(v & 0xffffffffu) : 0;
                 if (avail >= want) break;
                 __nanosleep(200);
@@ -319,7 +320,7 @@ __device__ __forceinline__ void fill_strip(const Win& Wsh, const Params& prm, co
     };
     auto publish = [&](int r31) {  // rows 1..r31 of this strip are complete (called by lane 31)
         __threadfence_block();
-        progress[g & 63] = ((unsigned long long)(g + 1) << 32) | (unsigned)r31;
+        progress[g & kProgMask] = ((unsigned long long)(g + 1) << 32) | (unsigned)r31;
     };
 
     const int nsteps = n1 + 31;
@@ -374,7 +375,10 @@ struct ColState {  // what a column offers to the columns right of it, for the c
 template <int P>
 __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& prm, const int cs, const int g,
                                                 FillSmemWide& sm, volatile unsigned long long* progress, const int lane,
-                                                const int start_lag) {
+                                                const int start_lag, const int R0, const int R1, const int dbg) {
+    // Rows R0+1 .. R1 of the strip (a panel; R0 = 0, R1 = n1 is the whole strip).  A panel that does not start at
+    // the top takes over from whoever filled the panel above through the window workspace: rows R0-2 .. R0 are
+    // persisted (host: popoa_host.cu) and the strip's own progress word says when they are there.
     constexpr int H = kFillRing, C = kWideCols, W = 32 * C, PB = 16;  // PB = rows per left-column prefetch block
     const int C0 = 1 + W * cs;
     const int n1 = Wsh.n1, n2 = Wsh.n2;
@@ -400,12 +404,12 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
         cinfo[c] = jv ? Wsh.info2[j] : (kInfoRegular | (1u << kInfoNearShift) | 0xffu);
         coff[c] = (jv && (cinfo[c] & kInfoPersist)) ? (uint32_t)slot2[j] * cstride : 0xffffffffu;
         upM[c] = kMinInf; upI[c][0] = upI[c][1] = upI[c][2] = kMinInf;
-        if (jv) {  // boundary row (alignment.hpp:814-894): M(0,j), I_k(0,j) = -inf
+        if (jv && R0 == 0) {  // boundary row (alignment.hpp:814-894): M(0,j), I_k(0,j) = -inf
             upM[c] = boundary_cell<P>(Wsh.depth2[j], prm).x;
             rowbuf[j] = make_int4(upM[c], kMinInf, kMinInf, kMinInf);
         }
     }
-    if (cs == 0) {  // boundary column as a predecessor column, and its diagonal input
+    if (cs == 0 && R0 == 0) {  // boundary column as a predecessor column, and its diagonal input
         for (int i = lane; i <= n1; i += 32) {
             const int m = i == 0 ? 0 : boundary_cell<P>(Wsh.depth1[i], prm).x;
             colbuf[i] = make_int4(m, kMinInf, kMinInf, kMinInf);
@@ -440,7 +444,7 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
     auto wait_rows = [&](int want) {
         if (avail < want) {
             for (;;) {
-                const unsigned long long v = progress[(g - 1) & 63];
+                const unsigned long long v = progress[(g - 1) & kProgMask];
                 avail = ((int)(v >> 32) == g) ? (int)(v & 0xffffffffu) : 0;
                 if (avail >= want) break;
                 __nanosleep(200);
@@ -450,7 +454,7 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
     };
     auto prefetch_block = [&](int b) {  // rows PB*b+1 .. PB*b+PB of the needed left columns -> buffer b&1
         const int row = PB * b + 1 + lane;
-        if (lane < PB && row <= n1) {
+        if (lane < PB && row <= R1) {
 #pragma unroll
             for (int d = 0; d < 3; ++d)
                 if (needL & (1u << d)) {
@@ -460,15 +464,39 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
         }
         cp_async_commit();
     };
-    wait_rows(min(max(start_lag, PB), n1));
-    prefetch_block(0);
+    // never wait for rows below the panel: the tile that fills them may be queued behind this one
+    wait_rows(min(R0 + max(start_lag, PB), R1));
+    if (R0 > 0) {  // the panel above must be complete before anything of this one is read (strip 0 has no other wait)
+        for (;;) {
+            const unsigned long long v = progress[g & kProgMask];
+            if ((int)(v >> 32) == g + 1 && (int)(v & 0xffffffffu) >= R0) break;
+            __nanosleep(200);
+        }
+        __threadfence_block();
+    }
+    prefetch_block(R0 / PB);
+    if (R0 > 0) {  // take over rows R0-2 .. R0 from the panel above
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const int row = R0 - t;
+            const uint32_t o = (uint32_t)Wsh.slot1[row] * rstride + (uint32_t)j0;
+            const uint32_t sa = (uint32_t)__cvta_generic_to_shared(sm.ringA) + (uint32_t)lane * 16u + (uint32_t)(row & (H - 1)) * (C * 32 * 16);
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                if (c < (int)nvalid) {
+                    const int4 v = rowbuf[o + c];
+                    sts_128(sa + c * (32 * 16), v);
+                    if (t == 0) { upM[c] = v.x; upI[c][0] = v.y; upI[c][1] = v.z; upI[c][2] = v.w; }
+                }
+        }
+    }
     cp_async_wait_all();
     __syncwarp();
 
     ColState out[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) { out[c].M = kMinInf; out[c].D[0] = out[c].D[1] = out[c].D[2] = kMinInf; out[c].E = kMinInf; }
-    uint32_t rinfo_next = (lane == 0) ? info1[1] : 0u;
+    uint32_t rinfo_next = (lane == 0) ? info1[R0 + 1] : 0u;
     // explicit 32-bit shared-window addresses: keeps ptxas from re-deriving them every step
     uint32_t saA = (uint32_t)__cvta_generic_to_shared(sm.ringA) + (uint32_t)lane * 16u;
     uint32_t saLv = (uint32_t)__cvta_generic_to_shared(&sm.leftv[0][0][0]);
@@ -531,6 +559,13 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
 #pragma unroll
     for (int c = 0; c < C - 1; ++c) lane_pers012 |= coff[c] != 0xffffffffu;
     const bool strip_pers012 = __any_sync(kFull, lane_pers012);
+    // A plain strip -- no column with a distance-3 / far predecessor, no persisted column other than a lane's
+    // last -- runs a lean step without any of that code: the four columns of a lane become one basic block
+    // (measured on windows without bubbles: 297 -> 368 GCUPS).
+    bool lane_cx = false;
+#pragma unroll
+    for (int c = 0; c < C; ++c) lane_cx |= cx[c];
+    const bool lean = !__any_sync(kFull, lane_cx) && !strip_pers012 && !(needS & 4u) && !(needL & 4u) && !(dbg & 2);
 
     auto shfl_col = [&](const ColState& v) {
         ColState o;
@@ -554,24 +589,25 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
         if (lane == 0) { S.M = t.x; S.D[0] = t.y; S.D[1] = t.z; S.D[2] = t.w; S.E = e; }
     };
 
-    auto step = [&](const int s, auto guard_tag) {
+    auto step = [&](const int s, auto guard_tag, auto lean_tag) {
         constexpr bool GUARD = decltype(guard_tag)::value;
+        constexpr bool LEAN = decltype(lean_tag)::value;
         const int r = 1 + s - lane;
         bool act = true;
-        if (GUARD) act = r >= 1 && r <= n1;
+        if (GUARD) act = r > R0 && r <= R1;
         // previous lane's columns for this row (it finished the row one step ago)
         ColState S0, S1, S2;  // its column 3, 2, 1
         S0 = shfl_col(out[3]);
         if (needS & 2u) S1 = shfl_col(out[2]);
-        if (needS & 4u) S2 = shfl_col(out[1]);
+        if (!LEAN && (needS & 4u)) S2 = shfl_col(out[1]);
         // lane 0 is on row s+1: rows PB*b+1.. live in buffer b&1 at index (row-1) % PB
         if (needL & 1u) take_left(S0, 0, s);
         if (needL & 6u) {
             if (needL & 2u) take_left(S1, 1, s);
-            if (needL & 4u) take_left(S2, 2, s);
+            if (!LEAN && (needL & 4u)) take_left(S2, 2, s);
         }
         const uint32_t rinfo = rinfo_next;
-        if (GUARD) rinfo_next = (r >= 0 && r < n1) ? info1[(uint32_t)(r + 1)] : 0u;
+        if (GUARD) rinfo_next = (r >= R0 && r < R1) ? info1[(uint32_t)(r + 1)] : 0u;
         else rinfo_next = info1[(uint32_t)(r + 1)];  // the info array is padded by one entry
         if (act) {
             const uint32_t rsA = saA + (uint32_t)(r & (H - 1)) * (C * 32 * 16);
@@ -627,12 +663,12 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
                 for (int k = 0; k < 3; ++k) L.D[k] = (k < P && cb1[c]) ? d1.D[k] : kMinInf;
                 L.E = cb1[c] ? d1.E : kMinInf;
                 if (cb2[c]) fold(L, d2);
-                if (cx[c]) {
+                if (!LEAN && cx[c]) {
                   if (farc == c) {  // fast far column
-                    if (r == 1) { Fv = farv[1]; Fe = fare[1]; }
+                    if (r == R0 + 1) { Fv = farv[r]; Fe = fare[r]; }
                     L.M = imax(L.M, Fv.x); L.D[0] = imax(L.D[0], Fv.y); L.D[1] = imax(L.D[1], Fv.z); L.D[2] = imax(L.D[2], Fv.w);
                     L.E = imax(L.E, Fe);
-                    const int rn = min(r + 1, n1);
+                    const int rn = min(r + 1, R1);  // not below the panel: those rows may not exist yet
                     Fv = farv[rn]; Fe = fare[rn];
                   }
                   if (crare[c]) {
@@ -678,7 +714,7 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
                 }
                 upM[c] = M; upI[c][0] = I[0]; upI[c][1] = I[1]; upI[c][2] = I[2];
             }
-            if (strip_pers012) {  // warp-uniform and rare: a column with a far successor among a lane's first three
+            if (!LEAN && strip_pers012) {  // warp-uniform and rare: a column with a far successor among a lane's first three
 #pragma unroll
                 for (int c = 0; c < C - 1; ++c)
                     if (coff[c] != 0xffffffffu) {
@@ -701,33 +737,33 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
     };
     auto publish = [&](int r31) {
         __threadfence_block();
-        progress[g & 63] = ((unsigned long long)(g + 1) << 32) | (unsigned)r31;
+        progress[g & kProgMask] = ((unsigned long long)(g + 1) << 32) | (unsigned)r31;
     };
 
-    const int nsteps = n1 + 31;
-    for (int s0 = 0; s0 < nsteps; s0 += PB) {  // PB-step blocks; lane 0 is on rows s0+1 .. s0+PB
+    const int nsteps = R1 + 31;
+    for (int s0 = R0; s0 < nsteps; s0 += PB) {  // PB-step blocks; lane 0 is on rows s0+1 .. s0+PB (R0 is a multiple of PB)
         const int s1 = min(s0 + PB, nsteps);
         {  // only lane 0 reads the prefetch buffers, so the next block can be requested right away
             const int b = s0 / PB + 1;
-            if (PB * b + 1 <= n1) {
-                wait_rows(min(PB * b + PB, n1));
+            if (PB * b + 1 <= R1) {
+                wait_rows(min(PB * b + PB, R1));
                 prefetch_block(b);
             }
         }
-        const bool inner = s0 >= 31 && s1 <= n1;
+        const bool inner = s0 >= R0 + 31 && s1 <= R1;
 #pragma unroll 1
         for (int q8 = s0; q8 < s1; q8 += 8) {
             const int e8 = min(q8 + 8, s1);
-            if (inner) {  // exactly 8 steps: unrolled in pairs so that the row registers ping-pong instead of being copied
+            if (inner && lean) {  // exactly 8 steps: unrolled in pairs so that the row registers ping-pong instead of being copied
 #pragma unroll 2
-                for (int s = q8; s < q8 + 8; ++s) step(s, std::false_type{});
-            } else {
+                for (int s = q8; s < q8 + 8; ++s) step(s, std::false_type{}, std::true_type{});
+            } else {  // the guarded step doubles as the generic one (one copy of it: instruction cache)
 #pragma unroll 1
-                for (int s = q8; s < e8; ++s) step(s, std::true_type{});
+                for (int s = q8; s < e8; ++s) step(s, std::true_type{}, std::false_type{});
             }
             if (lane == 31) {
                 const int r31 = e8 - 31;
-                if (r31 >= 1) publish(min(r31, n1));
+                if (r31 > R0) publish(min(r31, R1));
             }
         }
         cp_async_wait_all();
@@ -1132,12 +1168,25 @@ constexpr int kTileInt4 = (int)(sizeof(TileSmem) / sizeof(int4));
 
 struct CtaState {
     Win win[2];
-    unsigned long long progress[64];
+    unsigned long long progress[kProgMask + 1];
     int seq_win[8];      // window id of the CTA's k-th window (-1 = queue exhausted)
     int seq_nstrips[8];
     int seq_tag[8];      // k+1 once entry k is published
-    int strips_done[2];  // per workspace slot
+    int strips_done[2];  // per workspace slot: finished strips (or tiles, for a tiled window)
+    int tile_next[2];    // per workspace slot: next tile of a tiled window
 };
+
+// Tiled windows.  A strip that is slower than its neighbours (far predecessor columns, the generic step) holds back
+// every strip behind it for its whole length when strips are filled top to bottom in one piece.  Wide windows with
+// more than panel_rows rows are therefore cut into panels: a tile = (panel p, strip cs), handed out from a per-window
+// queue in the order of d = p * kTileSkew + cs (p ascending inside d).  Both predecessors of a tile, (p, cs-1) and
+// (p-1, cs), have a smaller d, so they were taken earlier and no wait can deadlock; with about one tile per panel in
+// flight, a tile's left neighbour is usually finished, and nothing waits for a slow strip.
+constexpr int kTileSkew = 11;
+constexpr int kMaxTiledStrips = kProgMask - 64;
+__device__ __forceinline__ bool window_tiled(const Win& W, int nstrips, int panel_rows) {
+    return W.cw == kWideCols && panel_rows > 0 && W.n1 > panel_rows + panel_rows / 4 && nstrips <= kMaxTiledStrips;
+}
 
 __device__ __forceinline__ unsigned smid() {
     unsigned v;
@@ -1157,7 +1206,7 @@ __global__ void __launch_bounds__(kThreads, 1) popoa_kernel(const LaunchArgs A) 
     __shared__ CtaState S;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const Params prm = A.prm;
-    if (tid < 64) S.progress[tid] = 0ull;
+    for (int i = tid; i <= kProgMask; i += kThreads) S.progress[i] = 0ull;
     if (tid < 8) S.seq_tag[tid] = 0;
     __syncthreads();
 
@@ -1172,9 +1221,35 @@ __global__ void __launch_bounds__(kThreads, 1) popoa_kernel(const LaunchArgs A) 
             if (w < 0) break;
             const int nstrips = ld_volatile(&S.seq_nstrips[k & 7]);
             const Win& W = S.win[k & 1];
+            if (window_tiled(W, nstrips, A.panel_rows)) {
+                const int H = A.panel_rows, T = (W.n1 + H - 1) / H, ntiles = T * nstrips;
+                int d = 0, p = 0, qi = 0;  // enumeration cursor: tile number qi is (p, d - p * kTileSkew)
+                for (;;) {
+                    int q = 0;
+                    if (lane == 0) q = atomicAdd(&S.tile_next[k & 1], 1);
+                    q = __shfl_sync(kFull, q, 0);
+                    if (q >= ntiles) break;
+                    while (qi < q) {
+                        do {
+                            if (++p >= T) { p = 0; ++d; }
+                        } while (d - p * kTileSkew < 0 || d - p * kTileSkew >= nstrips);
+                        ++qi;
+                    }
+                    const int cs = d - p * kTileSkew;
+                    fill_strip_wide<P>(W, prm, cs, G + cs, *reinterpret_cast<FillSmemWide*>(&sm), S.progress, lane, A.start_lag,
+                                       p * H, min((p + 1) * H, W.n1), A.debug_flags);
+                    if (lane == 0) {
+                        __threadfence_block();
+                        atomicAdd(&S.strips_done[k & 1], 1);
+                    }
+                    __syncwarp();
+                }
+                G += nstrips;
+                continue;
+            }
             int first = (warp - G % kFillWarps + kFillWarps) % kFillWarps;  // my first strip of this window
             for (int cs = first; cs < nstrips; cs += kFillWarps) {
-                if (W.cw == kWideCols) fill_strip_wide<P>(W, prm, cs, G + cs, *reinterpret_cast<FillSmemWide*>(&sm), S.progress, lane, A.start_lag);
+                if (W.cw == kWideCols) fill_strip_wide<P>(W, prm, cs, G + cs, *reinterpret_cast<FillSmemWide*>(&sm), S.progress, lane, A.start_lag, 0, W.n1, A.debug_flags);
                 else fill_strip<P>(W, prm, cs, G + cs, *reinterpret_cast<FillSmem*>(&sm), S.progress, lane, A.start_lag);
                 if (lane == 0) {
                     __threadfence_block();
@@ -1220,6 +1295,7 @@ __global__ void __launch_bounds__(kThreads, 1) popoa_kernel(const LaunchArgs A) 
                     nstrips = m.n1 >= 1 ? (int)((m.n2 + sw - 1) / sw) : 0;
                 }
                 S.strips_done[k & 1] = 0;
+                S.tile_next[k & 1] = 0;
                 S.seq_nstrips[k & 7] = nstrips;
                 S.seq_win[k & 7] = w;
                 __threadfence_block();
@@ -1234,9 +1310,11 @@ __global__ void __launch_bounds__(kThreads, 1) popoa_kernel(const LaunchArgs A) 
             const int w = ld_volatile(&S.seq_win[t & 7]);  // written by this warp
             if (w < 0) break;
             const int nstrips = ld_volatile(&S.seq_nstrips[t & 7]);
-            while (ld_volatile(&S.strips_done[t & 1]) < nstrips) __nanosleep(500);
-            __threadfence_block();
             const Win& W = S.win[t & 1];
+            int nwait = nstrips;
+            if (window_tiled(W, nstrips, A.panel_rows)) nwait *= (W.n1 + A.panel_rows - 1) / A.panel_rows;
+            while (ld_volatile(&S.strips_done[t & 1]) < nwait) __nanosleep(500);
+            __threadfence_block();
             tb_boundary<P>(W, prm, lane);
             if (!(A.debug_flags & 1))
                 traceback<P>(W, prm, *reinterpret_cast<TileSmem*>(smem), lane, A.score + w, A.aln + 2 * W.out, A.aln_len + w);

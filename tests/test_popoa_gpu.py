@@ -162,6 +162,48 @@ def test_wide_strips_irregular_graphs_vs_oracle(num_pw):
     _compare(batch, p, scores, alns, oracle, f"wide irregular P={num_pw}")
 
 
+_TILED_CHILD = r"""
+import sys
+import numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
+from centrolign_b200.batch import (AlignmentParameters, CpuChecker, batch_from_graph_pairs, concat_batches, graph_from_edges,
+                                   random_bubble_chain, sources_and_sinks, synth_windows)
+from centrolign_b200.popoa import po_poa_batch
+import test_popoa_gpu as t
+oracle = CpuChecker("port")
+rng = np.random.default_rng(77)
+pairs = []
+for k in range(40):
+    sides = []
+    for side in range(2):
+        n = int(rng.integers(420, 1400))
+        if k % 3 == 0: labels, edges = random_bubble_chain(rng, n, snp_rate=0.0, del_rate=0.0)   # low-entropy linear
+        elif k % 3 == 1: labels, edges = random_bubble_chain(rng, n, snp_rate=0.1, del_rate=0.04)
+        else: labels, edges = t._irregular_chain(rng, n)
+        src, snk = sources_and_sinks(len(labels), edges)
+        sides.append(graph_from_edges(labels, edges, src, snk))
+    pairs.append(tuple(sides))
+batch = concat_batches([batch_from_graph_pairs(pairs), synth_windows(6, first_index=50, seed=5, len_min=1500, len_max=3000)])
+for p in (t.PROD, t.PROD.truncated(1)):
+    scores, alns = po_poa_batch(batch, p)
+    t._compare(batch, p, scores, alns, oracle, "tiled P=%d" % p.num_pw)
+print("TILED-OK", batch.n_windows)
+"""
+
+
+def test_tiled_fill_small_panels():
+    """The tiled fill (wide windows cut into row panels, tiles handed out from a queue; popoa_kernels.cu) with a
+    panel height of 256 rows, so that windows of a few hundred rows already consist of several panels and every
+    hand-over (rows R0-2..R0 through the workspace, the boundary column of strip 0) is exercised.  The panel height
+    is read once per process (CLB_PANEL_ROWS), hence the child process."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CLB_PANEL_ROWS="256")
+    code = _TILED_CHILD.format(root=root, tests=os.path.join(root, "tests"))
+    res = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert res.returncode == 0 and "TILED-OK" in res.stdout, res.stdout[-3000:]
+
+
 @pytest.mark.skipif(not CpuChecker.available("reference"), reason="oracle/_ref/libclref.so did not travel")
 def test_live_against_unmodified_reference():
     ref = CpuChecker("reference")

@@ -1,4 +1,3 @@
-timeout 300 python -m pytest tests/test_popoa_gpu.py -x -q -m gpu 2>&1 | tail -3
-B="timeout 200 python bench.py --windows 8000 --no-cpu-baseline --no-e2e --no-other-paths"
-f(){ tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d[\"value\"],1), d[\"roofline\"][\"frac\"])"; }
-for L in libcentrolign_b200.so libclb_w13.so libclb_w14.so; do echo "== $L"; CLB_LIBRARY=$PWD/centrolign_b200/csrc/$L $B 2>&1 | f; done
+CLB_PANEL_ROWS=256 timeout 200 python tools/scratch/dbg2.py 2>&1 | tail -14
+echo "== tests panel default"; timeout 300 python -m pytest tests/test_popoa_gpu.py -x -q -m gpu 2>&1 | tail -3
+echo "== tests panel 256"; CLB_PANEL_ROWS=256 timeout 300 python -m pytest tests/test_popoa_gpu.py -x -q -m gpu 2>&1 | tail -3
