@@ -16,7 +16,7 @@ constexpr int kStrip = 32;              // columns per strip = lanes per warp
 constexpr int kRowBlock = 64;           // rows per traceback tile
 constexpr int kNear = 3;                // predecessors at most this far back are served from the shared-memory ring
 constexpr int kRingRows = 8;            // fill-kernel ring depth (>= 2*kNear+2)
-constexpr int kPanelRows = 1024;        // default panel height of tiled windows (multiple of kRowBlock; CLB_PANEL_ROWS overrides, 0 = off)
+constexpr int kPanelRows = 2048;        // default panel height of tiled windows (multiple of kRowBlock; CLB_PANEL_ROWS overrides, 0 = off)
 
 // per-node info word
 constexpr uint32_t kInfoLabelMask = 0xffu;

@@ -559,13 +559,12 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
 #pragma unroll
     for (int c = 0; c < C - 1; ++c) lane_pers012 |= coff[c] != 0xffffffffu;
     const bool strip_pers012 = __any_sync(kFull, lane_pers012);
-    // A plain strip -- no column with a distance-3 / far predecessor, no persisted column other than a lane's
-    // last -- runs a lean step without any of that code: the four columns of a lane become one basic block
-    // (measured on windows without bubbles: 297 -> 368 GCUPS).
+    // A plain strip -- no column with a distance-3 / far predecessor -- runs a lean step without any of that
+    // code: the four columns of a lane become one basic block (measured on windows without bubbles: 297 -> 368 GCUPS).
     bool lane_cx = false;
 #pragma unroll
     for (int c = 0; c < C; ++c) lane_cx |= cx[c];
-    const bool lean = !__any_sync(kFull, lane_cx) && !strip_pers012 && !(needS & 4u) && !(needL & 4u) && !(dbg & 2);
+    const bool lean = !__any_sync(kFull, lane_cx) && !(needS & 4u) && !(needL & 4u) && !(dbg & 2);
 
     auto shfl_col = [&](const ColState& v) {
         ColState o;
@@ -714,7 +713,7 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
                 }
                 upM[c] = M; upI[c][0] = I[0]; upI[c][1] = I[1]; upI[c][2] = I[2];
             }
-            if (!LEAN && strip_pers012) {  // warp-uniform and rare: a column with a far successor among a lane's first three
+            if (strip_pers012) {  // warp-uniform and rare: a column with a far successor among a lane's first three
 #pragma unroll
                 for (int c = 0; c < C - 1; ++c)
                     if (coff[c] != 0xffffffffu) {
@@ -755,7 +754,7 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
         for (int q8 = s0; q8 < s1; q8 += 8) {
             const int e8 = min(q8 + 8, s1);
             if (inner && lean) {  // exactly 8 steps: unrolled in pairs so that the row registers ping-pong instead of being copied
-#pragma unroll 2
+#pragma unroll 1
                 for (int s = q8; s < q8 + 8; ++s) step(s, std::false_type{}, std::true_type{});
             } else {  // the guarded step doubles as the generic one (one copy of it: instruction cache)
 #pragma unroll 1
