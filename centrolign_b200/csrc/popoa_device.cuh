@@ -16,7 +16,8 @@ constexpr int kStrip = 32;              // columns per strip = lanes per warp
 constexpr int kRowBlock = 64;           // rows per traceback tile
 constexpr int kNear = 3;                // predecessors at most this far back are served from the shared-memory ring
 constexpr int kRingRows = 8;            // fill-kernel ring depth (>= 2*kNear+2)
-constexpr int kPanelRows = 2048;        // default panel height of tiled windows (multiple of kRowBlock; CLB_PANEL_ROWS overrides, 0 = off)
+constexpr int kPanelRowsMax = 2048;     // panel height of tiled windows (default; a multiple of kRowBlock); in "auto" mode about
+constexpr int kPanelRowsMin = 512;      // n1/8 between these bounds (host and kernel call panel_rows_for); CLB_PANEL_ROWS, 0 = off
 
 // per-node info word
 constexpr uint32_t kInfoLabelMask = 0xffu;
@@ -70,8 +71,18 @@ struct LaunchArgs {
     int debug_flags;        // bit0: skip the traceback walk (profiling the fill alone; results are then invalid)
     int start_lag;          // rows a strip stays behind its left neighbour when it starts
     int slot_by_smid;       // 1: workspace slot pair chosen by %smid (kernels of several chunks share one workspace)
-    int panel_rows;         // > 0: wide windows with more rows are filled as (panel, strip) tiles; rows p*panel_rows-2..p*panel_rows are persisted
+    int panel_rows;         // panel_rows_for(n1, this): wide windows with more rows are filled as (panel, strip) tiles; rows p*H-2..p*H are persisted
 };
+
+// Panel height of a window with n1 rows; cfg < 0: automatic, 0: no tiling, > 0: fixed.
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline int panel_rows_for(int n1, int cfg) {
+    if (cfg >= 0) return cfg;
+    int h = (n1 / 8 + kRowBlock - 1) / kRowBlock * kRowBlock;
+    return h < kPanelRowsMin ? kPanelRowsMin : (h > kPanelRowsMax ? kPanelRowsMax : h);
+}
 
 // Workspace of one window: rowbuf {M,I_k} + colbuf {M,D_k} + boundary row + boundary column (16 B per
 // entry), then coleff (4 B per persisted-column entry: the column's effective diagonal input per row).

@@ -192,13 +192,16 @@ struct clb_batch {
 };
 
 namespace {
-// panel height of the tiled fill (LaunchArgs::panel_rows): read once; a multiple of 64 rows, 0 switches tiling off
-int panel_rows() {
+// panel configuration of the tiled fill (LaunchArgs::panel_rows, clb::panel_rows_for): read once.  CLB_PANEL_ROWS
+// sets the height (a multiple of 64 rows), 0 switches tiling off, "auto" = about n1/8 per window; unset = 2048 rows
+// (measured on configs[1]: 1024 / 2048 / 4096 / auto within 1.5 % of each other, 2048 best)
+int panel_cfg() {
     static const int v = [] {
         const char* e = getenv("CLB_PANEL_ROWS");
-        int h = e ? atoi(e) : clb::kPanelRows;
-        if (h < 0) h = 0;
-        return h / clb::kRowBlock * clb::kRowBlock;
+        if (!e) return clb::kPanelRowsMax;
+        if (!strcmp(e, "auto")) return -1;
+        const int h = atoi(e);
+        return h <= 0 ? 0 : h / clb::kRowBlock * clb::kRowBlock;
     }();
     return v;
 }
@@ -305,8 +308,8 @@ int flatten_side(const clb_graph_batch& g, int64_t w, int side, SideStage& st, c
         int_ops_deg += fill - first;
     }
     // tiled fill (popoa_kernels.cu): a panel takes rows R0-2 .. R0 over from the panel above through the workspace
-    if (side == 0 && panel_rows() > 0)
-        for (uint32_t r0 = (uint32_t)panel_rows(); r0 < n; r0 += (uint32_t)panel_rows())
+    if (const uint32_t H = side == 0 ? (uint32_t)clb::panel_rows_for((int)n, panel_cfg()) : 0u)
+        for (uint32_t r0 = H; r0 < n; r0 += H)
             for (uint32_t t = 0; t < 3; ++t) info[r0 - t] |= clb::kInfoPersist;
     uint32_t* sinks = st.sinks.h + kb;
     for (uint32_t k = 0; k < nsnk; ++k) {
@@ -624,7 +627,7 @@ static int launch_internal(clb_batch* b) {
         a.debug_flags = getenv("CLB_DEBUG_FLAGS") ? atoi(getenv("CLB_DEBUG_FLAGS")) : 0;
         a.start_lag = getenv("CLB_START_LAG") ? atoi(getenv("CLB_START_LAG")) : 64;
         a.slot_by_smid = b->shared_workspace ? 1 : 0;
-        a.panel_rows = panel_rows();
+        a.panel_rows = panel_cfg();
         CUDA_TRY(clb::launch_popoa(b->params.num_pw, a, b->grid, b->stream));
         b->stats.kernel_launches = 1;
     }

@@ -93,6 +93,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // per-fill-warp shared memory
 // (the start lag between neighbouring strips is a launch parameter, LaunchArgs::start_lag; 64 rows measured best)
+constexpr unsigned kPollNs = 200;  // poll interval of the strip hand-off waits (800 ns measured the same)
 constexpr int kProgMask = 511;  // progress words per CTA (one per strip in flight; a tiled window keeps all its strips live)
 constexpr int kFillRing = 4;    // ring rows: a row is read at most kNear steps after it was written
 struct __align__(16) FillSmem {
@@ -190,7 +191,7 @@ __device__ __forceinline__ void fill_strip(const Win& Wsh, const Params& prm, co
                 const unsigned long long v = progress[(g - 1) & kProgMask];
                 avail = ((int)(v >> 32) == g) ? (int)(v & 0xffffffffu) : 0;
                 if (avail >= want) break;
-                __nanosleep(200);
+                __nanosleep(kPollNs);
             }
             __threadfence_block();
         }
@@ -447,7 +448,7 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
                 const unsigned long long v = progress[(g - 1) & kProgMask];
                 avail = ((int)(v >> 32) == g) ? (int)(v & 0xffffffffu) : 0;
                 if (avail >= want) break;
-                __nanosleep(200);
+                __nanosleep(kPollNs);
             }
             __threadfence_block();
         }
@@ -1183,7 +1184,8 @@ struct CtaState {
 // flight, a tile's left neighbour is usually finished, and nothing waits for a slow strip.
 constexpr int kTileSkew = 11;
 constexpr int kMaxTiledStrips = kProgMask - 64;
-__device__ __forceinline__ bool window_tiled(const Win& W, int nstrips, int panel_rows) {
+__device__ __forceinline__ bool window_tiled(const Win& W, int nstrips, int panel_cfg) {
+    const int panel_rows = panel_rows_for(W.n1, panel_cfg);
     return W.cw == kWideCols && panel_rows > 0 && W.n1 > panel_rows + panel_rows / 4 && nstrips <= kMaxTiledStrips;
 }
 
@@ -1221,7 +1223,7 @@ __global__ void __launch_bounds__(kThreads, 1) popoa_kernel(const LaunchArgs A) 
             const int nstrips = ld_volatile(&S.seq_nstrips[k & 7]);
             const Win& W = S.win[k & 1];
             if (window_tiled(W, nstrips, A.panel_rows)) {
-                const int H = A.panel_rows, T = (W.n1 + H - 1) / H, ntiles = T * nstrips;
+                const int H = panel_rows_for(W.n1, A.panel_rows), T = (W.n1 + H - 1) / H, ntiles = T * nstrips;
                 int d = 0, p = 0, qi = 0;  // enumeration cursor: tile number qi is (p, d - p * kTileSkew)
                 for (;;) {
                     int q = 0;
@@ -1311,7 +1313,10 @@ __global__ void __launch_bounds__(kThreads, 1) popoa_kernel(const LaunchArgs A) 
             const int nstrips = ld_volatile(&S.seq_nstrips[t & 7]);
             const Win& W = S.win[t & 1];
             int nwait = nstrips;
-            if (window_tiled(W, nstrips, A.panel_rows)) nwait *= (W.n1 + A.panel_rows - 1) / A.panel_rows;
+            if (window_tiled(W, nstrips, A.panel_rows)) {
+                const int H = panel_rows_for(W.n1, A.panel_rows);
+                nwait *= (W.n1 + H - 1) / H;
+            }
             while (ld_volatile(&S.strips_done[t & 1]) < nwait) __nanosleep(500);
             __threadfence_block();
             tb_boundary<P>(W, prm, lane);
