@@ -374,8 +374,8 @@ def main():
                     "hbm": {"bound": "hbm", "achieved": hbm_bytes / step_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": hbm_bytes / step_s / 1e9 / hbm_peak, "traffic": None,
                             "bytes_model": "persisted rows/columns written once + flattened graph arrays read once", "peak_source": hbm_src,
-                            "traffic_ncu": "dram read+write 26.4 GB per launch on the 1480-window profile batch (2.39e10 cells) = 1.10 B/cell "
-                                           "vs 0.9 B/cell algorithmic (profiles/r01_ncu_v7.md)"}}
+                            "traffic_ncu": "dram read+write 27.3 GB per launch on the 1480-window profile batch (2.37e10 cells) = 1.15 B/cell "
+                                           "vs 0.9 B/cell algorithmic (profiles/r01_ncu_v9.md)"}}
         # ---- CPU baseline on a bounded sample, parity-checked against the GPU result ----
         cpu = None
         if not args.no_cpu_baseline:
