@@ -1,10 +1,5 @@
-timeout 300 python -m pytest tests/test_popoa_gpu.py -x -q -m gpu 2>&1 | tail -2
-B="timeout 200 python bench.py --windows 8000 --no-cpu-baseline --no-e2e --no-other-paths"
-S="timeout 200 python bench.py --windows 1480 --len-min 3000 --len-max 4000 --no-cpu-baseline --no-e2e --no-other-paths"
-f(){ tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d[\"value\"],1))"; }
-echo -n "main auto/800: "; $B 2>&1 | f
-echo -n "auto/200: "; CLB_LIBRARY=$PWD/centrolign_b200/csrc/libclb_p200.so $B 2>&1 | f
-echo -n "fixed2048/800: "; CLB_PANEL_ROWS=2048 $B 2>&1 | f
-echo -n "small: main auto/800: "; $S 2>&1 | f
-echo -n "small: fixed2048/800: "; CLB_PANEL_ROWS=2048 $S 2>&1 | f
-echo -n "small: auto/200: "; CLB_LIBRARY=$PWD/centrolign_b200/csrc/libclb_p200.so $S 2>&1 | f
+export CLB_PANEL_ROWS=256
+timeout 280 compute-sanitizer --tool initcheck --print-limit 100000 python tools/scratch/san.py > /tmp/init.txt 2>&1
+echo "device-side uninitialized reads: $(grep -c 'Uninitialized __global__ memory read' /tmp/init.txt)"; echo "host-side (cudaMemcpy source) reports: $(grep -c 'Host API memory access error' /tmp/init.txt)"; grep "parity\|ERROR SUMMARY" /tmp/init.txt
+grep -A3 'Uninitialized __global__ memory read' /tmp/init.txt | grep " at \|Device Frame" | sort | uniq -c | sort -rn | head -8
+timeout 200 compute-sanitizer --tool racecheck --print-limit 100 python tools/scratch/san.py 2>&1 | grep "Race reported\|and Read\|and Write\|RACECHECK SUMMARY" | sed 's/void clb:://; s/(const clb::Win.*int)//' | cut -c1-200 | sort | uniq -c | sort -rn | head -30
