@@ -201,7 +201,7 @@ int panel_cfg() {
         if (!e) return clb::kPanelRowsMax;
         if (!strcmp(e, "auto")) return -1;
         const int h = atoi(e);
-        return h <= 0 ? 0 : h / clb::kRowBlock * clb::kRowBlock;
+        return h <= 0 ? 0 : std::max(128, h / clb::kRowBlock * clb::kRowBlock);  // tiny panels only add hand-overs
     }();
     return v;
 }
