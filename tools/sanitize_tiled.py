@@ -1,5 +1,5 @@
 import sys
-sys.path.insert(0, "."); sys.path.insert(0, "tests")
+sys.path.insert(0, "."); sys.path.insert(0, "tests")  # run from the repo root: compute-sanitizer --tool memcheck python tools/sanitize_tiled.py
 import numpy as np
 from centrolign_b200.batch import *
 from centrolign_b200.popoa import po_poa_batch
