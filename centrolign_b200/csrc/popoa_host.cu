@@ -211,29 +211,10 @@ struct FlattenScratch {
     std::vector<uint8_t> is_src;
 };
 
-// Flatten one side of one window.  Returns CLB_OK / CLB_EINVAL / CLB_ECYCLE.
-int flatten_side(const clb_graph_batch& g, int64_t w, int side, SideStage& st, clb::WindowMeta& m, FlattenScratch& sc,
-                 int64_t& int_ops_deg /* sum of in-degrees incl. boundary edges */) {
-    const int64_t n0 = g.node_off[w];
-    const uint32_t n = (uint32_t)(g.node_off[w + 1] - n0);
-    const uint32_t* po = g.pred_off + n0 + w;
-    const uint32_t* pr = g.pred + g.edge_off[w];
-    const uint32_t E = (uint32_t)(g.edge_off[w + 1] - g.edge_off[w]);
-    const uint32_t nsrc = (uint32_t)(g.src_off[w + 1] - g.src_off[w]);
-    const uint32_t nsnk = (uint32_t)(g.snk_off[w + 1] - g.snk_off[w]);
-    const uint32_t* src = g.src + g.src_off[w];
-    const uint32_t* snk = g.snk + g.snk_off[w];
-    if (po[0] != 0 || po[n] != E) return CLB_EINVAL;
-    for (uint32_t v = 0; v < n; ++v)
-        if (po[v + 1] < po[v]) return CLB_EINVAL;
-    for (uint32_t k = 0; k < E; ++k)
-        if (pr[k] >= n) return CLB_EINVAL;
-    for (uint32_t k = 0; k < nsrc; ++k)
-        if (src[k] >= n) return CLB_EINVAL;
-    for (uint32_t k = 0; k < nsnk; ++k)
-        if (snk[k] >= n) return CLB_EINVAL;
-
-    // successor lists + Kahn order with a LIFO stack (keeps chains contiguous)
+// Topological numbering of one graph: successor lists + Kahn's algorithm with a stack (keeps chains contiguous).
+// Fills sc.tpos[v] = 1-based rank, orig[rank] = v (and leaves the successor lists in sc); returns the number of
+// nodes ranked (< n: the graph has a cycle).
+uint32_t topological_ranks(uint32_t n, const uint32_t* po, const uint32_t* pr, uint32_t E, FlattenScratch& sc, uint32_t* orig) {
     sc.succ_off.assign(n + 2, 0);
     sc.succ.resize(E + 1);
     sc.indeg.resize(n + 1);
@@ -245,16 +226,6 @@ int flatten_side(const clb_graph_batch& g, int64_t w, int side, SideStage& st, c
     for (uint32_t v = 0; v < n; ++v)
         for (uint32_t k = po[v]; k < po[v + 1]; ++k) sc.succ[sc.succ_off[pr[k] + 1]++] = v;
     // succ_off[v] .. succ_off[v+1] now delimit v's successors
-    const int64_t nb = (side == 0 ? m.node1 : m.node2);
-    const int64_t pb = (side == 0 ? m.poff1 : m.poff2);
-    const int64_t xb = (side == 0 ? m.pidx1 : m.pidx2);
-    const int64_t kb = (side == 0 ? m.snk1 : m.snk2);
-    uint32_t* info = st.info.h + nb;
-    int32_t* slot = st.slot.h + nb;
-    uint32_t* depth = st.depth.h + nb;
-    uint32_t* poff = st.poff.h + pb;
-    uint32_t* pidx = st.pidx.h + xb;
-    uint32_t* orig = st.orig.data() + nb;
     for (uint32_t v = 0; v < n; ++v) {
         sc.indeg[v] = po[v + 1] - po[v];
         if (sc.indeg[v] == 0) sc.stack.push_back(v);
@@ -281,6 +252,42 @@ int flatten_side(const clb_graph_batch& g, int64_t w, int side, SideStage& st, c
             if (--sc.indeg[sc.succ[k]] == 0) sc.stack.push_back(sc.succ[k]);
         if (sc.stack.size() - base > 1) std::stable_sort(sc.stack.begin() + (ptrdiff_t)base, sc.stack.end(), goes_later);
     }
+    return cnt;
+}
+
+// Flatten one side of one window.  Returns CLB_OK / CLB_EINVAL / CLB_ECYCLE.
+int flatten_side(const clb_graph_batch& g, int64_t w, int side, SideStage& st, clb::WindowMeta& m, FlattenScratch& sc,
+                 int64_t& int_ops_deg /* sum of in-degrees incl. boundary edges */) {
+    const int64_t n0 = g.node_off[w];
+    const uint32_t n = (uint32_t)(g.node_off[w + 1] - n0);
+    const uint32_t* po = g.pred_off + n0 + w;
+    const uint32_t* pr = g.pred + g.edge_off[w];
+    const uint32_t E = (uint32_t)(g.edge_off[w + 1] - g.edge_off[w]);
+    const uint32_t nsrc = (uint32_t)(g.src_off[w + 1] - g.src_off[w]);
+    const uint32_t nsnk = (uint32_t)(g.snk_off[w + 1] - g.snk_off[w]);
+    const uint32_t* src = g.src + g.src_off[w];
+    const uint32_t* snk = g.snk + g.snk_off[w];
+    if (po[0] != 0 || po[n] != E) return CLB_EINVAL;
+    for (uint32_t v = 0; v < n; ++v)
+        if (po[v + 1] < po[v]) return CLB_EINVAL;
+    for (uint32_t k = 0; k < E; ++k)
+        if (pr[k] >= n) return CLB_EINVAL;
+    for (uint32_t k = 0; k < nsrc; ++k)
+        if (src[k] >= n) return CLB_EINVAL;
+    for (uint32_t k = 0; k < nsnk; ++k)
+        if (snk[k] >= n) return CLB_EINVAL;
+
+    const int64_t nb = (side == 0 ? m.node1 : m.node2);
+    const int64_t pb = (side == 0 ? m.poff1 : m.poff2);
+    const int64_t xb = (side == 0 ? m.pidx1 : m.pidx2);
+    const int64_t kb = (side == 0 ? m.snk1 : m.snk2);
+    uint32_t* info = st.info.h + nb;
+    int32_t* slot = st.slot.h + nb;
+    uint32_t* depth = st.depth.h + nb;
+    uint32_t* poff = st.poff.h + pb;
+    uint32_t* pidx = st.pidx.h + xb;
+    uint32_t* orig = st.orig.data() + nb;
+    const uint32_t cnt = topological_ranks(n, po, pr, E, sc, orig);
     if (cnt != n) return CLB_ECYCLE;
     for (uint32_t k = 0; k < nsrc; ++k) sc.is_src[src[k]] = 1;
 
@@ -826,6 +833,22 @@ int clb_popoa_batch(int device, int32_t n_windows, const clb_graph_batch* g1, co
                 chunks.size(), t_create, t_upload, t2 - t0, t3 - t2, t_down, kernel_ms, now() - t0);
     (void)t1; (void)t4;
     return rc;
+}
+
+// Host-only diagnostic: the matrix index (1-based topological rank) flatten_side gives every node of one graph.
+int clb_topological_ranks(uint32_t n_nodes, const uint32_t* pred_off, const uint32_t* pred, uint32_t* rank_out) {
+    if (!pred_off || !rank_out || (n_nodes && pred_off[0] != 0)) return fail(CLB_EINVAL, "clb_topological_ranks: bad arguments");
+    const uint32_t E = n_nodes ? pred_off[n_nodes] : 0;
+    if (E && !pred) return fail(CLB_EINVAL, "clb_topological_ranks: bad arguments");
+    for (uint32_t v = 0; v < n_nodes; ++v)
+        if (pred_off[v + 1] < pred_off[v]) return fail(CLB_EINVAL, "clb_topological_ranks: predecessor offsets not monotone");
+    for (uint32_t k = 0; k < E; ++k)
+        if (pred[k] >= n_nodes) return fail(CLB_EINVAL, "clb_topological_ranks: predecessor id out of range");
+    FlattenScratch sc;
+    std::vector<uint32_t> orig((size_t)n_nodes + 1);
+    if (topological_ranks(n_nodes, pred_off, pred, E, sc, orig.data()) != n_nodes) return fail(CLB_ECYCLE, "clb_topological_ranks: the graph has a cycle");
+    for (uint32_t v = 0; v < n_nodes; ++v) rank_out[v] = sc.tpos[v];
+    return CLB_OK;
 }
 
 void clb_release_cached_memory(void) {

@@ -21,7 +21,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "li
 
 EXPORTS = ["clb_popoa_batch", "clb_batch_create", "clb_batch_upload", "clb_batch_run", "clb_batch_download",
            "clb_batch_destroy", "clb_batch_get_stats", "clb_int32_peak_tops", "clb_last_error", "clb_device_count",
-           "clb_release_cached_memory", "clb_pwfa_batch", "clb_chain_dp"]
+           "clb_release_cached_memory", "clb_pwfa_batch", "clb_chain_dp", "clb_topological_ranks"]
 ERROR_NAMES = {0: "CLB_OK", 1: "CLB_EINVAL", 2: "CLB_ECYCLE", 3: "CLB_ECUDA", 4: "CLB_ENOMEM", 5: "CLB_ESTATE"}
 
 
@@ -82,6 +82,8 @@ def load_library() -> ctypes.CDLL:
     lib.clb_batch_destroy.argtypes = [vp]
     lib.clb_batch_get_stats.restype = ctypes.c_int
     lib.clb_batch_get_stats.argtypes = [vp, ctypes.POINTER(BatchStats)]
+    lib.clb_topological_ranks.restype = ctypes.c_int
+    lib.clb_topological_ranks.argtypes = [ctypes.c_uint32, vp, vp, vp]
     lib.clb_int32_peak_tops.restype = ctypes.c_double
     lib.clb_int32_peak_tops.argtypes = [ctypes.c_int, ctypes.c_int]
     lib.clb_last_error.restype = ctypes.c_char_p
@@ -228,3 +230,21 @@ def pwfa_po_poa_batch(succ_batch: WindowBatch, params: AlignmentParameters, prun
                               ctypes.byref(stats) if stats is not None else None))
     del k1, k2
     return score, [pairs[int(aln_off[w]): int(aln_off[w]) + int(aln_len[w])] for w in range(nw)]
+
+
+def topological_ranks(pred_lists) -> "np.ndarray":
+    """Matrix index (1-based topological rank) the library's flattening code gives every node of a graph whose
+    predecessor lists are ``pred_lists`` (host only, no device needed; ``clb_topological_ranks``)."""
+    lib = load_library()
+    n = len(pred_lists)
+    off = np.zeros(n + 1, dtype=np.uint32)
+    off[1:] = np.cumsum([len(p) for p in pred_lists])
+    pred = np.asarray([q for p in pred_lists for q in p], dtype=np.uint32)
+    if pred.size == 0:
+        pred = np.zeros(1, dtype=np.uint32)
+    out = np.zeros(max(n, 1), dtype=np.uint32)
+    rc = lib.clb_topological_ranks(n, off.ctypes.data, pred.ctypes.data, out.ctypes.data)
+    if rc != 0:
+        lib.clb_last_error.restype = ctypes.c_char_p
+        raise ClbError(rc, (lib.clb_last_error() or b"").decode())
+    return out[:n]

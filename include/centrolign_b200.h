@@ -234,6 +234,14 @@ int clb_chain_dp(int device, const clb_chain_problem* problem, float* dp_out, in
  * returns achieved 10^12 INT32 lane-ops per second on `device`, <0 on error. */
 double clb_int32_peak_tops(int device, int use_dpx);
 
+/* Host-only diagnostic (no device needed): the 1-based matrix index -- topological rank -- the flattening code gives
+ * every node of one graph in predecessor-list form (the order replaces `topological_order`,
+ * include/centrolign/topological_order.hpp:11-60; DP values do not depend on which topological order is used,
+ * include/centrolign/alignment.hpp:806-807, but predecessor distances do -- DESIGN.md section 4).
+ * Returns CLB_OK, CLB_EINVAL or CLB_ECYCLE. */
+int clb_topological_ranks(uint32_t n_nodes, const uint32_t* pred_off /* [n_nodes+1] */, const uint32_t* pred,
+                          uint32_t* rank_out /* [n_nodes] */);
+
 /* Staging buffers (pinned host, device) are cached across calls; this frees the cache. */
 void clb_release_cached_memory(void);
 

@@ -53,3 +53,51 @@ def test_missing_library_fails_loudly(monkeypatch):
     g = graph_from_edges("A", [], [0], [0])
     with pytest.raises(popoa.ClbError):
         popoa.po_poa_batch(batch_from_graph_pairs([(g, g)]), AlignmentParameters())
+
+
+def _pred_lists(n, edges):
+    preds = [[] for _ in range(n)]
+    for a, b in edges:
+        preds[b].append(a)
+    return preds
+
+
+def test_topological_numbering_is_valid_and_keeps_bubbles_near():
+    """Host logic of the gap-fill path that needs no GPU: the numbering the flattening code gives the nodes
+    (clb_topological_ranks) is a topological order of any DAG, rejects cycles, and keeps both alleles of adjacent
+    SNP bubbles within distance 2 of their predecessors (a plain LIFO order leaves distance 3,
+    which sends the strip through the generic step of the fill kernel)."""
+    import numpy as np
+    from centrolign_b200.batch import random_bubble_chain, random_dag
+    _lib_or_skip()
+    rng = np.random.default_rng(3)
+    for t in range(60):
+        n = int(rng.integers(1, 60))
+        _, edges = random_dag(rng, n, int(rng.integers(0, 3 * n)))
+        ranks = popoa.topological_ranks(_pred_lists(n, edges))
+        assert sorted(ranks.tolist()) == list(range(1, n + 1))
+        assert all(ranks[a] < ranks[b] for a, b in edges)
+    for t in range(20):  # SNP bubbles at random, many of them adjacent: still a topological order
+        labels, edges = random_bubble_chain(rng, int(rng.integers(50, 400)), snp_rate=0.3, del_rate=0.0)
+        ranks = popoa.topological_ranks(_pred_lists(len(labels), edges)).astype(np.int64)
+        assert all(ranks[a] < ranks[b] for a, b in edges)
+    # isolated PAIRS of adjacent SNP bubbles (three in a row cannot all stay within distance 2 in any order)
+    length = 200
+    edges = [(i - 1, i) for i in range(1, length)]
+    n = length
+    for p in range(5, length - 5, 10):
+        for q in (p, p + 1):
+            edges += [(q - 1, n), (n, q + 1)]
+            n += 1
+    for seed in range(5):
+        e = list(edges)
+        np.random.default_rng(seed).shuffle(e)  # the edge order decides the successor order the stack sees
+        ranks = popoa.topological_ranks(_pred_lists(n, e)).astype(np.int64)
+        assert all(ranks[a] < ranks[b] for a, b in e)
+        assert max(ranks[b] - ranks[a] for a, b in e) <= 2, seed
+    with pytest.raises(popoa.ClbError) as ei:
+        popoa.topological_ranks([[1], [0]])
+    assert ei.value.code == 2
+    with pytest.raises(popoa.ClbError) as ei:
+        popoa.topological_ranks([[5]])
+    assert ei.value.code == 1
