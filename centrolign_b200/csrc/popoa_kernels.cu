@@ -18,6 +18,9 @@
 // a strip, published through the window workspace with a fence + progress word in shared memory and
 // prefetched by the consumer with cp.async.  DPX instructions (__viaddmax_s32, __vimax3_s32) carry
 // the three-piece affine recurrences.  No tensor cores: this is integer max-plus, not a GEMM.
+// Wide windows with many rows are filled as (row panel, strip) tiles from a per-window queue, so that a
+// slow strip does not hold back the strips behind it (see "Tiled windows" below), and strips without rare
+// predecessor columns run a lean copy of the step (fill_strip_wide).
 //
 // Traceback does not store the matrix.  The fill keeps only "persisted" rows {M,I_k} and
 // columns {M,D_k}: every 64th row / 32nd column plus any row / column that has a far successor.
