@@ -84,10 +84,19 @@ inline int panel_rows_for(int n1, int cfg) {
     return h < kPanelRowsMin ? kPanelRowsMin : (h > kPanelRowsMax ? kPanelRowsMax : h);
 }
 
-// Workspace of one window: rowbuf {M,I_k} + colbuf {M,D_k} + boundary row + boundary column (16 B per
+// Workspace of one window: rowbuf {M,H_k} + colbuf {M,D_k} + boundary row + boundary column (16 B per
 // entry), then coleff (4 B per persisted-column entry: the column's effective diagonal input per row).
+// A persisted ROW holds, per column, M and what the cell offers the rows below it: H_k = max(I_k - e_k, M - oe_k)
+// (the wide fill stores it with one 16-byte store per column; everything the traceback needs from a row outside
+// the recomputed tile follows from it, see popoa_kernels.cu "Traceback").  Rows are padded by kRowPad entries so that
+// a lane of the wide fill may store all of its four columns when the last ones lie beyond n2.
+constexpr uint32_t kRowPad = 3;
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline uint32_t row_stride(uint32_t n2) { return n2 + 1u + kRowPad; }
 inline int64_t workspace_int4(uint32_t n1, uint32_t n2, uint32_t nrslot, uint32_t ncslot) {
-    return (int64_t)nrslot * (n2 + 1) + (int64_t)ncslot * (n1 + 1) + (n2 + 1) + (n1 + 1);
+    return (int64_t)nrslot * row_stride(n2) + (int64_t)ncslot * (n1 + 1) + (n2 + 1) + (n1 + 1);
 }
 inline int64_t workspace_bytes(uint32_t n1, uint32_t n2, uint32_t nrslot, uint32_t ncslot) {
     return 16 * workspace_int4(n1, n2, nrslot, ncslot) + ((4 * (int64_t)ncslot * (n1 + 1) + 15) & ~int64_t(15));

@@ -426,7 +426,7 @@ static int create_internal(int device, int32_t n_windows, const clb_graph_batch*
         }
         if (N < 0 || E < 0 || S < 0 || K < 0) rc = CLB_EINVAL;
         SideStage& st = b->s[sd];
-        rc |= st.info.alloc_host(N + nw + 1) | st.slot.alloc_host(N + nw) | st.depth.alloc_host(N + nw) |  // info: +1 pad, read one past
+        rc |= st.info.alloc_host(N + nw + 2) | st.slot.alloc_host(N + nw) | st.depth.alloc_host(N + nw) |  // info: +2 pad, the fill reads up to two entries past a window
               st.poff.alloc_host(N + 2 * nw) | st.pidx.alloc_host(E + S) | st.sinks.alloc_host(K);
         st.orig.resize(N + nw);
     }

@@ -37,7 +37,10 @@
 
 namespace clb {
 
-constexpr int kWarps = 12;
+#ifndef CLB_WARPS
+#define CLB_WARPS 12
+#endif
+constexpr int kWarps = CLB_WARPS;  // fill warps + 1 traceback warp per CTA (one CTA per SM)
 constexpr int kThreads = kWarps * 32;
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -65,6 +68,17 @@ __device__ __forceinline__ void max4(int& m, int (&v)[3], const int4 a) {
     v[0] = imax(v[0], a.y);
     v[1] = imax(v[1], a.z);
     v[2] = imax(v[2], a.w);
+}
+
+// What a cell with gap state s (I_k or D_k) and value m offers its successors in piece k: max(s - e_k, m - oe_k).
+__device__ __forceinline__ int offer(const Params& prm, int s, int m, int k) { return __viaddmax_s32(s, -prm.e[k], m - prm.oe[k]); }
+template <int P>
+__device__ __forceinline__ int4 to_offered(const Params& prm, const int4 v) {  // {M, I_k} -> {M, H_k} (or {M, D_k} -> {M, G_k})
+    int4 o = make_int4(v.x, kMinInf, kMinInf, kMinInf);
+    o.y = offer(prm, v.y, v.x, 0);
+    if (P > 1) o.z = offer(prm, v.z, v.x, 1);
+    if (P > 2) o.w = offer(prm, v.w, v.x, 2);
+    return o;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -137,7 +151,7 @@ __device__ __forceinline__ void fill_strip(const Win& Wsh, const Params& prm, co
     int4* const rowbuf = Wsh.rowbuf;
     int4* const colbuf = Wsh.colbuf;
     int* const coleff = Wsh.coleff;
-    const uint32_t rstride = (uint32_t)n2 + 1u, cstride = (uint32_t)n1 + 1u;  // host guarantees 32-bit offsets
+    const uint32_t rstride = row_stride((uint32_t)n2), cstride = (uint32_t)n1 + 1u;  // host guarantees 32-bit offsets
 
     const int j = C0 + lane;
     const bool jvalid = j <= n2;
@@ -156,7 +170,7 @@ __device__ __forceinline__ void fill_strip(const Win& Wsh, const Params& prm, co
     int upM = kMinInf, upI[3] = {kMinInf, kMinInf, kMinInf};
     if (jvalid) {
         upM = boundary_cell<P>(Wsh.depth2[j], prm).x;  // M(0,j); I_k(0,j) = -inf
-        rowbuf[j] = make_int4(upM, kMinInf, kMinInf, kMinInf);
+        rowbuf[j] = to_offered<P>(prm, make_int4(upM, kMinInf, kMinInf, kMinInf));  // persisted rows hold {M, H_k}
     }
     if (cs == 0) {  // boundary column as a predecessor column: {M(i,0), -inf} and its diagonal input
         for (int i = lane; i <= n1; i += 32) {
@@ -241,6 +255,7 @@ __device__ __forceinline__ void fill_strip(const Win& Wsh, const Params& prm, co
             const int rs = (r & (H - 1)) * 32;
             // ---- effective predecessor row ----
             int eM = upM, eI[3] = {upI[0], upI[1], upI[2]};
+            int fH[3] = {kMinInf, kMinInf, kMinInf};  // offered by far predecessor rows (the workspace holds {M, H_k})
             if (!(rinfo & kInfoRegular)) {
                 if (!(rinfo & (1u << kInfoNearShift))) { eM = kMinInf; eI[0] = eI[1] = eI[2] = kMinInf; }
                 if (rinfo & (2u << kInfoNearShift)) max4(eM, eI, myA[rs ^ 64]);  // row r-2
@@ -251,7 +266,7 @@ __device__ __forceinline__ void fill_strip(const Win& Wsh, const Params& prm, co
                         for (uint32_t a = poff1[r]; a < rp1; ++a) {
                             const int p = (int)pidx1[a];
                             if (p >= 1 && r - p <= kNear) continue;
-                            max4(eM, eI, rowbuf[(uint32_t)slot1[p] * rstride + (uint32_t)j]);
+                            max4(eM, fH, rowbuf[(uint32_t)slot1[p] * rstride + (uint32_t)j]);
                         }
                     }
                 }
@@ -300,7 +315,7 @@ __device__ __forceinline__ void fill_strip(const Win& Wsh, const Params& prm, co
             int M = __viaddmax_s32(lEff, sub, kMinInf);
 #pragma unroll
             for (int k = 0; k < P; ++k) {
-                I[k] = __viaddmax_s32(eI[k], -prm.e[k], eM - prm.oe[k]);
+                I[k] = imax(__viaddmax_s32(eI[k], -prm.e[k], eM - prm.oe[k]), fH[k]);
                 D[k] = __viaddmax_s32(lD[k], -prm.e[k], lM - prm.oe[k]);
                 M = __vimax3_s32(M, I[k], D[k]);
             }
@@ -310,7 +325,7 @@ __device__ __forceinline__ void fill_strip(const Win& Wsh, const Params& prm, co
             if (rinfo & persist_mask) {
                 uint32_t slot = rinfo >> kInfoSlotShift;
                 if (slot == kInfoSlotEscape) slot = (uint32_t)slot1[r];
-                rowbuf[slot * rstride + (uint32_t)j] = cellA;
+                rowbuf[slot * rstride + (uint32_t)j] = to_offered<P>(prm, cellA);
             }
             if (hascol) {
                 colbuf[myoff + (uint32_t)r] = make_int4(M, D[0], D[1], D[2]);
@@ -359,31 +374,38 @@ __device__ __forceinline__ void fill_strip(const Win& Wsh, const Params& prm, co
 }
 
 // ------------------------------------------------------------------------------------------
-// DP fill, wide variant: strips of 128 columns, FOUR consecutive columns per lane.
-// The per-step overhead (shuffles, row info, loop, waits) is shared by 128 cells instead of 32,
-// a column's near predecessors inside the lane are plain registers, and the ones that fall into
-// the previous lane come over warp shuffles (lane-1 finished the same row one step earlier), so
-// no shared-memory traffic is needed for columns at all; rows still use a small ring.
+// DP fill, wide variant: strips of 128 columns, FOUR consecutive columns per lane, PUSH form.
+//
+// What a cell keeps for its successors is not {M, I_k, D_k} but what it OFFERS them:
+//     T_k = M - oe_k,   H_k = max(I_k - e_k, T_k)  (to the rows below),   G_k = max(D_k - e_k, T_k)  (to the columns right)
+// so that I_k(i,j) = max over predecessor rows of H_k and D_k(i,j) = max over predecessor columns of G_k: for the common
+// single-predecessor cell the gap states cost nothing, the three subtractions are shared by both directions, and all
+// seven values of the recurrence are still exactly the reference's (integer max/add; alignment.hpp:898-938 is itself a
+// push loop).  Per lane the row above lives in registers {M, H_k} x 4 columns and is updated IN PLACE; the values a
+// column offers to its right neighbours stay in registers inside the lane and cross lanes by shfl.up (lane-1 finished the
+// same row one step earlier).  Which neighbour columns feed a column (distance 1 / 2: SNP-sized bubbles) is lane-constant,
+// so it is not branched or predicated on but multiplied in: v*m + b with (m,b) = (1,0) or (0,-inf) -- IMADs, which run on
+// the FMA pipe next to the DPX instructions on the ALU pipe (measured: profiles/r02_pipe_rates.txt; each pipe issues 2
+// warp instructions per clock and SM, 3 together).  Rows with other predecessors than the row above fold the ring rows
+// into the registers under one divergent branch; persisted rows store {I_k} before and {M} after the cell update.
 // ------------------------------------------------------------------------------------------
 constexpr int kWideCols = 4;
 struct __align__(16) FillSmemWide {
-    int4 ringA[kFillRing * kWideCols * 32];  // [row & 3][c][lane]: {M, I_k} of the last rows, own columns
-    int4 leftv[3][2][16];                    // prefetched {M, D_k} of the 3 columns left of the strip, 16-row blocks
-    int lefte[3][2][16];
-};
-
-struct ColState {  // what a column offers to the columns right of it, for the current row
-    int M, D[3], E;  // E = diagonal input = max over predecessor rows of M
+    int4 ringA[kFillRing * kWideCols * 32];  // [row & 3][c][lane]: {M, H_k} of the last rows, own columns
+    int4 leftv[3][2][16];                    // the 3 columns left of the strip, 16-row blocks: lands as {M, D_k}, converted to {G_k, E}
+    int lefte[3][2][16];                     // landing zone of their diagonal input E
 };
 
 template <int P>
 __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& prm, const int cs, const int g,
-                                                FillSmemWide& sm, volatile unsigned long long* progress, const int lane,
+                                                FillSmemWide& sm, volatile unsigned long long* progress, const int lane_in,
                                                 const int start_lag, const int R0, const int R1, const int dbg) {
     // Rows R0+1 .. R1 of the strip (a panel; R0 = 0, R1 = n1 is the whole strip).  A panel that does not start at
     // the top takes over from whoever filled the panel above through the window workspace: rows R0-2 .. R0 are
     // persisted (host: popoa_host.cu) and the strip's own progress word says when they are there.
     constexpr int H = kFillRing, C = kWideCols, W = 32 * C, PB = 16;  // PB = rows per left-column prefetch block
+    int lane = lane_in;
+    asm volatile("mov.u32 %0, %0;" : "+r"(lane));  // a register, not a re-read of %tid in the row loop
     const int C0 = 1 + W * cs;
     const int n1 = Wsh.n1, n2 = Wsh.n2;
     const uint32_t* __restrict__ info1 = Wsh.info1;
@@ -393,24 +415,31 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
     int4* const rowbuf = Wsh.rowbuf;
     int4* const colbuf = Wsh.colbuf;
     int* const coleff = Wsh.coleff;
-    const uint32_t rstride = (uint32_t)n2 + 1u, cstride = (uint32_t)n1 + 1u;
+    const uint32_t rstride = row_stride((uint32_t)n2), cstride = (uint32_t)n1 + 1u;
     const int j0 = C0 + C * lane;
 
     // ---- per-column constants ----
-    uint32_t cinfo[C], coff[C];
-    int upM[C], upI[C][3];
+    uint32_t cbits = 0;   // per column c, bits 8c..8c+4: near1|regular, near2, near3, far, persisted
+    int cl[C];
+    int4 St[C];           // the row above: {M, H_k}, one aligned register quad per column (LDS.128 / STS.128 without moves)
     uint32_t nvalid = 0;  // number of this lane's columns that exist
+    uint32_t coff3 = 0xffffffffu;  // workspace offset of the lane's last column if it is persisted (the regular persisted columns are)
 #pragma unroll
     for (int c = 0; c < C; ++c) {
         const int j = j0 + c;
         const bool jv = j <= n2;
         nvalid += jv ? 1u : 0u;
-        cinfo[c] = jv ? Wsh.info2[j] : (kInfoRegular | (1u << kInfoNearShift) | 0xffu);
-        coff[c] = (jv && (cinfo[c] & kInfoPersist)) ? (uint32_t)slot2[j] * cstride : 0xffffffffu;
-        upM[c] = kMinInf; upI[c][0] = upI[c][1] = upI[c][2] = kMinInf;
+        const uint32_t ci = jv ? Wsh.info2[j] : (kInfoRegular | (1u << kInfoNearShift) | 0xffu);
+        cl[c] = (int)(ci & kInfoLabelMask);
+        // a regular column always takes its distance-1 neighbour (column 1's is the boundary column)
+        const bool c1 = (ci & ((1u << kInfoNearShift) | kInfoRegular)) != 0, c2 = (ci & (2u << kInfoNearShift)) != 0;
+        const bool pers = jv && (ci & kInfoPersist);
+        cbits |= ((c1 ? 1u : 0u) | (c2 ? 2u : 0u) | ((ci & (4u << kInfoNearShift)) ? 4u : 0u) | ((ci & kInfoFar) ? 8u : 0u) | (pers ? 16u : 0u)) << (8 * c);
+        if (c == C - 1 && pers) coff3 = (uint32_t)slot2[j] * cstride;
+        St[c] = make_int4(kMinInf, kMinInf, kMinInf, kMinInf);
         if (jv && R0 == 0) {  // boundary row (alignment.hpp:814-894): M(0,j), I_k(0,j) = -inf
-            upM[c] = boundary_cell<P>(Wsh.depth2[j], prm).x;
-            rowbuf[j] = make_int4(upM[c], kMinInf, kMinInf, kMinInf);
+            St[c] = to_offered<P>(prm, make_int4(boundary_cell<P>(Wsh.depth2[j], prm).x, kMinInf, kMinInf, kMinInf));
+            rowbuf[j] = St[c];
         }
     }
     if (cs == 0 && R0 == 0) {  // boundary column as a predecessor column, and its diagonal input
@@ -435,7 +464,7 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
     for (int c = 0; c < C; ++c)
 #pragma unroll
         for (int d = 1; d <= 3; ++d)
-            if (d > c && ((cinfo[c] >> (kInfoNearShift + d - 1)) & 1u)) nb |= 1u << (d - c - 1);
+            if (d > c && ((cbits >> (8 * c + d - 1)) & 1u)) nb |= 1u << (d - c - 1);
     const unsigned needS = __reduce_or_sync(kFull, nb);           // shuffles needed by any lane
     const unsigned needL = __shfl_sync(kFull, nb, 0);             // left columns needed by lane 0
     uint32_t xoffw[3] = {0, 0, 0};
@@ -468,6 +497,17 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
         }
         cp_async_commit();
     };
+    auto convert_block = [&](int b) {  // landed {M, D_k} + E -> {G_k, E}, in place (one lane per row)
+        if (lane < PB) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+                if (needL & (1u << d)) {
+                    const int4 p = to_offered<P>(prm, sm.leftv[d][b & 1][lane]);
+                    sm.leftv[d][b & 1][lane] = make_int4(p.y, p.z, p.w, sm.lefte[d][b & 1][lane]);
+                }
+        }
+        __syncwarp();
+    };
     // never wait for rows below the panel: the tile that fills them may be queued behind this one
     wait_rows(min(R0 + max(start_lag, PB), R1));
     if (R0 > 0) {  // the panel above must be complete before anything of this one is read (strip 0 has no other wait)
@@ -479,7 +519,7 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
         __threadfence_block();
     }
     prefetch_block(R0 / PB);
-    if (R0 > 0) {  // take over rows R0-2 .. R0 from the panel above
+    if (R0 > 0) {  // take over rows R0-2 .. R0 from the panel above (the workspace holds {M, H_k})
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
             const int row = R0 - t;
@@ -490,35 +530,21 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
                 if (c < (int)nvalid) {
                     const int4 v = rowbuf[o + c];
                     sts_128(sa + c * (32 * 16), v);
-                    if (t == 0) { upM[c] = v.x; upI[c][0] = v.y; upI[c][1] = v.z; upI[c][2] = v.w; }
+                    if (t == 0) St[c] = v;
                 }
         }
     }
     cp_async_wait_all();
     __syncwarp();
+    convert_block(R0 / PB);
 
-    ColState out[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) { out[c].M = kMinInf; out[c].D[0] = out[c].D[1] = out[c].D[2] = kMinInf; out[c].E = kMinInf; }
-    uint32_t rinfo_next = (lane == 0) ? info1[R0 + 1] : 0u;
+    // offered by this lane's columns 3, 2, 1 for the row just computed: {G_k} and the diagonal input E
+    int O3g[3] = {kMinInf, kMinInf, kMinInf}, O2g[3] = {kMinInf, kMinInf, kMinInf}, O1g[3] = {kMinInf, kMinInf, kMinInf};
+    int O3e = kMinInf, O2e = kMinInf, O1e = kMinInf;
     // explicit 32-bit shared-window addresses: keeps ptxas from re-deriving them every step
     uint32_t saA = (uint32_t)__cvta_generic_to_shared(sm.ringA) + (uint32_t)lane * 16u;
-    uint32_t saLv = (uint32_t)__cvta_generic_to_shared(&sm.leftv[0][0][0]);
-    uint32_t saLe = (uint32_t)__cvta_generic_to_shared(&sm.lefte[0][0][0]);
-    // opaque copies: stops ptxas from re-deriving the addresses (S2R + LEA + IMAD) inside the row loop
+    const uint32_t saLv = (uint32_t)__cvta_generic_to_shared(&sm.leftv[0][0][0]);
     asm volatile("mov.u32 %0, %0;" : "+r"(saA));
-    asm volatile("mov.u32 %0, %0;" : "+r"(saLv));
-    asm volatile("mov.u32 %0, %0;" : "+r"(saLe));
-    // per-column constant predicates
-    bool cb1[C], cb2[C], crare[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-        cb1[c] = (cinfo[c] & ((1u << kInfoNearShift) | kInfoRegular)) != 0 &&
-                 ((cinfo[c] & (1u << kInfoNearShift)) != 0 || (cinfo[c] & kInfoRegular) != 0);
-        // a regular column always takes its distance-1 neighbour (column 1's is the boundary column)
-        cb2[c] = (cinfo[c] & (2u << kInfoNearShift)) != 0;
-        crare[c] = (cinfo[c] & ((4u << kInfoNearShift) | kInfoFar)) != 0;
-    }
 
     // Far predecessor columns (long bubbles, the boundary column of a source).  The common shape -- one such
     // column in the lane, with ONE far predecessor that lies in an earlier strip or at least two lanes back --
@@ -528,16 +554,15 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
     int farc = -1;
     const int4* farv = colbuf;
     const int* fare = coleff;
-    bool slowfar[C], cx[C];
+    uint32_t slowbits = 0;  // bit c: column c walks its predecessor list
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-        slowfar[c] = false;
-        if (cinfo[c] & kInfoFar) {  // never set for a column beyond n2
+        if ((cbits >> (8 * c)) & 8u) {  // never set for a column beyond n2
             const int j = j0 + c;
             int nf = 0, qsel = 0;
-            const uint32_t b1 = Wsh.poff2[j + 1];
+            const uint32_t b1e = Wsh.poff2[j + 1];
 #pragma unroll 1
-            for (uint32_t b = Wsh.poff2[j]; b < b1; ++b) {
+            for (uint32_t b = Wsh.poff2[j]; b < b1e; ++b) {
                 const int q = (int)Wsh.pidx2[b];
                 if (q >= 1 && j - q <= kNear) continue;
                 ++nf;
@@ -548,49 +573,43 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
                 farv = colbuf + (size_t)((uint32_t)slot2[qsel] * cstride);
                 fare = coleff + (size_t)((uint32_t)slot2[qsel] * cstride);
             } else {
-                slowfar[c] = true;
+                slowbits |= 1u << c;
             }
         }
-        crare[c] = (cinfo[c] & (4u << kInfoNearShift)) != 0 || slowfar[c];
     }
-#pragma unroll
-    for (int c = 0; c < C; ++c) cx[c] = crare[c] || farc == c;
     int4 Fv = make_int4(kMinInf, kMinInf, kMinInf, kMinInf);
     int Fe = kMinInf;
 
-    // warp-uniform: does any lane of this strip persist one of its first three columns?
-    bool lane_pers012 = false;
+    // A plain strip -- no column with a distance-3 / far predecessor -- runs the lean step: none of the rare code,
+    // the four columns of a lane are one basic block.
+    const bool lean = !__any_sync(kFull, (cbits & 0x0c0c0c0cu) != 0) && !(needS & 4u) && !(needL & 4u) && !(dbg & 2);
+    // warp-uniform: does any lane of this strip persist one of its first three columns (a column with a far successor,
+    // or whose distance-2 successor lies in the next 32-column block)?  Their offsets; the stores sit behind one branch.
+    const bool strip_pers012 = __any_sync(kFull, (cbits & 0x00101010u) != 0);
+    uint32_t coff012[C - 1];
 #pragma unroll
-    for (int c = 0; c < C - 1; ++c) lane_pers012 |= coff[c] != 0xffffffffu;
-    const bool strip_pers012 = __any_sync(kFull, lane_pers012);
-    // A plain strip -- no column with a distance-3 / far predecessor -- runs a lean step without any of that
-    // code: the four columns of a lane become one basic block (measured on windows without bubbles: 297 -> 368 GCUPS).
-    bool lane_cx = false;
-#pragma unroll
-    for (int c = 0; c < C; ++c) lane_cx |= cx[c];
-    const bool lean = !__any_sync(kFull, lane_cx) && !(needS & 4u) && !(needL & 4u) && !(dbg & 2);
+    for (int c = 0; c < C - 1; ++c) coff012[c] = ((cbits >> (8 * c)) & 16u) ? (uint32_t)slot2[j0 + c] * cstride : 0xffffffffu;
+    const uint32_t rpersist = nvalid ? kInfoPersist : 0u;  // a lane entirely beyond n2 stores no rows
+    const bool lane0L1 = lane == 0 && (needL & 1u);        // lane 0 takes its left neighbour from the left-column buffer
 
-    auto shfl_col = [&](const ColState& v) {
-        ColState o;
-        o.M = __shfl_up_sync(kFull, v.M, 1);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) o.D[k] = (k < P) ? __shfl_up_sync(kFull, v.D[k], 1) : kMinInf;
-        o.E = __shfl_up_sync(kFull, v.E, 1);
-        return o;
+    // 7-way max of the recurrence (2P+1 values), DPX three-input maxima; the left-dependent values come last
+    auto cell_max = [&](int x, const int4& I, const int (&D)[3]) {
+        if (P == 1) return __vimax3_s32(x, I.y, D[0]);
+        if (P == 2) return __vimax3_s32(__vimax3_s32(x, I.y, I.z), D[0], D[1]);
+        return __vimax3_s32(__vimax3_s32(__vimax3_s32(x, I.y, I.z), D[0], D[1]), D[2], I.w);
     };
-    auto fold = [&](ColState& a, const ColState& b) {
-        a.M = imax(a.M, b.M);
-#pragma unroll
-        for (int k = 0; k < P; ++k) a.D[k] = imax(a.D[k], b.D[k]);
-        a.E = imax(a.E, b.E);
+    auto fold4 = [&](int4& a, const int4 b) {
+        a.x = imax(a.x, b.x); a.y = imax(a.y, b.y); a.z = imax(a.z, b.z); a.w = imax(a.w, b.w);
     };
-    // all lanes read lane 0's left-column entry (a broadcast, no divergence); lane 0 keeps it
-    auto take_left = [&](ColState& S, int d, int s) {
-        const uint32_t slot = (uint32_t)(d * 2 + ((s / PB) & 1)) * PB + (uint32_t)(s % PB);
-        const int4 t = lds_128(saLv + slot * 16u);
-        const int e = lds_32(saLe + slot * 4u);
-        if (lane == 0) { S.M = t.x; S.D[0] = t.y; S.D[1] = t.z; S.D[2] = t.w; S.E = e; }
-    };
+
+    // lane 0's entry of the left-column buffers for the row it is on: rows PB*b+1.. live in buffer b&1 at index (row-1) % PB,
+    // column d at leftv[d]; the address advances by one entry per step and flips buffers every PB steps
+    uint32_t laddr = saLv + (uint32_t)((R0 / PB) & 1) * (PB * 16u);
+    // row info words, requested two steps ahead so that no step waits for its own load
+    // (lane t enters the panel at step R0 + t on row R0 + 1; it has been loading since it was on row R0 - 1)
+    uint32_t rinfo_cur = 0u, rinfo_nxt = 0u;
+    if (lane == 0) rinfo_cur = info1[R0 + 1];
+    if (lane <= 1 && R0 + 2 - lane <= R1) rinfo_nxt = info1[R0 + 2 - lane];
 
     auto step = [&](const int s, auto guard_tag, auto lean_tag) {
         constexpr bool GUARD = decltype(guard_tag)::value;
@@ -598,144 +617,227 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
         const int r = 1 + s - lane;
         bool act = true;
         if (GUARD) act = r > R0 && r <= R1;
-        // previous lane's columns for this row (it finished the row one step ago)
-        ColState S0, S1, S2;  // its column 3, 2, 1
-        S0 = shfl_col(out[3]);
-        if (needS & 2u) S1 = shfl_col(out[2]);
-        if (!LEAN && (needS & 4u)) S2 = shfl_col(out[1]);
-        // lane 0 is on row s+1: rows PB*b+1.. live in buffer b&1 at index (row-1) % PB
-        if (needL & 1u) take_left(S0, 0, s);
-        if (needL & 6u) {
-            if (needL & 2u) take_left(S1, 1, s);
-            if (!LEAN && (needL & 4u)) take_left(S2, 2, s);
+        // requests first: lane 0's left-column entry (all lanes read it: a broadcast) and the info word two rows down
+        const int4 tl = lds_128(laddr);
+        laddr += 16u;
+        uint32_t rinfo_new;
+        if (GUARD) rinfo_new = (r + 1 >= R0 && r + 2 <= R1) ? info1[(uint32_t)(r + 2)] : 0u;
+        else rinfo_new = info1[(uint32_t)(r + 2)];  // r + 2 <= n1 + 1: the info array is padded by one entry
+        // previous lane's columns for this row (it finished the row one step ago); in lane 0, the columns left of the
+        // strip.  Columns that no lane needs are not shuffled: whatever value stands in for them is never selected.
+        int P3g[3] = {kMinInf, kMinInf, kMinInf}, P2g[3] = {O2g[0], O2g[1], O2g[2]}, P1g[3] = {O1g[0], O1g[1], O1g[2]};
+        int P3e, P2e = O2e, P1e = O1e;
+#pragma unroll
+        for (int k = 0; k < P; ++k) P3g[k] = __shfl_up_sync(kFull, O3g[k], 1);
+        P3e = __shfl_up_sync(kFull, O3e, 1);
+        if (needS & 2u) {
+#pragma unroll
+            for (int k = 0; k < P; ++k) P2g[k] = __shfl_up_sync(kFull, O2g[k], 1);
+            P2e = __shfl_up_sync(kFull, O2e, 1);
         }
-        const uint32_t rinfo = rinfo_next;
-        if (GUARD) rinfo_next = (r >= R0 && r < R1) ? info1[(uint32_t)(r + 1)] : 0u;
-        else rinfo_next = info1[(uint32_t)(r + 1)];  // the info array is padded by one entry
+        if (!LEAN && (needS & 4u)) {
+#pragma unroll
+            for (int k = 0; k < P; ++k) P1g[k] = __shfl_up_sync(kFull, O1g[k], 1);
+            P1e = __shfl_up_sync(kFull, O1e, 1);
+        }
+        if (lane0L1) { P3g[0] = tl.x; P3g[1] = tl.y; P3g[2] = tl.z; P3e = tl.w; }
+        if (needL & 6u) {
+            if (needL & 2u) {
+                const int4 t = lds_128(laddr + (2 * PB - 1) * 16);
+                if (lane == 0) { P2g[0] = t.x; P2g[1] = t.y; P2g[2] = t.z; P2e = t.w; }
+            }
+            if (!LEAN && (needL & 4u)) {
+                const int4 t = lds_128(laddr + (4 * PB - 1) * 16);
+                if (lane == 0) { P1g[0] = t.x; P1g[1] = t.y; P1g[2] = t.z; P1e = t.w; }
+            }
+        }
+        const uint32_t rinfo = rinfo_cur;
         if (act) {
             const uint32_t rsA = saA + (uint32_t)(r & (H - 1)) * (C * 32 * 16);
             const int rlabel = (int)(rinfo & kInfoLabelMask);
-            // ---- effective predecessor row, folded in place into the up registers ----
-            if (!(rinfo & kInfoRegular)) {
-                const bool rb1 = (rinfo & (1u << kInfoNearShift)) != 0;
+            // ---- rows that are not "one predecessor, the row above" ----
+            // The two SNP-bubble shapes are folded in WITHOUT a branch (with 32 lanes on 32 different rows some lane is
+            // on such a row in nine steps out of ten, so a branch would be taken by the whole warp anyway): the second
+            // allele (predecessor r-2 only) reloads its state from the ring, the node after the bubble (r-1 and r-2)
+            // takes the element-wise maximum; predicated loads and maxima, one basic block with the cells.
+            {
                 const uint32_t rs2 = saA + (uint32_t)((r - 2) & (H - 1)) * (C * 32 * 16);  // row r-2
-                if (rinfo & (2u << kInfoNearShift)) {
-                    if (!rb1) {  // second allele of a SNP bubble: row r-2 replaces row r-1
+                const uint32_t nb12 = rinfo & (3u << kInfoNearShift);
+                const uint32_t isB = (nb12 == (2u << kInfoNearShift)) ? 1u : 0u, isJ = (nb12 == (3u << kInfoNearShift)) ? 1u : 0u;
+                asm volatile(
+                    "{\n .reg .pred pb, pj;\n .reg .s32 t<16>;\n"
+                    " setp.ne.u32 pb, %17, 0;\n setp.ne.u32 pj, %18, 0;\n"
+                    " @pb ld.shared.v4.s32 {%0,%1,%2,%3}, [%16];\n"
+                    " @pb ld.shared.v4.s32 {%4,%5,%6,%7}, [%16+512];\n"
+                    " @pb ld.shared.v4.s32 {%8,%9,%10,%11}, [%16+1024];\n"
+                    " @pb ld.shared.v4.s32 {%12,%13,%14,%15}, [%16+1536];\n"
+                    " @pj ld.shared.v4.s32 {t0,t1,t2,t3}, [%16];\n"
+                    " @pj ld.shared.v4.s32 {t4,t5,t6,t7}, [%16+512];\n"
+                    " @pj ld.shared.v4.s32 {t8,t9,t10,t11}, [%16+1024];\n"
+                    " @pj ld.shared.v4.s32 {t12,t13,t14,t15}, [%16+1536];\n"
+                    " @pj max.s32 %0, %0, t0;\n @pj max.s32 %1, %1, t1;\n @pj max.s32 %2, %2, t2;\n @pj max.s32 %3, %3, t3;\n"
+                    " @pj max.s32 %4, %4, t4;\n @pj max.s32 %5, %5, t5;\n @pj max.s32 %6, %6, t6;\n @pj max.s32 %7, %7, t7;\n"
+                    " @pj max.s32 %8, %8, t8;\n @pj max.s32 %9, %9, t9;\n @pj max.s32 %10, %10, t10;\n @pj max.s32 %11, %11, t11;\n"
+                    " @pj max.s32 %12, %12, t12;\n @pj max.s32 %13, %13, t13;\n @pj max.s32 %14, %14, t14;\n @pj max.s32 %15, %15, t15;\n"
+                    "}\n"
+                    : "+r"(St[0].x), "+r"(St[0].y), "+r"(St[0].z), "+r"(St[0].w), "+r"(St[1].x), "+r"(St[1].y), "+r"(St[1].z), "+r"(St[1].w),
+                      "+r"(St[2].x), "+r"(St[2].y), "+r"(St[2].z), "+r"(St[2].w), "+r"(St[3].x), "+r"(St[3].y), "+r"(St[3].z), "+r"(St[3].w)
+                    : "r"(rs2), "r"(isB), "r"(isJ)
+                    : "memory");
+            }
+            // everything else -- a distance-3 or far predecessor, or no predecessor within two rows -- is uncommon
+            if ((rinfo & ((4u << kInfoNearShift) | kInfoFar)) || !(rinfo & (kInfoRegular | (3u << kInfoNearShift)))) {
+                if (!(rinfo & (kInfoRegular | (3u << kInfoNearShift)))) {
 #pragma unroll
-                        for (int c = 0; c < C; ++c) {
-                            const int4 t = lds_128(rs2 + c * (32 * 16));
-                            upM[c] = t.x; upI[c][0] = t.y; upI[c][1] = t.z; upI[c][2] = t.w;
-                        }
-                    } else {     // node after the bubble: both
-#pragma unroll
-                        for (int c = 0; c < C; ++c) max4(upM[c], upI[c], lds_128(rs2 + c * (32 * 16)));
-                    }
-                } else if (!rb1) {
-#pragma unroll
-                    for (int c = 0; c < C; ++c) { upM[c] = kMinInf; upI[c][0] = upI[c][1] = upI[c][2] = kMinInf; }
+                    for (int c = 0; c < C; ++c) St[c] = make_int4(kMinInf, kMinInf, kMinInf, kMinInf);
                 }
-                if (rinfo & ((4u << kInfoNearShift) | kInfoFar)) {
-                    if (rinfo & (4u << kInfoNearShift)) {
-                        const uint32_t rs3 = saA + (uint32_t)((r - 3) & (H - 1)) * (C * 32 * 16);
+                if (rinfo & (4u << kInfoNearShift)) {
+                    const uint32_t rs3 = saA + (uint32_t)((r - 3) & (H - 1)) * (C * 32 * 16);
 #pragma unroll
-                        for (int c = 0; c < C; ++c) max4(upM[c], upI[c], lds_128(rs3 + c * (32 * 16)));
-                    }
-                    if (rinfo & kInfoFar) {
-                        const uint32_t rp1 = Wsh.poff1[r + 1];
+                    for (int c = 0; c < C; ++c) fold4(St[c], lds_128(rs3 + c * (32 * 16)));
+                }
+                if (rinfo & kInfoFar) {
+                    const uint32_t rp1 = Wsh.poff1[r + 1];
 #pragma unroll 1
-                        for (uint32_t a = Wsh.poff1[r]; a < rp1; ++a) {
-                            const int p = (int)Wsh.pidx1[a];
-                            if (p >= 1 && r - p <= kNear) continue;
-                            const uint32_t o = (uint32_t)Wsh.slot1[p] * rstride + (uint32_t)j0;
+                    for (uint32_t a = Wsh.poff1[r]; a < rp1; ++a) {
+                        const int p = (int)Wsh.pidx1[a];
+                        if (p >= 1 && r - p <= kNear) continue;
+                        const uint32_t o = (uint32_t)Wsh.slot1[p] * rstride + (uint32_t)j0;
 #pragma unroll
-                            for (int c = 0; c < C; ++c)
-                                if (c < (int)nvalid) max4(upM[c], upI[c], rowbuf[o + c]);
-                        }
+                        for (int c = 0; c < C; ++c)
+                            if (c < (int)nvalid) fold4(St[c], rowbuf[o + c]);  // the workspace holds {M, H_k}
                     }
                 }
             }
-            ColState cur[C];
+            int G[C][3], eM[C], Dk[C][3];
+            auto column = [&](auto ctag) {
+                constexpr int c = decltype(ctag)::value;
+                eM[c] = St[c].x;  // effective M of the row above = diagonal input of the columns to the right
+                // ---- effective predecessor column: the distance-1 neighbour, the distance-2 neighbour, or both ----
+                int d1g[3], d2g[3], d1e, d2e;
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                // ---- effective predecessor column: distance 1 and 2 branch-free, the rest rarely ----
-                const ColState& d1 = (c == 0) ? S0 : cur[c > 0 ? c - 1 : 0];
-                const ColState& d2 = (c >= 2) ? cur[c >= 2 ? c - 2 : 0] : (c == 1 ? S0 : S1);
-                ColState L;
-                L.M = cb1[c] ? d1.M : kMinInf;
+                for (int k = 0; k < 3; ++k) {
+                    if constexpr (c == 0) { d1g[k] = P3g[k]; d2g[k] = P2g[k]; }
+                    else if constexpr (c == 1) { d1g[k] = G[0][k]; d2g[k] = P3g[k]; }
+                    else { d1g[k] = G[c - 1][k]; d2g[k] = G[c - 2][k]; }
+                }
+                if constexpr (c == 0) { d1e = P3e; d2e = P2e; }
+                else if constexpr (c == 1) { d1e = eM[0]; d2e = P3e; }
+                else { d1e = eM[c - 1]; d2e = eM[c - 2]; }
+                const bool c1 = (cbits >> (8 * c)) & 1u, c2 = (cbits >> (8 * c)) & 2u;
+                int D[3] = {kMinInf, kMinInf, kMinInf};
+                int E;
+                if (LEAN) {  // a lean strip knows three column shapes: (c1, !c2) regular, (!c1, c2) second allele, (c1, c2) after a bubble
 #pragma unroll
-                for (int k = 0; k < 3; ++k) L.D[k] = (k < P && cb1[c]) ? d1.D[k] : kMinInf;
-                L.E = cb1[c] ? d1.E : kMinInf;
-                if (cb2[c]) fold(L, d2);
-                if (!LEAN && cx[c]) {
-                  if (farc == c) {  // fast far column
-                    if (r == R0 + 1) { Fv = farv[r]; Fe = fare[r]; }
-                    L.M = imax(L.M, Fv.x); L.D[0] = imax(L.D[0], Fv.y); L.D[1] = imax(L.D[1], Fv.z); L.D[2] = imax(L.D[2], Fv.w);
-                    L.E = imax(L.E, Fe);
-                    const int rn = min(r + 1, R1);  // not below the panel: those rows may not exist yet
-                    Fv = farv[rn]; Fe = fare[rn];
-                  }
-                  if (crare[c]) {
-                    const uint32_t ci = cinfo[c];
-                    if (ci & (4u << kInfoNearShift)) {
-                        const ColState& d3 = (c >= 3) ? cur[0] : (c == 2 ? S0 : (c == 1 ? S1 : S2));
-                        fold(L, d3);
+                    for (int k = 0; k < P; ++k) {
+                        D[k] = c1 ? d1g[k] : d2g[k];
+                        if (c1 && c2) D[k] = imax(D[k], d2g[k]);
                     }
-                    if (slowfar[c]) {
+                    E = c1 ? d1e : d2e;
+                    if (c1 && c2) E = imax(E, d2e);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < P; ++k) D[k] = imax(c1 ? d1g[k] : kMinInf, c2 ? d2g[k] : kMinInf);
+                    E = imax(c1 ? d1e : kMinInf, c2 ? d2e : kMinInf);
+                }
+                if (!LEAN && ((cbits >> (8 * c)) & 12u)) {
+                    if (farc == c) {  // fast far column
+                        if (r == R0 + 1) { Fv = farv[r]; Fe = fare[r]; }
+                        const int4 fp = to_offered<P>(prm, Fv);
+                        D[0] = imax(D[0], fp.y); D[1] = imax(D[1], fp.z); D[2] = imax(D[2], fp.w);
+                        E = imax(E, Fe);
+                        const int rn = min(r + 1, R1);  // not below the panel: those rows may not exist yet
+                        Fv = farv[rn]; Fe = fare[rn];
+                    }
+                    if ((cbits >> (8 * c)) & 4u) {  // distance 3
+                        int d3e;
+#pragma unroll
+                        for (int k = 0; k < P; ++k) {
+                            int d3g;
+                            if constexpr (c >= 3) d3g = G[c - 3][k];
+                            else if constexpr (c == 2) d3g = P3g[k];
+                            else if constexpr (c == 1) d3g = P2g[k];
+                            else d3g = P1g[k];
+                            D[k] = imax(D[k], d3g);
+                        }
+                        if constexpr (c >= 3) d3e = eM[c - 3];
+                        else if constexpr (c == 2) d3e = P3e;
+                        else if constexpr (c == 1) d3e = P2e;
+                        else d3e = P1e;
+                        E = imax(E, d3e);
+                    }
+                    if (slowbits & (1u << c)) {
                         const int j = j0 + c;
-                        const uint32_t b1 = Wsh.poff2[j + 1];
+                        const uint32_t b1e = Wsh.poff2[j + 1];
 #pragma unroll 1
-                        for (uint32_t b = Wsh.poff2[j]; b < b1; ++b) {
+                        for (uint32_t b = Wsh.poff2[j]; b < b1e; ++b) {
                             const int q = (int)Wsh.pidx2[b];
                             if (q >= 1 && j - q <= kNear) continue;
                             const uint32_t o = (uint32_t)Wsh.slot2[q] * cstride + (uint32_t)r;
-                            const int4 t = colbuf[o];
-                            L.M = imax(L.M, t.x); L.D[0] = imax(L.D[0], t.y); L.D[1] = imax(L.D[1], t.z); L.D[2] = imax(L.D[2], t.w);
-                            L.E = imax(L.E, coleff[o]);
+                            const int4 t = to_offered<P>(prm, colbuf[o]);
+                            D[0] = imax(D[0], t.y); D[1] = imax(D[1], t.z); D[2] = imax(D[2], t.w);
+                            E = imax(E, coleff[o]);
                         }
                     }
-                  }
                 }
                 // ---- the cell ----
-                const int sub = (rlabel == (int)(cinfo[c] & kInfoLabelMask)) ? prm.match : -prm.mismatch;
-                const int eM = upM[c];
-                int I[3] = {kMinInf, kMinInf, kMinInf};
-                cur[c].D[0] = cur[c].D[1] = cur[c].D[2] = kMinInf;
-                int M = __viaddmax_s32(L.E, sub, kMinInf);
+                const int x = (rlabel == cl[c]) ? E + prm.match : E - prm.mismatch;
+                const int Mn = cell_max(x, St[c], D);
+                {
+                    const int T = Mn - prm.oe[0];
+                    G[c][0] = __viaddmax_s32(D[0], -prm.e[0], T);
+                    St[c].y = __viaddmax_s32(St[c].y, -prm.e[0], T);
+                }
+                G[c][1] = G[c][2] = kMinInf;
+                if (P > 1) {
+                    const int T = Mn - prm.oe[1];
+                    G[c][1] = __viaddmax_s32(D[1], -prm.e[1], T);
+                    St[c].z = __viaddmax_s32(St[c].z, -prm.e[1], T);
+                }
+                if (P > 2) {
+                    const int T = Mn - prm.oe[2];
+                    G[c][2] = __viaddmax_s32(D[2], -prm.e[2], T);
+                    St[c].w = __viaddmax_s32(St[c].w, -prm.e[2], T);
+                }
+                St[c].x = Mn;
+                sts_128(rsA + c * (32 * 16), St[c]);
+                if constexpr (c == C - 1) {
+                    if (coff3 != 0xffffffffu) {  // the regular persisted columns (every 32nd) are a lane's last
+                        colbuf[coff3 + (uint32_t)r] = make_int4(Mn, D[0], D[1], D[2]);
+                        coleff[coff3 + (uint32_t)r] = eM[c];
+                    }
+                }
 #pragma unroll
-                for (int k = 0; k < P; ++k) {
-                    I[k] = __viaddmax_s32(upI[c][k], -prm.e[k], eM - prm.oe[k]);
-                    cur[c].D[k] = __viaddmax_s32(L.D[k], -prm.e[k], L.M - prm.oe[k]);
-                    M = __vimax3_s32(M, I[k], cur[c].D[k]);
-                }
-                cur[c].M = M;
-                cur[c].E = eM;
-                const int4 cellA = make_int4(M, I[0], I[1], I[2]);
-                sts_128(rsA + c * (32 * 16), cellA);
-                if (c == C - 1 && coff[c] != 0xffffffffu) {  // the regular persisted columns (every 32nd) are a lane's last
-                    colbuf[coff[c] + (uint32_t)r] = make_int4(M, cur[c].D[0], cur[c].D[1], cur[c].D[2]);
-                    coleff[coff[c] + (uint32_t)r] = eM;
-                }
-                upM[c] = M; upI[c][0] = I[0]; upI[c][1] = I[1]; upI[c][2] = I[2];
-            }
-            if (strip_pers012) {  // warp-uniform and rare: a column with a far successor among a lane's first three
+                for (int k = 0; k < 3; ++k) Dk[c][k] = D[k];
+            };
+            column(std::integral_constant<int, 0>{});
+            column(std::integral_constant<int, 1>{});
+            column(std::integral_constant<int, 2>{});
+            column(std::integral_constant<int, 3>{});
+            if (strip_pers012) {  // warp-uniform and uncommon
 #pragma unroll
                 for (int c = 0; c < C - 1; ++c)
-                    if (coff[c] != 0xffffffffu) {
-                        colbuf[coff[c] + (uint32_t)r] = make_int4(cur[c].M, cur[c].D[0], cur[c].D[1], cur[c].D[2]);
-                        coleff[coff[c] + (uint32_t)r] = cur[c].E;
+                    if (coff012[c] != 0xffffffffu) {
+                        colbuf[coff012[c] + (uint32_t)r] = make_int4(St[c].x, Dk[c][0], Dk[c][1], Dk[c][2]);
+                        coleff[coff012[c] + (uint32_t)r] = eM[c];
                     }
             }
-            if (rinfo & kInfoPersist) {  // persisted row: the new row is in the up registers
+            {   // persisted row: {M, H_k} of the lane's four columns (rows are padded: columns beyond n2 land in the padding)
                 uint32_t rslot = rinfo >> kInfoSlotShift;
-                if (rslot == kInfoSlotEscape) rslot = (uint32_t)Wsh.slot1[r];
-                int4* const rp = rowbuf + (size_t)(rslot * rstride + (uint32_t)j0);  // one address, immediate offsets
+                if ((rinfo & rpersist) && rslot == kInfoSlotEscape) rslot = (uint32_t)Wsh.slot1[r];
+                int4* const rp = rowbuf + (size_t)(rslot * rstride + (uint32_t)j0);
+                if (rinfo & rpersist) {
 #pragma unroll
-                for (int c = 0; c < C; ++c)
-                    if (c < (int)nvalid) rp[c] = make_int4(upM[c], upI[c][0], upI[c][1], upI[c][2]);
+                    for (int c = 0; c < C; ++c) rp[c] = St[c];
+                }
             }
 #pragma unroll
-            for (int c = 0; c < C; ++c) out[c] = cur[c];
+            for (int k = 0; k < 3; ++k) { O3g[k] = G[3][k]; O2g[k] = G[2][k]; if (!LEAN) O1g[k] = G[1][k]; }
+            O3e = eM[3]; O2e = eM[2];
+            if (!LEAN) O1e = eM[1];
         }
+        rinfo_cur = rinfo_nxt;
+        rinfo_nxt = rinfo_new;
         __syncwarp();
     };
     auto publish = [&](int r31) {
@@ -746,18 +848,18 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
     const int nsteps = R1 + 31;
     for (int s0 = R0; s0 < nsteps; s0 += PB) {  // PB-step blocks; lane 0 is on rows s0+1 .. s0+PB (R0 is a multiple of PB)
         const int s1 = min(s0 + PB, nsteps);
-        {  // only lane 0 reads the prefetch buffers, so the next block can be requested right away
-            const int b = s0 / PB + 1;
-            if (PB * b + 1 <= R1) {
-                wait_rows(min(PB * b + PB, R1));
-                prefetch_block(b);
-            }
+        const int bnext = s0 / PB + 1;
+        const bool more = PB * bnext + 1 <= R1;
+        if (more) {  // only lane 0 reads the prefetch buffers, so the next block can be requested right away
+            wait_rows(min(PB * bnext + PB, R1));
+            prefetch_block(bnext);
         }
+        laddr = saLv + (uint32_t)((s0 / PB) & 1) * (PB * 16u);
         const bool inner = s0 >= R0 + 31 && s1 <= R1;
 #pragma unroll 1
         for (int q8 = s0; q8 < s1; q8 += 8) {
             const int e8 = min(q8 + 8, s1);
-            if (inner && lean) {  // exactly 8 steps: unrolled in pairs so that the row registers ping-pong instead of being copied
+            if (inner && lean) {
 #pragma unroll 1
                 for (int s = q8; s < q8 + 8; ++s) step(s, std::false_type{}, std::true_type{});
             } else {  // the guarded step doubles as the generic one (one copy of it: instruction cache)
@@ -771,6 +873,7 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
         }
         cp_async_wait_all();
         __syncwarp();
+        if (more) convert_block(bnext);
     }
 }
 
@@ -797,7 +900,7 @@ __device__ __forceinline__ int4 boundary_cell(uint32_t depth, const Params& prm)
 // and the boundary entries of persisted rows / columns.  Run by the traceback warp.
 template <int P>
 __device__ void tb_boundary(const Win& W, const Params& prm, int lane) {
-    const int64_t rstride = (int64_t)W.n2 + 1, cstride = (int64_t)W.n1 + 1;
+    const int64_t rstride = (int64_t)row_stride((uint32_t)W.n2), cstride = (int64_t)W.n1 + 1;
     const int4 corner = make_int4(0, kMinInf, kMinInf, kMinInf);
     for (int j = lane; j <= W.n2; j += 32) {
         const int4 b = j == 0 ? corner : boundary_cell<P>(W.depth2[j], prm);
@@ -848,7 +951,7 @@ __device__ __forceinline__ void tile_strip(const Win& Wsh, const Params& prm, co
     const int4* const rowbuf = Wsh.rowbuf;
     const int4* const colbuf = Wsh.colbuf;
     const int* const coleff = Wsh.coleff;
-    const uint32_t rstride = (uint32_t)n2 + 1u, cstride = (uint32_t)n1 + 1u;
+    const uint32_t rstride = row_stride((uint32_t)n2), cstride = (uint32_t)n1 + 1u;
     const int nrows = R1 - R0 + 1;
 
     const int j = C0 + lane;
@@ -882,12 +985,13 @@ __device__ __forceinline__ void tile_strip(const Win& Wsh, const Params& prm, co
                 sm.lefte[d][idx] = coleff[o];
             }
     }
-    int upM = kMinInf, upI[3] = {kMinInf, kMinInf, kMinInf};
+    // the row above as {M, H_k}: what it offers this row (rows outside the tile come from the workspace in that form)
+    int upM = kMinInf, upH[3] = {kMinInf, kMinInf, kMinInf};
     if (jvalid) {
         const int s0 = slot1[R0 - 1];
         if (s0 >= 0) {
             const int4 a = rowbuf[(uint32_t)s0 * rstride + (uint32_t)j];
-            upM = a.x; upI[0] = a.y; upI[1] = a.z; upI[2] = a.w;
+            upM = a.x; upH[0] = a.y; upH[1] = a.z; upH[2] = a.w;
         }
     }
     __syncwarp();
@@ -909,16 +1013,16 @@ __device__ __forceinline__ void tile_strip(const Win& Wsh, const Params& prm, co
             const int li = r - R0;
             const uint32_t rinfo = sm.rinfo[li];
             const int rs = (r & (H - 1)) * 32;
-            // ---- effective predecessor row ----
-            int eM = upM, eI[3] = {upI[0], upI[1], upI[2]};
+            // ---- effective predecessor row: I_k(r,j) = max over predecessor rows of H_k, diagonal input eM likewise ----
+            int eM = upM, eH[3] = {upH[0], upH[1], upH[2]};
             if (!(rinfo & kInfoRegular)) {
-                if (!(rinfo & (1u << kInfoNearShift))) { eM = kMinInf; eI[0] = eI[1] = eI[2] = kMinInf; }
+                if (!(rinfo & (1u << kInfoNearShift))) { eM = kMinInf; eH[0] = eH[1] = eH[2] = kMinInf; }
 #pragma unroll
                 for (int d = 2; d <= 3; ++d) {
                     if (rinfo & ((1u << (d - 1)) << kInfoNearShift)) {
-                        const int p = r - d;
-                        const int4 v = p >= R0 ? myA[(p & (H - 1)) * 32] : rowbuf[(uint32_t)slot1[p] * rstride + (uint32_t)j];
-                        max4(eM, eI, v);
+                        const int p = r - d;  // inside the tile: shared memory holds {M, I_k}; above it: the workspace, {M, H_k}
+                        const int4 v = p >= R0 ? to_offered<P>(prm, myA[(p & (H - 1)) * 32]) : rowbuf[(uint32_t)slot1[p] * rstride + (uint32_t)j];
+                        max4(eM, eH, v);
                     }
                 }
                 if (rinfo & kInfoFar) {
@@ -927,7 +1031,7 @@ __device__ __forceinline__ void tile_strip(const Win& Wsh, const Params& prm, co
                     for (uint32_t a = poff1[r]; a < rp1; ++a) {
                         const int p = (int)pidx1[a];
                         if (p >= 1 && r - p <= kNear) continue;
-                        max4(eM, eI, rowbuf[(uint32_t)slot1[p] * rstride + (uint32_t)j]);
+                        max4(eM, eH, rowbuf[(uint32_t)slot1[p] * rstride + (uint32_t)j]);
                     }
                 }
             }
@@ -973,13 +1077,15 @@ __device__ __forceinline__ void tile_strip(const Win& Wsh, const Params& prm, co
             int M = __viaddmax_s32(lEff, sub, kMinInf);
 #pragma unroll
             for (int k = 0; k < P; ++k) {
-                I[k] = __viaddmax_s32(eI[k], -prm.e[k], eM - prm.oe[k]);
+                I[k] = eH[k];
                 D[k] = __viaddmax_s32(lD[k], -prm.e[k], lM - prm.oe[k]);
                 M = __vimax3_s32(M, I[k], D[k]);
             }
             myA[rs] = make_int4(M, I[0], I[1], I[2]);
             myB[rs] = make_int4(eM, D[0], D[1], D[2]);
-            upM = M; upI[0] = I[0]; upI[1] = I[1]; upI[2] = I[2];
+            upM = M;
+#pragma unroll
+            for (int k = 0; k < P; ++k) upH[k] = offer(prm, I[k], M, k);
             outM = M; outD[0] = D[0]; outD[1] = D[1]; outD[2] = D[2];
             outEff = eM;
         }
@@ -1007,12 +1113,20 @@ struct Walker {
         if (s >= 0) return W.rowbuf[(uint32_t)s * rstride + (uint32_t)j].x;
         return W.colbuf[(uint32_t)W.slot2[j] * cstride + (uint32_t)i].x;
     }
+    // I_k(i,j) of the CURRENT cell: always on the boundary or inside the recomputed tile
     __device__ int cI(int i, int j, int k) const {
         if (i == 0) return kMinInf;
-        int4 v;
-        if (j == 0) v = W.bcol[i];
-        else if (in_tile(i, j)) v = sm.A[(i & (kRowBlock - 1)) * 32 + (j - tv.C0)];
-        else v = W.rowbuf[(uint32_t)W.slot1[i] * rstride + (uint32_t)j];
+        const int4 v = (j == 0) ? W.bcol[i] : sm.A[(i & (kRowBlock - 1)) * 32 + (j - tv.C0)];
+        return k == 0 ? v.y : (k == 1 ? v.z : v.w);
+    }
+    // "I_k(p,j) - e_k" of a PREDECESSOR row p, for the extension test of alignment.hpp:1101-1116.  A row outside the tile
+    // is in the workspace as H_k = max(I_k - e_k, M - oe_k); the reference tests the opening (cur == M(p,j) - oe_k)
+    // before the extension for the same predecessor, so when this value is compared the opening has already failed,
+    // and then cur == I_k - e_k  <=>  cur == H_k  (cur >= H_k >= M - oe_k != cur rules the other branch of the max out).
+    __device__ int cIext(int p, int j, int k) const {
+        if (p == 0) return kMinInf;
+        if (j == 0 || in_tile(p, j)) return cI(p, j, k) - prm.e[k];
+        const int4 v = W.rowbuf[(uint32_t)W.slot1[p] * rstride + (uint32_t)j];
         return k == 0 ? v.y : (k == 1 ? v.z : v.w);
     }
     __device__ int cD(int i, int j, int k) const {
@@ -1048,7 +1162,7 @@ template <int P>
 __device__ void traceback(const Win& W, const Params& prm, TileSmem& sm, int lane, int64_t* score_out, int32_t* aln,
                           uint32_t* len_out) {
     const int n1 = W.n1, n2 = W.n2;
-    const uint32_t rstride = (uint32_t)n2 + 1u;
+    const uint32_t rstride = row_stride((uint32_t)n2);
     // ---- best sink pair: first maximum in caller order, strict '>' (alignment.hpp:979-1008) ----
     long long npairs;
     if (n1 != 0 && n2 != 0) npairs = (long long)W.nsnk1 * W.nsnk2;
@@ -1127,7 +1241,7 @@ __device__ void traceback(const Win& W, const Params& prm, TileSmem& sm, int lan
                     for (int a = 0; a < p1.n; ++a) {
                         const int p = p1.at(a);
                         if (cur == wk.cM(p, cj) - prm.oe[k]) { comp = 0; ni = p; nj = cj; break; }
-                        if (cur == wk.cI(p, cj, k) - prm.e[k]) { ni = p; nj = cj; break; }
+                        if (cur == wk.cIext(p, cj, k)) { ni = p; nj = cj; break; }
                     }
                 } else {
                     o[0] = -1; o[1] = cj - 1;
@@ -1185,7 +1299,7 @@ struct CtaState {
 // queue in the order of d = p * kTileSkew + cs (p ascending inside d).  Both predecessors of a tile, (p, cs-1) and
 // (p-1, cs), have a smaller d, so they were taken earlier and no wait can deadlock; with about one tile per panel in
 // flight, a tile's left neighbour is usually finished, and nothing waits for a slow strip.
-constexpr int kTileSkew = 11;
+constexpr int kTileSkew = kWarps - 1;
 constexpr int kMaxTiledStrips = kProgMask - 64;
 __device__ __forceinline__ bool window_tiled(const Win& W, int nstrips, int panel_cfg) {
     const int panel_rows = panel_rows_for(W.n1, panel_cfg);
@@ -1225,10 +1339,16 @@ __global__ void __launch_bounds__(kThreads, 1) popoa_kernel(const LaunchArgs A) 
             if (w < 0) break;
             const int nstrips = ld_volatile(&S.seq_nstrips[k & 7]);
             const Win& W = S.win[k & 1];
-            if (window_tiled(W, nstrips, A.panel_rows)) {
-                const int H = panel_rows_for(W.n1, A.panel_rows), T = (W.n1 + H - 1) / H, ntiles = T * nstrips;
-                int d = 0, p = 0, qi = 0;  // enumeration cursor: tile number qi is (p, d - p * kTileSkew)
-                for (;;) {
+            // One work loop for both schedules (a single call site per fill routine: the step code exists once).
+            // Tiled windows hand out (panel, strip) tiles from the per-window queue; the others give every warp the
+            // strips cs = first, first + kFillWarps, ... top to bottom.
+            const bool tiled = window_tiled(W, nstrips, A.panel_rows);
+            const int H = tiled ? panel_rows_for(W.n1, A.panel_rows) : max(W.n1, 1);
+            const int T = tiled ? (W.n1 + H - 1) / H : 1, ntiles = T * nstrips;
+            int d = 0, p = 0, qi = 0;  // enumeration cursor of the tile queue: tile number qi is (p, d - p * kTileSkew)
+            int cs = (warp - G % kFillWarps + kFillWarps) % kFillWarps;  // my first strip of an untiled window
+            for (;;) {
+                if (tiled) {
                     int q = 0;
                     if (lane == 0) q = atomicAdd(&S.tile_next[k & 1], 1);
                     q = __shfl_sync(kFull, q, 0);
@@ -1239,27 +1359,21 @@ __global__ void __launch_bounds__(kThreads, 1) popoa_kernel(const LaunchArgs A) 
                         } while (d - p * kTileSkew < 0 || d - p * kTileSkew >= nstrips);
                         ++qi;
                     }
-                    const int cs = d - p * kTileSkew;
+                    cs = d - p * kTileSkew;
+                } else if (cs >= nstrips) {
+                    break;
+                }
+                if (W.cw == kWideCols)
                     fill_strip_wide<P>(W, prm, cs, G + cs, *reinterpret_cast<FillSmemWide*>(&sm), S.progress, lane, A.start_lag,
                                        p * H, min((p + 1) * H, W.n1), A.debug_flags);
-                    if (lane == 0) {
-                        __threadfence_block();
-                        atomicAdd(&S.strips_done[k & 1], 1);
-                    }
-                    __syncwarp();
-                }
-                G += nstrips;
-                continue;
-            }
-            int first = (warp - G % kFillWarps + kFillWarps) % kFillWarps;  // my first strip of this window
-            for (int cs = first; cs < nstrips; cs += kFillWarps) {
-                if (W.cw == kWideCols) fill_strip_wide<P>(W, prm, cs, G + cs, *reinterpret_cast<FillSmemWide*>(&sm), S.progress, lane, A.start_lag, 0, W.n1, A.debug_flags);
-                else fill_strip<P>(W, prm, cs, G + cs, *reinterpret_cast<FillSmem*>(&sm), S.progress, lane, A.start_lag);
+                else
+                    fill_strip<P>(W, prm, cs, G + cs, *reinterpret_cast<FillSmem*>(&sm), S.progress, lane, A.start_lag);
                 if (lane == 0) {
                     __threadfence_block();
                     atomicAdd(&S.strips_done[k & 1], 1);
                 }
                 __syncwarp();
+                if (!tiled) cs += kFillWarps;
             }
             G += nstrips;
         }
@@ -1288,7 +1402,7 @@ __global__ void __launch_bounds__(kThreads, 1) popoa_kernel(const LaunchArgs A) 
                     const int64_t pair = A.slot_by_smid ? (int64_t)smid() : (int64_t)blockIdx.x;
                     int4* ws = reinterpret_cast<int4*>(A.workspace + (pair * 2 + (k & 1)) * A.slot_bytes);
                     W.rowbuf = ws;
-                    W.colbuf = W.rowbuf + (int64_t)m.nrslot * (m.n2 + 1);
+                    W.colbuf = W.rowbuf + (int64_t)m.nrslot * row_stride(m.n2);
                     W.brow = W.colbuf + (int64_t)m.ncslot * (m.n1 + 1);
                     W.bcol = W.brow + (m.n2 + 1);
                     W.coleff = reinterpret_cast<int*>(W.bcol + (m.n1 + 1));

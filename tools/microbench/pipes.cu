@@ -9,12 +9,12 @@
 #define UNROLL 8
 
 enum Kind { K_VIADDMNMX_RRR, K_VIADDMNMX_RCR, K_VIMNMX3, K_VIMNMX2, K_IADD, K_IMAD, K_SEL, K_ISETP_SEL, K_MIX_DPX_IMAD, K_MIX_DPX_IADD,
-            K_MIX_DPX_MNMX2, K_SHFL, K_LDS128, K_MIX_DPX_IMAD2, K_CELL, K_PREDOFF, K_LOP3, K_MIX_MNMX2_IMAD, K_NKINDS };
+            K_MIX_DPX_MNMX2, K_SHFL, K_LDS128, K_MIX_DPX_IMAD2, K_CELL, K_PREDOFF, K_LOP3, K_MIX_MNMX2_IMAD, K_MIX_DPXC_IMADC, K_MIX_DPX_IADDC, K_MIX_DPXC_IADDC, K_MIX_2DPXC_IADDC, K_MIX_MNMX2_IADDC, K_NKINDS };
 static const char* kNames[] = {"VIADDMNMX r,r,r", "VIADDMNMX r,c,r", "VIMNMX3", "VIMNMX (2-in)", "IADD3", "IMAD (x*y+z)", "SEL", "ISETP+SEL",
                                "VIADDMNMX + IMAD 1:1", "VIADDMNMX + IADD3 1:1", "VIADDMNMX + VIMNMX2 1:1", "SHFL.UP", "LDS.128",
-                               "VIADDMNMX + 2 IMAD", "bare cell (11 ALU + 8 IMAD)", "predicated-off VIMNMX", "LOP3", "VIMNMX2 + IMAD 1:1"};
+                               "VIADDMNMX + 2 IMAD", "bare cell (11 ALU + 8 IMAD)", "predicated-off VIMNMX", "LOP3", "VIMNMX2 + IMAD 1:1", "VIADDMNMX r,c,r + IMAD r,c,c", "VIADDMNMX r,r,r + IADD r,c", "VIADDMNMX r,c,r + IADD r,c", "2 VIADDMNMX r,c,r + IADD r,c", "VIMNMX2 + IADD r,c"};
 // instructions counted per chain-update
-static const int kInstr[] = {1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 1, 1, 3, 19, 1, 1, 2};
+static const int kInstr[] = {1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 1, 1, 3, 19, 1, 1, 2, 2, 2, 2, 3, 2};
 
 __constant__ int cst[8];
 
@@ -54,6 +54,11 @@ __global__ void __launch_bounds__(1024) probe(int* out, int iters, int seed, int
                 }
                 if (K == K_PREDOFF) asm volatile("{.reg .pred p; setp.eq.s32 p, %2, 12345; @p max.s32 %0, %0, %1;}" : "+r"(a[k]) : "r"(o), "r"(one));
                 if (K == K_LOP3) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[k]) : "r"(o), "r"(d));
+                if (K == K_MIX_DPXC_IMADC) { a[k] = __viaddmax_s32(a[k], cst[1], o); asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(b[k]) : "r"(cst[7]), "r"(cst[2])); }
+                if (K == K_MIX_DPX_IADDC) { a[k] = __viaddmax_s32(a[k], d, o); asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(b[k]) : "r"(cst[7]), "r"(cst[2])); }
+                if (K == K_MIX_DPXC_IADDC) { a[k] = __viaddmax_s32(a[k], cst[1], o); asm volatile("mad.lo.s32 %0, %0, 1, %1;" : "+r"(b[k]) : "r"(cst[2])); }
+                if (K == K_MIX_2DPXC_IADDC) { a[k] = __viaddmax_s32(a[k], cst[1], o); b[k] = __viaddmax_s32(b[k], cst[3], a[(k+2)%NCH]); asm volatile("mad.lo.s32 %0, %0, 1, %1;" : "+r"(b[(k+3)%NCH]) : "r"(cst[2])); }
+                if (K == K_MIX_MNMX2_IADDC) { asm volatile("max.s32 %0, %0, %1;" : "+r"(a[k]) : "r"(o)); asm volatile("mad.lo.s32 %0, %0, 1, %1;" : "+r"(b[k]) : "r"(cst[2])); }
                 if (K == K_MIX_MNMX2_IMAD) { asm volatile("max.s32 %0, %0, %1;" : "+r"(a[k]) : "r"(o)); asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(b[k]) : "r"(one), "r"(d)); }
             }
             if (K == K_CELL) {
@@ -124,6 +129,6 @@ int main() {
     printf("\n");
 #define ROW(K) { printf("%-30s", kNames[K]); for (int w : wps) printf(" %7.3f", run<K>(w, p.multiProcessorCount, ghz)); printf("\n"); }
     ROW(K_VIADDMNMX_RRR) ROW(K_VIADDMNMX_RCR) ROW(K_VIMNMX3) ROW(K_VIMNMX2) ROW(K_IADD) ROW(K_IMAD) ROW(K_SEL) ROW(K_ISETP_SEL) ROW(K_LOP3)
-    ROW(K_MIX_DPX_IMAD) ROW(K_MIX_DPX_IADD) ROW(K_MIX_DPX_MNMX2) ROW(K_MIX_MNMX2_IMAD) ROW(K_MIX_DPX_IMAD2) ROW(K_SHFL) ROW(K_LDS128) ROW(K_PREDOFF) ROW(K_CELL)
+    ROW(K_MIX_DPX_IMAD) ROW(K_MIX_DPX_IADD) ROW(K_MIX_DPX_MNMX2) ROW(K_MIX_MNMX2_IMAD) ROW(K_MIX_DPX_IMAD2) ROW(K_MIX_DPXC_IMADC) ROW(K_MIX_DPX_IADDC) ROW(K_MIX_DPXC_IADDC) ROW(K_MIX_2DPXC_IADDC) ROW(K_MIX_MNMX2_IADDC) ROW(K_SHFL) ROW(K_LDS128) ROW(K_PREDOFF) ROW(K_CELL)
     return 0;
 }
