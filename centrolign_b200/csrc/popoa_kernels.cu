@@ -586,10 +586,19 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
     // warp-uniform: does any lane of this strip persist one of its first three columns (a column with a far successor,
     // or whose distance-2 successor lies in the next 32-column block)?  Their offsets; the stores sit behind one branch.
     const bool strip_pers012 = __any_sync(kFull, (cbits & 0x00101010u) != 0);
-    uint32_t coff012[C - 1];
-#pragma unroll
-    for (int c = 0; c < C - 1; ++c) coff012[c] = ((cbits >> (8 * c)) & 16u) ? (uint32_t)slot2[j0 + c] * cstride : 0xffffffffu;
     const uint32_t rpersist = nvalid ? kInfoPersist : 0u;  // a lane entirely beyond n2 stores no rows
+    const bool slot_escape = n1 >= (int)kInfoSlotEscape;    // warp-uniform: row slots may exceed the info word's field
+    // lane-constant column shapes of the lean step and the labels, in registers of their own (re-deriving them from the
+    // packed words costs a dozen instructions per step)
+    int cB[C], cJ[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        cB[c] = ((cbits >> (8 * c)) & 1u) ? 0 : 1;        // no distance-1 predecessor: a second allele
+        cJ[c] = (((cbits >> (8 * c)) & 3u) == 3u) ? 1 : 0; // distance 1 and 2: the node after a bubble
+        asm volatile("mov.u32 %0, %0;" : "+r"(cB[c]));
+        asm volatile("mov.u32 %0, %0;" : "+r"(cJ[c]));
+        asm volatile("mov.u32 %0, %0;" : "+r"(cl[c]));
+    }
     const bool lane0L1 = lane == 0 && (needL & 1u);        // lane 0 takes its left neighbour from the left-column buffer
 
     // 7-way max of the recurrence (2P+1 values), DPX three-input maxima; the left-dependent values come last
@@ -615,14 +624,12 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
         constexpr bool GUARD = decltype(guard_tag)::value;
         constexpr bool LEAN = decltype(lean_tag)::value;
         const int r = 1 + s - lane;
-        bool act = true;
-        if (GUARD) act = r > R0 && r <= R1;
+        const bool act = r > R0 && r <= R1;  // lanes outside the panel (pipeline fill / drain) idle
         // requests first: lane 0's left-column entry (all lanes read it: a broadcast) and the info word two rows down
         const int4 tl = lds_128(laddr);
         laddr += 16u;
-        uint32_t rinfo_new;
-        if (GUARD) rinfo_new = (r + 1 >= R0 && r + 2 <= R1) ? info1[(uint32_t)(r + 2)] : 0u;
-        else rinfo_new = info1[(uint32_t)(r + 2)];  // r + 2 <= n1 + 1: the info array is padded by one entry
+        // (lanes that have not entered the panel yet read a harmless entry; the info array is padded by two entries)
+        const uint32_t rinfo_new = info1[(uint32_t)min(max(r + 2, 0), R1 + 2)];
         // previous lane's columns for this row (it finished the row one step ago); in lane 0, the columns left of the
         // strip.  Columns that no lane needs are not shuffled: whatever value stands in for them is never selected.
         int P3g[3] = {kMinInf, kMinInf, kMinInf}, P2g[3] = {O2g[0], O2g[1], O2g[2]}, P1g[3] = {O1g[0], O1g[1], O1g[2]};
@@ -709,7 +716,7 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
                     }
                 }
             }
-            int G[C][3], eM[C], Dk[C][3];
+            int G[C][3], eM[C];
             auto column = [&](auto ctag) {
                 constexpr int c = decltype(ctag)::value;
                 eM[c] = St[c].x;  // effective M of the row above = diagonal input of the columns to the right
@@ -728,13 +735,14 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
                 int D[3] = {kMinInf, kMinInf, kMinInf};
                 int E;
                 if (LEAN) {  // a lean strip knows three column shapes: (c1, !c2) regular, (!c1, c2) second allele, (c1, c2) after a bubble
+                    const bool pB = cB[c] != 0, pJ = cJ[c] != 0;
 #pragma unroll
                     for (int k = 0; k < P; ++k) {
-                        D[k] = c1 ? d1g[k] : d2g[k];
-                        if (c1 && c2) D[k] = imax(D[k], d2g[k]);
+                        D[k] = pB ? d2g[k] : d1g[k];
+                        if (pJ) D[k] = imax(D[k], d2g[k]);
                     }
-                    E = c1 ? d1e : d2e;
-                    if (c1 && c2) E = imax(E, d2e);
+                    E = pB ? d2e : d1e;
+                    if (pJ) E = imax(E, d2e);
                 } else {
 #pragma unroll
                     for (int k = 0; k < P; ++k) D[k] = imax(c1 ? d1g[k] : kMinInf, c2 ? d2g[k] : kMinInf);
@@ -806,25 +814,25 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
                         colbuf[coff3 + (uint32_t)r] = make_int4(Mn, D[0], D[1], D[2]);
                         coleff[coff3 + (uint32_t)r] = eM[c];
                     }
+                } else {
+                    if (strip_pers012) {  // warp-uniform and uncommon
+                        if ((cbits >> (8 * c)) & 16u) {
+                            const uint32_t o = (uint32_t)slot2[j0 + c] * cstride + (uint32_t)r;
+                            colbuf[o] = make_int4(Mn, D[0], D[1], D[2]);
+                            coleff[o] = eM[c];
+                        }
+                    }
                 }
-#pragma unroll
-                for (int k = 0; k < 3; ++k) Dk[c][k] = D[k];
             };
             column(std::integral_constant<int, 0>{});
             column(std::integral_constant<int, 1>{});
             column(std::integral_constant<int, 2>{});
             column(std::integral_constant<int, 3>{});
-            if (strip_pers012) {  // warp-uniform and uncommon
-#pragma unroll
-                for (int c = 0; c < C - 1; ++c)
-                    if (coff012[c] != 0xffffffffu) {
-                        colbuf[coff012[c] + (uint32_t)r] = make_int4(St[c].x, Dk[c][0], Dk[c][1], Dk[c][2]);
-                        coleff[coff012[c] + (uint32_t)r] = eM[c];
-                    }
-            }
             {   // persisted row: {M, H_k} of the lane's four columns (rows are padded: columns beyond n2 land in the padding)
                 uint32_t rslot = rinfo >> kInfoSlotShift;
-                if ((rinfo & rpersist) && rslot == kInfoSlotEscape) rslot = (uint32_t)Wsh.slot1[r];
+                if (slot_escape) {
+                    if ((rinfo & rpersist) && rslot == kInfoSlotEscape) rslot = (uint32_t)Wsh.slot1[r];
+                }
                 int4* const rp = rowbuf + (size_t)(rslot * rstride + (uint32_t)j0);
                 if (rinfo & rpersist) {
 #pragma unroll
@@ -845,9 +853,10 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
         progress[g & kProgMask] = ((unsigned long long)(g + 1) << 32) | (unsigned)r31;
     };
 
+    // PB-step blocks; lane 0 is on rows s0+1 .. s0+PB (R0 is a multiple of PB).  Lean and generic strips have loops of
+    // their own, so that what only the generic step keeps across steps is not live in the lean loop.
     const int nsteps = R1 + 31;
-    for (int s0 = R0; s0 < nsteps; s0 += PB) {  // PB-step blocks; lane 0 is on rows s0+1 .. s0+PB (R0 is a multiple of PB)
-        const int s1 = min(s0 + PB, nsteps);
+    auto block_head = [&](int s0) {
         const int bnext = s0 / PB + 1;
         const bool more = PB * bnext + 1 <= R1;
         if (more) {  // only lane 0 reads the prefetch buffers, so the next block can be requested right away
@@ -855,25 +864,45 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
             prefetch_block(bnext);
         }
         laddr = saLv + (uint32_t)((s0 / PB) & 1) * (PB * 16u);
-        const bool inner = s0 >= R0 + 31 && s1 <= R1;
-#pragma unroll 1
-        for (int q8 = s0; q8 < s1; q8 += 8) {
-            const int e8 = min(q8 + 8, s1);
-            if (inner && lean) {
-#pragma unroll 1
-                for (int s = q8; s < q8 + 8; ++s) step(s, std::false_type{}, std::true_type{});
-            } else {  // the guarded step doubles as the generic one (one copy of it: instruction cache)
-#pragma unroll 1
-                for (int s = q8; s < e8; ++s) step(s, std::true_type{}, std::false_type{});
-            }
-            if (lane == 31) {
-                const int r31 = e8 - 31;
-                if (r31 > R0) publish(min(r31, R1));
-            }
-        }
+        return more;
+    };
+    auto block_tail = [&](int s0, bool more) {
         cp_async_wait_all();
         __syncwarp();
-        if (more) convert_block(bnext);
+        if (more) convert_block(s0 / PB + 1);
+    };
+    auto publish_after = [&](int e8) {
+        if (lane == 31) {
+            const int r31 = e8 - 31;
+            if (r31 > R0) publish(min(r31, R1));
+        }
+    };
+    if (lean) {
+        for (int s0 = R0; s0 < nsteps; s0 += PB) {
+            const int s1 = min(s0 + PB, nsteps);
+            const bool more = block_head(s0);
+#pragma unroll 1
+            for (int q8 = s0; q8 < s1; q8 += 8) {
+                const int e8 = min(q8 + 8, s1);
+#pragma unroll 1
+                for (int s = q8; s < e8; ++s) step(s, std::false_type{}, std::true_type{});
+                publish_after(e8);
+            }
+            block_tail(s0, more);
+        }
+    } else {
+        for (int s0 = R0; s0 < nsteps; s0 += PB) {
+            const int s1 = min(s0 + PB, nsteps);
+            const bool more = block_head(s0);
+#pragma unroll 1
+            for (int q8 = s0; q8 < s1; q8 += 8) {
+                const int e8 = min(q8 + 8, s1);
+#pragma unroll 1
+                for (int s = q8; s < e8; ++s) step(s, std::true_type{}, std::false_type{});
+                publish_after(e8);
+            }
+            block_tail(s0, more);
+        }
     }
 }
 
@@ -921,13 +950,18 @@ __device__ void tb_boundary(const Win& W, const Params& prm, int lane) {
 // Traceback (the CTA's traceback warp).  Mirrors alignment.hpp:979-1138 on recomputed cell values.
 // ------------------------------------------------------------------------------------------
 struct TileView {
-    int R0, R1, C0;  // tile rows R0..R1, columns C0..C0+31; R0 = 0 means "no tile"
+    int R0, R1, C0;  // rows R0..R1 of the tile are in shared memory, columns C0..C0+31; R0 = 0 means "no tile"
+    int B0;          // first row of the recomputation (the 64-row block): base of the cached row info words
+    int W0;          // the walk may stand on rows W0..R1: its near predecessors (up to kNear rows up) must be in shared memory too
 };
 
-// shared memory of the traceback warp
+// shared memory of the traceback warp.  A tile is recomputed from the top of its 64-row block down to the row the
+// walk is on, but only its last kTileKeep rows are kept (a ring): the walk re-enters the recomputation when it
+// climbs above them.  Half the shared memory of keeping all 64 rows, which the fill warps' L1 gets.
+constexpr int kTileKeep = 32;
 struct __align__(16) TileSmem {
-    int4 A[kRowBlock * 32];       // {M, I_k}       [row & 63][lane]
-    int4 B[kRowBlock * 32];       // {diag in, D_k} [row & 63][lane]
+    int4 A[kTileKeep * 32];       // {M, I_k}       [row & 31][lane]: the LAST kTileKeep rows of the recomputed tile
+    int4 B[kTileKeep * 32];       // {diag in, D_k} [row & 31][lane]
     int4 leftv[3][kRowBlock];     // {M, D_k} of the 3 columns left of the tile, rows R0..R1
     int lefte[3][kRowBlock];      // their diagonal input
     uint32_t rinfo[kRowBlock];    // info words of the tile's rows
@@ -940,7 +974,7 @@ struct __align__(16) TileSmem {
 template <int P>
 __device__ __forceinline__ void tile_strip(const Win& Wsh, const Params& prm, const int C0, const int R0, const int R1,
                                            TileSmem& sm, const int lane) {
-    constexpr int H = kRowBlock;
+    constexpr int H = kTileKeep;
     const int n1 = Wsh.n1, n2 = Wsh.n2;
     const uint32_t* __restrict__ info1 = Wsh.info1;
     const int32_t* __restrict__ slot1 = Wsh.slot1;
@@ -1104,11 +1138,12 @@ struct Walker {
     __device__ bool in_tile(int i, int j) const {
         return tv.R0 > 0 && i >= tv.R0 && i <= tv.R1 && j >= tv.C0 && j < tv.C0 + kStrip && j <= W.n2;
     }
+    __device__ bool walkable(int i, int j) const { return i >= tv.W0 && in_tile(i, j); }
     // M(i,j); the corner reads as -inf in every traceback test (it is never a match)
     __device__ int cM(int i, int j) const {
         if (i == 0) return j == 0 ? kMinInf : W.brow[j].x;
         if (j == 0) return W.bcol[i].x;
-        if (in_tile(i, j)) return sm.A[(i & (kRowBlock - 1)) * 32 + (j - tv.C0)].x;
+        if (in_tile(i, j)) return sm.A[(i & (kTileKeep - 1)) * 32 + (j - tv.C0)].x;
         const int s = W.slot1[i];
         if (s >= 0) return W.rowbuf[(uint32_t)s * rstride + (uint32_t)j].x;
         return W.colbuf[(uint32_t)W.slot2[j] * cstride + (uint32_t)i].x;
@@ -1116,7 +1151,7 @@ struct Walker {
     // I_k(i,j) of the CURRENT cell: always on the boundary or inside the recomputed tile
     __device__ int cI(int i, int j, int k) const {
         if (i == 0) return kMinInf;
-        const int4 v = (j == 0) ? W.bcol[i] : sm.A[(i & (kRowBlock - 1)) * 32 + (j - tv.C0)];
+        const int4 v = (j == 0) ? W.bcol[i] : sm.A[(i & (kTileKeep - 1)) * 32 + (j - tv.C0)];
         return k == 0 ? v.y : (k == 1 ? v.z : v.w);
     }
     // "I_k(p,j) - e_k" of a PREDECESSOR row p, for the extension test of alignment.hpp:1101-1116.  A row outside the tile
@@ -1133,11 +1168,11 @@ struct Walker {
         if (j == 0) return kMinInf;
         int4 v;
         if (i == 0) v = W.brow[j];
-        else if (in_tile(i, j)) v = sm.B[(i & (kRowBlock - 1)) * 32 + (j - tv.C0)];
+        else if (in_tile(i, j)) v = sm.B[(i & (kTileKeep - 1)) * 32 + (j - tv.C0)];
         else v = W.colbuf[(uint32_t)W.slot2[j] * cstride + (uint32_t)i];
         return k == 0 ? v.y : (k == 1 ? v.z : v.w);
     }
-    __device__ uint32_t rinfo(int i) const { return (tv.R0 > 0 && i >= tv.R0 && i <= tv.R1) ? sm.rinfo[i - tv.R0] : W.info1[i]; }
+    __device__ uint32_t rinfo(int i) const { return (tv.R0 > 0 && i >= tv.B0 && i <= tv.R1) ? sm.rinfo[i - tv.B0] : W.info1[i]; }
     __device__ uint32_t cinfo(int j) const { return (tv.R0 > 0 && j >= tv.C0 && j < tv.C0 + kStrip && j <= W.n2) ? sm.cinfo[j - tv.C0] : W.info2[j]; }
 };
 
@@ -1197,21 +1232,22 @@ __device__ void traceback(const Win& W, const Params& prm, TileSmem& sm, int lan
     }
     if (lane == 0) *score_out = (ci >= 0) ? (long long)best : 0;
 
-    Walker<P> wk{W, prm, sm, TileView{0, 0, 0}, rstride, (uint32_t)n1 + 1u};
+    Walker<P> wk{W, prm, sm, TileView{0, 0, 0, 0, 0}, rstride, (uint32_t)n1 + 1u};
     const int cap = n1 + n2;
     int len = 0, comp = 0;
     while (ci >= 0) {  // warp-uniform: ci/cj are broadcast from lane 0 below
-        if (ci >= 1 && cj >= 1 && !wk.in_tile(ci, cj)) {
+        if (ci >= 1 && cj >= 1 && !wk.walkable(ci, cj)) {
             const int R0 = 1 + ((ci - 1) / kRowBlock) * kRowBlock;
             const int C0 = 1 + ((cj - 1) / kStrip) * kStrip;
             __syncwarp();
             tile_strip<P>(W, prm, C0, R0, ci, sm, lane);
             __syncwarp();
-            wk.tv = TileView{R0, ci, C0};
+            const int keep0 = max(R0, ci - (kTileKeep - 1));  // rows above the block are persisted, rows above keep0 inside it are not
+            wk.tv = TileView{keep0, ci, C0, R0, keep0 == R0 ? R0 : keep0 + kNear};
         }
         if (lane == 0) {
             // walk while the current cell is on the boundary or inside the recomputed tile
-            while (ci >= 0 && (ci == 0 || cj == 0 || wk.in_tile(ci, cj)) && len < cap) {
+            while (ci >= 0 && (ci == 0 || cj == 0 || wk.walkable(ci, cj)) && len < cap) {
                 const int M = wk.cM(ci, cj);
                 if (comp == 0) {
                     for (int k = 0; k < P; ++k) {
@@ -1319,11 +1355,11 @@ __global__ void nsmid_kernel(unsigned* out) {
 __device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 
 template <int P>
-__global__ void __launch_bounds__(kThreads, 1) popoa_kernel(const LaunchArgs A) {
+__global__ void __launch_bounds__(kThreads, 1) popoa_kernel(const __grid_constant__ LaunchArgs A) {
     extern __shared__ int4 smem[];
     __shared__ CtaState S;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const Params prm = A.prm;
+    const Params& prm = A.prm;  // __grid_constant__: the parameters are constant-bank operands, not registers
     for (int i = tid; i <= kProgMask; i += kThreads) S.progress[i] = 0ull;
     if (tid < 8) S.seq_tag[tid] = 0;
     __syncthreads();
