@@ -31,6 +31,8 @@
 #include <cuda_runtime.h>
 #include <limits.h>
 
+#include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 #include "popoa_device.cuh"
@@ -586,6 +588,9 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
     // warp-uniform: does any lane of this strip persist one of its first three columns (a column with a far successor,
     // or whose distance-2 successor lies in the next 32-column block)?  Their offsets; the stores sit behind one branch.
     const bool strip_pers012 = __any_sync(kFull, (cbits & 0x00101010u) != 0);
+    uint32_t coff012[C - 1];  // their workspace offsets
+#pragma unroll
+    for (int c = 0; c < C - 1; ++c) coff012[c] = ((cbits >> (8 * c)) & 16u) ? (uint32_t)slot2[j0 + c] * cstride : 0xffffffffu;
     const uint32_t rpersist = nvalid ? kInfoPersist : 0u;  // a lane entirely beyond n2 stores no rows
     const bool slot_escape = n1 >= (int)kInfoSlotEscape;    // warp-uniform: row slots may exceed the info word's field
     // lane-constant column shapes of the lean step and the labels, in registers of their own (re-deriving them from the
@@ -614,11 +619,11 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
     // lane 0's entry of the left-column buffers for the row it is on: rows PB*b+1.. live in buffer b&1 at index (row-1) % PB,
     // column d at leftv[d]; the address advances by one entry per step and flips buffers every PB steps
     uint32_t laddr = saLv + (uint32_t)((R0 / PB) & 1) * (PB * 16u);
-    // row info words, requested two steps ahead so that no step waits for its own load
-    // (lane t enters the panel at step R0 + t on row R0 + 1; it has been loading since it was on row R0 - 1)
-    uint32_t rinfo_cur = 0u, rinfo_nxt = 0u;
-    if (lane == 0) rinfo_cur = info1[R0 + 1];
-    if (lane <= 1 && R0 + 2 - lane <= R1) rinfo_nxt = info1[R0 + 2 - lane];
+    // Row info words travel down the lanes with the wavefront (lane t is on the row lane t-1 was on a step earlier):
+    // one shuffle per step, and lane 0 takes the word of its new row, which every lane requested (one broadcast
+    // address) three steps earlier -- no step waits for a load.
+    uint32_t rinfo_cur = (lane == 0) ? info1[R0 + 1] : 0u;                 // row of this lane in the coming step
+    uint32_t rq1 = info1[min(R0 + 2, R1 + 1)], rq2 = info1[min(R0 + 3, R1 + 2)];  // lane 0's rows one and two steps ahead
 
     auto step = [&](const int s, auto guard_tag, auto lean_tag) {
         constexpr bool GUARD = decltype(guard_tag)::value;
@@ -628,8 +633,7 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
         // requests first: lane 0's left-column entry (all lanes read it: a broadcast) and the info word two rows down
         const int4 tl = lds_128(laddr);
         laddr += 16u;
-        // (lanes that have not entered the panel yet read a harmless entry; the info array is padded by two entries)
-        const uint32_t rinfo_new = info1[(uint32_t)min(max(r + 2, 0), R1 + 2)];
+        const uint32_t rq3 = info1[(uint32_t)min(s + 4, R1 + 2)];  // lane 0's row three steps ahead (the info array is padded by two entries)
         // previous lane's columns for this row (it finished the row one step ago); in lane 0, the columns left of the
         // strip.  Columns that no lane needs are not shuffled: whatever value stands in for them is never selected.
         int P3g[3] = {kMinInf, kMinInf, kMinInf}, P2g[3] = {O2g[0], O2g[1], O2g[2]}, P1g[3] = {O1g[0], O1g[1], O1g[2]};
@@ -816,8 +820,8 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
                     }
                 } else {
                     if (strip_pers012) {  // warp-uniform and uncommon
-                        if ((cbits >> (8 * c)) & 16u) {
-                            const uint32_t o = (uint32_t)slot2[j0 + c] * cstride + (uint32_t)r;
+                        if (coff012[c] != 0xffffffffu) {
+                            const uint32_t o = coff012[c] + (uint32_t)r;
                             colbuf[o] = make_int4(Mn, D[0], D[1], D[2]);
                             coleff[o] = eM[c];
                         }
@@ -844,8 +848,11 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
             O3e = eM[3]; O2e = eM[2];
             if (!LEAN) O1e = eM[1];
         }
-        rinfo_cur = rinfo_nxt;
-        rinfo_nxt = rinfo_new;
+        {   // next step: every lane moves one row down
+            const uint32_t up = __shfl_up_sync(kFull, rinfo, 1);
+            rinfo_cur = (lane == 0) ? rq1 : up;
+            rq1 = rq2; rq2 = rq3;
+        }
         __syncwarp();
     };
     auto publish = [&](int r31) {
@@ -1494,7 +1501,10 @@ int popoa_smem_bytes() { return (kTileInt4 + kFillWarps * (int)(sizeof(FillSmemA
 int popoa_threads() { return kThreads; }
 
 cudaError_t launch_popoa(int num_pw, const LaunchArgs& args, int grid, cudaStream_t stream) {
-    const int smem = popoa_smem_bytes();
+    int smem = popoa_smem_bytes();
+#ifdef CLB_PROFILE
+    if (const char* e = getenv("CLB_SMEM_PAD_KB")) smem = std::min(smem + 1024 * atoi(e), 227 * 1024 - 6 * 1024);  // experiment: shrink the L1 share
+#endif
     cudaError_t err;
     switch (num_pw) {
         case 1:
