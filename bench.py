@@ -27,6 +27,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))  # tests/checkers.py: the CPU checkers of the cpu_baseline / reference legs
 
 METRIC = "GCUPS (graph DP cell updates/s), batched PO-to-PO gap-fill windows"
 UNIT = "GCUPS"
@@ -127,8 +128,9 @@ def run_reference_arm(args, rank, world):
         return
     from concurrent.futures import ThreadPoolExecutor
 
-    from centrolign_b200.batch import AlignmentParameters, CpuChecker, select_windows, synth_windows
+    from centrolign_b200.batch import AlignmentParameters, select_windows, synth_windows
 
+    from checkers import CpuChecker
     kind = "reference" if CpuChecker.available("reference") else "port"
     chk = CpuChecker(kind)
     cores = os.cpu_count() or 1
@@ -179,8 +181,8 @@ def other_paths(device):
     pwfa_po_poa (clb_pwfa_batch) and the sparse anchor-chaining DP (clb_chain_dp)."""
     import tempfile
 
-    from centrolign_b200.batch import AlignmentParameters, CpuChecker, select_windows, successor_form, synth_windows
-    from centrolign_b200.chain import ChainStats, chain_dp, chain_oracle, read_chain_bin
+    from centrolign_b200.batch import AlignmentParameters, select_windows, successor_form, synth_windows
+    from centrolign_b200.chain import ChainStats, chain_dp, read_chain_bin
     from centrolign_b200.popoa import PwfaStats, pwfa_po_poa_batch
 
     out = {}
@@ -193,6 +195,7 @@ def other_paths(device):
     t0 = time.perf_counter()
     scores, alns = pwfa_po_poa_batch(sb, params, 50, device=device, stats=st)
     wall = time.perf_counter() - t0
+    from checkers import CpuChecker
     kind = "reference" if CpuChecker.available("reference") else "port"
     chk = CpuChecker(kind)
     idx = np.linspace(0, nw - 1, 6).astype(int)
@@ -233,6 +236,7 @@ def other_paths(device):
         wall = (time.perf_counter() - t0) * 1e3
         assert np.array_equal(chain, prob.expect_chain), f"chaining ({kind_name}): GPU chain differs from the reference's"
         t0 = time.perf_counter()
+        from checkers import chain_oracle
         ochain = chain_oracle(prob)[0]
         oracle_ms = (time.perf_counter() - t0) * 1e3
         assert np.array_equal(chain, ochain)
@@ -253,7 +257,7 @@ def main():
 
     import torch
 
-    from centrolign_b200.batch import AlignmentParameters, CpuChecker, select_windows, synth_windows
+    from centrolign_b200.batch import AlignmentParameters, select_windows, synth_windows
     from centrolign_b200.popoa import DeviceBatch, load_library, po_poa_batch
 
     if not torch.cuda.is_available():
@@ -379,6 +383,7 @@ def main():
         # ---- CPU baseline on a bounded sample, parity-checked against the GPU result ----
         cpu = None
         if not args.no_cpu_baseline:
+            from checkers import CpuChecker
             kind = "reference" if CpuChecker.available("reference") else "port"
             chk = CpuChecker(kind)
             picks = cpu_sample(batch, cells, budget_cells=int(5e8), max_cells=int(1.2e8))

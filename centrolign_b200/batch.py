@@ -320,94 +320,3 @@ def sources_and_sinks(n: int, edges) -> Tuple[List[int], List[int]]:
         outdeg[a] += 1
         indeg[b] += 1
     return [v for v in range(n) if indeg[v] == 0], [v for v in range(n) if outdeg[v] == 0]
-
-
-# ----------------------------------------------------------------------------------------
-# CPU checkers (TEST INFRASTRUCTURE): the C oracle and, when built, the real reference.
-# Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may call these.
-# ----------------------------------------------------------------------------------------
-_ORACLE_DIR = os.path.join(os.path.dirname(_HERE), "oracle")
-
-_u32p = ctypes.POINTER(ctypes.c_uint32)
-_u8p = ctypes.POINTER(ctypes.c_uint8)
-_SIDE_ARGS = [ctypes.c_uint32, _u8p, _u32p, _u32p, ctypes.c_uint32, _u32p, ctypes.c_uint32, _u32p]
-
-
-def _bind_checker(lib, name, extra=(), tail=()):
-    fn = getattr(lib, name)
-    fn.restype = ctypes.c_int
-    fn.argtypes = [ctypes.c_int, _u32p, *extra, *_SIDE_ARGS, *_SIDE_ARGS, ctypes.POINTER(ctypes.c_int64),
-                   ctypes.POINTER(ctypes.c_int32), _u32p, *tail]
-    return fn
-
-
-class CpuChecker:
-    """ctypes front for ``oracle/libcloracle.so`` (kind='port') or
-    ``oracle/_ref/libclref.so`` (kind='reference', the unmodified reference)."""
-
-    def __init__(self, kind: str = "port"):
-        self.kind = kind
-        if kind == "port":
-            path, sym = os.path.join(_ORACLE_DIR, "libcloracle.so"), "clo_po_poa"
-        elif kind == "reference":
-            path, sym = os.path.join(_ORACLE_DIR, "_ref", "libclref.so"), "clref_po_poa"
-        else:
-            raise ValueError(kind)
-        if not os.path.exists(path):
-            raise FileNotFoundError(path)
-        self.lib = ctypes.CDLL(path)
-        self._po_poa = _bind_checker(self.lib, sym)
-        self._pwfa = _bind_checker(self.lib, "clref_pwfa_po_poa", (ctypes.c_int64,)) if kind == "reference" else None
-        self._pwfa_succ = _bind_checker(self.lib, "clo_pwfa_po_poa" if kind == "port" else "clref_pwfa_po_poa_succ",
-                                        (ctypes.c_int64,), (ctypes.POINTER(ctypes.c_int64),))
-
-    @staticmethod
-    def available(kind: str) -> bool:
-        p = os.path.join(_ORACLE_DIR, "libcloracle.so") if kind == "port" else os.path.join(_ORACLE_DIR, "_ref", "libclref.so")
-        return os.path.exists(p)
-
-    @staticmethod
-    def _side(side: GraphSide, w: int):
-        lab, po, pr, src, snk = (np.ascontiguousarray(a) for a in side.window(w))
-        keep = (lab, po, pr, src, snk)
-
-        def p32(a):
-            return a.ctypes.data_as(_u32p)
-
-        return keep, [len(lab), lab.ctypes.data_as(_u8p), p32(po), p32(pr), len(src), p32(src), len(snk), p32(snk)]
-
-    def po_poa(self, batch: WindowBatch, w: int, params: AlignmentParameters, prune_limit=None):
-        """Returns (score, alignment[int32 (len,2)], -1 = gap) for window ``w``."""
-        k1, a1 = self._side(batch.g1, w)
-        k2, a2 = self._side(batch.g2, w)
-        pk = params.packed()
-        score = ctypes.c_int64(0)
-        cap = max(1, batch.g1.n(w) + batch.g2.n(w))
-        aln = np.empty((cap, 2), np.int32)
-        ln = ctypes.c_uint32(0)
-        extra = [] if prune_limit is None else [ctypes.c_int64(prune_limit)]
-        fn = self._po_poa if prune_limit is None else self._pwfa
-        rc = fn(params.num_pw, pk.ctypes.data_as(_u32p), *extra, *a1, *a2, ctypes.byref(score),
-                aln.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), ctypes.byref(ln))
-        if rc != 0:
-            raise RuntimeError(f"{self.kind} checker failed with code {rc}")
-        return int(score.value), aln[: ln.value].copy()
-
-    def pwfa_po_poa(self, succ_batch: WindowBatch, w: int, params: AlignmentParameters, prune_limit: int, stats=None):
-        """``pwfa_po_poa`` (alignment.hpp:2299-2338) on window ``w`` of a batch in ``successor_form``.
-        Returns (score, alignment); ``stats`` (int64[3], port only) receives settled states, dequeued
-        entries and the final WFA score."""
-        k1, a1 = self._side(succ_batch.g1, w)
-        k2, a2 = self._side(succ_batch.g2, w)
-        pk = params.packed()
-        score = ctypes.c_int64(0)
-        cap = max(1, succ_batch.g1.n(w) + succ_batch.g2.n(w))
-        aln = np.empty((cap, 2), np.int32)
-        ln = ctypes.c_uint32(0)
-        st = stats if stats is not None else np.zeros(3, np.int64)
-        rc = self._pwfa_succ(params.num_pw, pk.ctypes.data_as(_u32p), ctypes.c_int64(prune_limit), *a1, *a2,
-                             ctypes.byref(score), aln.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), ctypes.byref(ln),
-                             st.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)))
-        if rc != 0:
-            raise RuntimeError(f"{self.kind} pwfa checker failed with code {rc}")
-        return int(score.value), aln[: ln.value].copy()

@@ -136,39 +136,3 @@ def problems_from_arrays(raw, prefix: str = "") -> Dict[str, ChainProblem]:
                                  {} if meta is None else dict(zip(("nodes1", "nodes2", "chains1", "chains2", "match_sets", "pairs"),
                                                                   np.asarray(meta).tolist())))
     return out
-
-
-# ----------------------------------------------------------------------------------------
-# CPU checker (TEST INFRASTRUCTURE): oracle/chain_oracle.c.  Only tests/, __graft_entry__.smoke()
-# and bench.py's CPU legs may call this.
-# ----------------------------------------------------------------------------------------
-def chain_oracle(problem: ChainProblem):
-    """The C restatement of the reference's chaining DP (oracle/libcloracle.so :: clo_chain_dp) on the same flat
-    problem.  Returns (chain ranks, dp values, back-pointers, optimum)."""
-    import os
-
-    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "libcloracle.so")
-    lib = ctypes.CDLL(path)
-    vp = ctypes.c_void_p
-    lib.clo_chain_dp.restype = ctypes.c_int
-    lib.clo_chain_dp.argtypes = ([ctypes.c_int, vp, vp, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int64, vp, vp, vp,
-                                  ctypes.c_float, ctypes.c_int64] + [vp] * 14 + [vp, vp, vp, ctypes.POINTER(ctypes.c_int64),
-                                                                              ctypes.POINTER(ctypes.c_float)])
-    keep = {k: np.ascontiguousarray(problem.arrays[k], dt) for k, dt in _FIELDS}
-    go = np.asarray(list(problem.gap_open) + [0.0] * 3, np.float64)[:3].copy()
-    ge = np.asarray(list(problem.gap_extend) + [0.0] * 3, np.float64)[:3].copy()
-    m = problem.n_match
-    dp = np.zeros(max(1, m), np.float32)
-    bp = np.full(max(1, m), -1, np.int64)
-    chain = np.zeros(m + 1, np.int64)
-    n = ctypes.c_int64(0)
-    opt = ctypes.c_float(0)
-    order = ["end_off", "end_match", "qry_off", "qry_match", "qry_chain1", "ins_off", "ins_p1", "ins_p2", "ins_shift", "ins_offset",
-             "ins_active", "qa1", "qa2", "qoff"]
-    rc = lib.clo_chain_dp(problem.num_pw, go.ctypes.data, ge.ctypes.data, problem.scale, problem.n_chain1, problem.n_chain2, m,
-                          keep["weight"].ctypes.data, keep["dp_init"].ctypes.data, keep["final_term"].ctypes.data,
-                          problem.min_score, problem.n_step, *[keep[k].ctypes.data for k in order], dp.ctypes.data, bp.ctypes.data,
-                          chain.ctypes.data, ctypes.byref(n), ctypes.byref(opt))
-    if rc != 0:
-        raise RuntimeError(f"chain oracle failed with code {rc}")
-    return chain[: n.value].copy(), dp[:m], bp[:m], float(opt.value)

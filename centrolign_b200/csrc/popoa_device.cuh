@@ -68,7 +68,7 @@ struct LaunchArgs {
     int32_t* aln;           // pairs, written backwards from the end of each window's region
     uint32_t* aln_len;      // [n_windows]
     Params prm;
-    int debug_flags;        // bit0: skip the traceback walk (profiling the fill alone; results are then invalid)
+    int debug_flags;        // bit1: generic fill step everywhere; bit0 (-DCLB_PROFILE builds only): skip the traceback walk, results invalid
     int start_lag;          // rows a strip stays behind its left neighbour when it starts
     int slot_by_smid;       // 1: workspace slot pair chosen by %smid (kernels of several chunks share one workspace)
     int panel_rows;         // panel_rows_for(n1, this): wide windows with more rows are filled as (panel, strip) tiles; rows p*H-2..p*H are persisted

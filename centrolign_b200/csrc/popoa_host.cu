@@ -582,6 +582,9 @@ static int upload_internal(clb_batch* b, char* shared_ws, int64_t shared_slot_by
     size_t qcap = 0;
     b->d_queue = (int32_t*)g_cache.dev_alloc(b->device, sizeof(int32_t), &qcap, false);
     if (!b->d_queue) return fail(CLB_ENOMEM, "device allocation failed (queue)");
+    // A chunk whose largest window needs more than the shared slot (the slot was sized from the chunk with the most
+    // cells; elongated or persist-heavy windows can need more with fewer cells) gets a workspace of its own below.
+    if (shared_ws && b->max_ws_bytes > shared_slot_bytes) shared_ws = nullptr;
     if (shared_ws) {
         b->shared_workspace = true;
         b->d_workspace = shared_ws;
@@ -644,7 +647,12 @@ static int launch_internal(clb_batch* b) {
             a.prm.oe[k] = k < b->params.num_pw ? (int)(b->params.gap_open[k] + b->params.gap_extend[k]) : 0;
             a.prm.e[k] = k < b->params.num_pw ? (int)b->params.gap_extend[k] : 0;
         }
+        // bit 1: force the generic fill step everywhere (results unchanged; tests use it to cover that path).
+        // bit 0 (skip the traceback walk: results invalid, profiling the fill alone) exists only in -DCLB_PROFILE builds.
         a.debug_flags = getenv("CLB_DEBUG_FLAGS") ? atoi(getenv("CLB_DEBUG_FLAGS")) : 0;
+#ifndef CLB_PROFILE
+        a.debug_flags &= ~1;
+#endif
         a.start_lag = getenv("CLB_START_LAG") ? atoi(getenv("CLB_START_LAG")) : 64;
         a.slot_by_smid = b->shared_workspace ? 1 : 0;
         a.panel_rows = panel_cfg();
@@ -750,7 +758,7 @@ int clb_popoa_batch(int device, int32_t n_windows, const clb_graph_batch* g1, co
     // CLB_CHUNK_MIN_NODES lowers the node threshold (tests exercise the chunked path on small batches)
     const int64_t chunk_min_nodes = getenv("CLB_CHUNK_MIN_NODES") ? atoll(getenv("CLB_CHUNK_MIN_NODES")) : (int64_t(1) << 24);
     const bool chunked = n_windows >= 1024 && tot_nodes >= chunk_min_nodes && !getenv("CLB_NO_CHUNKS");
-    if (!chunked) {
+    auto one_batch = [&]() {
         clb_batch* b = nullptr;
         int rc = clb_batch_create(device, n_windows, g1, g2, params, &b);
         t1 = now();
@@ -765,7 +773,8 @@ int clb_popoa_batch(int device, int32_t n_windows, const clb_graph_batch* g1, co
             fprintf(stderr, "[clb] create %.3f s, upload %.3f s, run %.3f s, download %.3f s, destroy %.3f s\n", t1 - t0,
                     t2 - t1, t3 - t2, t4 - t3, now() - t4);
         return rc;
-    }
+    };
+    if (!chunked) return one_batch();
     if (check_side(g1) || check_side(g2) || !params) return fail(CLB_EINVAL, "null graph arrays");
     // windows by matrix size, largest first
     std::vector<int32_t> ord(n_windows);
@@ -806,9 +815,12 @@ int clb_popoa_batch(int device, int32_t n_windows, const clb_graph_batch* g1, co
         if (c == 0) {  // chunk 0 holds the largest windows: its slot size serves every chunk
             const int nsm = clb::popoa_nsmid();
             if (nsm <= 0) { rc = fail(CLB_ECUDA, "could not query the SM id space"); break; }
-            shared_slot = chunks[0]->max_ws_bytes;
+            shared_slot = (chunks[0]->max_ws_bytes + 255) & ~int64_t(255);
             shared_ws = (char*)g_cache.dev_alloc(device, (size_t)nsm * 2 * shared_slot, &shared_cap, true);
-            if (!shared_ws) { rc = fail(CLB_ENOMEM, "device allocation failed (shared workspace)"); break; }
+            if (!shared_ws) {  // one slot pair per SM does not fit: the single-batch path shrinks its grid to what does
+                clb_batch_destroy(chunks[0]);
+                return one_batch();
+            }
         }
         rc = upload_internal(chunks[c], shared_ws, shared_slot);
         if (rc == CLB_OK) rc = launch_internal(chunks[c]);

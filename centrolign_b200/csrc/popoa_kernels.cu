@@ -1480,7 +1480,9 @@ __global__ void __launch_bounds__(kThreads, 1) popoa_kernel(const __grid_constan
             while (ld_volatile(&S.strips_done[t & 1]) < nwait) __nanosleep(500);
             __threadfence_block();
             tb_boundary<P>(W, prm, lane);
+#ifdef CLB_PROFILE
             if (!(A.debug_flags & 1))
+#endif
                 traceback<P>(W, prm, *reinterpret_cast<TileSmem*>(smem), lane, A.score + w, A.aln + 2 * W.out, A.aln_len + w);
             __syncwarp();
             if (!ended) fetch();  // hands slot t&1 to window t+2

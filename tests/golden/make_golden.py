@@ -11,7 +11,7 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
-from centrolign_b200.batch import (AlignmentParameters, CpuChecker, batch_from_graph_pairs, concat_batches,  # noqa: E402
+from centrolign_b200.batch import (AlignmentParameters, batch_from_graph_pairs, concat_batches,  # noqa: E402
                                    graph_from_edges, random_bubble_chain, random_dag, sources_and_sinks, synth_windows)
 
 PARAM_SETS = [
@@ -66,6 +66,8 @@ def random_window(rng, kind):
 
 
 def main():
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from checkers import CpuChecker
     ref = CpuChecker("reference")
     rng = np.random.default_rng(20261017)
     pairs = []

@@ -15,7 +15,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 sys.path.insert(0, os.path.dirname(HERE))
-from centrolign_b200.batch import (AlignmentParameters, CpuChecker, concat_batches, successor_form,  # noqa: E402
+from centrolign_b200.batch import (AlignmentParameters, concat_batches, successor_form,  # noqa: E402
                                    synth_windows)
 from golden_io import load_golden  # noqa: E402
 
@@ -23,6 +23,7 @@ PRUNE_LIMITS = [0, 3, 50, 10 ** 6]  # Stitcher passes 2*wfa_pruning_dist = 50 (s
 
 
 def main():
+    from checkers import CpuChecker
     ref = CpuChecker("reference")
     base, params, pidx, _, _ = load_golden()
     hor = synth_windows(10, first_index=40, seed=11, len_min=150, len_max=2500, alt_len=61, alt_period=500)

@@ -5,7 +5,8 @@ between equal-scoring chains included, which is where the reference's search-tre
 import numpy as np
 import pytest
 
-from centrolign_b200.chain import ChainProblem, ChainStats, chain_dp, chain_oracle
+from centrolign_b200.chain import ChainProblem, ChainStats, chain_dp
+from checkers import chain_oracle  # test infrastructure: tests/checkers.py
 from golden_io import load_chain_golden
 
 pytestmark = pytest.mark.gpu

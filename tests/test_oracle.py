@@ -8,8 +8,9 @@
 import numpy as np
 import pytest
 
-from centrolign_b200.batch import (AlignmentParameters, CpuChecker, batch_from_graph_pairs, graph_from_edges,
+from centrolign_b200.batch import (AlignmentParameters, batch_from_graph_pairs, graph_from_edges,
                                    successor_form, synth_windows)
+from checkers import CpuChecker  # test infrastructure: tests/checkers.py
 from golden_io import REFERENCE_UNIT_GOLDENS, TIEBREAK_PROBES, load_chain_golden, load_golden, load_pwfa_golden
 
 
@@ -115,7 +116,7 @@ def test_pwfa_live_against_reference(oracle):
 def test_chain_oracle_reproduces_reference_chains():
     """tests/golden/chain_golden.npz: flat problems + the chains Anchorer::sparse_chain_dp /
     sparse_affine_chain_dp of the unmodified reference returned (anchorer.hpp:1511-1750, 1812-2471)."""
-    from centrolign_b200.chain import chain_oracle
+    from checkers import chain_oracle
 
     gold = load_chain_golden()
     assert len(gold) >= 4

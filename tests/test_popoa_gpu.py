@@ -5,10 +5,11 @@ scores and identical alignments are required."""
 import numpy as np
 import pytest
 
-from centrolign_b200.batch import (AlignmentParameters, CpuChecker, batch_from_graph_pairs, concat_batches,
+from centrolign_b200.batch import (AlignmentParameters, batch_from_graph_pairs, concat_batches,
                                    graph_from_edges, random_bubble_chain, random_dag, select_windows,
                                    sources_and_sinks, synth_windows)
 from centrolign_b200.popoa import DeviceBatch, po_poa_batch
+from checkers import CpuChecker  # test infrastructure: tests/checkers.py
 from golden_io import REFERENCE_UNIT_GOLDENS, TIEBREAK_PROBES, load_golden
 
 pytestmark = pytest.mark.gpu
@@ -166,9 +167,10 @@ _TILED_CHILD = r"""
 import sys
 import numpy as np
 sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
-from centrolign_b200.batch import (AlignmentParameters, CpuChecker, batch_from_graph_pairs, concat_batches, graph_from_edges,
+from centrolign_b200.batch import (AlignmentParameters, batch_from_graph_pairs, concat_batches, graph_from_edges,
                                    random_bubble_chain, sources_and_sinks, synth_windows)
 from centrolign_b200.popoa import po_poa_batch
+from checkers import CpuChecker
 import test_popoa_gpu as t
 oracle = CpuChecker("port")
 rng = np.random.default_rng(77)
@@ -303,3 +305,41 @@ def test_chunked_one_shot_matches_single_batch(monkeypatch):
         assert all(np.array_equal(x, y) for x, y in zip(a, ref_a))
     for w in range(0, batch.n_windows, 97):
         assert_valid_and_rescore(batch, w, PROD, int(ref_s[w]), ref_a[w])
+
+
+def test_chunked_one_shot_late_chunk_needs_larger_workspace(monkeypatch):
+    """A window's workspace grows with its persisted rows / columns and its elongation, not only with its cell count: the
+    chunked one-shot path sizes the shared slot from the chunk with the largest windows, so a persist-heavy or elongated
+    window of a LATER chunk must get a workspace of its own (popoa_host.cu upload_internal) instead of overrunning its slot."""
+    rng = np.random.default_rng(99)
+    pairs = []
+    for n1, n2 in ((260, 9), (9, 260), (300, 300)):  # elongated: few cells, long persisted columns / rows
+        for _ in range(3):
+            sides = []
+            for n in (n1, n2):
+                labels, edges = random_bubble_chain(rng, n, snp_rate=0.1, del_rate=0.03)
+                if n >= 200:  # many far edges: nearly every row / column is persisted
+                    edges = list(edges) + [(int(a), int(a) + 5 + int(rng.integers(0, 40))) for a in rng.integers(0, n - 50, size=n // 3)]
+                src, snk = sources_and_sinks(len(labels), edges)
+                sides.append(graph_from_edges(labels, edges, src, snk))
+            pairs.append(tuple(sides))
+    odd = batch_from_graph_pairs(pairs)
+    batch = concat_batches([
+        synth_windows(1100, first_index=9000, seed=13, len_min=100, len_max=400),
+        synth_windows(8, first_index=9500, seed=13, len_min=420, len_max=450),  # chunk 0: most cells, few persisted rows
+        odd,
+    ])
+    monkeypatch.setenv("CLB_NO_CHUNKS", "1")
+    ref_s, ref_a = po_poa_batch(batch, PROD)
+    ref_s = ref_s.copy()
+    ref_a = [a.copy() for a in ref_a]
+    monkeypatch.delenv("CLB_NO_CHUNKS")
+    monkeypatch.setenv("CLB_CHUNK_MIN_NODES", "1")
+    s, a = po_poa_batch(batch, PROD)
+    assert np.array_equal(s, ref_s)
+    assert all(np.array_equal(x, y) for x, y in zip(a, ref_a))
+    oracle = CpuChecker("port")
+    first_odd = batch.n_windows - odd.n_windows
+    for w in range(first_odd, batch.n_windows):
+        so, ao = oracle.po_poa(batch, w, PROD)
+        assert so == s[w] and np.array_equal(ao, a[w]), f"window {w} differs from the oracle"

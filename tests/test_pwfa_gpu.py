@@ -5,9 +5,10 @@ defined by its dequeue order, so identical alignments and scores are required, n
 import numpy as np
 import pytest
 
-from centrolign_b200.batch import (AlignmentParameters, CpuChecker, batch_from_graph_pairs, concat_batches,
+from centrolign_b200.batch import (AlignmentParameters, batch_from_graph_pairs, concat_batches,
                                    graph_from_edges, select_windows, successor_form, synth_windows)
 from centrolign_b200.popoa import ClbError, PwfaStats, pwfa_po_poa_batch
+from checkers import CpuChecker  # test infrastructure: tests/checkers.py
 from golden_io import REFERENCE_UNIT_GOLDENS, load_pwfa_golden
 
 pytestmark = pytest.mark.gpu

@@ -7,8 +7,9 @@ import numpy as np
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from centrolign_b200.batch import AlignmentParameters, CpuChecker, successor_form, synth_windows
+from centrolign_b200.batch import AlignmentParameters, successor_form, synth_windows
 from centrolign_b200.sharding import balanced_partition, run_sharded, stream_shard
+from checkers import CpuChecker  # test infrastructure: tests/checkers.py
 
 
 def test_balanced_partition_properties():

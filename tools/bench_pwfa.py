@@ -12,7 +12,8 @@ import time
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from centrolign_b200.batch import AlignmentParameters, CpuChecker, select_windows, successor_form, synth_windows  # noqa: E402
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from centrolign_b200.batch import AlignmentParameters, select_windows, successor_form, synth_windows  # noqa: E402
 from centrolign_b200.popoa import PwfaStats, pwfa_po_poa_batch  # noqa: E402
 
 
@@ -39,6 +40,7 @@ def main():
         if best is None or wall < best[0]:
             best = (wall, st.kernel_ms, st)
     wall, kms, st = best
+    from checkers import CpuChecker
     kind = "reference" if CpuChecker.available("reference") else "port"
     chk = CpuChecker(kind)
     idx = np.linspace(0, a.windows - 1, a.cpu_sample).astype(int)

@@ -4,6 +4,7 @@ import numpy as np
 from centrolign_b200.batch import *
 from centrolign_b200.popoa import po_poa_batch
 import test_popoa_gpu as t
+from checkers import CpuChecker
 oracle = CpuChecker("port")
 rng = np.random.default_rng(5)
 pairs = []

@@ -5,7 +5,7 @@
 B="timeout 200 python bench.py --windows ${WINDOWS:-8000} --no-cpu-baseline --no-e2e --no-other-paths"
 f(){ tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value'],1), round(d['roofline']['frac'],4))"; }
 echo -n "configs[1] as specified:        "; $B 2>&1 | f
-echo -n "traceback walk skipped:         "; CLB_DEBUG_FLAGS=1 $B 2>&1 | f
+echo -n "traceback walk skipped:         "; CLB_DEBUG_FLAGS=1 $B 2>&1 | f   # needs a -DCLB_PROFILE build (CLB_LIBRARY=...), else identical to the first line
 echo -n "lean step disabled:             "; CLB_DEBUG_FLAGS=2 $B 2>&1 | f
 echo -n "tiling off (CLB_PANEL_ROWS=0):  "; CLB_PANEL_ROWS=0 $B 2>&1 | f
 echo -n "no 171-node bubbles:            "; $B --alt-period 0 2>&1 | f
