@@ -48,15 +48,29 @@ def parse_args():
     ap.add_argument("--snp-rate", type=float, default=0.05)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-other-paths", action="store_true", help="skip the short pwfa / chaining measurements")
+    ap.add_argument("--no-other-paths", action="store_true", help="skip the short pwfa / chaining / end-to-end MSA measurements")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --windows per GPU (the driver's 1->8 run); strong: ONE batch of --windows windows dealt to the ranks "
+                         "in cell-balanced bins (clb_balanced_partition, the rule of clb_popoa_batch_multi)")
+    ap.add_argument("--workload", default="configs1", choices=["configs1", "pipeline"],
+                    help="configs1: BASELINE configs[1]; pipeline: window sizes of the reference's own Stitcher (SURVEY section 6: "
+                         "median 9 cells), reported as windows/s beside GCUPS")
     return ap.parse_args()
 
 
+REFERENCE_SAMPLE = ("reference arm: per step max(4*cores, 64) windows of the same generator with backbone <= 3 kbp (so that one 28 B/cell "
+                    "table per host thread fits in RAM), all host threads each running the single-threaded reference po_poa; the "
+                    "reference's per-cell rate is size-independent within 0.020-0.035 GCUPS/thread (BASELINE.md section 2)")
+
+
 def workload_config(args, world):
-    return {"workload": f"configs[1]: batched inter-anchor windows, {args.windows} synthetic PO-to-PO gap-fill problems per GPU, "
+    per = "per GPU" if args.scaling == "weak" else f"in total, dealt to {world} rank(s) in cell-balanced bins"
+    return {"workload": f"configs[1]: batched inter-anchor windows, {args.windows} synthetic PO-to-PO gap-fill problems {per}, "
                         f"backbone {args.len_min:.0f}-{args.len_max:.0f} bp log-uniform (~1-20 k nodes/side), 5% SNP bubbles, "
                         "171-node bubble per 2 kbp, NumPW=3 production parameters 20/80/{60,800,2500}/{30,5,1}",
-            "windows_per_gpu": args.windows, "num_pw": 3, "seed": SEED, "sharding": f"independent windows, {world} rank(s), no collective",
+            "windows_per_gpu": args.windows if args.scaling == "weak" else args.windows // max(1, world), "num_pw": 3, "seed": SEED,
+            "sharding": f"independent windows, {world} rank(s), no collective ({args.scaling} scaling)",
+            "reference_sample": REFERENCE_SAMPLE,
             "l2_policy": "inputs (GBs of CSR + workspace) exceed the 126 MB L2; no flush needed"}
 
 
@@ -209,6 +223,12 @@ def other_paths(device):
                           "windows_per_s": nw / (st.kernel_ms * 1e-3), "e2e_windows_per_s": nw / wall,
                           "search_states_per_s": st.states / (st.kernel_ms * 1e-3), "entries_per_warp_step": st.dequeued / max(1, st.steps),
                           "gpu_launches": int(st.kernel_launches),
+                          "roofline": {"bound": "latency of the dependent global accesses of one warp step (hash probe -> node record -> "
+                                                "FIFO append, ~3 L2 round trips), hidden by resident windows: one warp per window",
+                                       "achieved": st.kernel_ms * 1e3 / max(1, st.steps) * min(nw, 148 * 16), "unit": "us per warp step x resident windows",
+                                       "peak": 3 * 0.13, "peak_source": "3 dependent L2 round trips of ~250 cycles at 1.965 GHz (B300_MICROARCH.md L2 hit latency)",
+                                       "frac": (3 * 0.13) / max(1e-9, st.kernel_ms * 1e3 / max(1, st.steps) * min(nw, 148 * 16)),
+                                       "note": "issue slots and HBM are idle (profiles/r01_ncu_pwfa.md: issue 4 %, DRAM 0.7 %); throughput scales with the batch"},
                           "cpu_baseline": {"kind": kind, "cores": 1, "windows_per_s": 1.0 / cpu_s,
                                            "sample": f"{len(idx)} windows, each equal to the GPU result (score + alignment)"}}
     # ---- chaining: a pairwise HOR problem made by the reference's own match finder where its objects travelled ----
@@ -243,8 +263,66 @@ def other_paths(device):
         chain_out[kind_name] = {"matches": prob.n_match, "steps": prob.n_step, "kernel_ms": cst.kernel_ms, "build_ms": cst.build_ms,
                                 "e2e_ms": wall, "matches_per_s": prob.n_match / (cst.kernel_ms * 1e-3), "reference_cpu_ms": prob.ref_ms,
                                 "oracle_cpu_ms": oracle_ms, "chain_len": int(len(chain)), "equal_to_reference": True,
-                                "gpu_launches": int(cst.kernel_launches)}
+                                "gpu_launches": int(cst.kernel_launches),
+                                "roofline": {"bound": "dependent L2 round trips per step of the strictly sequential DP over graph-1 nodes "
+                                                      "(insert -> barrier -> query -> barrier)",
+                                             "achieved": cst.kernel_ms * 1e3 / max(1, prob.n_step), "unit": "us per step",
+                                             "peak": 4 * 0.13, "peak_source": "4 dependent L2 round trips of ~250 cycles at 1.965 GHz per step "
+                                                                             "(B300_MICROARCH.md L2 hit latency 234-262 cycles)",
+                                             "frac": (4 * 0.13) / max(1e-9, cst.kernel_ms * 1e3 / max(1, prob.n_step))}}
     out["chain_dp"] = chain_out
+    return out
+
+
+E2E_CASES = [
+    # name, what, make_hor_fasta args (n_seqs, length, seed, hor_indels), CLI options, Newick tree or None
+    ("configs[0]_pair_100k", "configs[0] at full size, default options: two 100 kbp HOR arrays -> CIGAR", [2, 100000, 1, 0], [], None),
+    ("configs[2]_scaled_tree", "configs[2] scaled: four 6 kbp HOR arrays with HOR indels, Newick guide tree, default options -> GFA",
+     [4, 6000, 5, 1], [], "((seq0,seq1),(seq2,seq3));"),
+    ("configs[4]_scaled_cyclic", "configs[4] scaled: three 6 kbp arrays with HOR indels, -c with cyclizing size 1000 -> cyclic GFA",
+     [3, 6000, 9, 3], ["-c", "-y", "1000"], None),
+]
+
+
+def e2e_msa(device):
+    """End-to-end MSA wall time and output identity (BASELINE.json metric, second half): the reference CLI built from its
+    own unmodified sources (oracle/_ref/centrolign_ref) next to the same sources built with the shadow headers
+    (oracle/_ref/centrolign_b200: chaining DP, po_poa and pwfa_po_poa on the GPU), same input, outputs compared by md5."""
+    import hashlib
+    import tempfile
+
+    clis = {k: os.path.join(ROOT, "oracle", "_ref", "centrolign_" + k) for k in ("ref", "b200")}
+    if not all(os.path.exists(c) for c in clis.values()):
+        return {"unavailable": "oracle/_ref/centrolign_{ref,b200} did not travel (built by `make -C integration` where /root/reference exists)"}
+    out = {"what": "wall seconds of the whole CLI run (process start to exit, GPU context creation included), reference = 1 host thread "
+                   "(the reference is single-threaded); identical = md5 of stdout (CIGAR / GFA) equal"}
+    env = dict(os.environ, CLB_COUNT_CALLS="1", CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(device)))
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, what, fa_args, opts, tree in E2E_CASES:
+            fa = os.path.join(tmp, name + ".fa")
+            subprocess.run([sys.executable, os.path.join(ROOT, "integration", "make_hor_fasta.py"), fa] + [str(a) for a in fa_args], check=True)
+            o = list(opts)
+            if tree:
+                nwk = os.path.join(tmp, name + ".nwk")
+                open(nwk, "w").write(tree + "\n")
+                o += ["-T", nwk]
+            row = {"what": what, "options": " ".join(o[: len(opts)]) or "(defaults)"}
+            for k in ("b200", "ref"):
+                t0 = time.perf_counter()
+                try:
+                    res = subprocess.run([clis[k], "-v", "0"] + o + [fa], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, timeout=600)
+                except subprocess.TimeoutExpired:
+                    row[k] = {"seconds": None, "error": "timeout 600 s"}
+                    continue
+                row[k] = {"seconds": round(time.perf_counter() - t0, 2), "returncode": res.returncode, "output_bytes": len(res.stdout),
+                          "md5": hashlib.md5(res.stdout).hexdigest()}
+                if k == "b200":
+                    row[k]["gpu_calls"] = [l for l in res.stderr.decode().splitlines() if l.startswith("[clb]")]
+            ok = all("md5" in row[k] and row[k]["returncode"] == 0 for k in ("b200", "ref"))
+            row["identical"] = bool(ok and row["b200"]["md5"] == row["ref"]["md5"] and row["ref"]["output_bytes"] > 0)
+            if ok and row["b200"]["seconds"]:
+                row["speedup"] = round(row["ref"]["seconds"] / row["b200"]["seconds"], 2)
+            out[name] = row
     return out
 
 
@@ -276,7 +354,7 @@ def main():
         import psutil
 
         avail = psutil.virtual_memory().available / max(1, world)
-        fit = int(avail * 0.6 / 0.8e6)
+        fit = int(avail * 0.6 / 0.8e6) * (world if args.scaling == "strong" else 1)
         if fit < args.windows:
             if rank == 0:
                 print(f"[bench] host RAM allows {fit} windows per rank, not {args.windows}: reducing", file=sys.stderr)
@@ -288,8 +366,19 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         args.windows = int(t.item())
     t_gen = time.perf_counter()
-    batch = synth_windows(args.windows, first_index=rank * args.windows, seed=SEED, len_min=args.len_min, len_max=args.len_max,
-                          snp_rate=args.snp_rate, alt_period=args.alt_period)
+    if args.scaling == "strong" and world > 1:
+        # ONE batch of args.windows windows: every rank computes the same cell-balanced assignment from the backbone
+        # lengths (node counts are proportional to them) and generates only its own share
+        from centrolign_b200.batch import synth_backbone_lengths
+        from centrolign_b200.popoa import balanced_partition_c
+
+        lens = synth_backbone_lengths(args.windows, 0, SEED, args.len_min, args.len_max)
+        part = balanced_partition_c(lens * lens, world)
+        batch = synth_windows(0, seed=SEED, len_min=args.len_min, len_max=args.len_max, snp_rate=args.snp_rate,
+                              alt_period=args.alt_period, indices=np.nonzero(part == rank)[0])
+    else:
+        batch = synth_windows(args.windows, first_index=rank * args.windows, seed=SEED, len_min=args.len_min, len_max=args.len_max,
+                              snp_rate=args.snp_rate, alt_period=args.alt_period)
     t_gen = time.perf_counter() - t_gen
     cells = batch.cells()
     my_cells = float(cells.sum())
@@ -371,15 +460,16 @@ def main():
         hbm_bytes = float(st.persist_bytes + st.h2d_bytes)
         roofline = {"bound": "int32", "kernel": "popoa_kernel<3> (fused DP fill + traceback, 1 launch per step)",
                     "achieved": achieved, "peak": peak, "unit": "TOP/s", "frac": achieved / peak if peak > 0 else None,
-                    "traffic": None,
+                    "traffic": hbm_bytes,
                     "ops_per_launch": int(st.int_ops), "ops_model": "SURVEY 8d: a*b+1+4P(a+b)+2P INT32 add/max per cell (32 for a linear cell at P=3)",
                     "peak_source": f"measured in this run by clb_int32_peak_tops: DPX viaddmax {peak_dpx:.1f}, add+max {peak_plain:.1f} TOP/s "
                                    "(nominal 148 SM x 128 lanes x 1.965 GHz = 37.2)",
                     "hbm": {"bound": "hbm", "achieved": hbm_bytes / step_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                            "frac": hbm_bytes / step_s / 1e9 / hbm_peak, "traffic": None,
+                            "frac": hbm_bytes / step_s / 1e9 / hbm_peak, "traffic": hbm_bytes,
                             "bytes_model": "persisted rows/columns written once + flattened graph arrays read once", "peak_source": hbm_src,
-                            "traffic_ncu": "dram read+write 27.3 GB per launch on the 1480-window profile batch (2.37e10 cells) = 1.15 B/cell "
-                                           "vs 0.9 B/cell algorithmic (profiles/r01_ncu_v9.md)"}}
+                            "traffic_model": "bytes per launch = persisted rows {M,H_k} and columns {M,D_k}+E written once (persist_bytes) + "
+                                             "flattened graph arrays read once (h2d_bytes); ncu cross-check on the 1480-window profile batch: "
+                                             "dram read+write 27.2 GB per launch for 2.37e10 cells = 1.15 B/cell (profiles/r02_ncu_popoa.md)"}}
         # ---- CPU baseline on a bounded sample, parity-checked against the GPU result ----
         cpu = None
         if not args.no_cpu_baseline:
@@ -399,7 +489,7 @@ def main():
                              f"{t_cpu:.1f} s single-threaded; score+alignment of every sampled window equal to the GPU's",
                    "host_cores": os.cpu_count()}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": kernel_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": kernel_ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "int32", "data": "synthetic", "config": workload_config(args, world),
                 "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
                 "e2e": None if e2e_ms_max is None else {"value": total_cells * args.steps / (e2e_ms_max * 1e-3) / 1e9, "unit": UNIT,
@@ -414,6 +504,10 @@ def main():
                 line["other_paths"] = other_paths(local)
             except Exception as exc:  # the headline metric stands on its own
                 line["other_paths"] = {"error": str(exc)[:300]}
+            try:
+                line["other_paths"]["e2e_msa"] = e2e_msa(local)
+            except Exception as exc:
+                line["other_paths"]["e2e_msa"] = {"error": str(exc)[:300]}
         print(json.dumps(line), flush=True)
     if use_dist:
         dist.barrier()

@@ -247,17 +247,28 @@ def _load_synth():
     lib.clsynth_generate.restype = ctypes.POINTER(_SynthBatch)
     lib.clsynth_generate.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.c_uint64, ctypes.c_double, ctypes.c_double,
                                      ctypes.c_double, ctypes.c_int64, ctypes.c_int64]
+    lib.clsynth_generate_list.restype = ctypes.POINTER(_SynthBatch)
+    lib.clsynth_generate_list.argtypes = [ctypes.c_int64, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_double, ctypes.c_double,
+                                          ctypes.c_double, ctypes.c_int64, ctypes.c_int64]
+    lib.clsynth_backbone_lengths.restype = None
+    lib.clsynth_backbone_lengths.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.c_uint64, ctypes.c_double, ctypes.c_double, ctypes.c_void_p]
     lib.clsynth_free.argtypes = [ctypes.POINTER(_SynthBatch)]
     return lib
 
 
 def synth_windows(n_windows: int, first_index: int = 0, seed: int = 20261017, len_min: float = 880.0,
                   len_max: float = 17600.0, snp_rate: float = 0.05, alt_len: int = 171,
-                  alt_period: int = 2000) -> WindowBatch:
+                  alt_period: int = 2000, indices=None) -> WindowBatch:
     """BASELINE.json configs[1] windows: backbone length log-uniform in
-    [len_min, len_max] (=> ~1 k - 20 k nodes per side with bubbles), seed = window index."""
+    [len_min, len_max] (=> ~1 k - 20 k nodes per side with bubbles), seed = window index.
+    ``indices`` (int64 array) selects arbitrary windows of the stream instead of a contiguous range: a shard of one batch."""
     lib = _load_synth()
-    ptr = lib.clsynth_generate(n_windows, first_index, seed, len_min, len_max, snp_rate, alt_len, alt_period)
+    if indices is not None:
+        idx = np.ascontiguousarray(indices, np.int64)
+        n_windows = int(len(idx))
+        ptr = lib.clsynth_generate_list(n_windows, idx.ctypes.data, seed, len_min, len_max, snp_rate, alt_len, alt_period)
+    else:
+        ptr = lib.clsynth_generate(n_windows, first_index, seed, len_min, len_max, snp_rate, alt_len, alt_period)
     B = ptr.contents
     nw = n_windows
 
@@ -279,6 +290,14 @@ def synth_windows(n_windows: int, first_index: int = 0, seed: int = 20261017, le
                                arr(B.snk[s], int(snk_off[-1]), np.uint32)))
     lib.clsynth_free(ptr)
     return WindowBatch(sides[0], sides[1])
+
+
+def synth_backbone_lengths(n_windows: int, first_index: int = 0, seed: int = 20261017, len_min: float = 880.0,
+                           len_max: float = 17600.0) -> np.ndarray:
+    """Backbone lengths of a range of stream windows without generating them (cell-balanced sharding of one batch)."""
+    out = np.zeros(n_windows, np.int64)
+    _load_synth().clsynth_backbone_lengths(n_windows, first_index, seed, len_min, len_max, out.ctypes.data)
+    return out
 
 
 # ----------------------------------------------------------------------------------------

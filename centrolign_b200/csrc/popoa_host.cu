@@ -847,6 +847,67 @@ int clb_popoa_batch(int device, int32_t n_windows, const clb_graph_batch* g1, co
     return rc;
 }
 
+// Longest-processing-time-first assignment by cell count; ties go to the lowest part.  The same rule as
+// centrolign_b200/sharding.py balanced_partition (tests compare the two).
+int clb_balanced_partition(int32_t n_windows, const int64_t* cells, int n_parts, int32_t* part_out) {
+    if (n_windows < 0 || n_parts < 1 || (n_windows > 0 && (!cells || !part_out))) return fail(CLB_EINVAL, "clb_balanced_partition: bad arguments");
+    std::vector<int32_t> ord(n_windows);
+    for (int32_t w = 0; w < n_windows; ++w) ord[w] = w;
+    std::stable_sort(ord.begin(), ord.end(), [&](int32_t a, int32_t c) { return cells[a] > cells[c]; });
+    std::vector<int64_t> load(n_parts, 0);
+    for (int32_t w : ord) {
+        int best = 0;
+        for (int k = 1; k < n_parts; ++k)
+            if (load[k] < load[best]) best = k;
+        part_out[w] = best;
+        load[best] += cells[w];
+    }
+    return CLB_OK;
+}
+
+int clb_popoa_batch_multi(int n_devices, const int* devices, int32_t n_windows, const clb_graph_batch* g1,
+                          const clb_graph_batch* g2, const clb_params* params, int64_t* score_out, const int64_t* aln_off,
+                          int32_t* aln_pairs, uint32_t* aln_len, int32_t* part_out) {
+    if (n_devices < 1 || !devices) return fail(CLB_EINVAL, "clb_popoa_batch_multi: no devices");
+    for (int a = 0; a < n_devices; ++a)
+        for (int c = a + 1; c < n_devices; ++c)
+            if (devices[a] == devices[c]) return fail(CLB_EINVAL, "clb_popoa_batch_multi: a device is listed twice");
+    if (n_devices == 1 || n_windows <= 1) {
+        if (part_out) for (int32_t w = 0; w < n_windows; ++w) part_out[w] = 0;
+        return clb_popoa_batch(devices[0], n_windows, g1, g2, params, score_out, aln_off, aln_pairs, aln_len);
+    }
+    if (n_windows < 0 || check_side(g1) || check_side(g2) || !params) return fail(CLB_EINVAL, "null graph arrays");
+    std::vector<int64_t> cells(n_windows);
+    for (int32_t w = 0; w < n_windows; ++w)
+        cells[w] = (g1->node_off[w + 1] - g1->node_off[w] + 1) * (g2->node_off[w + 1] - g2->node_off[w] + 1);
+    std::vector<int32_t> part(n_windows);
+    int rc = clb_balanced_partition(n_windows, cells.data(), n_devices, part.data());
+    if (rc != CLB_OK) return rc;
+    if (part_out) memcpy(part_out, part.data(), n_windows * sizeof(int32_t));
+    std::vector<std::vector<int32_t>> sel(n_devices);
+    for (int32_t w = 0; w < n_windows; ++w) sel[part[w]].push_back(w);
+    // one host thread (and CUDA context) per device; each writes only its own windows' entries of the output arrays
+    std::vector<int> rcs(n_devices, CLB_OK);
+    std::vector<std::string> errs(n_devices);
+    std::vector<std::thread> pool;
+    for (int k = 0; k < n_devices; ++k)
+        pool.emplace_back([&, k] {
+            if (sel[k].empty()) return;
+            clb_batch* b = nullptr;
+            int r = create_internal(devices[k], n_windows, g1, g2, params, sel[k].data(), (int32_t)sel[k].size(), &b);
+            if (r == CLB_OK) r = clb_batch_upload(b);
+            if (r == CLB_OK) r = clb_batch_run(b);
+            if (r == CLB_OK) r = clb_batch_download(b, score_out, aln_off, aln_pairs, aln_len);
+            clb_batch_destroy(b);
+            rcs[k] = r;
+            if (r != CLB_OK) errs[k] = g_err;  // thread-local: hand it to the caller's thread
+        });
+    for (auto& t : pool) t.join();
+    for (int k = 0; k < n_devices; ++k)
+        if (rcs[k] != CLB_OK) return fail(rcs[k], "device " + std::to_string(devices[k]) + ": " + errs[k]);
+    return CLB_OK;
+}
+
 // Host-only diagnostic: the matrix index (1-based topological rank) flatten_side gives every node of one graph.
 int clb_topological_ranks(uint32_t n_nodes, const uint32_t* pred_off, const uint32_t* pred, uint32_t* rank_out) {
     if (!pred_off || !rank_out || (n_nodes && pred_off[0] != 0)) return fail(CLB_EINVAL, "clb_topological_ranks: bad arguments");

@@ -142,8 +142,34 @@ typedef struct {
  * Backbone length of a window is log-uniform in [len_min, len_max]; node counts come out
  * ~13.5 % larger (bubbles).  Returns a heap-allocated batch; release with clsynth_free.
  */
+static clsynth_batch* generate_impl(int64_t n_windows, int64_t first_index, const int64_t* index_list, uint64_t seed, double len_min,
+                                    double len_max, double snp_rate, int64_t alt_len, int64_t alt_period);
+
 clsynth_batch* clsynth_generate(int64_t n_windows, int64_t first_index, uint64_t seed, double len_min,
                                 double len_max, double snp_rate, int64_t alt_len, int64_t alt_period) {
+    return generate_impl(n_windows, first_index, NULL, seed, len_min, len_max, snp_rate, alt_len, alt_period);
+}
+
+/* The windows with the stream indices index_list[0..n_windows-1] (any order): a shard of one batch. */
+clsynth_batch* clsynth_generate_list(int64_t n_windows, const int64_t* index_list, uint64_t seed, double len_min,
+                                     double len_max, double snp_rate, int64_t alt_len, int64_t alt_period) {
+    return generate_impl(n_windows, 0, index_list, seed, len_min, len_max, snp_rate, alt_len, alt_period);
+}
+
+/* Backbone length of the windows first_index .. first_index+n-1 without generating them (cell-balanced sharding
+   needs the sizes of the whole batch on every rank; node counts are ~13.5 % above the backbone length). */
+void clsynth_backbone_lengths(int64_t n_windows, int64_t first_index, uint64_t seed, double len_min, double len_max, int64_t* out) {
+    for (int64_t w = 0; w < n_windows; ++w) {
+        rng_t r = {seed ^ (0xD1B54A32D192ED03ull * (uint64_t)(first_index + w + 1))};
+        rng_next(&r);
+        double L = exp(log(len_min) + rng_unit(&r) * (log(len_max) - log(len_min)));
+        int64_t len0 = (int64_t)(L + 0.5);
+        out[w] = len0 < 2 ? 2 : len0;
+    }
+}
+
+static clsynth_batch* generate_impl(int64_t n_windows, int64_t first_index, const int64_t* index_list, uint64_t seed, double len_min,
+                                    double len_max, double snp_rate, int64_t alt_len, int64_t alt_period) {
     clsynth_batch* B = (clsynth_batch*)calloc(1, sizeof(clsynth_batch));
     B->n_windows = n_windows;
     caps_t caps[2] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
@@ -162,7 +188,8 @@ clsynth_batch* clsynth_generate(int64_t n_windows, int64_t first_index, uint64_t
     uint32_t* outdeg = NULL;
     size_t cap_cnt = 0;
     for (int64_t w = 0; w < n_windows; ++w) {
-        rng_t r = {seed ^ (0xD1B54A32D192ED03ull * (uint64_t)(first_index + w + 1))};
+        const int64_t stream_index = index_list ? index_list[w] : first_index + w;
+        rng_t r = {seed ^ (0xD1B54A32D192ED03ull * (uint64_t)(stream_index + 1))};
         rng_next(&r);
         double L = exp(log(len_min) + rng_unit(&r) * (log(len_max) - log(len_min)));
         size_t len0 = (size_t)(L + 0.5);

@@ -24,6 +24,7 @@
 #define CENTROLIGN_B200_PO_POA_HPP
 
 #include <cstdint>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -56,13 +57,14 @@ struct AlignmentParameters {
 // Accumulates windows (graph pairs) in the flat layout of clb_graph_batch.
 class PoPoaBatch {
 public:
-    explicit PoPoaBatch(int device = 0) : device_(device) {
-        for (int s = 0; s < 2; ++s) {
-            node_off_[s].push_back(0); edge_off_[s].push_back(0); src_off_[s].push_back(0); snk_off_[s].push_back(0);
-        }
-    }
+    explicit PoPoaBatch(int device = 0) : devices_(1, device) { init(); }
+    // Several GPUs of one box: the windows are dealt to the devices in cell-balanced bins (clb_popoa_batch_multi; the
+    // windows of a stitch are independent, stitcher.hpp:157-203) and the results come back in window order.
+    // CLB_DEVICES="0,1,2,3" in the environment gives a default-constructed Stitcher recorder the same list.
+    explicit PoPoaBatch(const std::vector<int>& devices) : devices_(devices.empty() ? std::vector<int>(1, 0) : devices) { init(); }
 
     size_t size() const { return node_off_[0].size() - 1; }
+    const std::vector<int>& devices() const { return devices_; }
 
     // one window = the argument list of the reference's po_poa, minus the parameters
     template <class Graph>
@@ -97,8 +99,10 @@ public:
             aln_off[w + 1] = aln_off[w] + (node_off_[0][w + 1] - node_off_[0][w]) + (node_off_[1][w + 1] - node_off_[1][w]);
         std::vector<int32_t> pairs(2 * (size_t)aln_off[nw] + 2);
         std::vector<uint32_t> len(nw, 0);
-        const int rc = clb_popoa_batch(device_, (int32_t)nw, &g[0], &g[1], &p, score.data(), aln_off.data(), pairs.data(),
-                                       len.data());
+        const int rc = devices_.size() == 1
+                           ? clb_popoa_batch(devices_[0], (int32_t)nw, &g[0], &g[1], &p, score.data(), aln_off.data(), pairs.data(), len.data())
+                           : clb_popoa_batch_multi((int)devices_.size(), devices_.data(), (int32_t)nw, &g[0], &g[1], &p, score.data(),
+                                                   aln_off.data(), pairs.data(), len.data(), nullptr);
         if (rc != CLB_OK) throw std::runtime_error(std::string("centrolign_b200: ") + clb_last_error());
         alignments.assign(nw, AlignmentT());
         for (size_t w = 0; w < nw; ++w) {
@@ -115,6 +119,11 @@ public:
     }
 
 private:
+    void init() {
+        for (int s = 0; s < 2; ++s) {
+            node_off_[s].push_back(0); edge_off_[s].push_back(0); src_off_[s].push_back(0); snk_off_[s].push_back(0);
+        }
+    }
     template <class Graph>
     void add_side(int s, const Graph& graph, const std::vector<uint64_t>& sources, const std::vector<uint64_t>& sinks) {
         const uint64_t n = graph.node_size();
@@ -136,11 +145,26 @@ private:
         snk_off_[s].push_back(snk_off_[s].back() + (int64_t)sinks.size());
     }
 
-    int device_;
+    std::vector<int> devices_;
     std::vector<int64_t> node_off_[2], edge_off_[2], src_off_[2], snk_off_[2];
     std::vector<uint8_t> label_[2];
     std::vector<uint32_t> pred_off_[2], pred_[2], src_[2], snk_[2];
 };
+
+// Device list of the process: CLB_DEVICES="0,1,..." (ordinals), else device 0.  The Stitcher recorder uses it, so a
+// reference binary built with the shadow headers spreads every stitch over the listed GPUs without a source change.
+inline std::vector<int> default_devices() {
+    std::vector<int> out;
+    if (const char* e = std::getenv("CLB_DEVICES")) {
+        int cur = -1;
+        for (const char* c = e;; ++c) {
+            if (*c >= '0' && *c <= '9') cur = (cur < 0 ? 0 : cur * 10) + (*c - '0');
+            else { if (cur >= 0) out.push_back(cur); cur = -1; if (!*c) break; }
+        }
+    }
+    if (out.empty()) out.push_back(0);
+    return out;
+}
 
 // Drop-in for the reference's po_poa: same arguments, same result.
 template <int NumPW, class Graph, class Params, class AlignmentT = Alignment>

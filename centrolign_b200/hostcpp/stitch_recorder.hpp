@@ -36,7 +36,7 @@ public:
     void begin() {
         active_ = true;
         for (int k = 0; k < CLB_MAX_PW; ++k) {
-            batch_[k] = PoPoaBatch();
+            batch_[k] = PoPoaBatch(default_devices());  // CLB_DEVICES: several GPUs of the box share every stitch
             wbatch_[k] = PwfaBatch();
             have_params_[k] = false;
         }

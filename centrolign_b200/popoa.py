@@ -21,7 +21,8 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "li
 
 EXPORTS = ["clb_popoa_batch", "clb_batch_create", "clb_batch_upload", "clb_batch_run", "clb_batch_download",
            "clb_batch_destroy", "clb_batch_get_stats", "clb_int32_peak_tops", "clb_last_error", "clb_device_count",
-           "clb_release_cached_memory", "clb_pwfa_batch", "clb_chain_dp", "clb_topological_ranks"]
+           "clb_release_cached_memory", "clb_pwfa_batch", "clb_chain_dp", "clb_topological_ranks", "clb_popoa_batch_multi",
+           "clb_balanced_partition"]
 ERROR_NAMES = {0: "CLB_OK", 1: "CLB_EINVAL", 2: "CLB_ECYCLE", 3: "CLB_ECUDA", 4: "CLB_ENOMEM", 5: "CLB_ESTATE"}
 
 
@@ -82,6 +83,10 @@ def load_library() -> ctypes.CDLL:
     lib.clb_batch_destroy.argtypes = [vp]
     lib.clb_batch_get_stats.restype = ctypes.c_int
     lib.clb_batch_get_stats.argtypes = [vp, ctypes.POINTER(BatchStats)]
+    lib.clb_popoa_batch_multi.restype = ctypes.c_int
+    lib.clb_popoa_batch_multi.argtypes = [ctypes.c_int, vp, i32, gp, gp, pp, vp, vp, vp, vp, vp]
+    lib.clb_balanced_partition.restype = ctypes.c_int
+    lib.clb_balanced_partition.argtypes = [i32, vp, ctypes.c_int, vp]
     lib.clb_topological_ranks.restype = ctypes.c_int
     lib.clb_topological_ranks.argtypes = [ctypes.c_uint32, vp, vp, vp]
     lib.clb_int32_peak_tops.restype = ctypes.c_double
@@ -199,6 +204,37 @@ def po_poa_batch(batch: WindowBatch, params: AlignmentParameters, device: int = 
                                aln_off.ctypes.data, pairs.ctypes.data, aln_len.ctypes.data))
     del k1, k2
     return score, [pairs[int(aln_off[w]): int(aln_off[w]) + int(aln_len[w])] for w in range(nw)]
+
+
+def po_poa_batch_multi(batch: WindowBatch, params: AlignmentParameters, devices, return_parts: bool = False):
+    """``clb_popoa_batch_multi``: the windows dealt to several GPUs of one box in cell-balanced bins (one host thread
+    per device inside the library), results in window order.  ``devices`` is a list of device ordinals."""
+    lib = load_library()
+    p = _c_params(params)
+    g1, k1 = _c_side(batch.g1)
+    g2, k2 = _c_side(batch.g2)
+    nw = batch.n_windows
+    aln_off = np.zeros(nw + 1, np.int64)
+    np.cumsum(batch.aln_capacity(), out=aln_off[1:])
+    score = np.zeros(nw, np.int64)
+    aln_len = np.zeros(nw, np.uint32)
+    pairs = np.empty((max(1, int(aln_off[-1])), 2), np.int32)
+    devs = np.ascontiguousarray(list(devices), np.int32)
+    parts = np.zeros(max(1, nw), np.int32)
+    _check(lib.clb_popoa_batch_multi(len(devs), devs.ctypes.data, nw, ctypes.byref(g1), ctypes.byref(g2), ctypes.byref(p),
+                                     score.ctypes.data, aln_off.ctypes.data, pairs.ctypes.data, aln_len.ctypes.data, parts.ctypes.data))
+    del k1, k2
+    alns = [pairs[int(aln_off[w]): int(aln_off[w]) + int(aln_len[w])] for w in range(nw)]
+    return (score, alns, parts[:nw]) if return_parts else (score, alns)
+
+
+def balanced_partition_c(cells, n_parts: int) -> np.ndarray:
+    """``clb_balanced_partition`` (host only): part index per window, longest-processing-time-first by cell count."""
+    lib = load_library()
+    c = np.ascontiguousarray(cells, np.int64)
+    out = np.zeros(max(1, len(c)), np.int32)
+    _check(lib.clb_balanced_partition(len(c), c.ctypes.data, n_parts, out.ctypes.data))
+    return out[: len(c)]
 
 
 def po_poa(graph1, graph2, params: AlignmentParameters, device: int = 0):

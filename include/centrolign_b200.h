@@ -87,6 +87,24 @@ int clb_popoa_batch(int device, int32_t n_windows, const clb_graph_batch* g1, co
                     uint32_t* aln_len);
 
 /*
+ * The same call over several GPUs of one box (BASELINE.json north_star: "work is sharded across the 8 GPUs of one box by
+ * cell-balanced window bins ... results return through pinned host memory").  The windows of a stitch are independent
+ * (include/centrolign/stitcher.hpp:157-203 reads only its own SubGraphInfo pair per window), so they are dealt to the
+ * devices longest-first by DP cell count (n1+1)*(n2+1) (the measure of stitcher.hpp:241), one host thread and CUDA
+ * context per device runs the single-device path on its share, and every window's result lands in the caller's arrays at
+ * the same place as with clb_popoa_batch -- no device-to-device traffic, no collective.  devices[] lists distinct device
+ * ordinals; n_devices == 1 is clb_popoa_batch.  If part_out is not NULL it receives, per window, the index into devices[]
+ * the window ran on.
+ */
+int clb_popoa_batch_multi(int n_devices, const int* devices, int32_t n_windows, const clb_graph_batch* g1,
+                          const clb_graph_batch* g2, const clb_params* params, int64_t* score_out, const int64_t* aln_off,
+                          int32_t* aln_pairs, uint32_t* aln_len, int32_t* part_out);
+
+/* Host-only: the cell-balanced assignment clb_popoa_batch_multi uses (longest-processing-time-first; ties to the lowest
+ * part), part_out[w] in [0, n_parts). */
+int clb_balanced_partition(int32_t n_windows, const int64_t* cells, int n_parts, int32_t* part_out);
+
+/*
  * Staged form of the same call, for callers that keep a batch resident in HBM
  * (bench.py times clb_batch_run alone for the device-resident figure):
  *   create   : validate + renumber each graph topologically into pinned host staging

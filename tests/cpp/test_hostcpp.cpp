@@ -63,6 +63,32 @@ int main(int argc, char** argv) {
     std::vector<int64_t> scores;
     batch.align<3>(prod, alns, &scores);
     if (alns.size() != 3 || scores[2] != 6 * 20) { std::fprintf(stderr, "FAILED batch: self alignment score %lld\n", (long long)scores[2]); ++bad; }
+    // several GPUs of the box: the same windows dealt to every visible device in cell-balanced bins, results in window order
+    {
+        std::vector<int> devs;
+        for (int d = 0; d < clb_device_count(); ++d) devs.push_back(d);
+        PoPoaBatch multi(devs);
+        for (int rep = 0; rep < 5; ++rep) {
+            multi.add(g1, g2, {7}, {0}, {6}, {7});
+            multi.add(g2, g1, {0}, {7}, {7}, {6});
+            multi.add(g1, g1, {7}, {7}, {6}, {6});
+        }
+        std::vector<Alignment> malns;
+        std::vector<int64_t> mscores;
+        multi.align<3>(prod, malns, &mscores);
+        for (size_t w = 0; w < malns.size(); ++w)
+            if (!(malns[w] == alns[w % 3]) || mscores[w] != scores[w % 3]) { std::fprintf(stderr, "FAILED multi-device batch, window %zu on %zu device(s)\n", w, devs.size()); ++bad; break; }
+        std::printf("multi-device batch: %zu windows over %zu device(s)\n", malns.size(), devs.size());
+        // a device listed twice is an argument error
+        bool threw2 = false;
+        if (!devs.empty()) {
+            PoPoaBatch twice(std::vector<int>(2, devs[0]));
+            twice.add(g1, g2, {7}, {0}, {6}, {7});
+            twice.add(g2, g1, {0}, {7}, {7}, {6});
+            try { std::vector<Alignment> x; twice.align<3>(prod, x); } catch (const std::runtime_error&) { threw2 = true; }
+            if (!threw2) { std::fprintf(stderr, "FAILED: duplicate device did not raise\n"); ++bad; }
+        }
+    }
     // cyclic input is an error, not a crash (the reference asserts, topological_order.hpp:56)
     MiniGraph cyc = bubbles("ACGTGCA");
     cyc.add_edge(6, 0);

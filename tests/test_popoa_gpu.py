@@ -343,3 +343,23 @@ def test_chunked_one_shot_late_chunk_needs_larger_workspace(monkeypatch):
     for w in range(first_odd, batch.n_windows):
         so, ao = oracle.po_poa(batch, w, PROD)
         assert so == s[w] and np.array_equal(ao, a[w]), f"window {w} differs from the oracle"
+
+
+def test_multi_device_call_matches_single_device():
+    """clb_popoa_batch_multi over every visible GPU (one on the test box: the threaded path with a single bin is still
+    exercised through the two-window minimum) returns what clb_popoa_batch returns, in window order."""
+    import torch
+
+    from centrolign_b200.popoa import po_poa_batch_multi
+
+    batch = synth_windows(40, first_index=700, seed=21, len_min=60, len_max=700)
+    ref_s, ref_a = po_poa_batch(batch, PROD)
+    devs = list(range(torch.cuda.device_count()))
+    s, a, parts = po_poa_batch_multi(batch, PROD, devs, return_parts=True)
+    assert np.array_equal(s, ref_s) and all(np.array_equal(x, y) for x, y in zip(a, ref_a))
+    assert parts.min() >= 0 and parts.max() < len(devs)
+    if len(devs) > 1:
+        loads = np.bincount(parts, weights=batch.cells().astype(np.float64), minlength=len(devs))
+        assert loads.min() > 0 and loads.max() - loads.min() <= batch.cells().max()
+    with pytest.raises(Exception):
+        po_poa_batch_multi(batch, PROD, [0, 0])

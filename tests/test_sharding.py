@@ -78,3 +78,24 @@ def test_world_size_2_gloo_matches_single_process():
     want_ws, want_wa = _pwfa_oracle_runner(successor_form(batch), AlignmentParameters())
     assert wscores == want_ws.tolist()
     assert walns == [a.tolist() for a in want_wa]
+
+
+def test_c_partition_matches_python_partition():
+    """clb_balanced_partition (what clb_popoa_batch_multi deals windows to devices with) is the same
+    longest-processing-time-first rule as sharding.balanced_partition."""
+    from centrolign_b200.popoa import balanced_partition_c
+    from centrolign_b200.sharding import balanced_partition
+
+    rng = np.random.default_rng(5)
+    for n, parts in ((0, 3), (1, 4), (57, 2), (1000, 8), (33, 5)):
+        cells = (rng.integers(1, 2000, n) ** 2).astype(np.int64)
+        if n > 10:
+            cells[rng.integers(0, n, n // 3)] = cells[0]  # ties
+        got = balanced_partition_c(cells, parts)
+        want = np.zeros(n, np.int32)
+        for k, ids in enumerate(balanced_partition(cells, parts)):
+            want[ids] = k
+        assert np.array_equal(got, want)
+        if n >= 57:
+            loads = np.bincount(got, weights=cells.astype(np.float64), minlength=parts)
+            assert loads.max() - loads.min() <= cells.max()  # LPT bound
