@@ -52,9 +52,6 @@ def parse_args():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --windows per GPU (the driver's 1->8 run); strong: ONE batch of --windows windows dealt to the ranks "
                          "in cell-balanced bins (clb_balanced_partition, the rule of clb_popoa_batch_multi)")
-    ap.add_argument("--workload", default="configs1", choices=["configs1", "pipeline"],
-                    help="configs1: BASELINE configs[1]; pipeline: window sizes of the reference's own Stitcher (SURVEY section 6: "
-                         "median 9 cells), reported as windows/s beside GCUPS")
     return ap.parse_args()
 
 
@@ -271,6 +268,53 @@ def other_paths(device):
                                                                              "(B300_MICROARCH.md L2 hit latency 234-262 cycles)",
                                              "frac": (4 * 0.13) / max(1e-9, cst.kernel_ms * 1e3 / max(1, prob.n_step))}}
     out["chain_dp"] = chain_out
+    return out
+
+
+def pipeline_windows(device):
+    """Windows of the size the reference's own Stitcher sends to po_poa (SURVEY.md section 6, 2 x 93 kbp HOR arrays:
+    median 9 cells, p90 49, p99 169, max 18 549): windows/s through clb_popoa_batch with host buffers, with the
+    warp-per-window kernel (popoa_small_kernels.cu) and, for comparison, with every window forced through the
+    CTA-per-window strip kernel; the reference on one core on a sample, parity-checked."""
+    from centrolign_b200.batch import AlignmentParameters, concat_batches, select_windows, synth_windows
+    from centrolign_b200.popoa import po_poa_batch
+
+    params = AlignmentParameters()
+    nw = 200000
+    mix = [(0.55, 2.0, 2.4), (0.35, 2.4, 7.0), (0.09, 7.0, 13.0), (0.01, 13.0, 135.0)]  # share, backbone length range per side
+    batch = concat_batches([synth_windows(int(nw * f), first_index=k * 10 ** 7, seed=SEED + 1, len_min=lo, len_max=hi, alt_period=0)
+                            for k, (f, lo, hi) in enumerate(mix)])
+    cells = batch.cells()
+    out = {"windows": int(batch.n_windows), "cells": float(cells.sum()), "cells_median": float(np.median(cells)),
+           "cells_p90": float(np.percentile(cells, 90)), "cells_p99": float(np.percentile(cells, 99)), "cells_max": float(cells.max())}
+    res = {}
+    for name, env in (("warp_per_window", None), ("cta_per_window", "1")):
+        if env:
+            os.environ["CLB_NO_SMALL_WINDOWS"] = env
+        try:
+            po_poa_batch(batch, params, device=device)  # warm-up
+            t0 = time.perf_counter()
+            res[name] = po_poa_batch(batch, params, device=device)
+            dt = time.perf_counter() - t0
+        finally:
+            os.environ.pop("CLB_NO_SMALL_WINDOWS", None)
+        out[name] = {"seconds": dt, "windows_per_s": batch.n_windows / dt, "ns_per_cell": dt * 1e9 / float(cells.sum()),
+                     "includes": "host flattening, H2D, kernels, D2H, id translation"}
+    assert np.array_equal(res["warp_per_window"][0], res["cta_per_window"][0])
+    assert all(np.array_equal(a, b) for a, b in zip(res["warp_per_window"][1], res["cta_per_window"][1])), "the two kernels disagree"
+    out["speedup_over_cta_per_window"] = out["cta_per_window"]["seconds"] / out["warp_per_window"]["seconds"]
+    from checkers import CpuChecker
+    kind = "reference" if CpuChecker.available("reference") else "port"
+    chk = CpuChecker(kind)
+    idx = np.linspace(0, batch.n_windows - 1, 3000).astype(int)
+    t0 = time.perf_counter()
+    for w in idx:
+        s, a = chk.po_poa(batch, int(w), params)
+        assert s == res["warp_per_window"][0][w] and np.array_equal(a, res["warp_per_window"][1][w]), f"pipeline window {w} differs from the CPU {kind}"
+    dt = time.perf_counter() - t0
+    out["cpu_baseline"] = {"kind": kind, "cores": 1, "windows_per_s": len(idx) / dt, "ns_per_cell": dt * 1e9 / float(cells[idx].sum()),
+                           "sample": f"{len(idx)} windows evenly spaced, each equal to the GPU result; includes the ctypes call per window",
+                           "reference_in_pipeline_ns_per_cell": 134}
     return out
 
 
@@ -504,6 +548,10 @@ def main():
                 line["other_paths"] = other_paths(local)
             except Exception as exc:  # the headline metric stands on its own
                 line["other_paths"] = {"error": str(exc)[:300]}
+            try:
+                line["other_paths"]["pipeline_windows"] = pipeline_windows(local)
+            except Exception as exc:
+                line["other_paths"]["pipeline_windows"] = {"error": str(exc)[:300]}
             try:
                 line["other_paths"]["e2e_msa"] = e2e_msa(local)
             except Exception as exc:

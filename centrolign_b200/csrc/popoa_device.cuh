@@ -19,6 +19,12 @@ constexpr int kRingRows = 8;            // fill-kernel ring depth (>= 2*kNear+2)
 constexpr int kPanelRowsMax = 2048;     // panel height of tiled windows (default; a multiple of kRowBlock); in "auto" mode about
 constexpr int kPanelRowsMin = 512;      // n1/8 between these bounds (host and kernel call panel_rows_for); CLB_PANEL_ROWS, 0 = off
 
+// Windows whose whole matrix has at most kSmallCells cells go to popoa_small_kernel (one warp per window, the matrix in
+// shared memory: 2 x 16 B per cell, kSmallWarps warps per CTA = 192 KB); the reference's own Stitcher windows are
+// almost all of this kind (median 9 cells, p99 169).
+constexpr int kSmallCells = 384;
+constexpr int kSmallWarps = 16;
+
 // per-node info word
 constexpr uint32_t kInfoLabelMask = 0xffu;
 constexpr uint32_t kInfoRegular = 1u << 8;  // exactly one predecessor and it is index-1

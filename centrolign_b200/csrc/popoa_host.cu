@@ -26,6 +26,7 @@
 
 namespace clb {
 cudaError_t launch_popoa(int num_pw, const LaunchArgs& args, int grid, cudaStream_t stream);
+cudaError_t launch_popoa_small(int num_pw, const LaunchArgs& args, int first, int count, int grid, cudaStream_t stream);  // popoa_small_kernels.cu
 int popoa_smem_bytes();
 double int32_probe(int use_dpx, int sm_count);
 int popoa_nsmid();
@@ -188,6 +189,8 @@ struct clb_batch {
     std::vector<int64_t> out_off;  // pair offset per window in the device output
     std::vector<int32_t> sel;      // caller window id of batch window k (empty = identity)
     bool shared_workspace = false; // workspace owned by the caller of the chunked one-shot path; slots by SM id
+    int32_t n_big = 0;             // order[0 .. n_big) go to popoa_kernel, the rest (matrices of <= kSmallCells cells) to popoa_small_kernel
+    int sm_count = 0;
     int64_t max_ws_bytes = 0;      // largest single-window workspace of this batch
 };
 
@@ -522,9 +525,18 @@ static int create_internal(int device, int32_t n_windows, const clb_graph_batch*
         return ((int64_t)ma.n1 + 1) * ((int64_t)ma.n2 + 1) > ((int64_t)mc.n1 + 1) * ((int64_t)mc.n2 + 1);
     });
     if (nw) memcpy(b->order.h, ord.data(), nw * sizeof(int32_t));
+    // small windows (sorted to the end of the order) take the warp-per-window kernel and need no workspace
+    b->n_big = (int32_t)nw;
+    if (!getenv("CLB_NO_SMALL_WINDOWS"))
+        while (b->n_big > 0) {
+            const clb::WindowMeta& m = b->meta.h[ord[b->n_big - 1]];
+            if (((int64_t)m.n1 + 1) * ((int64_t)m.n2 + 1) > clb::kSmallCells) break;
+            --b->n_big;
+        }
     b->slot_bytes = 16;
     b->stats.persist_bytes = 0;
-    for (int64_t w = 0; w < nw; ++w) {
+    for (int64_t k = 0; k < b->n_big; ++k) {
+        const int64_t w = ord[k];
         const clb::WindowMeta& m = b->meta.h[w];
         const int64_t ws = clb::workspace_bytes(m.n1, m.n2, m.nrslot, m.ncslot);
         if (clb::workspace_int4(m.n1, m.n2, m.nrslot, m.ncslot) >= (int64_t(1) << 31)) {
@@ -561,6 +573,7 @@ static int upload_internal(clb_batch* b, char* shared_ws, int64_t shared_slot_by
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, b->device));
     if (prop.major < 10) return fail(CLB_ECUDA, "device is not sm_100-class; this library ships sm_100a code only");
+    b->sm_count = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&b->ev0));
     CUDA_TRY(cudaEventCreate(&b->ev1));
@@ -589,7 +602,7 @@ static int upload_internal(clb_batch* b, char* shared_ws, int64_t shared_slot_by
         b->shared_workspace = true;
         b->d_workspace = shared_ws;
         b->slot_bytes = shared_slot_bytes;
-        b->grid = std::max(1, std::min<int>(b->nw, prop.multiProcessorCount));
+        b->grid = std::max(1, std::min<int>(b->n_big, prop.multiProcessorCount));
         CUDA_TRY(cudaStreamSynchronize(b->stream));
         b->stats.h2d_bytes = h2d;
         b->stats.workspace_bytes = 0;
@@ -600,7 +613,7 @@ static int upload_internal(clb_batch* b, char* shared_ws, int64_t shared_slot_by
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
     free_b += g_cache.dev_cached(b->device);  // cached blocks are reusable (or trimmed on demand)
-    int grid = std::max(1, std::min<int>(b->nw, prop.multiProcessorCount));
+    int grid = std::max(1, std::min<int>(b->n_big, prop.multiProcessorCount));
     const int64_t budget = (int64_t)(free_b * 0.92);
     if (b->slot_bytes > budget) return fail(CLB_ENOMEM, "a single window's workspace exceeds device memory");
     // two workspace slots per CTA: one window being filled, the previous one being traced back
@@ -656,8 +669,17 @@ static int launch_internal(clb_batch* b) {
         a.start_lag = getenv("CLB_START_LAG") ? atoi(getenv("CLB_START_LAG")) : 64;
         a.slot_by_smid = b->shared_workspace ? 1 : 0;
         a.panel_rows = panel_cfg();
-        CUDA_TRY(clb::launch_popoa(b->params.num_pw, a, b->grid, b->stream));
-        b->stats.kernel_launches = 1;
+        a.n_windows = b->n_big;  // the strip / tile kernel takes the windows above kSmallCells ...
+        if (b->n_big > 0) {
+            CUDA_TRY(clb::launch_popoa(b->params.num_pw, a, b->grid, b->stream));
+            b->stats.kernel_launches += 1;
+        }
+        if (b->nw > b->n_big) {  // ... one warp per window takes the rest
+            const int count = b->nw - b->n_big;
+            const int sgrid = std::max(1, std::min(b->sm_count, (count + clb::kSmallWarps - 1) / clb::kSmallWarps));
+            CUDA_TRY(clb::launch_popoa_small(b->params.num_pw, a, b->n_big, count, sgrid, b->stream));
+            b->stats.kernel_launches += 1;
+        }
     }
     CUDA_TRY(cudaEventRecord(b->ev1, b->stream));
     return CLB_OK;

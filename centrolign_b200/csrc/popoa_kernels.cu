@@ -626,7 +626,7 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
     uint32_t rq1 = info1[min(R0 + 2, R1 + 1)], rq2 = info1[min(R0 + 3, R1 + 2)];  // lane 0's rows one and two steps ahead
 
     auto step = [&](const int s, auto guard_tag, auto lean_tag) {
-        constexpr bool GUARD = decltype(guard_tag)::value;
+        (void)guard_tag;
         constexpr bool LEAN = decltype(lean_tag)::value;
         const int r = 1 + s - lane;
         const bool act = r > R0 && r <= R1;  // lanes outside the panel (pipeline fill / drain) idle

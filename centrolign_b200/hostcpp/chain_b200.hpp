@@ -153,9 +153,26 @@ void collect_events(ChainProblem& P, const MBank& bank, const FwdEdges& forward_
 
 }  // namespace detail
 
-// The gap measures of sparse_affine_chain_dp (anchorer.hpp:1875-2000), same integer and float types.
+// Gap geometry of sparse_affine_chain_dp.  The reference measures the indel between an END point (a node pair a chain
+// element stops on, or a source pair) and a START point (the node pair the next element begins on, or a sink pair) as a
+// difference of diagonals on a pair of paths (p1, p2) through the end point (anchorer.hpp:1875-1892):
+//     end diagonal    d_end(p1,p2)   = index_on(e1,p1) - index_on(e2,p2)
+//     reach diagonal  d_reach(p1,p2) = (predecessor_index(s1,p1) + D1(s1,p1)) - (predecessor_index(s2,p2) + D2(s2,p2))
+// (the same two quantities the flat problem carries per match as ins_shift and qa1 - qa2), keeps the difference of smallest
+// absolute value over the path pairs, and, for SETS of end / start points, folds over their product.  Here that is ONE
+// routine, `closest`, over (pointer, count) views; the four shapes of the reference (:1937-2000 node->node, sources->node,
+// node->sinks, sources->sinks) are its calls with one-element views.  Two details decide results and are kept: the
+// product is walked starts-outer / ends-inner (:1985-1988; the one-sided shapes are that order with a trivial loop), and a
+// candidate replaces the running value only if its ABSOLUTE value is below the running SIGNED value (:1954, :1971,
+// :1991), so a negative running value is final.
 template <typename IntShift, typename ScoreFloat, class XMerge, class SwitchDists, size_t NumPW>
-struct GapMeasure {
+struct GapGeometry {
+    struct Nodes {  // a view of node ids
+        const uint64_t* ptr;
+        size_t n;
+        Nodes(const uint64_t& one) : ptr(&one), n(1) {}
+        Nodes(const std::vector<uint64_t>& v) : ptr(v.data()), n(v.size()) {}
+    };
     const XMerge& xmerge1;
     const XMerge& xmerge2;
     const SwitchDists& switch_dists1;
@@ -164,79 +181,81 @@ struct GapMeasure {
     const std::array<double, NumPW>& gap_extend;
     double local_scale;
 
-    IntShift basic_source_shift(uint64_t src_id1, uint64_t src_id2, uint64_t path1, uint64_t path2) const {  // :1875-1877
-        return xmerge1.index_on(src_id1, path1) - xmerge2.index_on(src_id2, path2);
+    static IntShift unreachable() { return std::numeric_limits<IntShift>::max(); }
+
+    IntShift end_diagonal(uint64_t e1, uint64_t e2, uint64_t p1, uint64_t p2) const {
+        return xmerge1.index_on(e1, p1) - xmerge2.index_on(e2, p2);
     }
-    IntShift basic_query_shift(uint64_t query_id1, uint64_t query_id2, uint64_t path1, uint64_t path2) const {  // :1886-1889
-        return (xmerge1.predecessor_index(query_id1, path1) - xmerge2.predecessor_index(query_id2, path2) +
-                switch_dists1.distance(query_id1, path1) - switch_dists2.distance(query_id2, path2));
+    IntShift reach_diagonal(uint64_t s1, uint64_t s2, uint64_t p1, uint64_t p2) const {
+        return (xmerge1.predecessor_index(s1, p1) - xmerge2.predecessor_index(s2, p2) + switch_dists1.distance(s1, p1) -
+                switch_dists2.distance(s2, p2));
     }
-    ScoreFloat score_gap(IntShift gap) const {  // :1906-1918
-        ScoreFloat score = std::numeric_limits<ScoreFloat>::lowest();
-        if (gap == 0) {
-            score = 0.0;
-        } else if (gap != std::numeric_limits<IntShift>::max()) {
-            for (size_t pw = 0; pw < NumPW; ++pw)
-                score = std::max<ScoreFloat>(score, -local_scale * (gap_open[pw] + gap_extend[pw] * std::abs(gap)));
-        }
-        return score;
-    }
-    IntShift measure_gap(uint64_t prev_id1, uint64_t prev_id2, uint64_t curr_id1, uint64_t curr_id2) const {  // :1919-1936
-        IntShift gap = std::numeric_limits<IntShift>::max();
-        if ((prev_id1 == curr_id1 || xmerge1.reachable(prev_id1, curr_id1)) &&
-            (prev_id2 == curr_id2 || xmerge2.reachable(prev_id2, curr_id2))) {
-            for (auto p1 : xmerge1.chains_on(prev_id1)) {
-                for (auto p2 : xmerge2.chains_on(prev_id2)) {
-                    IntShift gap_here = basic_source_shift(prev_id1, prev_id2, p1, p2) - basic_query_shift(curr_id1, curr_id2, p1, p2);
-                    if (std::abs(gap_here) < std::abs(gap)) gap = gap_here;
+    // one end point to one start point: the diagonal difference of smallest absolute value over the path pairs through
+    // the end point (first such pair in chains_on order), `unreachable()` if either graph has no walk between them
+    IntShift between(uint64_t e1, uint64_t e2, uint64_t s1, uint64_t s2) const {
+        IntShift best = unreachable();
+        const bool walk1 = e1 == s1 || xmerge1.reachable(e1, s1), walk2 = e2 == s2 || xmerge2.reachable(e2, s2);
+        if (walk1 && walk2)
+            for (auto p1 : xmerge1.chains_on(e1))
+                for (auto p2 : xmerge2.chains_on(e2)) {
+                    const IntShift d = end_diagonal(e1, e2, p1, p2) - reach_diagonal(s1, s2, p1, p2);
+                    if (std::abs(d) < std::abs(best)) best = d;
                 }
-            }
-        }
-        return gap;
+        return best;
     }
-    std::pair<IntShift, ScoreFloat> measure_gap_nn(uint64_t p1, uint64_t p2, uint64_t c1, uint64_t c2) const {  // :1937-1943
-        std::pair<IntShift, ScoreFloat> r;
-        r.first = measure_gap(p1, p2, c1, c2);
-        r.second = score_gap(r.first);
-        return r;
-    }
-    // the set variants compare |gap_here| with the signed running value, as the reference does (:1954, :1971, :1991)
-    std::pair<IntShift, ScoreFloat> measure_gap_sn(const std::vector<uint64_t>& prev1, const std::vector<uint64_t>& prev2,
-                                                   uint64_t curr_id1, uint64_t curr_id2) const {  // :1946-1961
-        std::pair<IntShift, ScoreFloat> r(std::numeric_limits<IntShift>::max(), std::numeric_limits<ScoreFloat>::lowest());
-        for (uint64_t prev_id1 : prev1)
-            for (uint64_t prev_id2 : prev2) {
-                IntShift gap_here = measure_gap(prev_id1, prev_id2, curr_id1, curr_id2);
-                if (std::abs(gap_here) < r.first) r.first = gap_here;
-            }
-        r.second = score_gap(r.first);
-        return r;
-    }
-    std::pair<IntShift, ScoreFloat> measure_gap_ns(uint64_t prev_id1, uint64_t prev_id2, const std::vector<uint64_t>& curr1,
-                                                   const std::vector<uint64_t>& curr2) const {  // :1963-1978
-        std::pair<IntShift, ScoreFloat> r(std::numeric_limits<IntShift>::max(), std::numeric_limits<ScoreFloat>::lowest());
-        for (uint64_t curr_id1 : curr1)
-            for (uint64_t curr_id2 : curr2) {
-                IntShift gap_here = measure_gap(prev_id1, prev_id2, curr_id1, curr_id2);
-                if (std::abs(gap_here) < r.first) r.first = gap_here;
-            }
-        r.second = score_gap(r.first);
-        return r;
-    }
-    std::pair<IntShift, ScoreFloat> measure_gap_ss(const std::vector<uint64_t>& prev1, const std::vector<uint64_t>& prev2,
-                                                   const std::vector<uint64_t>& curr1, const std::vector<uint64_t>& curr2) const {  // :1980-2000
-        std::pair<IntShift, ScoreFloat> r(std::numeric_limits<IntShift>::max(), std::numeric_limits<ScoreFloat>::lowest());
-        for (uint64_t curr_id1 : curr1)
-            for (uint64_t curr_id2 : curr2)
-                for (uint64_t prev_id1 : prev1)
-                    for (uint64_t prev_id2 : prev2) {
-                        IntShift gap_here = measure_gap(prev_id1, prev_id2, curr_id1, curr_id2);
-                        if (std::abs(gap_here) < r.first) r.first = gap_here;
+    // sets of end points to sets of start points
+    IntShift closest(Nodes ends1, Nodes ends2, Nodes starts1, Nodes starts2) const {
+        IntShift running = unreachable();
+        for (size_t a = 0; a < starts1.n; ++a)
+            for (size_t b = 0; b < starts2.n; ++b)
+                for (size_t c = 0; c < ends1.n; ++c)
+                    for (size_t d = 0; d < ends2.n; ++d) {
+                        const IntShift g = between(ends1.ptr[c], ends2.ptr[d], starts1.ptr[a], starts2.ptr[b]);
+                        if (std::abs(g) < running) running = g;
                     }
-        r.second = score_gap(r.first);
-        return r;
+        return running;
+    }
+    // score of an indel of `gap` diagonals: the best gap piece, 0 for no gap, lowest() if unreachable (:1906-1918)
+    ScoreFloat score(IntShift gap) const {
+        if (gap == 0) return ScoreFloat(0.0);
+        ScoreFloat best = std::numeric_limits<ScoreFloat>::lowest();
+        if (gap != unreachable())
+            for (size_t pw = 0; pw < NumPW; ++pw)
+                best = std::max<ScoreFloat>(best, -local_scale * (gap_open[pw] + gap_extend[pw] * std::abs(gap)));
+        return best;
+    }
+    std::pair<IntShift, ScoreFloat> measured(Nodes ends1, Nodes ends2, Nodes starts1, Nodes starts2) const {
+        const IntShift g = closest(ends1, ends2, starts1, starts2);
+        return std::make_pair(g, score(g));
     }
 };
+
+// Gap lengths and scores between the elements of a finished chain (what anchorer.hpp:2443-2468 records in the anchors):
+// one measurement per junction -- sources to the first anchor, anchor to anchor, last anchor to the sinks -- written to
+// the records on both sides of the junction.
+template <typename IntShift, class Anchors, class XMerge, class SwitchDists, size_t NumPW>
+void annotate_gaps(Anchors& chain, const XMerge& xmerge1, const XMerge& xmerge2, const SwitchDists& switch_dists1,
+                   const SwitchDists& switch_dists2, const std::array<double, NumPW>& gap_open,
+                   const std::array<double, NumPW>& gap_extend, double local_scale, const std::vector<uint64_t>* sources1,
+                   const std::vector<uint64_t>* sources2, const std::vector<uint64_t>* sinks1, const std::vector<uint64_t>* sinks2) {
+    if (chain.empty()) return;
+    GapGeometry<IntShift, float, XMerge, SwitchDists, NumPW> geo{xmerge1, xmerge2, switch_dists1, switch_dists2, gap_open, gap_extend, local_scale};
+    if (sources1) {
+        const auto lead = geo.measured(*sources1, *sources2, chain.front().walk1.front(), chain.front().walk2.front());
+        chain.front().gap_before = lead.first;
+        chain.front().gap_score_before = lead.second;
+    }
+    for (size_t i = 0; i + 1 < chain.size(); ++i) {
+        const auto mid = geo.measured(chain[i].walk1.back(), chain[i].walk2.back(), chain[i + 1].walk1.front(), chain[i + 1].walk2.front());
+        chain[i].gap_after = chain[i + 1].gap_before = mid.first;
+        chain[i].gap_score_after = chain[i + 1].gap_score_before = mid.second;
+    }
+    if (sinks1) {
+        const auto trail = geo.measured(chain.back().walk1.back(), chain.back().walk2.back(), *sinks1, *sinks2);
+        chain.back().gap_after = trail.first;
+        chain.back().gap_score_after = trail.second;
+    }
+}
 
 // Flat problem of sparse_affine_chain_dp.  `weight_of(match_set)` is the reference's
 // score_function->anchor_weight(count1, count2, walks1.front().size(), full_length) (anchorer.hpp:2023-2024).
@@ -253,8 +272,8 @@ ChainProblem build_affine_chain_problem(const MBank& bank, const FwdEdges& forwa
     static_assert(NumPW >= 1 && NumPW <= CLB_MAX_PW, "1..3 gap pieces");
     typedef float ScoreFloat;  // the reference instantiates ScoreFloat = float (anchorer.hpp:1217)
     const ScoreFloat mininf = std::numeric_limits<ScoreFloat>::lowest();
-    GapMeasure<IntShift, ScoreFloat, XMerge, SwitchDists, NumPW> gaps{xmerge1, xmerge2, switch_dists1, switch_dists2,
-                                                                     gap_open, gap_extend, local_scale};
+    GapGeometry<IntShift, ScoreFloat, XMerge, SwitchDists, NumPW> geo{xmerge1, xmerge2, switch_dists1, switch_dists2,
+                                                                      gap_open, gap_extend, local_scale};
     ChainProblem P;
     P.num_pw = (int)NumPW;
     for (size_t k = 0; k < NumPW; ++k) {
@@ -274,17 +293,17 @@ ChainProblem build_affine_chain_problem(const MBank& bank, const FwdEdges& forwa
         ScoreFloat weight = weight_of(match_set);
         P.weight.push_back(weight);
         if (sources1) {  // anchorer.hpp:2026-2039
-            ScoreFloat lead_indel_score = gaps.measure_gap_sn(*sources1, *sources2, start1, start2).second;
+            ScoreFloat lead_indel_score = geo.measured(*sources1, *sources2, start1, start2).second;
             if (lead_indel_score == mininf) weight = mininf;
             else weight += lead_indel_score;
         }
         P.dp_init.push_back(weight);
-        P.final_term.push_back(sinks1 ? gaps.measure_gap_ns(end1, end2, *sinks1, *sinks2).second : ScoreFloat(0.0));  // :2431-2438
+        P.final_term.push_back(sinks1 ? geo.measured(end1, end2, *sinks1, *sinks2).second : ScoreFloat(0.0));  // :2431-2438
         for (auto p1 : xmerge1.chains_on(end1))  // anchorer.hpp:2043-2048, 2309-2318
             for (auto p2 : xmerge2.chains_on(end2)) {
                 P.ins_p1.push_back((uint32_t)p1);
                 P.ins_p2.push_back((uint32_t)p2);
-                P.ins_shift.push_back((int32_t)gaps.basic_source_shift(end1, end2, p1, p2));
+                P.ins_shift.push_back((int32_t)geo.end_diagonal(end1, end2, p1, p2));
                 P.ins_offset.push_back((uint32_t)xmerge2.index_on(end2, p2));
             }
         P.ins_off.push_back((int64_t)P.ins_p1.size());
@@ -301,7 +320,7 @@ ChainProblem build_affine_chain_problem(const MBank& bank, const FwdEdges& forwa
         }
     }
     P.min_score = 0.0f;
-    if (sources1 && sinks1) P.min_score = gaps.measure_gap_ss(*sources1, *sources2, *sinks1, *sinks2).second;  // :2419-2424
+    if (sources1 && sinks1) P.min_score = geo.measured(*sources1, *sources2, *sinks1, *sinks2).second;  // :2419-2424
     detail::collect_events(P, bank, forward_edges, graph1, ranks, order1);
     return P;
 }

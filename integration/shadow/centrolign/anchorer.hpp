@@ -6,8 +6,8 @@
 // Anchorer::anchor_chain selects (reference: include/centrolign/anchorer.hpp:1271-1278 and :1286-1291, with
 // BGraph = BaseGraph, XMerge = PathMerge<uint32_t, uint8_t> as chosen by Core, include/centrolign/core.hpp:336-338,
 // and NumPW = 3).  Name lookup in the reference's own `_gen_sparse_affine` / `_gen_sparse` calls then picks the
-// specializations: same signature, same call sites, no reference line edited.  All other instantiations (bit-packed
-// containers under restrain_memory, 64-bit variants, ChainMerge) keep running the reference's generic code.
+// specializations: same signature, same call sites, no reference line edited.  The bit-packed instantiation that
+// restrain_memory selects (:1263-1264) is specialized the same way; the 64-bit variants keep the reference's generic code.
 //
 // The specializations build what the reference builds before its main loop (MatchBank, forward edges,
 // post-switch distances, topological order -- the reference's own classes), hand the flat problem to
@@ -21,6 +21,10 @@
 #include "centrolign/chain_merge.hpp"
 #include "centrolign/forward_edges.hpp"
 #include "centrolign/match_bank.hpp"
+#include "centrolign/packed_forward_edges.hpp"
+#include "centrolign/packed_match_bank.hpp"
+#include "centrolign/packed_vector.hpp"
+#include "centrolign/vector_support.hpp"
 #include "centrolign/path_merge.hpp"
 #include "centrolign/post_switch_distances.hpp"
 #include "centrolign/topological_order.hpp"
@@ -41,6 +45,10 @@ typedef MatchBank<uint32_t, uint16_t, float> Bank;
 typedef ForwardEdges<XMerge::node_id_t, XMerge::chain_id_t> FwdEdges;
 typedef std::vector<std::pair<int32_t, Bank::match_id_t>> ShiftMatchVector;
 typedef std::vector<std::pair<uint32_t, Bank::match_id_t>> DistMatchVector;
+// the bit-packed containers of restrain_memory (anchorer.hpp:1236-1248)
+typedef PackedMatchBank<uint32_t, float> PackedBank;
+typedef VectorPair<SignedPackedVector, PackedVector, int32_t, PackedBank::match_id_t> PackedShiftMatchVector;
+typedef VectorPair<PackedVector, PackedVector, uint32_t, PackedBank::match_id_t> PackedDistMatchVector;
 
 // anchors of a chain of match ranks: the loop body of traceback_sparse_dp (anchorer.hpp:2510-2527), forward order
 inline std::vector<anchor_t> anchors_of(const std::vector<int64_t>& chain, const centrolign_b200::ChainProblem& P,
@@ -66,72 +74,62 @@ inline std::vector<anchor_t> anchors_of(const std::vector<int64_t>& chain, const
 
 }  // namespace b200_chain
 
-// ---- sparse_affine_chain_dp, production instantiation (anchorer.hpp:1276-1277) ----
-template <>
-inline std::vector<anchor_t>
-Anchorer::sparse_affine_chain_dp<uint32_t, uint16_t, uint32_t, int32_t, uint32_t, float, b200_chain::ShiftMatchVector,
-                                 b200_chain::DistMatchVector, std::vector<uint32_t>, std::vector<uint32_t>, b200_chain::Bank,
-                                 b200_chain::FwdEdges, BaseGraph, b200_chain::XMerge, 3>(
-    const std::vector<match_set_t>& match_sets, const BaseGraph& graph1, const BaseGraph& graph2,
-    const b200_chain::XMerge& xmerge1, const b200_chain::XMerge& xmerge2, const std::array<double, 3>& gap_open,
-    const std::array<double, 3>& gap_extend, double local_scale, size_t num_match_sets, bool suppress_verbose_logging,
-    const std::vector<uint64_t>* sources1, const std::vector<uint64_t>* sources2, const std::vector<uint64_t>* sinks1,
-    const std::vector<uint64_t>* sinks2, const std::unordered_set<std::tuple<size_t, size_t, size_t>>* masked_matches) const {
-    using namespace b200_chain;
-    const double t0 = now_s();
-    Bank match_bank(graph1, match_sets, num_match_sets, true, masked_matches);                 // anchorer.hpp:1861
-    PostSwitchDistances<std::vector<uint32_t>> switch_dists1(graph1, xmerge1), switch_dists2(graph2, xmerge2);  // :1871-1872
-    std::vector<bool> mask_to, mask_from;
-    std::tie(mask_to, mask_from) = generate_forward_edge_masks(graph1, match_sets, num_match_sets);  // :2267-2269
-    FwdEdges forward_edges(xmerge1, &mask_to, &mask_from);
-    const auto order1 = topological_order(graph1);  // :2290
-    auto weight_of = [&](const match_set_t& ms) -> float {
-        return score_function->anchor_weight(ms.count1, ms.count2, ms.walks1.front().size(), ms.full_length);
-    };
-    const double t1 = now_s();
-    auto P = centrolign_b200::build_affine_chain_problem<int32_t>(match_bank, forward_edges, switch_dists1, switch_dists2, graph1,
-                                                                  order1, xmerge1, xmerge2, match_sets, num_match_sets, gap_open,
-                                                                  gap_extend, local_scale, sources1, sources2, sinks1, sinks2, weight_of);
-    const double t2 = now_s();
-    float opt_value = 0.0f;
-    auto traceback = anchors_of(P.solve(0, &opt_value), P, match_sets);
-    if (getenv("CLB_TIMING") && P.n_match() > 10000)
-        fprintf(stderr, "[clb] affine chaining of %zu matches: reference-side tables %.3f s, flat problem %.3f s, clb_chain_dp %.3f s\n",
-                P.n_match(), t1 - t0, t2 - t1, now_s() - t2);
-    annotate_scores(traceback);  // :2536
-    // gap length and score between the anchors (:2443-2468)
-    centrolign_b200::GapMeasure<int32_t, float, XMerge, PostSwitchDistances<std::vector<uint32_t>>, 3> gaps{
-        xmerge1, xmerge2, switch_dists1, switch_dists2, gap_open, gap_extend, local_scale};
-    for (size_t i = 0; i < traceback.size(); ++i) {
-        auto& anchor = traceback[i];
-        if (i == 0) {
-            if (sources1) {
-                auto gap = gaps.measure_gap_sn(*sources1, *sources2, anchor.walk1.front(), anchor.walk2.front());
-                anchor.gap_before = gap.first;
-                anchor.gap_score_before = gap.second;
-            }
-        } else {
-            auto& prev_anchor = traceback[i - 1];
-            auto gap = gaps.measure_gap_nn(prev_anchor.walk1.back(), prev_anchor.walk2.back(), anchor.walk1.front(), anchor.walk2.front());
-            prev_anchor.gap_after = gap.first;
-            prev_anchor.gap_score_after = gap.second;
-            anchor.gap_before = gap.first;
-            anchor.gap_score_before = gap.second;
-        }
-        if (i + 1 == traceback.size()) {
-            if (sinks1) {
-                auto gap = gaps.measure_gap_ns(anchor.walk1.back(), anchor.walk2.back(), *sinks1, *sinks2);
-                anchor.gap_after = gap.first;
-                anchor.gap_score_after = gap.second;
-            }
-        }
+// ---- sparse_affine_chain_dp: the 32-bit instantiations Anchorer::anchor_chain selects (anchorer.hpp:1258-1278) ----
+//   * production:        std::vector-backed containers (:1276-1277);
+//   * restrain_memory:   bit-packed MatchBank / forward edges / distance vectors (:1263-1264) -- what Core switches to for
+//                        merges of many paths (core.hpp:194), i.e. the largest chaining calls of a progressive alignment.
+// Both build the same flat problem: packed and unpacked containers answer every query identically and iterate in the
+// same order (packed_match_bank.hpp:146-163, packed_forward_edges.hpp:86-101).  The 64-bit instantiations (:1267-1268,
+// :1281-1282: >= 2^32 anchors or a diagonal difference >= 2^31) keep the reference's generic code: the flat problem and the
+// device search structures index matches with 32 bits, and a problem of that size does not fit one GPU's HBM anyway.
+#define CLB_AFFINE_CHAIN_SPECIALIZATION(SHIFT_MATCH_VEC, DIST_MATCH_VEC, DIST_VEC, ANCHOR_VEC, MBANK, FWD)                         \
+    template <>                                                                                                                    \
+    inline std::vector<anchor_t>                                                                                                   \
+    Anchorer::sparse_affine_chain_dp<uint32_t, uint16_t, uint32_t, int32_t, uint32_t, float, SHIFT_MATCH_VEC, DIST_MATCH_VEC,      \
+                                     DIST_VEC, ANCHOR_VEC, MBANK, FWD, BaseGraph, b200_chain::XMerge, 3>(                          \
+        const std::vector<match_set_t>& match_sets, const BaseGraph& graph1, const BaseGraph& graph2,                              \
+        const b200_chain::XMerge& xmerge1, const b200_chain::XMerge& xmerge2, const std::array<double, 3>& gap_open,               \
+        const std::array<double, 3>& gap_extend, double local_scale, size_t num_match_sets, bool suppress_verbose_logging,         \
+        const std::vector<uint64_t>* sources1, const std::vector<uint64_t>* sources2, const std::vector<uint64_t>* sinks1,         \
+        const std::vector<uint64_t>* sinks2, const std::unordered_set<std::tuple<size_t, size_t, size_t>>* masked_matches) const { \
+        using namespace b200_chain;                                                                                                \
+        const double t0 = now_s();                                                                                                 \
+        MBANK match_bank(graph1, match_sets, num_match_sets, true, masked_matches);                   /* anchorer.hpp:1861 */      \
+        PostSwitchDistances<DIST_VEC> switch_dists1(graph1, xmerge1), switch_dists2(graph2, xmerge2); /* :1871-1872 */             \
+        std::vector<bool> mask_to, mask_from;                                                                                      \
+        std::tie(mask_to, mask_from) = generate_forward_edge_masks(graph1, match_sets, num_match_sets); /* :2267-2269 */           \
+        FWD forward_edges(xmerge1, &mask_to, &mask_from);                                                                          \
+        const auto order1 = topological_order(graph1); /* :2290 */                                                                 \
+        auto weight_of = [&](const match_set_t& ms) -> float {                                                                     \
+            return score_function->anchor_weight(ms.count1, ms.count2, ms.walks1.front().size(), ms.full_length);                  \
+        };                                                                                                                         \
+        const double t1 = now_s();                                                                                                 \
+        auto P = centrolign_b200::build_affine_chain_problem<int32_t>(match_bank, forward_edges, switch_dists1, switch_dists2,     \
+                                                                      graph1, order1, xmerge1, xmerge2, match_sets, num_match_sets, \
+                                                                      gap_open, gap_extend, local_scale, sources1, sources2,       \
+                                                                      sinks1, sinks2, weight_of);                                  \
+        const double t2 = now_s();                                                                                                 \
+        float opt_value = 0.0f;                                                                                                    \
+        auto traceback = anchors_of(P.solve(0, &opt_value), P, match_sets);                                                        \
+        if (getenv("CLB_TIMING") && P.n_match() > 10000)                                                                           \
+            fprintf(stderr, "[clb] affine chaining of %zu matches (" #MBANK "): reference-side tables %.3f s, flat problem %.3f s, " \
+                            "clb_chain_dp %.3f s\n", P.n_match(), t1 - t0, t2 - t1, now_s() - t2);                                 \
+        annotate_scores(traceback); /* :2536 */                                                                                    \
+        /* gap length and score between the anchors (:2443-2468) */                                                               \
+        centrolign_b200::annotate_gaps<int32_t>(traceback, xmerge1, xmerge2, switch_dists1, switch_dists2, gap_open, gap_extend,   \
+                                                local_scale, sources1, sources2, sinks1, sinks2);                                  \
+        if (!suppress_verbose_logging) {                                                                                           \
+            logging::log(logging::Debug, "Optimal chain consists of " + std::to_string(traceback.size()) + " matches with score " + \
+                                             (opt_value == std::numeric_limits<float>::lowest() ? std::string("-inf")              \
+                                                                                                : std::to_string(opt_value)));     \
+        }                                                                                                                          \
+        return traceback;                                                                                                          \
     }
-    if (!suppress_verbose_logging) {
-        logging::log(logging::Debug, "Optimal chain consists of " + std::to_string(traceback.size()) + " matches with score " +
-                                         (opt_value == std::numeric_limits<float>::lowest() ? std::string("-inf") : std::to_string(opt_value)));
-    }
-    return traceback;
-}
+CLB_AFFINE_CHAIN_SPECIALIZATION(b200_chain::ShiftMatchVector, b200_chain::DistMatchVector, std::vector<uint32_t>, std::vector<uint32_t>,
+                                b200_chain::Bank, b200_chain::FwdEdges)
+CLB_AFFINE_CHAIN_SPECIALIZATION(b200_chain::PackedShiftMatchVector, b200_chain::PackedDistMatchVector, PackedVector, PackedVector,
+                                b200_chain::PackedBank, PackedForwardEdges)
+#undef CLB_AFFINE_CHAIN_SPECIALIZATION
 
 // ---- sparse_chain_dp, production instantiation (anchorer.hpp:1291), for the two reachability structures Core uses with
 // it: PathMerge<uint32_t, uint8_t> in the alignment subproblems (core.hpp:336-338) and ChainMerge in the per-sequence

@@ -22,9 +22,9 @@ pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.path.exists(CLI), reaso
 @pytest.mark.parametrize("name", sorted(GOLD))
 def test_cli_output_is_byte_identical(name, tmp_path):
     case = GOLD[name]
-    if "-c" in case["options"] and not os.environ.get("CLB_RUN_SLOW"):
-        pytest.skip("cyclizing case: 6.5 min on the GPU box (13 min for the reference); set CLB_RUN_SLOW=1 -- "
-                    "last run byte-identical, see profiles/README.md")
+    if case.get("reference_seconds", 0) > 300 and not os.environ.get("CLB_RUN_SLOW"):
+        pytest.skip("large cyclizing case: 6.5 min on the GPU box (13 min for the reference); set CLB_RUN_SLOW=1.  The small "
+                    "cyclizing case msa3_2k5_cyclic runs in every test run")
     fa = str(tmp_path / (name + ".fa"))
     subprocess.run([sys.executable, os.path.join(ROOT, "integration", "make_hor_fasta.py"), fa] + [str(a) for a in case["fasta_args"]],
                    check=True)
@@ -32,7 +32,7 @@ def test_cli_output_is_byte_identical(name, tmp_path):
     env = dict(os.environ, CLB_COUNT_CALLS="1")
     sys.path.insert(0, os.path.join(ROOT, "integration"))
     from make_e2e_golden import run_cli
-    res = run_cli(CLI, case["options"], fa, case.get("config_overrides") or {}, str(tmp_path), env=env)
+    res = run_cli(CLI, case["options"], fa, case.get("config_overrides") or {}, str(tmp_path), env=env, tree=case.get("tree"))
     assert res.returncode == 0, res.stderr.decode()[-2000:]
     assert len(res.stdout) == case["output_bytes"]
     assert hashlib.md5(res.stdout).hexdigest() == case["output_md5"], "CIGAR/GFA differs from the unmodified reference"

@@ -363,3 +363,43 @@ def test_multi_device_call_matches_single_device():
         assert loads.min() > 0 and loads.max() - loads.min() <= batch.cells().max()
     with pytest.raises(Exception):
         po_poa_batch_multi(batch, PROD, [0, 0])
+
+
+def test_small_and_strip_kernels_agree_on_every_fixture_window(monkeypatch):
+    """Windows of at most 384 matrix cells take the warp-per-window kernel (popoa_small_kernels.cu), larger ones the strip
+    kernel.  Both must reproduce the reference fixture; with CLB_NO_SMALL_WINDOWS every window is forced through the
+    strip kernel, so each fixture window is checked on both paths."""
+    batch, params, pidx, scores, alns = load_golden()
+    cells = batch.cells()
+    assert (cells <= 384).sum() > 50 and (cells > 384).sum() > 50  # the fixture exercises both routes
+    for force_strip in (False, True):
+        if force_strip:
+            monkeypatch.setenv("CLB_NO_SMALL_WINDOWS", "1")
+        for k, p in enumerate(params):
+            idx = np.nonzero(pidx == k)[0]
+            got_s, got_a = po_poa_batch(select_windows(batch, idx), p)
+            for n, w in enumerate(idx):
+                assert got_s[n] == scores[w], f"window {w} (force_strip={force_strip}): score {got_s[n]} != {scores[w]}"
+                assert np.array_equal(got_a[n], alns[w]), f"window {w} (force_strip={force_strip}): alignment differs"
+
+
+def test_small_window_kernel_random_dags_vs_oracle():
+    """Thousands of tiny random DAG windows (the size the Stitcher really produces), all three parameter widths,
+    through the warp-per-window kernel, each compared with the oracle."""
+    oracle = CpuChecker("port")
+    rng = np.random.default_rng(2024)
+    pairs = []
+    for t in range(1500):
+        sides = []
+        for _ in range(2):
+            n = int(rng.integers(1, 19))
+            labels, edges = random_dag(rng, n, int(rng.integers(0, 2 * n + 1)), alphabet="AC")
+            src, snk = sources_and_sinks(len(labels), edges)
+            sides.append(graph_from_edges(labels, edges, src, snk))
+        pairs.append(tuple(sides))
+    batch = batch_from_graph_pairs(pairs)
+    assert (batch.cells() <= 384).all()
+    for num_pw in (1, 2, 3):
+        p = PROD.truncated(num_pw)
+        scores, alns = po_poa_batch(batch, p)
+        _compare(batch, p, scores, alns, oracle, f"small random DAGs, NumPW={num_pw}")
