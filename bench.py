@@ -267,6 +267,32 @@ def other_paths(device):
                                              "peak": 4 * 0.13, "peak_source": "4 dependent L2 round trips of ~250 cycles at 1.965 GHz per step "
                                                                              "(B300_MICROARCH.md L2 hit latency 234-262 cycles)",
                                              "frac": (4 * 0.13) / max(1e-9, cst.kernel_ms * 1e3 / max(1, prob.n_step))}}
+    # ---- batched entry point: fill-in sized problems (anchorer.hpp:619-699 makes thousands of them per alignment) ----
+    try:
+        from centrolign_b200.chain import chain_dp_batch
+        from golden_io import load_chain_golden
+
+        gold = load_chain_golden()
+        small = [gold[c][k] for c in sorted(gold) for k in sorted(gold[c]) if gold[c][k].n_match <= 2000]
+        if small:
+            reps = max(1, 2000 // len(small))
+            many = small * reps
+            chain_dp_batch(many[: len(small)], device=device)  # warm-up
+            bst = ChainStats()
+            t0 = time.perf_counter()
+            got = chain_dp_batch(many, device=device, stats=bst)
+            t_batch = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            ones = [chain_dp(p, device=device) for p in many[: 4 * len(small)]]
+            t_one = (time.perf_counter() - t0) / (4 * len(small)) * len(many)
+            assert all(np.array_equal(a[0], b[0]) for a, b in zip(got, ones)), "batched chaining differs from the single calls"
+            chain_out["batched_fill_in"] = {"problems": len(many), "matches_total": int(sum(p.n_match for p in many)),
+                                            "batch_call_ms": t_batch * 1e3, "kernel_ms": bst.kernel_ms, "gpu_launches": int(bst.kernel_launches),
+                                            "one_by_one_ms_extrapolated": t_one * 1e3, "speedup": t_one / t_batch,
+                                            "what": "clb_chain_dp_batch: host layout per problem, ONE staging copy, ONE launch (a CTA per problem), "
+                                                    "ONE read-back; one_by_one = clb_chain_dp per problem (timed on a fifth of them)"}
+    except Exception as exc:
+        chain_out["batched_fill_in"] = {"error": str(exc)[:200]}
     out["chain_dp"] = chain_out
     return out
 

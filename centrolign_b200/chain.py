@@ -72,13 +72,13 @@ def _bind(lib):
     lib.clb_chain_dp.restype = ctypes.c_int
     lib.clb_chain_dp.argtypes = [ctypes.c_int, ctypes.POINTER(_CProblem), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                  ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ChainStats)]
+    lib.clb_chain_dp_batch.restype = ctypes.c_int
+    lib.clb_chain_dp_batch.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ChainStats)]
     lib._chain_bound = True
 
 
-def chain_dp(problem: ChainProblem, device: int = 0, stats: Optional[ChainStats] = None):
-    """Run the chaining DP + traceback on the GPU.  Returns (chain ranks, dp values, back-pointers, optimum)."""
-    lib = load_library()
-    _bind(lib)
+def _c_problem(problem: ChainProblem):
     keep = {k: np.ascontiguousarray(problem.arrays[k], dt) for k, dt in _FIELDS}
     cp = _CProblem()
     cp.num_pw = problem.num_pw
@@ -89,6 +89,36 @@ def chain_dp(problem: ChainProblem, device: int = 0, stats: Optional[ChainStats]
     cp.n_match, cp.n_step, cp.min_score = problem.n_match, problem.n_step, problem.min_score
     for k, _ in _FIELDS:
         setattr(cp, k, keep[k].ctypes.data)
+    return cp, keep
+
+
+def chain_dp_batch(problems, device: int = 0, stats: Optional[ChainStats] = None):
+    """``clb_chain_dp_batch``: many independent problems in one call (one launch for all that fit shared memory).
+    Returns a list of (chain ranks, dp values, back-pointers, optimum), one per problem."""
+    lib = load_library()
+    _bind(lib)
+    n = len(problems)
+    cps = [_c_problem(p) for p in problems]
+    ms = [p.n_match for p in problems]
+    dps = [np.zeros(max(1, m), np.float32) for m in ms]
+    bps = [np.full(max(1, m), -1, np.int64) for m in ms]
+    chains = [np.zeros(m + 1, np.int64) for m in ms]
+    lens = np.zeros(max(1, n), np.int64)
+    opts = np.zeros(max(1, n), np.float32)
+    PP = ctypes.POINTER(_CProblem) * max(1, n)
+    VP = ctypes.c_void_p * max(1, n)
+    parr = PP(*[ctypes.pointer(c[0]) for c in cps]) if n else PP()
+    _check(lib.clb_chain_dp_batch(device, n, parr, VP(*[a.ctypes.data for a in dps]), VP(*[a.ctypes.data for a in bps]),
+                                  VP(*[a.ctypes.data for a in chains]), lens.ctypes.data, opts.ctypes.data,
+                                  ctypes.byref(stats) if stats is not None else None))
+    return [(chains[k][: int(lens[k])].copy(), dps[k][: ms[k]], bps[k][: ms[k]], float(opts[k])) for k in range(n)]
+
+
+def chain_dp(problem: ChainProblem, device: int = 0, stats: Optional[ChainStats] = None):
+    """Run the chaining DP + traceback on the GPU.  Returns (chain ranks, dp values, back-pointers, optimum)."""
+    lib = load_library()
+    _bind(lib)
+    cp, keep = _c_problem(problem)
     m = problem.n_match
     dp = np.zeros(max(1, m), np.float32)
     bp = np.full(max(1, m), -1, np.int64)

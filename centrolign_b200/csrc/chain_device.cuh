@@ -115,6 +115,9 @@ struct ChainArgs {
     int rank_stride;
     const char* arena_base;  // the arena all pointers above point into, and its size
     int64_t arena_bytes;
+    int64_t copy_bytes;      // shared-memory kernels: this many bytes are copied from arena_base, the rest of the arena starts as zero
+    float* out_dp;           // batched launch: compact result arrays of the problem (nullptr: results go back into dp / backptr)
+    uint32_t* out_backptr;
     int split_phases;  // debug: separate barrier between update_dp and the next step's insertions
 };
 

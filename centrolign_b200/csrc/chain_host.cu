@@ -32,6 +32,7 @@
 
 namespace clb {
 cudaError_t launch_chain(const ChainArgs& args, int grid, int prepare_grid, cudaStream_t stream, cudaEvent_t after_prepare);
+cudaError_t launch_chain_small_batch(const ChainArgs* d_args, int n, int smem_bytes, cudaStream_t stream);
 int chain_max_grid(int device);
 int host_fail(int code, const std::string& msg);
 }  // namespace clb
@@ -121,6 +122,28 @@ void parallel_sort(std::vector<SortKey>& keys) {
     }
 }
 
+// A batch of small problems being collected by clb_chain_dp_batch: every problem whose arena fits shared memory is
+// laid out as usual, its copy segments are appended to ONE staging buffer, and its kernel arguments are recorded with
+// arena-relative pointers; flush() then needs one H2D copy, one launch (a CTA per problem) and one D2H copy for all.
+struct DeferredProblem {
+    clb::ChainArgs args;        // pointers relative to the problem's arena (offset from 0)
+    size_t arena_off = 0;       // of the problem's copy region in the combined buffer
+    size_t res_off = 0;         // of its results (match-count floats / words) in the compact result buffers
+    int64_t n_match = 0;
+    const clb_chain_problem* p = nullptr;
+    float* dp_out = nullptr;
+    int64_t* backptr_out = nullptr;
+    int64_t* chain_out = nullptr;
+    int64_t* chain_len = nullptr;
+    float* opt_score = nullptr;
+};
+struct BatchCtx {
+    std::vector<char> staging;  // concatenated copy regions (256-byte aligned)
+    std::vector<DeferredProblem> items;
+    size_t res_total = 0;
+    int max_smem = 0;
+};
+
 struct ArenaPlan {
     struct Seg {
         size_t off, bytes;
@@ -146,8 +169,47 @@ struct ArenaPlan {
 
 }  // namespace
 
+// the reference's traceback on the final DP values and back-pointers (anchorer.hpp:2483-2534)
+static int chain_traceback(const clb_chain_problem* p, const float* h_dp, const uint32_t* h_bp, float* dp_out, int64_t* backptr_out,
+                           int64_t* chain_out, int64_t* chain_len, float* opt_score) {
+    const float kLowest = std::numeric_limits<float>::lowest();
+    const int64_t M = p->n_match;
+    float opt_value = kLowest;
+    int64_t opt = -1;
+    for (int64_t m = 0; m < M; ++m) {
+        float dp_val = h_dp[m];
+        const float fin = p->final_term[m];
+        if (fin == kLowest) dp_val = fin;
+        else dp_val += fin;
+        if (dp_val > opt_value && dp_val > p->min_score) {
+            opt_value = dp_val;
+            opt = m;
+        }
+    }
+    int64_t len = 0;
+    for (int64_t here = opt; here >= 0; here = h_bp[here] == 0xffffffffu ? -1 : (int64_t)h_bp[here]) {
+        if (len >= M) return host_fail(CLB_ECUDA, "internal: back-pointer cycle");
+        chain_out[len++] = here;
+    }
+    std::reverse(chain_out, chain_out + len);
+    *chain_len = len;
+    if (opt_score) *opt_score = opt_value;
+    if (dp_out) memcpy(dp_out, h_dp, M * sizeof(float));
+    if (backptr_out)
+        for (int64_t m = 0; m < M; ++m) backptr_out[m] = h_bp[m] == 0xffffffffu ? -1 : (int64_t)h_bp[m];
+    return CLB_OK;
+}
+
+static int chain_dp_impl(int device, const clb_chain_problem* p, float* dp_out, int64_t* backptr_out, int64_t* chain_out,
+                         int64_t* chain_len, float* opt_score, clb_chain_stats* stats, BatchCtx* ctx);
+
 extern "C" int clb_chain_dp(int device, const clb_chain_problem* p, float* dp_out, int64_t* backptr_out, int64_t* chain_out,
                             int64_t* chain_len, float* opt_score, clb_chain_stats* stats) {
+    return chain_dp_impl(device, p, dp_out, backptr_out, chain_out, chain_len, opt_score, stats, nullptr);
+}
+
+static int chain_dp_impl(int device, const clb_chain_problem* p, float* dp_out, int64_t* backptr_out, int64_t* chain_out,
+                         int64_t* chain_len, float* opt_score, clb_chain_stats* stats, BatchCtx* ctx) {
     const double t_start = now_ms();
     if (stats) memset(stats, 0, sizeof(*stats));
     struct CallTimer {  // evidence for integration tests that the GPU path really ran, and what it cost
@@ -176,6 +238,38 @@ extern "C" int clb_chain_dp(int device, const clb_chain_problem* p, float* dp_ou
     if (p->n_match < 0 || p->n_step < 0 || p->n_chain1 < 0 || p->n_chain2 < 0) return host_fail(CLB_EINVAL, "negative sizes");
     if (p->n_match > 0 && (p->n_chain1 < 1 || p->n_chain2 < 1)) return host_fail(CLB_EINVAL, "matches but no chains");
     if (p->n_match >= (int64_t(1) << 31)) return host_fail(CLB_EINVAL, "more than 2^31 matches");
+    if (const char* dump_dir = getenv("CLB_DUMP_DIR")) {  // debugging aid: every problem a caller sends, in the format of oracle/chain_shim.cpp
+        static std::atomic<int> seq(0);
+        if (p->n_match > 0 && p->ins_off && p->end_off && p->qry_off) {
+            const std::string path = std::string(dump_dir) + "/chain_" + std::to_string(seq++) + ".bin";
+            if (FILE* f = fopen(path.c_str(), "wb")) {
+                const std::string kind = p->num_pw == 0 ? "gapfree" : "affine";
+                auto put = [&](const std::string& name, uint32_t code, const void* data, uint64_t n, size_t elem) {
+                    const std::string full = kind + "." + name;
+                    const uint32_t len = (uint32_t)full.size();
+                    fwrite(&len, 4, 1, f); fwrite(full.data(), 1, len, f); fwrite(&code, 4, 1, f); fwrite(&n, 8, 1, f);
+                    if (n) fwrite(data, elem, n, f);
+                };
+                const int64_t M_ = p->n_match, S_ = p->n_step, E_ = p->ins_off[M_], NE = p->end_off[S_], NQ = p->qry_off[S_];
+                const double prm[11] = {(double)p->num_pw, p->gap_open[0], p->gap_open[1], p->gap_open[2], p->gap_extend[0], p->gap_extend[1],
+                                        p->gap_extend[2], p->scale, (double)p->n_chain1, (double)p->n_chain2, 0.0};
+                put("params", 4, prm, 11, 8);
+                put("min_score", 0, &p->min_score, 1, 4);
+                put("expect_chain", 3, nullptr, 0, 8);
+                put("weight", 0, p->weight, M_, 4); put("dp_init", 0, p->dp_init, M_, 4); put("final_term", 0, p->final_term, M_, 4);
+                put("end_off", 3, p->end_off, S_ + 1, 8); put("end_match", 2, p->end_match, NE, 4);
+                put("qry_off", 3, p->qry_off, S_ + 1, 8); put("qry_match", 2, p->qry_match, NQ, 4); put("qry_chain1", 2, p->qry_chain1, NQ, 4);
+                put("ins_off", 3, p->ins_off, M_ + 1, 8); put("ins_p1", 2, p->ins_p1, E_, 4); put("ins_p2", 2, p->ins_p2, E_, 4);
+                put("ins_shift", 1, p->ins_shift, E_, 4); put("ins_offset", 2, p->ins_offset, E_, 4);
+                std::vector<uint32_t> act(E_, 1u);
+                if (p->ins_active) for (int64_t e = 0; e < E_; ++e) act[e] = p->ins_active[e];
+                put("ins_active", 2, act.data(), E_, 4);
+                put("qa1", 1, p->qa1, (uint64_t)M_ * p->n_chain1, 4); put("qa2", 1, p->qa2, (uint64_t)M_ * p->n_chain2, 4);
+                put("qoff", 2, p->qoff, (uint64_t)M_ * p->n_chain2, 4);
+                fclose(f);
+            }
+        }
+    }
     const bool layout_only = getenv("CLB_CHAIN_LAYOUT_ONLY") != nullptr;  // host-layout timing without a device (no results)
     int ndev = 0;
     if (!layout_only) {
@@ -444,6 +538,61 @@ extern "C" int clb_chain_dp(int device, const clb_chain_problem* p, float* dp_ou
             else rank_stride = 0;
         }
         const size_t total = plan.copy_bytes + plan.zero_bytes;
+        if (ctx && total <= (size_t)clb::kChainSmallArena && !getenv("CLB_CHAIN_NO_SMALL")) {
+            // batched small problem: stage the copy region, record arena-relative arguments, finish in flush()
+            DeferredProblem d;
+            d.arena_off = ctx->staging.size();
+            ctx->staging.resize(d.arena_off + plan.copy_bytes);
+            for (const auto& sg : plan.segs)
+                if (sg.bytes) memcpy(ctx->staging.data() + d.arena_off + sg.off, sg.src, sg.bytes);
+            char* const base = nullptr;           // arena-relative: flush() adds the device address of the problem's copy region
+            char* const zr0 = base + plan.copy_bytes;
+            clb::ChainArgs& b = d.args;
+            b = clb::ChainArgs{};
+            b.num_pw = P; b.n_chain1 = C1; b.n_chain2 = C2; b.scale = p->scale;
+            for (int k = 0; k < 3; ++k) {
+                b.gap_open[k] = p->gap_open[k];
+                b.gap_extend[k] = p->gap_extend[k];
+                b.scale_ext[k] = p->scale * p->gap_extend[k];
+            }
+            b.n_match = M; b.n_step = S; b.n_entry = E; b.n_inner = n_inner; b.n_qry = n_qry;
+            b.dp = (float*)(base + o_dp); b.backptr = (uint32_t*)(base + o_bp);
+            b.sins_off = (const int64_t*)(base + o_sins); b.ins = (const clb::InsRec*)(base + o_ins);
+            b.qry_off = (const int64_t*)(base + o_qoff); b.qry_match = (const uint32_t*)(base + o_qm);
+            b.weight = (const float*)(base + o_w); b.qry_chain1 = (const uint32_t*)(base + o_qc1);
+            b.qa1 = (const int32_t*)(base + o_qa1); b.qa2 = (const int32_t*)(base + o_qa2); b.qoff = (const uint32_t*)(base + o_qo);
+            b.pair_grp_off = (const int64_t*)(base + o_pg); b.grp_shift = (const int32_t*)(base + o_gs);
+            b.grp_base = (const uint32_t*)(base + o_gb); b.grp_n = (const uint32_t*)(base + o_gn); b.pair_base = (const uint32_t*)(base + o_pb);
+            b.gf_key = (const uint32_t*)(base + o_gk); b.gf_match = (const uint32_t*)(base + o_gm);
+            b.or_shift = (const int32_t*)(base + o_os); b.or_off = (const uint32_t*)(base + o_oo); b.or_match = (const uint32_t*)(base + o_om);
+            b.in_base = (const uint32_t*)(base + o_ib); b.in_n = (const uint32_t*)(base + o_in); b.in_off = (const uint32_t*)(base + o_io);
+            b.ent_rank = (const uint32_t*)(base + o_er);
+            b.qrec = (clb::QueryRec*)(zr0 + z_qrec);
+            b.gf_ord = (uint32_t*)(zr0 + z_gford); b.gf_best = (unsigned long long*)(zr0 + z_gfbest);
+            b.or_ord = (uint32_t*)(zr0 + z_orord); b.bit = (unsigned long long*)(zr0 + z_bit);
+            b.rank_pool = rank_stride ? (uint32_t*)(zr0 + z_ranks) : nullptr;
+            b.rank_stride = rank_stride;
+            b.cand_best = (unsigned long long*)(zr0 + z_cbest); b.cand_bp = (uint32_t*)(zr0 + z_cbp); b.counters = (unsigned long long*)(zr0 + z_cnt);
+            b.arena_base = base;
+            b.arena_bytes = (int64_t)total;
+            b.copy_bytes = (int64_t)plan.copy_bytes;
+            d.res_off = ctx->res_total;
+            ctx->res_total += (size_t)M;
+            ctx->max_smem = std::max(ctx->max_smem, (int)((total + 15) / 16 * 16));
+            d.n_match = M; d.p = p; d.dp_out = dp_out; d.backptr_out = backptr_out; d.chain_out = chain_out; d.chain_len = chain_len;
+            d.opt_score = opt_score;
+            ctx->items.push_back(d);
+            if (stats) {
+                stats->build_ms = t_built - t_start;
+                stats->steps = S;
+                stats->inserts = (int64_t)ins.size();
+                stats->queries = n_qry * C2;
+                stats->tree_bytes = (int64_t)total;
+                stats->h2d_bytes = (int64_t)plan.copy_bytes;
+                stats->d2h_bytes = M * 8;
+            }
+            return CLB_OK;
+        }
         keep = total <= kArenaKeep;
         CHAIN_TRY(cudaSetDevice(device));
         if (!ar.stream) {
@@ -506,6 +655,8 @@ extern "C" int clb_chain_dp(int device, const clb_chain_problem* p, float* dp_ou
                                          : (warps_per_step > 64.0 ? std::min<int>(max_grid, (int)(warps_per_step / 12.0) + 1) : 1);
         a.arena_base = ar.d;
         a.arena_bytes = (int64_t)total;
+        a.copy_bytes = (int64_t)total;  // the single-problem path copies the zeroed region too
+        a.out_dp = nullptr; a.out_backptr = nullptr;
         if (total <= (size_t)clb::kChainSmallArena && !getenv("CLB_CHAIN_NO_SMALL") && !getenv("CLB_CHAIN_GRID")) grid = 0;
         const int prepare_grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_qry * C2 + 7) / 8, 8 * (int64_t)max_grid));
         CHAIN_TRY(cudaEventRecord(ar.ev0, ar.stream));
@@ -539,35 +690,8 @@ extern "C" int clb_chain_dp(int device, const clb_chain_problem* p, float* dp_ou
             stats->kernel_launches = (grid == 0 || n_qry == 0) ? 1 : 2;
         }
     }
-    // ---- traceback_sparse_dp (anchorer.hpp:2483-2534) ----
-    {
-        float opt_value = kLowest;
-        int64_t opt = -1;
-        for (int64_t m = 0; m < M; ++m) {
-            float dp_val = h_dp[m];
-            const float fin = p->final_term[m];
-            if (fin == kLowest) dp_val = fin;
-            else dp_val += fin;
-            if (dp_val > opt_value && dp_val > p->min_score) {
-                opt_value = dp_val;
-                opt = m;
-            }
-        }
-        int64_t len = 0;
-        for (int64_t here = opt; here >= 0; here = h_bp[here] == 0xffffffffu ? -1 : (int64_t)h_bp[here]) {
-            if (len >= M) {
-                rc = host_fail(CLB_ECUDA, "internal: back-pointer cycle");
-                goto cleanup;
-            }
-            chain_out[len++] = here;
-        }
-        std::reverse(chain_out, chain_out + len);
-        *chain_len = len;
-        if (opt_score) *opt_score = opt_value;
-        if (dp_out) memcpy(dp_out, h_dp.data(), M * sizeof(float));
-        if (backptr_out)
-            for (int64_t m = 0; m < M; ++m) backptr_out[m] = h_bp[m] == 0xffffffffu ? -1 : (int64_t)h_bp[m];
-    }
+    rc = chain_traceback(p, h_dp.data(), h_bp.data(), dp_out, backptr_out, chain_out, chain_len, opt_score);
+    if (rc != CLB_OK) goto cleanup;
     if (stats) stats->total_ms = now_ms() - t_start;
 cleanup:
     if (!keep || rc != CLB_OK) {  // large arenas are not kept: other calls of the library size themselves by free memory
@@ -578,6 +702,113 @@ cleanup:
     }
     return rc;
 #undef CHAIN_TRY
+}
+
+// Many independent chaining problems in one call.  The Anchorer's fill-in pass (anchorer.hpp:619-699) chains the
+// matches inside every gap of the main chain separately -- thousands of problems of a few dozen matches each; one at a
+// time each pays a layout, a staging copy, a launch on ONE SM and a read-back.  Here every problem that fits shared
+// memory is laid out on the host, all of them are staged in one buffer and solved by ONE launch with a CTA per problem
+// (chain_small_batch_kernel), and the results come back in one copy; larger problems run through clb_chain_dp.
+extern "C" int clb_chain_dp_batch(int device, int64_t n_problems, const clb_chain_problem* const* problems, float* const* dp_out,
+                                  int64_t* const* backptr_out, int64_t* const* chain_out, int64_t* chain_len, float* opt_score,
+                                  clb_chain_stats* stats) {
+    const double t_start = now_ms();
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (n_problems < 0 || (n_problems > 0 && (!problems || !chain_out || !chain_len))) return host_fail(CLB_EINVAL, "clb_chain_dp_batch: null arguments");
+    BatchCtx ctx;
+    clb_chain_stats one{};
+    for (int64_t k = 0; k < n_problems; ++k) {
+        if (!problems[k] || !chain_out[k]) return host_fail(CLB_EINVAL, "clb_chain_dp_batch: null problem or output");
+        const int rc = chain_dp_impl(device, problems[k], dp_out ? dp_out[k] : nullptr, backptr_out ? backptr_out[k] : nullptr, chain_out[k],
+                                     &chain_len[k], opt_score ? &opt_score[k] : nullptr, stats ? &one : nullptr, &ctx);
+        if (rc != CLB_OK) return rc;
+        if (stats) {
+            stats->build_ms += one.build_ms; stats->kernel_ms += one.kernel_ms; stats->steps += one.steps; stats->inserts += one.inserts;
+            stats->queries += one.queries; stats->tree_bytes += one.tree_bytes; stats->h2d_bytes += one.h2d_bytes;
+            stats->d2h_bytes += one.d2h_bytes; stats->kernel_launches += one.kernel_launches;
+        }
+    }
+    const int64_t nb = (int64_t)ctx.items.size();
+    if (nb > 0) {
+        int rc = CLB_OK;
+        char* d_arena = nullptr;
+        clb::ChainArgs* d_args = nullptr;
+        float* d_dp = nullptr;
+        uint32_t* d_bp = nullptr;
+        cudaStream_t stream = nullptr;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        std::vector<clb::ChainArgs> h_args((size_t)nb);
+        std::vector<float> h_dp(ctx.res_total);
+        std::vector<uint32_t> h_bp(ctx.res_total);
+#define BATCH_TRY(expr)                                                                                                \
+    do {                                                                                                               \
+        cudaError_t _e = (expr);                                                                                       \
+        if (_e != cudaSuccess) {                                                                                       \
+            rc = host_fail(_e == cudaErrorMemoryAllocation ? CLB_ENOMEM : CLB_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+            goto batch_cleanup;                                                                                        \
+        }                                                                                                              \
+    } while (0)
+        BATCH_TRY(cudaSetDevice(device));
+        BATCH_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        BATCH_TRY(cudaEventCreate(&e0));
+        BATCH_TRY(cudaEventCreate(&e1));
+        BATCH_TRY(cudaMalloc((void**)&d_arena, std::max<size_t>(ctx.staging.size(), 256)));
+        BATCH_TRY(cudaMalloc((void**)&d_args, (size_t)nb * sizeof(clb::ChainArgs)));
+        BATCH_TRY(cudaMalloc((void**)&d_dp, std::max<size_t>(ctx.res_total, 1) * 4));
+        BATCH_TRY(cudaMalloc((void**)&d_bp, std::max<size_t>(ctx.res_total, 1) * 4));
+        for (int64_t k = 0; k < nb; ++k) {
+            clb::ChainArgs a = ctx.items[k].args;
+            const ptrdiff_t shift = (d_arena + ctx.items[k].arena_off) - (char*)nullptr;
+#define CLB_SHIFT(f) a.f = reinterpret_cast<decltype(a.f)>(reinterpret_cast<char*>(const_cast<void*>(static_cast<const void*>(a.f))) + shift)
+            CLB_SHIFT(dp); CLB_SHIFT(backptr); CLB_SHIFT(sins_off); CLB_SHIFT(ins); CLB_SHIFT(qry_off); CLB_SHIFT(qry_match);
+            CLB_SHIFT(qrec); CLB_SHIFT(weight); CLB_SHIFT(qry_chain1); CLB_SHIFT(qa1); CLB_SHIFT(qa2); CLB_SHIFT(qoff);
+            CLB_SHIFT(pair_grp_off); CLB_SHIFT(grp_shift); CLB_SHIFT(grp_base); CLB_SHIFT(grp_n); CLB_SHIFT(pair_base);
+            CLB_SHIFT(gf_key); CLB_SHIFT(gf_match); CLB_SHIFT(gf_ord); CLB_SHIFT(gf_best); CLB_SHIFT(or_shift); CLB_SHIFT(or_off);
+            CLB_SHIFT(or_match); CLB_SHIFT(or_ord); CLB_SHIFT(in_base); CLB_SHIFT(in_n); CLB_SHIFT(in_off); CLB_SHIFT(bit);
+            CLB_SHIFT(ent_rank); CLB_SHIFT(cand_best); CLB_SHIFT(cand_bp); CLB_SHIFT(counters); CLB_SHIFT(arena_base);
+            if (a.rank_pool) CLB_SHIFT(rank_pool);
+#undef CLB_SHIFT
+            a.out_dp = d_dp + ctx.items[k].res_off;
+            a.out_backptr = d_bp + ctx.items[k].res_off;
+            h_args[(size_t)k] = a;
+        }
+        {
+            const double t_staged = now_ms();
+            BATCH_TRY(cudaMemcpyAsync(d_arena, ctx.staging.data(), ctx.staging.size(), cudaMemcpyHostToDevice, stream));
+            BATCH_TRY(cudaMemcpyAsync(d_args, h_args.data(), (size_t)nb * sizeof(clb::ChainArgs), cudaMemcpyHostToDevice, stream));
+            BATCH_TRY(cudaEventRecord(e0, stream));
+            BATCH_TRY(clb::launch_chain_small_batch(d_args, (int)nb, ctx.max_smem, stream));
+            BATCH_TRY(cudaEventRecord(e1, stream));
+            BATCH_TRY(cudaMemcpyAsync(h_dp.data(), d_dp, ctx.res_total * 4, cudaMemcpyDeviceToHost, stream));
+            BATCH_TRY(cudaMemcpyAsync(h_bp.data(), d_bp, ctx.res_total * 4, cudaMemcpyDeviceToHost, stream));
+            BATCH_TRY(cudaStreamSynchronize(stream));
+            float ms = 0.f;
+            BATCH_TRY(cudaEventElapsedTime(&ms, e0, e1));
+            if (stats) {
+                stats->kernel_ms += ms;
+                stats->kernel_launches += 1;
+            }
+            if (getenv("CLB_TIMING"))
+                fprintf(stderr, "[clb] chain batch: %lld of %lld problems in one launch, %.1f MB staged, kernel %.2f ms, copies+sync %.2f ms\n",
+                        (long long)nb, (long long)n_problems, ctx.staging.size() / 1e6, ms, now_ms() - t_staged - ms);
+        }
+        for (int64_t k = 0; k < nb && rc == CLB_OK; ++k) {
+            const DeferredProblem& d = ctx.items[k];
+            rc = chain_traceback(d.p, h_dp.data() + d.res_off, h_bp.data() + d.res_off, d.dp_out, d.backptr_out, d.chain_out, d.chain_len, d.opt_score);
+        }
+    batch_cleanup:
+        if (d_arena) cudaFree(d_arena);
+        if (d_args) cudaFree(d_args);
+        if (d_dp) cudaFree(d_dp);
+        if (d_bp) cudaFree(d_bp);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        if (stream) cudaStreamDestroy(stream);
+#undef BATCH_TRY
+        if (rc != CLB_OK) return rc;
+    }
+    if (stats) stats->total_ms = now_ms() - t_start;
+    return CLB_OK;
 }
 
 namespace clb {

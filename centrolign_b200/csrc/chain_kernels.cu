@@ -545,12 +545,12 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainArgs A) {
 
 // Small problems: one CTA copies the whole arena into shared memory, rebases the pointers, prepares the queries,
 // runs the same step loop on shared memory and copies the DP values and back-pointers out again.
-__global__ void __launch_bounds__(kThreads, 1) chain_small_kernel(const ChainArgs G) {
-    __shared__ WarpScratch scratch[kWarps];
-    extern __shared__ uint4 arena_smem[];
+__device__ __forceinline__ void chain_small_body(const ChainArgs& G, WarpScratch* scratch, uint4* arena_smem) {
     const char* gbase = G.arena_base;
-    for (int64_t i = threadIdx.x; i < (G.arena_bytes + 15) / 16; i += kThreads)
+    const int64_t ncopy = (G.copy_bytes + 15) / 16, nall = (G.arena_bytes + 15) / 16;
+    for (int64_t i = threadIdx.x; i < ncopy; i += kThreads)
         arena_smem[i] = __ldg(reinterpret_cast<const uint4*>(gbase) + i);
+    for (int64_t i = ncopy + threadIdx.x; i < nall; i += kThreads) arena_smem[i] = make_uint4(0u, 0u, 0u, 0u);
     ChainArgs A = G;
     char* sbase = reinterpret_cast<char*>(arena_smem);
 #define CLB_REBASE(f) A.f = reinterpret_cast<decltype(A.f)>(sbase + (reinterpret_cast<const char*>(G.f) - gbase))
@@ -567,10 +567,41 @@ __global__ void __launch_bounds__(kThreads, 1) chain_small_kernel(const ChainArg
     __syncthreads();
     chain_steps<true>(A, scratch);
     __syncthreads();
+    float* const odp = G.out_dp ? G.out_dp : G.dp;
+    uint32_t* const obp = G.out_backptr ? G.out_backptr : G.backptr;
     for (int64_t m = threadIdx.x; m < G.n_match; m += kThreads) {
-        G.dp[m] = A.dp[m];
-        G.backptr[m] = A.backptr[m];
+        odp[m] = A.dp[m];
+        obp[m] = A.backptr[m];
     }
+}
+
+// Small problems: one CTA copies the whole arena into shared memory, rebases the pointers, prepares the queries,
+// runs the same step loop on shared memory and copies the DP values and back-pointers out again.
+__global__ void __launch_bounds__(kThreads, 1) chain_small_kernel(const ChainArgs G) {
+    __shared__ WarpScratch scratch[kWarps];
+    extern __shared__ uint4 arena_smem[];
+    chain_small_body(G, scratch, arena_smem);
+}
+
+// The same for a batch of independent problems: CTA b solves problem b (clb_chain_dp_batch).
+__global__ void __launch_bounds__(kThreads, 1) chain_small_batch_kernel(const ChainArgs* __restrict__ problems) {
+    __shared__ WarpScratch scratch[kWarps];
+    extern __shared__ uint4 arena_smem[];
+    __shared__ ChainArgs G;
+    if (threadIdx.x == 0) G = problems[blockIdx.x];
+    __syncthreads();
+    chain_small_body(G, scratch, arena_smem);
+}
+
+cudaError_t launch_chain_small_batch(const ChainArgs* d_args, int n, int smem_bytes, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e0 = cudaFuncSetAttribute(chain_small_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmallArena);
+        if (e0 != cudaSuccess) return e0;
+        attr_set = true;
+    }
+    chain_small_batch_kernel<<<n, kThreads, (size_t)smem_bytes, stream>>>(d_args);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_chain(const ChainArgs& args, int grid, int prepare_grid, cudaStream_t stream, cudaEvent_t after_prepare) {

@@ -770,6 +770,26 @@ int clb_popoa_batch(int device, int32_t n_windows, const clb_graph_batch* g1, co
         calls += 1;
         windows += n_windows;
     }
+    if (const char* dump_dir = getenv("CLB_DUMP_DIR")) {  // debugging aid: every batch a caller sends, for tools/check_dump.py
+        static std::atomic<int> seq(0);
+        if (n_windows > 0 && g1 && g2 && params) {
+            const std::string path = std::string(dump_dir) + "/popoa_" + std::to_string(seq++) + ".bin";
+            if (FILE* f = fopen(path.c_str(), "wb")) {
+                const int64_t nw64 = n_windows;
+                fwrite(&nw64, 8, 1, f);
+                fwrite(params, sizeof(*params), 1, f);
+                for (const clb_graph_batch* g : {g1, g2}) {
+                    const int64_t N = g->node_off[n_windows], E = g->edge_off[n_windows], S = g->src_off[n_windows], K = g->snk_off[n_windows];
+                    const int64_t hdr[4] = {N, E, S, K};
+                    fwrite(hdr, 8, 4, f);
+                    fwrite(g->node_off, 8, n_windows + 1, f); fwrite(g->label, 1, N, f); fwrite(g->edge_off, 8, n_windows + 1, f);
+                    fwrite(g->pred_off, 4, N + n_windows, f); fwrite(g->pred, 4, E, f); fwrite(g->src_off, 8, n_windows + 1, f);
+                    fwrite(g->src, 4, S, f); fwrite(g->snk_off, 8, n_windows + 1, f); fwrite(g->snk, 4, K, f);
+                }
+                fclose(f);
+            }
+        }
+    }
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t0 = now(), t1 = t0, t2 = t0, t3 = t0, t4 = t0;
     // Large batches go through in chunks (largest windows first, geometrically growing host work), each with its

@@ -248,6 +248,19 @@ typedef struct clb_chain_stats {
 int clb_chain_dp(int device, const clb_chain_problem* problem, float* dp_out, int64_t* backptr_out, int64_t* chain_out,
                  int64_t* chain_len, float* opt_score, clb_chain_stats* stats /* may be NULL */);
 
+/*
+ * Many independent chaining problems in one call: the Anchorer's fill-in pass (include/centrolign/anchorer.hpp:619-699)
+ * chains the matches inside every gap of the main chain separately, thousands of problems of a few dozen matches each.
+ * Every problem whose search structures fit one SM's shared memory is staged into one buffer and solved by ONE kernel
+ * launch with a CTA per problem; the others go through clb_chain_dp one by one.  Per problem k the outputs have the
+ * meaning of clb_chain_dp: dp_out[k] / backptr_out[k] may be NULL (and the arrays themselves may be NULL), chain_out[k]
+ * has capacity n_match of problem k, chain_len[k] and opt_score[k] (array may be NULL) receive the chain length and optimum.
+ * stats (may be NULL) accumulates over the batch.
+ */
+int clb_chain_dp_batch(int device, int64_t n_problems, const clb_chain_problem* const* problems, float* const* dp_out,
+                       int64_t* const* backptr_out, int64_t* const* chain_out, int64_t* chain_len, float* opt_score,
+                       clb_chain_stats* stats /* may be NULL */);
+
 /* Measured INT32 issue-rate probe (a dependent-free add/max loop on every SM):
  * returns achieved 10^12 INT32 lane-ops per second on `device`, <0 on error. */
 double clb_int32_peak_tops(int device, int use_dpx);

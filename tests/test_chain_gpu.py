@@ -94,3 +94,33 @@ def test_handmade_edge_cases(num_pw):
     empty.arrays = {k: v[:0] if k not in ("end_off", "qry_off", "ins_off") else v[:1] for k, v in empty.arrays.items()}
     chain, dp, bp, opt = chain_dp(empty)  # no matches at all: the empty chain
     assert len(chain) == 0
+
+
+def test_batched_call_equals_one_by_one():
+    """clb_chain_dp_batch (one launch, a CTA per problem for everything that fits shared memory; the rest one by one)
+    must return, per problem, exactly what clb_chain_dp returns: chains, every DP value, every back-pointer."""
+    from centrolign_b200.chain import ChainStats, chain_dp_batch
+
+    probs = []
+    for case in sorted(GOLD):
+        for kind in sorted(GOLD[case]):
+            probs.append(GOLD[case][kind])
+    for num_pw in (0, 1, 3):  # tiny problems, incl. one without matches
+        probs += [_handmade(num_pw), _handmade(num_pw, with_query=False), _handmade(num_pw, n=1)]
+        empty = _handmade(num_pw, n=1)
+        empty.arrays = {k: v[:0] if k not in ("end_off", "qry_off", "ins_off") else v[:1] for k, v in empty.arrays.items()}
+        probs.append(empty)
+    probs = probs * 3  # several CTAs' worth
+    st = ChainStats()
+    got = chain_dp_batch(probs, stats=st)
+    assert len(got) == len(probs)
+    n_small = 0
+    for prob, (chain, dp, bp, opt) in zip(probs, got):
+        rchain, rdp, rbp, ropt = chain_dp(prob)
+        assert np.array_equal(chain, rchain) and opt == ropt
+        assert np.array_equal(dp.view(np.uint32), rdp.view(np.uint32)) and np.array_equal(bp, rbp)
+        if prob.expect_chain is not None and len(prob.expect_chain):
+            assert np.array_equal(chain, prob.expect_chain)
+        n_small += 1
+    assert st.kernel_launches >= 1
+    assert chain_dp_batch([]) == []
