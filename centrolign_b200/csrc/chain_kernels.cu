@@ -286,8 +286,10 @@ __device__ __forceinline__ void chain_steps(const ChainArgs& A, WarpScratch* scr
     cg::grid_group grid = cg::this_grid();
     const bool multi = !SM && gridDim.x > 1;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int64_t gwarp = (int64_t)blockIdx.x * kWarps + wib, nwarp = (int64_t)gridDim.x * kWarps;
-    const int64_t gthread = (int64_t)blockIdx.x * kThreads + threadIdx.x, nthread = (int64_t)gridDim.x * kThreads;
+    // the shared-memory flavour is one CTA per problem whatever the grid is (a batch launch has one CTA per problem)
+    const int64_t cta = SM ? 0 : (int64_t)blockIdx.x, nctas = SM ? 1 : (int64_t)gridDim.x;
+    const int64_t gwarp = cta * kWarps + wib, nwarp = nctas * kWarps;
+    const int64_t gthread = cta * kThreads + threadIdx.x, nthread = nctas * kThreads;
     const int C2 = A.n_chain2, P = A.num_pw, T = 2 * A.num_pw;
     const int n_type = P > 0 ? 3 : 1;        // work items per (query, chain2): gap-free tree, even pieces, odd pieces
     const uint32_t slots = (uint32_t)(T + 1);  // candidate slots per (query, chain2), in the reference's order
