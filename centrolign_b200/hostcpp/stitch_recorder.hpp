@@ -17,6 +17,9 @@
 #include <utility>
 #include <vector>
 
+#include <stdexcept>
+#include <string>
+
 #include "po_poa_b200.hpp"
 
 namespace centrolign_b200 {
@@ -32,6 +35,19 @@ public:
     }
 
     bool active() const { return active_; }
+
+    // Scope guard for a recording: if the reference's stitch throws (src/stitcher.cpp:36 does, and the GPU wrappers do on
+    // CLB errors) the recorder is switched off again, so that later po_poa calls on this thread are aligned, not recorded.
+    struct Scope {
+        StitchRecorder& rec;
+        explicit Scope(StitchRecorder& r) : rec(r) { rec.begin(); }
+        ~Scope() { rec.abandon(); }
+    };
+    void abandon() {
+        active_ = false;
+        windows_.clear();
+        translations_.clear();
+    }
 
     void begin() {
         active_ = true;
@@ -100,6 +116,12 @@ public:
     AlignmentT finish(AlignmentT&& stitched) {
         active_ = false;
         if (windows_.empty()) return std::move(stitched);
+        size_t n_markers = 0;
+        for (const Pair& p : stitched) n_markers += (p.node_id1 == uint64_t(-1) && p.node_id2 == uint64_t(-1)) ? 1 : 0;
+        if (n_markers != windows_.size() || translations_.size() != windows_.size())
+            throw std::runtime_error("centrolign_b200: the stitched alignment holds " + std::to_string(n_markers) + " window markers for " +
+                                     std::to_string(windows_.size()) + " recorded windows and " + std::to_string(translations_.size()) +
+                                     " translations");
         std::vector<AlignmentT> out[CLB_MAX_PW], wout[CLB_MAX_PW];
         if (batch_[0].size()) batch_[0].template align<1, GenericParams, AlignmentT>(params_[0], out[0]);
         if (batch_[1].size()) batch_[1].template align<2, GenericParams, AlignmentT>(params_[1], out[1]);

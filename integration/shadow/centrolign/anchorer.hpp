@@ -50,6 +50,19 @@ typedef PackedMatchBank<uint32_t, float> PackedBank;
 typedef VectorPair<SignedPackedVector, PackedVector, int32_t, PackedBank::match_id_t> PackedShiftMatchVector;
 typedef VectorPair<PackedVector, PackedVector, uint32_t, PackedBank::match_id_t> PackedDistMatchVector;
 
+// The flat problem holds, per match, one query shift per path of graph 1 and two words per path of graph 2 (qa1 / qa2 /
+// qoff), and indexes tree entries with 32 bits.  A merge of hundreds of paths with millions of matches would need tens of
+// GB for them on the host, in pinned staging and on the device; such a problem stays on the reference's CPU code
+// (CLB_CHAIN_MAX_TABLE_GB, default 16).
+inline bool flat_problem_too_large(const std::vector<match_set_t>& match_sets, size_t num_match_sets, size_t chains1, size_t chains2) {
+    static const double budget_gb = getenv("CLB_CHAIN_MAX_TABLE_GB") ? atof(getenv("CLB_CHAIN_MAX_TABLE_GB")) : 16.0;
+    double matches = 0.0;
+    for (size_t s = 0; s < num_match_sets && s < match_sets.size(); ++s)
+        matches += (double)match_sets[s].walks1.size() * (double)match_sets[s].walks2.size();
+    const double table_bytes = matches * 4.0 * ((double)chains1 + 2.0 * (double)chains2);
+    return table_bytes > budget_gb * 1e9 || matches >= 2147483648.0;  // (the library indexes matches with 31 bits)
+}
+
 // anchors of a chain of match ranks: the loop body of traceback_sparse_dp (anchorer.hpp:2510-2527), forward order
 inline std::vector<anchor_t> anchors_of(const std::vector<int64_t>& chain, const centrolign_b200::ChainProblem& P,
                                         const std::vector<match_set_t>& match_sets) {
@@ -93,6 +106,16 @@ inline std::vector<anchor_t> anchors_of(const std::vector<int64_t>& chain, const
         const std::vector<uint64_t>* sources1, const std::vector<uint64_t>* sources2, const std::vector<uint64_t>* sinks1,         \
         const std::vector<uint64_t>* sinks2, const std::unordered_set<std::tuple<size_t, size_t, size_t>>* masked_matches) const { \
         using namespace b200_chain;                                                                                                \
+        if (flat_problem_too_large(match_sets, num_match_sets, xmerge1.chain_size(), xmerge2.chain_size()))                        \
+            /* the per-match x per-path tables of the flat problem would not fit: the reference's own generic code, through its   \
+               64-bit instantiation (anchorer.hpp:1281-1282), which this header does not specialize */                            \
+            return sparse_affine_chain_dp<uint64_t, uint32_t, uint64_t, int64_t, uint64_t, float,                                  \
+                                          std::vector<std::pair<int64_t, MatchBank<uint64_t, uint32_t, float>::match_id_t>>,       \
+                                          std::vector<std::pair<uint64_t, MatchBank<uint64_t, uint32_t, float>::match_id_t>>,      \
+                                          std::vector<uint64_t>, std::vector<uint64_t>, MatchBank<uint64_t, uint32_t, float>,     \
+                                          b200_chain::FwdEdges, BaseGraph, b200_chain::XMerge, 3>(                                 \
+                match_sets, graph1, graph2, xmerge1, xmerge2, gap_open, gap_extend, local_scale, num_match_sets,                  \
+                suppress_verbose_logging, sources1, sources2, sinks1, sinks2, masked_matches);                                    \
         const double t0 = now_s();                                                                                                 \
         MBANK match_bank(graph1, match_sets, num_match_sets, true, masked_matches);                   /* anchorer.hpp:1861 */      \
         PostSwitchDistances<DIST_VEC> switch_dists1(graph1, xmerge1), switch_dists2(graph2, xmerge2); /* :1871-1872 */             \

@@ -85,7 +85,7 @@ public:
                      const BGraph2& graph2, const SentinelTableau& tableau1, const SentinelTableau& tableau2,
                      XMerge1& chain_merge1, XMerge2& chain_merge2) const {
         auto& rec = centrolign_b200::StitchRecorder<Alignment>::instance();
-        rec.begin();
+        centrolign_b200::StitchRecorder<Alignment>::Scope recording(rec);  // switched off again if anything below throws
         Alignment with_markers = StitcherReference::stitch(anchor_segments, graph1, graph2, tableau1, tableau2,
                                                            chain_merge1, chain_merge2);
         return rec.finish(std::move(with_markers));
@@ -94,7 +94,7 @@ public:
     template <class BGraph, class XMerge>
     Alignment internal_stitch(const std::vector<anchor_t>& anchors, const BGraph& graph, const XMerge& xmerge) const {
         auto& rec = centrolign_b200::StitchRecorder<Alignment>::instance();
-        rec.begin();
+        centrolign_b200::StitchRecorder<Alignment>::Scope recording(rec);
         Alignment with_markers = StitcherReference::internal_stitch(anchors, graph, xmerge);
         return rec.finish(std::move(with_markers));
     }
