@@ -303,7 +303,7 @@ def pipeline_windows(device):
     warp-per-window kernel (popoa_small_kernels.cu) and, for comparison, with every window forced through the
     CTA-per-window strip kernel; the reference on one core on a sample, parity-checked."""
     from centrolign_b200.batch import AlignmentParameters, concat_batches, select_windows, synth_windows
-    from centrolign_b200.popoa import po_poa_batch
+    from centrolign_b200.popoa import DeviceBatch, po_poa_batch
 
     params = AlignmentParameters()
     nw = 200000
@@ -326,9 +326,26 @@ def pipeline_windows(device):
             os.environ.pop("CLB_NO_SMALL_WINDOWS", None)
         out[name] = {"seconds": dt, "windows_per_s": batch.n_windows / dt, "ns_per_cell": dt * 1e9 / float(cells.sum()),
                      "includes": "host flattening, H2D, kernels, D2H, id translation"}
+        if env:
+            os.environ["CLB_NO_SMALL_WINDOWS"] = env
+        try:  # the kernels alone, on a batch resident in HBM (CUDA events of clb_batch_run)
+            db = DeviceBatch(batch, params, device=device)
+            db.upload()
+            db.run()
+            kms = []
+            for _ in range(3):
+                db.run()
+                kms.append(db.stats().kernel_ms)
+            out[name]["kernel_ms"] = float(np.median(kms))
+            out[name]["kernel_windows_per_s"] = batch.n_windows / (float(np.median(kms)) * 1e-3)
+            out[name]["kernel_launches"] = int(db.stats().kernel_launches)
+            db.close()
+        finally:
+            os.environ.pop("CLB_NO_SMALL_WINDOWS", None)
     assert np.array_equal(res["warp_per_window"][0], res["cta_per_window"][0])
     assert all(np.array_equal(a, b) for a, b in zip(res["warp_per_window"][1], res["cta_per_window"][1])), "the two kernels disagree"
     out["speedup_over_cta_per_window"] = out["cta_per_window"]["seconds"] / out["warp_per_window"]["seconds"]
+    out["kernel_speedup_over_cta_per_window"] = out["cta_per_window"]["kernel_ms"] / out["warp_per_window"]["kernel_ms"]
     from checkers import CpuChecker
     kind = "reference" if CpuChecker.available("reference") else "port"
     chk = CpuChecker(kind)
