@@ -757,19 +757,23 @@ int clb_batch_get_stats(const clb_batch* b, clb_batch_stats* out) {
     return CLB_OK;
 }
 
+// evidence for integration tests that the GPU path really ran (CLB_COUNT_CALLS): calls and windows, printed at exit
+static void count_popoa_call(int64_t n_windows) {
+    if (!getenv("CLB_COUNT_CALLS")) return;
+    static std::atomic<int64_t> calls(0), windows(0);
+    static std::once_flag once;
+    std::call_once(once, [] {
+        atexit([] { fprintf(stderr, "[clb] calls %lld windows %lld\n", (long long)calls.load(), (long long)windows.load()); });
+    });
+    calls += 1;
+    windows += n_windows;
+}
+
 int clb_popoa_batch(int device, int32_t n_windows, const clb_graph_batch* g1, const clb_graph_batch* g2,
                     const clb_params* params, int64_t* score_out, const int64_t* aln_off, int32_t* aln_pairs,
                     uint32_t* aln_len) {
     const bool timing = getenv("CLB_TIMING") != nullptr;
-    if (getenv("CLB_COUNT_CALLS")) {  // evidence for integration tests that the GPU path really ran
-        static std::atomic<int64_t> calls(0), windows(0);
-        static std::once_flag once;
-        std::call_once(once, [] {
-            atexit([] { fprintf(stderr, "[clb] calls %lld windows %lld\n", (long long)calls.load(), (long long)windows.load()); });
-        });
-        calls += 1;
-        windows += n_windows;
-    }
+    count_popoa_call(n_windows);
     if (const char* dump_dir = getenv("CLB_DUMP_DIR")) {  // debugging aid: every batch a caller sends, for tools/check_dump.py
         static std::atomic<int> seq(0);
         if (n_windows > 0 && g1 && g2 && params) {
@@ -919,6 +923,7 @@ int clb_popoa_batch_multi(int n_devices, const int* devices, int32_t n_windows, 
         return clb_popoa_batch(devices[0], n_windows, g1, g2, params, score_out, aln_off, aln_pairs, aln_len);
     }
     if (n_windows < 0 || check_side(g1) || check_side(g2) || !params) return fail(CLB_EINVAL, "null graph arrays");
+    count_popoa_call(n_windows);
     std::vector<int64_t> cells(n_windows);
     for (int32_t w = 0; w < n_windows; ++w)
         cells[w] = (g1->node_off[w + 1] - g1->node_off[w] + 1) * (g2->node_off[w + 1] - g2->node_off[w] + 1);

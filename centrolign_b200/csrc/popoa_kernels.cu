@@ -1334,6 +1334,8 @@ struct CtaState {
     int seq_tag[8];      // k+1 once entry k is published
     int strips_done[2];  // per workspace slot: finished strips (or tiles, for a tiled window)
     int tile_next[2];    // per workspace slot: next tile of a tiled window
+    int warps_left[2];   // per workspace slot: fill warps that are done with the slot's window (strips or not); the slot and
+                         // its window view are handed to the next window only when all of them have left
 };
 
 // Tiled windows.  A strip that is slower than its neighbours (far predecessor columns, the generic step) holds back
@@ -1369,6 +1371,7 @@ __global__ void __launch_bounds__(kThreads, 1) popoa_kernel(const __grid_constan
     const Params& prm = A.prm;  // __grid_constant__: the parameters are constant-bank operands, not registers
     for (int i = tid; i <= kProgMask; i += kThreads) S.progress[i] = 0ull;
     if (tid < 8) S.seq_tag[tid] = 0;
+    if (tid < 2) S.warps_left[tid] = 0;
     __syncthreads();
 
     if (warp < kFillWarps) {
@@ -1418,6 +1421,8 @@ __global__ void __launch_bounds__(kThreads, 1) popoa_kernel(const __grid_constan
                 __syncwarp();
                 if (!tiled) cs += kFillWarps;
             }
+            __syncwarp();
+            if (lane == 0) atomicAdd(&S.warps_left[k & 1], 1);  // this warp will not look at S.win[k & 1] / the k-th queue entry again
             G += nstrips;
         }
     } else {
@@ -1428,6 +1433,10 @@ __global__ void __launch_bounds__(kThreads, 1) popoa_kernel(const __grid_constan
             const int k = fetched++;
             int w = -1;
             if (lane == 0) {
+                if (k >= 2) {  // every fill warp must have left window k-2 before its view and workspace slot are reused
+                    while (ld_volatile(&S.warps_left[k & 1]) < kFillWarps) __nanosleep(200);
+                }
+                S.warps_left[k & 1] = 0;
                 const int qi = atomicAdd(A.queue, 1);
                 w = qi < A.n_windows ? A.order[qi] : -1;
                 int nstrips = 0;

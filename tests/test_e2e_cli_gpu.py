@@ -64,3 +64,20 @@ def test_cli_output_is_byte_identical(name, tmp_path):
     # batched: one call per stitch() and NumPW, not one per window (stitch_recorder.hpp)
     # cyclizing mode realigns many small induced subproblems: several stitches with a handful of windows each
     assert n_calls > 0 and n_windows >= (2 if "-c" in case["options"] else 20) * n_calls
+
+
+def test_cli_over_all_visible_gpus_is_byte_identical(tmp_path):
+    """CLB_DEVICES lists every visible GPU: each Stitcher::stitch is dealt to them in cell-balanced bins
+    (clb_popoa_batch_multi) and the CLI still prints the reference's bytes."""
+    import torch
+
+    case = GOLD["msa3_40k"]
+    fa = str(tmp_path / "msa3_40k.fa")
+    subprocess.run([sys.executable, os.path.join(ROOT, "integration", "make_hor_fasta.py"), fa] + [str(a) for a in case["fasta_args"]], check=True)
+    env = dict(os.environ, CLB_COUNT_CALLS="1", CLB_DEVICES=",".join(str(d) for d in range(torch.cuda.device_count())))
+    sys.path.insert(0, os.path.join(ROOT, "integration"))
+    from make_e2e_golden import run_cli
+    res = run_cli(CLI, case["options"], fa, {}, str(tmp_path), env=env)
+    assert res.returncode == 0, res.stderr.decode()[-2000:]
+    assert hashlib.md5(res.stdout).hexdigest() == case["output_md5"]
+    assert any(l.startswith("[clb] calls") for l in res.stderr.decode().splitlines())
