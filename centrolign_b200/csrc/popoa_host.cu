@@ -28,6 +28,7 @@ namespace clb {
 cudaError_t launch_popoa(int num_pw, const LaunchArgs& args, int grid, cudaStream_t stream);
 cudaError_t launch_popoa_small(int num_pw, const LaunchArgs& args, int first, int count, int grid, cudaStream_t stream);  // popoa_small_kernels.cu
 int popoa_smem_bytes();
+void popoa_wait_profile(bool reset);  // -DCLB_PROFILE builds: where the warps of popoa_kernel wait
 double int32_probe(int use_dpx, int sm_count);
 int popoa_nsmid();
 void chain_release_cache();  // chain_host.cu
@@ -688,6 +689,7 @@ static int launch_internal(clb_batch* b) {
 static int wait_internal(clb_batch* b) {
     CUDA_TRY(cudaSetDevice(b->device));
     CUDA_TRY(cudaStreamSynchronize(b->stream));
+    if (getenv("CLB_WAIT_PROFILE")) clb::popoa_wait_profile(false);  // prints and clears the counters (no-op outside -DCLB_PROFILE builds)
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
     b->stats.kernel_ms = ms;

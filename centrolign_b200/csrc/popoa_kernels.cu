@@ -32,6 +32,7 @@
 #include <limits.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <type_traits>
 
@@ -45,6 +46,16 @@ namespace clb {
 constexpr int kWarps = CLB_WARPS;  // fill warps + 1 traceback warp per CTA (one CTA per SM)
 constexpr int kThreads = kWarps * 32;
 constexpr unsigned kFull = 0xffffffffu;
+
+// -DCLB_PROFILE builds: cycles the warps spend in their waits, by kind (printed by the host when CLB_WAIT_PROFILE is set)
+#ifdef CLB_PROFILE
+__device__ unsigned long long g_wait_cycles[8];  // 0 left-strip rows, 1 panel above, 2 next window, 3 traceback waits for the fill, 4 fill total, 5 traceback busy
+#define CLB_WAIT_BEGIN const long long _wt0 = clock64()
+#define CLB_WAIT_END(kind) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_wait_cycles[kind], (unsigned long long)(clock64() - _wt0)); } while (0)
+#else
+#define CLB_WAIT_BEGIN do {} while (0)
+#define CLB_WAIT_END(kind) do {} while (0)
+#endif
 
 // window view, resolved once per window into shared memory
 struct Win {
@@ -478,6 +489,7 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
     int avail = cs == 0 ? INT_MAX : 0;
     auto wait_rows = [&](int want) {
         if (avail < want) {
+            CLB_WAIT_BEGIN;
             for (;;) {
                 const unsigned long long v = progress[(g - 1) & kProgMask];
                 avail = ((int)(v >> 32) == g) ? (int)(v & 0xffffffffu) : 0;
@@ -485,6 +497,7 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
                 __nanosleep(kPollNs);
             }
             __threadfence_block();
+            CLB_WAIT_END(0);
         }
     };
     auto prefetch_block = [&](int b) {  // rows PB*b+1 .. PB*b+PB of the needed left columns -> buffer b&1
@@ -513,12 +526,14 @@ __device__ __forceinline__ void fill_strip_wide(const Win& Wsh, const Params& pr
     // never wait for rows below the panel: the tile that fills them may be queued behind this one
     wait_rows(min(R0 + max(start_lag, PB), R1));
     if (R0 > 0) {  // the panel above must be complete before anything of this one is read (strip 0 has no other wait)
+        CLB_WAIT_BEGIN;
         for (;;) {
             const unsigned long long v = progress[g & kProgMask];
             if ((int)(v >> 32) == g + 1 && (int)(v & 0xffffffffu) >= R0) break;
             __nanosleep(200);
         }
         __threadfence_block();
+        CLB_WAIT_END(1);
     }
     prefetch_block(R0 / PB);
     if (R0 > 0) {  // take over rows R0-2 .. R0 from the panel above (the workspace holds {M, H_k})
@@ -1376,10 +1391,15 @@ __global__ void __launch_bounds__(kThreads, 1) popoa_kernel(const __grid_constan
 
     if (warp < kFillWarps) {
         // ================= fill warps =================
+        CLB_WAIT_BEGIN;
         FillSmemAny& sm = *reinterpret_cast<FillSmemAny*>(smem + kTileInt4 + warp * (int)(sizeof(FillSmemAny) / sizeof(int4)));
         int G = 0;  // running strip number at the start of window k
         for (int k = 0;; ++k) {
-            while (ld_volatile(&S.seq_tag[k & 7]) != k + 1) __nanosleep(200);
+            {
+                CLB_WAIT_BEGIN;
+                while (ld_volatile(&S.seq_tag[k & 7]) != k + 1) __nanosleep(200);
+                CLB_WAIT_END(2);
+            }
             __threadfence_block();
             const int w = ld_volatile(&S.seq_win[k & 7]);
             if (w < 0) break;
@@ -1425,6 +1445,7 @@ __global__ void __launch_bounds__(kThreads, 1) popoa_kernel(const __grid_constan
             if (lane == 0) atomicAdd(&S.warps_left[k & 1], 1);  // this warp will not look at S.win[k & 1] / the k-th queue entry again
             G += nstrips;
         }
+        CLB_WAIT_END(4);
     } else {
         // ================= traceback warp =================
         int fetched = 0;
@@ -1486,14 +1507,20 @@ __global__ void __launch_bounds__(kThreads, 1) popoa_kernel(const __grid_constan
                 const int H = panel_rows_for(W.n1, A.panel_rows);
                 nwait *= (W.n1 + H - 1) / H;
             }
-            while (ld_volatile(&S.strips_done[t & 1]) < nwait) __nanosleep(500);
+            {
+                CLB_WAIT_BEGIN;
+                while (ld_volatile(&S.strips_done[t & 1]) < nwait) __nanosleep(500);
+                CLB_WAIT_END(3);
+            }
             __threadfence_block();
+            CLB_WAIT_BEGIN;
             tb_boundary<P>(W, prm, lane);
 #ifdef CLB_PROFILE
             if (!(A.debug_flags & 1))
 #endif
                 traceback<P>(W, prm, *reinterpret_cast<TileSmem*>(smem), lane, A.score + w, A.aln + 2 * W.out, A.aln_len + w);
             __syncwarp();
+            CLB_WAIT_END(5);
             if (!ended) fetch();  // hands slot t&1 to window t+2
         }
     }
@@ -1508,6 +1535,23 @@ int popoa_nsmid() {  // size of the %smid id space (>= number of SMs)
     cudaFree(d);
     return e == cudaSuccess ? (int)h : -1;
 }
+#ifdef CLB_PROFILE
+void popoa_wait_profile(bool reset) {
+    unsigned long long h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (!reset) {
+        cudaMemcpyFromSymbol(h, g_wait_cycles, sizeof(h));
+        const double fill = (double)h[4] > 0 ? (double)h[4] : 1.0;
+        fprintf(stderr, "[clb] fill-warp cycles %.3g: waiting for the left strip %.1f %%, for the panel above %.1f %%, for the next window %.1f %%; "
+                        "traceback warp: waiting for the fill %.3g cycles, busy %.3g cycles (%.1f %% of a fill warp's time)\n",
+                fill, 100.0 * h[0] / fill, 100.0 * h[1] / fill, 100.0 * h[2] / fill, (double)h[3], (double)h[5], 100.0 * h[5] / (fill / kFillWarps));
+    }
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaMemcpyToSymbol(g_wait_cycles, z, sizeof(z));
+}
+#else
+void popoa_wait_profile(bool) {}
+#endif
+
 int popoa_smem_bytes() { return (kTileInt4 + kFillWarps * (int)(sizeof(FillSmemAny) / sizeof(int4))) * (int)sizeof(int4); }
 int popoa_threads() { return kThreads; }
 
