@@ -354,8 +354,14 @@ int flatten_side(const clb_graph_batch& g, int64_t w, int side, SideStage& st, c
     return CLB_OK;
 }
 
-int check_side(const clb_graph_batch* g) {
+int check_side(const clb_graph_batch* g, int64_t n_windows = -1) {
     if (!g || !g->node_off || !g->edge_off || !g->pred_off || !g->src_off || !g->snk_off) return CLB_EINVAL;
+    if (n_windows > 0) {  // the payload arrays may only be null when they are empty
+        if (g->node_off[n_windows] > 0 && !g->label) return CLB_EINVAL;
+        if (g->edge_off[n_windows] > 0 && !g->pred) return CLB_EINVAL;
+        if (g->src_off[n_windows] > 0 && !g->src) return CLB_EINVAL;
+        if (g->snk_off[n_windows] > 0 && !g->snk) return CLB_EINVAL;
+    }
     return CLB_OK;
 }
 
@@ -400,7 +406,7 @@ static int create_internal(int device, int32_t n_windows, const clb_graph_batch*
     *out = nullptr;
     if (n_windows < 0 || !params || params->num_pw < 1 || params->num_pw > CLB_MAX_PW)
         return fail(CLB_EINVAL, "bad n_windows or num_pw (must be 1..3)");
-    if (n_windows > 0 && (check_side(g1) || check_side(g2))) return fail(CLB_EINVAL, "null graph arrays");
+    if (n_windows > 0 && (check_side(g1, n_windows) || check_side(g2, n_windows))) return fail(CLB_EINVAL, "null graph arrays");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(CLB_ECUDA, "no CUDA device: the gap-fill path has no CPU fallback");

@@ -185,8 +185,14 @@ int flatten_side(const clb_graph_batch& g, int64_t w, int4* info, uint32_t* next
     return CLB_OK;
 }
 
-int check_side(const clb_graph_batch* g) {
+int check_side(const clb_graph_batch* g, int64_t n_windows = -1) {
     if (!g || !g->node_off || !g->edge_off || !g->pred_off || !g->src_off || !g->snk_off) return CLB_EINVAL;
+    if (n_windows > 0) {  // the payload arrays may only be null when they are empty
+        if (g->node_off[n_windows] > 0 && !g->label) return CLB_EINVAL;
+        if (g->edge_off[n_windows] > 0 && !g->pred) return CLB_EINVAL;
+        if (g->src_off[n_windows] > 0 && !g->src) return CLB_EINVAL;
+        if (g->snk_off[n_windows] > 0 && !g->snk) return CLB_EINVAL;
+    }
     return CLB_OK;
 }
 
@@ -199,7 +205,7 @@ extern "C" int clb_pwfa_batch(int device, int32_t n_windows, const clb_succ_grap
     if (n_windows < 0 || !params || params->num_pw < 1 || params->num_pw > CLB_MAX_PW)
         return host_fail(CLB_EINVAL, "bad window count or NumPW outside 1..3");
     if (prune_limit < 0) return host_fail(CLB_EINVAL, "prune_limit must be >= 0");
-    if (n_windows > 0 && (check_side(g1) || check_side(g2))) return host_fail(CLB_EINVAL, "null graph arrays");
+    if (n_windows > 0 && (check_side(g1, n_windows) || check_side(g2, n_windows))) return host_fail(CLB_EINVAL, "null graph arrays");
     if (n_windows > 0 && (!score_out || !aln_off || !aln_pairs || !aln_len)) return host_fail(CLB_EINVAL, "null output arrays");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return host_fail(CLB_ECUDA, "no CUDA device available (there is no CPU fallback)");

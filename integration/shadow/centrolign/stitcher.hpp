@@ -27,6 +27,8 @@
 #include "centrolign/logging.hpp"
 #include "centrolign/partition_client.hpp"
 
+#include <algorithm>
+
 #include "stitch_recorder.hpp"
 
 namespace centrolign {
@@ -50,6 +52,16 @@ Alignment pwfa_po_poa_b200(const Graph& graph1, const Graph& graph2, const std::
                            const std::vector<uint64_t>& sources2, const std::vector<uint64_t>& sinks1,
                            const std::vector<uint64_t>& sinks2, const AlignmentParameters<NumPW>& params,
                            int64_t prune_limit, int64_t* score_out = nullptr) {
+    // The device search keeps WFA scores in 29 bits (pwfa_host.cu); a window whose worst-case score does not fit -- more than
+    // ~200 k nodes with the production parameters, i.e. only with a user-raised max_wfa_size -- keeps the reference's 64-bit CPU
+    // code instead of failing the whole batch.  Conservative bound: penalties before the division by their gcd (alignment.hpp:1959-2033).
+    {
+        uint64_t max_pen = 2ull * ((uint64_t)params.match + params.mismatch);
+        for (int k = 0; k < NumPW; ++k)
+            max_pen = std::max<uint64_t>(max_pen, 2ull * params.gap_open[k] + 2ull * params.gap_extend[k] + params.match);
+        if ((uint64_t)(graph1.node_size() + graph2.node_size() + 2) * (max_pen + 1) >= (uint64_t(1) << 29))
+            return pwfa_po_poa<NumPW>(graph1, graph2, sources1, sources2, sinks1, sinks2, params, prune_limit, score_out);
+    }
     auto& rec = centrolign_b200::StitchRecorder<Alignment>::instance();
     if (rec.active() && !score_out)
         return rec.record_pwfa<NumPW>(graph1, graph2, sources1, sources2, sinks1, sinks2, params, prune_limit);
