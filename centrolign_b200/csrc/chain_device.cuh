@@ -32,7 +32,7 @@ namespace clb {
 
 constexpr int kChainMaxTrees = 6;            // 2 * NumPW orthogonal value sets
 constexpr uint32_t kChainNone = 0xffffffffu;
-constexpr int kChainSmallArena = 200 * 1024;   // problems whose whole arena fits run from shared memory
+constexpr int kChainSmallArena = 216 * 1024;   // problems whose whole arena fits run from shared memory
 
 // One tree insertion (a match end on one path pair), in the reference's insertion order; the index of the
 // record is the insertion sequence number that breaks ties inside the gap-free trees.
@@ -58,8 +58,8 @@ struct QueryRec {
     uint32_t gf_S, gf_bits;   // prefix walk over keys < offset
     uint32_t or_base, or_n;
     uint32_t ev_S, ev_bits;   // even pieces: shift > q (suffix walk)
+    uint32_t or_base2, or_n2; // or_base, or_n again: every kind of work item reads two 16-byte quarters of the record
     uint32_t od_S, od_bits;   // odd pieces:  shift < q (prefix walk)
-    uint32_t pad[2];
 };
 
 struct ChainArgs {
@@ -73,6 +73,7 @@ struct ChainArgs {
     int64_t n_step;
     const int64_t* sins_off;   // [n_step+1] insertions of the step
     const InsRec* ins;
+    int64_t n_ins;
     const int64_t* qry_off;    // [n_step+1]
     const uint32_t* qry_match;
     QueryRec* qrec;            // [n_qry * n_chain2]
@@ -107,7 +108,8 @@ struct ChainArgs {
     int64_t n_entry;
     // per-step candidate exchange
     unsigned long long* cand_best;  // [2][n_match] by step parity: pack(value, ~order), 0 = none
-    uint32_t* cand_bp;              // [max queries per step * n_chain2 * (2*num_pw+1)]
+    uint32_t* cand_bp;              // [2][cand_bp_stride] by step parity, cand_bp_stride = max queries per step * n_chain2 * (2*num_pw+1)
+    int64_t cand_bp_stride;
     unsigned long long* counters;   // [0] tree queries answered
     // ranks of the subtree blocks of every orthogonal walk, computed by the preparation kernel: per (query, chain2,
     // parity) rank_stride words, one per subtree block in walk order; nullptr = computed on the fly
@@ -118,7 +120,8 @@ struct ChainArgs {
     int64_t copy_bytes;      // shared-memory kernels: this many bytes are copied from arena_base, the rest of the arena starts as zero
     float* out_dp;           // batched launch: compact result arrays of the problem (nullptr: results go back into dp / backptr)
     uint32_t* out_backptr;
-    int split_phases;  // debug: separate barrier between update_dp and the next step's insertions
+    int sync_mode;     // how the phases of a step are separated: 0 one CTA (__syncthreads), 1 one thread-block cluster
+                       // (barrier.cluster), 2 cooperative grid (grid.sync)
 };
 
 }  // namespace clb

@@ -31,7 +31,7 @@
 #include "chain_device.cuh"
 
 namespace clb {
-cudaError_t launch_chain(const ChainArgs& args, int grid, int prepare_grid, cudaStream_t stream, cudaEvent_t after_prepare);
+cudaError_t launch_chain(ChainArgs args, int grid, int cluster, int prepare_grid, cudaStream_t stream, cudaEvent_t after_prepare);
 cudaError_t launch_chain_small_batch(const ChainArgs* d_args, int n, int smem_bytes, cudaStream_t stream);
 int chain_max_grid(int device);
 int host_fail(int code, const std::string& msg);
@@ -73,6 +73,7 @@ struct DeviceArena {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp = nullptr;
 };
 constexpr size_t kArenaKeep = size_t(1) << 30;
+constexpr int kChainClusterMax = 16;  // CTAs of the cluster a mid-sized problem runs in (non-portable size; launch_chain halves it if refused)
 std::mutex g_arena_mu;
 std::map<int, DeviceArena> g_arenas;
 
@@ -519,7 +520,7 @@ static int chain_dp_impl(int device, const clb_chain_problem* p, float* dp_out, 
         const size_t z_qrec = plan.zero((size_t)n_qry * C2 * sizeof(clb::QueryRec));
         const size_t z_gford = plan.zero((size_t)E * 4), z_gfbest = plan.zero((size_t)E * 8);
         const size_t z_orord = plan.zero((size_t)T * E * 4), z_bit = plan.zero((size_t)T * n_inner * 8);
-        const size_t z_cbest = plan.zero((size_t)M * 16), z_cbp = plan.zero((size_t)(max_q * C2 * (T + 1)) * 4), z_cnt = plan.zero(8);
+        const size_t z_cbest = plan.zero((size_t)M * 16), z_cbp = plan.zero((size_t)(max_q * C2 * (T + 1)) * 4 * 2), z_cnt = plan.zero(8);
         // subtree-block ranks of every orthogonal walk (2 * (depth + 1) blocks at most), if memory allows
         int rank_stride = 0;
         size_t z_ranks = 0;
@@ -555,7 +556,8 @@ static int chain_dp_impl(int device, const clb_chain_problem* p, float* dp_out, 
                 b.gap_extend[k] = p->gap_extend[k];
                 b.scale_ext[k] = p->scale * p->gap_extend[k];
             }
-            b.n_match = M; b.n_step = S; b.n_entry = E; b.n_inner = n_inner; b.n_qry = n_qry;
+            b.n_match = M; b.n_step = S; b.n_entry = E; b.n_inner = n_inner; b.n_qry = n_qry; b.n_ins = (int64_t)ins.size();
+            b.cand_bp_stride = max_q * C2 * (T + 1); b.sync_mode = 0;
             b.dp = (float*)(base + o_dp); b.backptr = (uint32_t*)(base + o_bp);
             b.sins_off = (const int64_t*)(base + o_sins); b.ins = (const clb::InsRec*)(base + o_ins);
             b.qry_off = (const int64_t*)(base + o_qoff); b.qry_match = (const uint32_t*)(base + o_qm);
@@ -629,7 +631,8 @@ static int chain_dp_impl(int device, const clb_chain_problem* p, float* dp_out, 
             a.gap_extend[k] = p->gap_extend[k];
             a.scale_ext[k] = p->scale * p->gap_extend[k];  // anchorer.hpp:2330: local_scale * gap_extend[pw / 2] (* shift on the device)
         }
-        a.n_match = M; a.n_step = S; a.n_entry = E; a.n_inner = n_inner; a.n_qry = n_qry;
+        a.n_match = M; a.n_step = S; a.n_entry = E; a.n_inner = n_inner; a.n_qry = n_qry; a.n_ins = (int64_t)ins.size();
+        a.cand_bp_stride = max_q * C2 * (T + 1);
         a.dp = (float*)(ar.d + o_dp); a.backptr = (uint32_t*)(ar.d + o_bp);
         a.sins_off = (const int64_t*)(ar.d + o_sins); a.ins = (const clb::InsRec*)(ar.d + o_ins);
         a.qry_off = (const int64_t*)(ar.d + o_qoff); a.qry_match = (const uint32_t*)(ar.d + o_qm);
@@ -646,13 +649,22 @@ static int chain_dp_impl(int device, const clb_chain_problem* p, float* dp_out, 
         a.or_ord = (uint32_t*)(zr + z_orord); a.bit = (unsigned long long*)(zr + z_bit);
         a.rank_pool = rank_stride ? (uint32_t*)(zr + z_ranks) : nullptr;
         a.rank_stride = rank_stride;
-        a.split_phases = getenv("CLB_CHAIN_SPLIT_PHASES") ? 1 : 0;
         a.cand_best = (unsigned long long*)(zr + z_cbest); a.cand_bp = (uint32_t*)(zr + z_cbp); a.counters = (unsigned long long*)(zr + z_cnt);
-        // grid: one CTA unless a step has enough independent warps of work to pay for grid-wide barriers
-        const double warps_per_step = S ? ((double)ins.size() + (double)n_qry * C2 * (P > 0 ? 3 : 1)) / (double)S : 0.0;
+        // How the phases of a step are separated.  A step has `warps_per_step` independent warp-sized work items on average:
+        // a handful run in one CTA (__syncthreads), a few dozen to a few hundred in ONE thread-block cluster (hardware
+        // cluster barrier, the items of a step spread over its SMs), more in a cooperative grid (grid.sync).
+        const double warps_per_step = S ? ((double)ins.size() + (double)n_qry * C2) * (T + 1) / (double)S : 0.0;
         const int max_grid = clb::chain_max_grid(device);
-        grid = getenv("CLB_CHAIN_GRID") ? std::max(1, std::min(max_grid, atoi(getenv("CLB_CHAIN_GRID"))))
-                                         : (warps_per_step > 64.0 ? std::min<int>(max_grid, (int)(warps_per_step / 12.0) + 1) : 1);
+        int cluster = 1;
+        if (getenv("CLB_CHAIN_GRID")) {
+            grid = std::max(1, std::min(max_grid, atoi(getenv("CLB_CHAIN_GRID"))));
+        } else if (getenv("CLB_CHAIN_CLUSTER")) {
+            cluster = std::max(1, std::min(16, atoi(getenv("CLB_CHAIN_CLUSTER"))));
+        } else if (warps_per_step > 512.0) {
+            grid = std::min<int>(max_grid, (int)(warps_per_step / 12.0) + 1);
+        } else if (warps_per_step > 24.0) {
+            while (cluster < kChainClusterMax && cluster * 16 < warps_per_step) cluster *= 2;
+        }
         a.arena_base = ar.d;
         a.arena_bytes = (int64_t)total;
         a.copy_bytes = (int64_t)total;  // the single-problem path copies the zeroed region too
@@ -660,7 +672,7 @@ static int chain_dp_impl(int device, const clb_chain_problem* p, float* dp_out, 
         if (total <= (size_t)clb::kChainSmallArena && !getenv("CLB_CHAIN_NO_SMALL") && !getenv("CLB_CHAIN_GRID")) grid = 0;
         const int prepare_grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_qry * C2 + 7) / 8, 8 * (int64_t)max_grid));
         CHAIN_TRY(cudaEventRecord(ar.ev0, ar.stream));
-        CHAIN_TRY(clb::launch_chain(a, grid, prepare_grid, ar.stream, ar.evp));
+        CHAIN_TRY(clb::launch_chain(a, grid, cluster, prepare_grid, ar.stream, ar.evp));
         CHAIN_TRY(cudaEventRecord(ar.ev1, ar.stream));
         CHAIN_TRY(cudaMemcpyAsync(h_dp.data(), a.dp, M * sizeof(float), cudaMemcpyDeviceToHost, ar.stream));
         CHAIN_TRY(cudaMemcpyAsync(h_bp.data(), a.backptr, M * sizeof(uint32_t), cudaMemcpyDeviceToHost, ar.stream));
@@ -675,8 +687,8 @@ static int chain_dp_impl(int device, const clb_chain_problem* p, float* dp_out, 
         if (getenv("CLB_TIMING")) {
             float pms = 0.f;
             cudaEventElapsedTime(&pms, ar.ev0, ar.evp);
-            fprintf(stderr, "[clb] chain: build %.1f ms, prepare kernel %.2f ms, DP kernel %.2f ms (grid %d, %lld steps, rank pool %s)\n",
-                    t_built - t_start, pms, ms - pms, grid, (long long)S, rank_stride ? "on" : "off");
+            fprintf(stderr, "[clb] chain: build %.1f ms, prepare kernel %.2f ms, DP kernel %.2f ms (grid %d, cluster %d, %lld steps, %.0f warp items per step, rank pool %s)\n",
+                    t_built - t_start, pms, ms - pms, grid, cluster, (long long)S, warps_per_step, rank_stride ? "on" : "off");
         }
         if (stats) {
             stats->build_ms = t_built - t_start;

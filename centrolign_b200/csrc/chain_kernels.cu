@@ -34,7 +34,6 @@ namespace {
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
-constexpr int kMaxBlocks = 132;  // entries of one tree walk: 1 + 4 * depth, depth <= 32
 
 __device__ __forceinline__ float mininf() { return -3.402823466e+38f; }  // numeric_limits<float>::lowest()
 
@@ -67,15 +66,6 @@ __device__ __forceinline__ uint4 ld_const4(const uint4* p) {
     if (SM) return *p;
     return __ldg(p);
 }
-
-struct WalkEntry {
-    uint32_t node;  // heap index
-    uint32_t kind;  // 0: the node itself, 1: the whole subtree of `node`
-};
-
-struct WarpScratch {
-    WalkEntry blk[kMaxBlocks];
-};
 
 // The walk shared by MaxSearchTree::range_max (max_search_tree.hpp:361-444) and the outer level of
 // OrthogonalMaxSearchTree::range_max (orthogonal_max_search_tree.hpp:340-470), for one-sided key ranges:
@@ -133,37 +123,39 @@ __device__ void walk_shape(uint32_t n, bool prefix, const InRange& in_range, int
     bits_out = bits;
 }
 
-// Expands a stored walk into the blocks the reference tests, in its order: S, the left walk, the right walk
-// (each taken node followed by the subtree hanging off the walk).  Pure arithmetic; uniform, lane 0 writes.
-__device__ int walk_blocks(uint32_t n, bool prefix, uint32_t S, uint32_t bits, WalkEntry* blk, int lane) {
-    int nb = 0;
-    auto push = [&](uint32_t node, uint32_t kind) {
-        if (lane == 0 && nb < kMaxBlocks) blk[nb] = WalkEntry{node, kind};
-        ++nb;
-    };
-    push(S, 0);
-    uint32_t lc = 2 * S + 1, rc = 2 * S + 2;
-    int i = 0;
-    while (lc < n) {  // leftward: right subtrees hang entirely inside the range
-        if (prefix || ((bits >> i++) & 1u)) {
-            push(lc, 0);
-            if (2 * lc + 2 < n) push(2 * lc + 2, 1);
-            lc = 2 * lc + 1;
-        } else {
-            lc = 2 * lc + 2;
-        }
+// Expands a stored walk into the blocks the reference tests.  Its order is: S, then the left walk, then the right walk,
+// every taken node followed by the subtree hanging off the walk on the inner side.  The j-th node of either walk has a
+// closed form (heap indices + 1 are the bit strings of the root paths), so lane j of a warp finds its two nodes and two
+// subtrees without walking:
+//   unconditional side (left walk of a prefix range, right walk of a suffix range): always outward;
+//   conditional side: decision bit i says whether node i is in range (taken, continue outward) or not (continue inward).
+struct WalkStep {
+    uint32_t node, sub;  // heap indices of the walk node and of the subtree root hanging inside the range
+    bool node_ok, sub_ok;
+};
+__device__ __forceinline__ WalkStep walk_step(uint32_t n, bool prefix, uint32_t S, uint32_t bits, int side, int j) {
+    const bool cond = (side == 1) == prefix;
+    const unsigned long long x0 = 2ull * ((unsigned long long)S + 1ull) + (unsigned)side;  // heap index + 1 of the walk's first node
+    unsigned long long x;
+    bool taken = true;
+    if (!cond) {
+        x = side == 0 ? (x0 << j) : (((x0 + 1ull) << j) - 1ull);
+    } else {
+        const uint32_t path = side == 0 ? ~bits : bits;  // child bit per step: left walk taken -> 0, right walk taken -> 1
+        x = (x0 << j) | (unsigned long long)(j ? (__brev(path) >> (32 - j)) : 0u);
+        taken = (bits >> j) & 1u;
     }
-    while (rc < n) {  // rightward: left subtrees hang entirely inside
-        if (!prefix || ((bits >> i++) & 1u)) {
-            push(rc, 0);
-            if (2 * rc + 1 < n) push(2 * rc + 1, 1);
-            rc = 2 * rc + 2;
-        } else {
-            rc = 2 * rc + 1;
-        }
-    }
-    return nb;
+    WalkStep w;
+    const bool exists = j < 31 && x <= (unsigned long long)n;
+    const unsigned long long xs = side == 0 ? 2ull * x + 1ull : 2ull * x;  // left walk: right child; right walk: left child
+    w.node_ok = exists && taken;
+    w.sub_ok = w.node_ok && xs <= (unsigned long long)n;
+    w.node = (uint32_t)(x - 1ull);
+    w.sub = (uint32_t)(xs - 1ull);
+    return w;
 }
+// position of a block in the reference's test order (only the order matters): S = 0, left walk, right walk
+__device__ __forceinline__ uint32_t walk_key(int side, int j, int kind) { return 1u + 64u * (unsigned)side + 2u * (unsigned)j + (unsigned)kind; }
 
 // first index in [lo, hi) whose value is >= q, by 32-ary search over the warp (uniform result)
 template <bool SM>
@@ -211,7 +203,7 @@ __device__ __forceinline__ uint32_t count_less(const uint32_t* a, uint32_t n, ui
 
 // Everything about a (query, path of graph 2) pair that does not depend on DP values (anchorer.hpp:2374-2381).
 template <bool SM>
-__device__ void prepare_queries(const ChainArgs& A, WalkEntry* blk, int lane, int64_t gwarp, int64_t nwarp) {
+__device__ void prepare_queries(const ChainArgs& A, int lane, int64_t gwarp, int64_t nwarp) {
     const int C1 = A.n_chain1, C2 = A.n_chain2;
     for (int64_t qc = gwarp; qc < A.n_qry * C2; qc += nwarp) {
         const int64_t k = qc / C2;
@@ -225,7 +217,6 @@ __device__ void prepare_queries(const ChainArgs& A, WalkEntry* blk, int lane, in
         r.gf_base = r.gf_n = r.or_base = r.or_n = 0;
         r.gf_S = r.ev_S = r.od_S = kChainNone;
         r.gf_bits = r.ev_bits = r.od_bits = 0;
-        r.pad[0] = r.pad[1] = 0;
         if (r.offset != 0) {
             const int64_t pair = (int64_t)c1 * C2 + c2;
             const int64_t g1 = A.pair_grp_off[pair + 1];
@@ -249,80 +240,100 @@ __device__ void prepare_queries(const ChainArgs& A, WalkEntry* blk, int lane, in
                         for (int par = 0; par < 2; ++par) {
                             const uint32_t S = par ? r.od_S : r.ev_S;
                             if (S == kChainNone) continue;
-                            __syncwarp();
-                            const int nb = walk_blocks(r.or_n, par == 1, S, par ? r.od_bits : r.ev_bits, blk, lane);
-                            __syncwarp();
+                            const uint32_t bits = par ? r.od_bits : r.ev_bits;
                             uint32_t* pool = A.rank_pool + ((int64_t)qc * 2 + par) * A.rank_stride;
-                            int seen = 0;  // subtree blocks before this group of 32
-                            for (int b0 = 0; b0 < nb && b0 < kMaxBlocks; b0 += 32) {
-                                const int b = b0 + lane;
-                                const bool sub = b < nb && b < kMaxBlocks && blk[b].kind == 1;
-                                const unsigned subm = __ballot_sync(kFull, sub);
-                                if (sub) {
-                                    const int j = seen + __popc(subm & ((1u << lane) - 1));
-                                    const uint32_t node = blk[b].node;
-                                    if (j < A.rank_stride)
-                                        pool[j] = count_less<SM>(A.in_off + ld_const<SM>(&A.in_base[r.or_base + node]), ld_const<SM>(&A.in_n[r.or_base + node]), r.offset);
-                                }
-                                seen += __popc(subm);
+                            const WalkStep wl = walk_step(r.or_n, par == 1, S, bits, 0, lane), wr = walk_step(r.or_n, par == 1, S, bits, 1, lane);
+                            const unsigned lm = __ballot_sync(kFull, wl.sub_ok), rm = __ballot_sync(kFull, wr.sub_ok);
+                            const unsigned below = (1u << lane) - 1u;
+                            for (int side = 0; side < 2; ++side) {  // subtree blocks in walk order: the left walk's, then the right walk's
+                                const WalkStep& w = side ? wr : wl;
+                                const int j = side ? __popc(lm) + __popc(rm & below) : __popc(lm & below);
+                                if (w.sub_ok && j < A.rank_stride)
+                                    pool[j] = count_less<SM>(A.in_off + ld_const<SM>(&A.in_base[r.or_base + w.sub]), ld_const<SM>(&A.in_n[r.or_base + w.sub]), r.offset);
                             }
                         }
                     }
                 }
             }
         }
+        r.or_base2 = r.or_base;
+        r.or_n2 = r.or_n;
         if (lane == 0) A.qrec[qc] = r;
     }
 }
 
 __global__ void __launch_bounds__(256) chain_prepare_kernel(const ChainArgs A) {
-    __shared__ WarpScratch prep_scratch[8];
-    prepare_queries<false>(A, prep_scratch[threadIdx.x >> 5].blk, threadIdx.x & 31,
-                           ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, ((int64_t)gridDim.x * blockDim.x) >> 5);
+    prepare_queries<false>(A, threadIdx.x & 31, ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, ((int64_t)gridDim.x * blockDim.x) >> 5);
+}
+
+// 16-byte loads of DP-independent records that are issued one phase before they are needed (the next step's first work
+// item of this warp): volatile so that the compiler keeps them where they are written.
+__device__ __forceinline__ uint4 ld_early(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int64_t ld_early(const int64_t* p) {
+    int64_t v;
+    asm volatile("ld.global.nc.s64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_early(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+// warp-wide maximum of (hi, lo) pairs in lexicographic order, hi == 0 means "nothing"; returns the lane that holds it
+// (kFull lanes must call), or -1
+__device__ __forceinline__ int warp_argmax(uint32_t hi, uint32_t lo, uint32_t& hi_out) {
+    const uint32_t mh = __reduce_max_sync(kFull, hi);
+    hi_out = mh;
+    if (mh == 0) return -1;
+    const uint32_t ml = __reduce_max_sync(kFull, hi == mh ? lo : 0u);
+    return __ffs(__ballot_sync(kFull, hi == mh && lo == ml)) - 1;
 }
 
 template <bool SM>
-__device__ __forceinline__ void chain_steps(const ChainArgs& A, WarpScratch* scratch) {
+__device__ __forceinline__ void chain_steps(const ChainArgs& A) {
     cg::grid_group grid = cg::this_grid();
-    const bool multi = !SM && gridDim.x > 1;
+    const int mode = SM ? 0 : A.sync_mode;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    // the shared-memory flavour is one CTA per problem whatever the grid is (a batch launch has one CTA per problem)
-    const int64_t cta = SM ? 0 : (int64_t)blockIdx.x, nctas = SM ? 1 : (int64_t)gridDim.x;
-    const int64_t gwarp = cta * kWarps + wib, nwarp = nctas * kWarps;
-    const int64_t gthread = cta * kThreads + threadIdx.x, nthread = nctas * kThreads;
+    // the shared-memory flavour is one CTA per problem whatever the grid is (a batch launch has one CTA per problem);
+    // with several CTAs, consecutive work items of a step go to different CTAs (a step has a few dozen items)
+    const uint32_t nctas = mode == 0 ? 1u : gridDim.x, cta = mode == 0 ? 0u : blockIdx.x;
+    const uint32_t gwarp = (uint32_t)wib * nctas + cta, nwarp = nctas * kWarps;
+    const uint32_t gthread = cta * kThreads + threadIdx.x, nthread = nctas * kThreads;
     const int C2 = A.n_chain2, P = A.num_pw, T = 2 * A.num_pw;
-    const int n_type = P > 0 ? 3 : 1;        // work items per (query, chain2): gap-free tree, even pieces, odd pieces
-    const uint32_t slots = (uint32_t)(T + 1);  // candidate slots per (query, chain2), in the reference's order
-    WalkEntry* blk = scratch[wib].blk;
+    // work items: an insertion has one item for the gap-free tree of its diagonal and one per orthogonal value set; a
+    // (query, chain2) pair has one item for the gap-free tree and one per (piece, parity), in the reference's candidate order
+    const uint32_t n_kind = (uint32_t)(T + 1);
+    const uint32_t slots = n_kind;
     unsigned long long n_tree_queries = 0;
+    constexpr bool kEarly = !SM;  // records of the next step are fetched one phase ahead (global memory only)
 
     auto barrier = [&]() {
-        if (multi) grid.sync();
-        else __syncthreads();
+        if (mode == 0) __syncthreads();
+        else if (mode == 1) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+        else grid.sync();
     };
-    unsigned long long* post_to = A.cand_best;
-    auto post = [&](uint32_t m, int64_t qc, uint32_t slot, float cand, uint32_t bp) {  // lane 0 only
-        const uint32_t order = (uint32_t)qc * slots + slot;
-        A.cand_bp[order] = bp;
-        atomicMax(&post_to[m], pack(cand, ~order));
-    };
-
-    // update_dp of the winners of one step (match_bank.hpp:171-184).  Runs in the same phase as the insertions of
-    // the next step; a match may be queried in one step and end in the next, so an insertion takes the maximum of
-    // the stored value and the pending winner (effective_dp).  The candidate words are double-buffered by step
-    // parity and cleared one phase later, so nothing a concurrent reader looks at is ever reset under it.
-    auto apply_winners = [&](int64_t q0, int64_t q1, const unsigned long long* cand) {
-        for (int64_t qi = gthread; qi < q1 - q0; qi += nthread) {
-            const uint32_t m = A.qry_match[q0 + qi];
+    // update_dp of the winners of the previous step (match_bank.hpp:171-184).  Runs beside the queries of the current step,
+    // which never read DP values; an insertion of the current step took the maximum of the stored value and the pending
+    // winner (effective_dp).  The candidate words are double-buffered by step parity; the thread that applies a winner
+    // also clears its word, a full step before that buffer is posted to again.
+    auto apply_winners = [&](int64_t q0, int64_t q1, unsigned long long* cand, const uint32_t* cand_bp) {
+        for (uint32_t qi = gthread; qi < (uint32_t)(q1 - q0); qi += nthread) {
+            const uint32_t m = ld_const<SM>(&A.qry_match[q0 + qi]);
             const unsigned long long pk = ld_live<SM>(&cand[m]);
             if (!pk) continue;
             const uint32_t order = ~(uint32_t)pk;
-            if ((int64_t)(order / ((uint32_t)C2 * slots)) != qi) continue;  // the winner was posted by another query of this match
+            if (order / ((uint32_t)C2 * slots) != qi) continue;  // the winner was posted by another query of this match
             const float v = funord((uint32_t)(pk >> 32));
             if (v > ld_live<SM>(&A.dp[m])) {
                 A.dp[m] = v;
-                A.backptr[m] = ld_live<SM>(&A.cand_bp[order]);
+                A.backptr[m] = ld_live<SM>(&cand_bp[order]);
             }
+            cand[m] = 0;
         }
     };
     auto effective_dp = [&](uint32_t m, const unsigned long long* cand) -> float {
@@ -334,40 +345,102 @@ __device__ __forceinline__ void chain_steps(const ChainArgs& A, WarpScratch* scr
         }
         return dpv;
     };
+    // the two records of this warp's first work items of a step
+    struct InsEarly { uint4 a, b; uint32_t ib, cn, rank; };
+    struct QryEarly { uint4 r0, rs; };
+    auto ins_item = [&](uint32_t it, int64_t i0, int64_t& i, uint32_t& u) {
+        const uint32_t ii = it / n_kind;
+        u = it - ii * n_kind;
+        i = i0 + ii;
+    };
+    auto fetch_ins = [&](int64_t i0, InsEarly& e) {
+        int64_t i; uint32_t u;
+        ins_item(gwarp, i0, i, u);
+        if (i < A.n_ins) {
+            e.a = ld_early(reinterpret_cast<const uint4*>(&A.ins[i]));
+            e.b = ld_early(reinterpret_cast<const uint4*>(&A.ins[i]) + 1);
+        }
+    };
+    auto fetch_levels = [&](int64_t i0, InsEarly& e) {  // needs e.a, e.b
+        int64_t i; uint32_t u;
+        ins_item(gwarp, i0, i, u);
+        if (i < A.n_ins && u > 0 && lane < (int)e.b.w) {
+            const uint32_t a = ((e.b.x + 1) >> lane) - 1;
+            e.ib = ld_early(&A.in_base[e.a.w + a]);
+            e.cn = ld_early(&A.in_n[e.a.w + a]);
+            e.rank = ld_early(&A.ent_rank[e.b.z + lane]);
+        }
+    };
+    auto qry_second = [&](uint32_t type) -> int { return type == 0 ? 1 : 2 + (int)((type - 1) & 1u); };
+    auto fetch_qry = [&](int64_t q0, QryEarly& e) {
+        const uint32_t qc = gwarp / n_kind, type = gwarp - qc * n_kind;
+        const int64_t idx = q0 * C2 + qc;
+        if (idx < A.n_qry * C2) {
+            const uint4* rp = reinterpret_cast<const uint4*>(&A.qrec[idx]);
+            e.r0 = ld_early(rp);
+            e.rs = ld_early(rp + qry_second(type));
+        }
+    };
 
+    const int64_t S = A.n_step;
+    if (S <= 0) return;
+    int64_t i0 = A.sins_off[0], i1 = A.sins_off[1], q0 = A.qry_off[0], q1 = A.qry_off[1];
     int64_t pq0 = 0, pq1 = 0;  // queries of the previous step, whose winners are still to be applied
-    for (int64_t s = 0; s < A.n_step; ++s) {
-        // ---------------- update_dp of the previous step + A: inserts (anchorer.hpp:2301-2345) ----------------
-        const int64_t i0 = A.sins_off[s], i1 = A.sins_off[s + 1];
-        const int64_t q0 = A.qry_off[s], q1 = A.qry_off[s + 1];
+    InsEarly ie = {}, ie_next = {};
+    QryEarly qe = {}, qe_next = {};
+    if (kEarly) {
+        fetch_ins(i0, ie);
+        fetch_levels(i0, ie);
+        fetch_qry(q0, qe);
+    }
+    for (int64_t s = 0; s < S; ++s) {
         unsigned long long* cand_prev = A.cand_best + ((s + 1) & 1) * A.n_match;  // posted in step s-1
         unsigned long long* cand_cur = A.cand_best + (s & 1) * A.n_match;         // posted in this step
-        if (pq0 != pq1) {
-            apply_winners(pq0, pq1, cand_prev);
-            if (A.split_phases) barrier();
+        uint32_t* bp_prev = A.cand_bp + ((s + 1) & 1) * A.cand_bp_stride;
+        uint32_t* bp_cur = A.cand_bp + (s & 1) * A.cand_bp_stride;
+        const int64_t s2 = s + 2 <= S ? s + 2 : S;
+        int64_t i2, q2;  // used by the next step
+        if (kEarly) {
+            i2 = ld_early(&A.sins_off[s2]);
+            q2 = ld_early(&A.qry_off[s2]);
+        } else {
+            i2 = A.sins_off[s2];
+            q2 = A.qry_off[s2];
         }
-        for (int64_t i = i0 + gwarp; i < i1; i += nwarp) {
-            const uint4 ra = ld_const4<SM>(reinterpret_cast<const uint4*>(&A.ins[i]));
-            const uint4 rb = ld_const4<SM>(reinterpret_cast<const uint4*>(&A.ins[i]) + 1);
+        if (kEarly) {
+            fetch_ins(i1, ie_next);
+            fetch_qry(q1, qe_next);
+        }
+        // -------------------------------- A: inserts (anchorer.hpp:2301-2345) --------------------------------
+        const uint32_t n_ins_items = (uint32_t)(i1 - i0) * n_kind;
+        for (uint32_t it = gwarp; it < n_ins_items; it += nwarp) {
+            int64_t i; uint32_t u;
+            ins_item(it, i0, i, u);
+            const bool early = kEarly && it == gwarp;
+            const uint4 ra = early ? ie.a : ld_const4<SM>(reinterpret_cast<const uint4*>(&A.ins[i]));
+            const uint4 rb = early ? ie.b : ld_const4<SM>(reinterpret_cast<const uint4*>(&A.ins[i]) + 1);
             const uint32_t m = ra.x, gf_base = ra.y, gf_node = ra.z, or_base = ra.w, or_node = rb.x, rank_off = rb.z;
             const int shift = (int)rb.y, nr = (int)rb.w;
-            int64_t ib = 0;
-            uint32_t cn = 0, rank = 0;
-            if (P > 0 && lane < nr) {  // lane = level: the node itself and its ancestors below the outer spines
-                const uint32_t a = ((or_node + 1) >> lane) - 1;
-                ib = ld_const<SM>(&A.in_base[or_base + a]);
-                cn = ld_const<SM>(&A.in_n[or_base + a]);
-                rank = ld_const<SM>(&A.ent_rank[rank_off + lane]);
+            uint32_t ib = 0, cn = 0, rank = 0;
+            if (u > 0 && lane < nr) {  // lane = level: the node itself and its ancestors below the outer spines
+                if (early) {
+                    ib = ie.ib; cn = ie.cn; rank = ie.rank;
+                } else {
+                    const uint32_t a = ((or_node + 1) >> lane) - 1;
+                    ib = ld_const<SM>(&A.in_base[or_base + a]);
+                    cn = ld_const<SM>(&A.in_n[or_base + a]);
+                    rank = ld_const<SM>(&A.ent_rank[rank_off + lane]);
+                }
             }
             const float dpv = effective_dp(m, cand_prev);
             if (!(dpv > mininf())) continue;  // entering lowest() changes nothing in the reference's trees
-            {   // gap-free tree of the entry's diagonal: lanes = the node and its ancestors
+            if (u == 0) {  // gap-free tree of the entry's diagonal: lanes = the node and its ancestors
                 if (lane == 0) A.gf_ord[gf_base + gf_node] = ford(dpv);
                 const uint32_t anc = (gf_node + 1) >> lane;
                 if (anc) atomicMax(&A.gf_best[gf_base + anc - 1], pack(dpv, ~(uint32_t)i));
-            }
-            for (int t = 0; t < T; ++t) {
+            } else {
                 // anchorer.hpp:2328-2335: odd pieces add, even pieces subtract local_scale * gap_extend * shift
+                const int t = (int)u - 1;
                 const double gap = __dmul_rn(A.scale_ext[t >> 1], (double)shift);
                 const float v = __double2float_rn((t & 1) ? __dadd_rn((double)dpv, gap) : __dsub_rn((double)dpv, gap));
                 if (!(v > mininf())) continue;  // anchorer.hpp:2338
@@ -379,175 +452,136 @@ __device__ __forceinline__ void chain_steps(const ChainArgs& A, WarpScratch* scr
                 }
             }
         }
-        if (i0 != i1 || pq0 != pq1) barrier();
-        // the previous step's candidate words are spent now: clear them while this step's queries run
-        const bool cleared = pq0 != pq1;
-        for (int64_t qi = gthread; qi < pq1 - pq0; qi += nthread) cand_prev[A.qry_match[pq0 + qi]] = 0;
-        pq0 = q0;
-        pq1 = q1;
-        if (q0 == q1) {
-            if (cleared) barrier();  // the clears must land before that buffer is posted to again
-            continue;
-        }
+        if (i0 != i1) barrier();
+        if (kEarly) fetch_levels(i1, ie_next);
 
-        // ------------------------------ B: queries (anchorer.hpp:2352-2416) ------------------------------
-        post_to = cand_cur;
-        const int64_t n_items = (q1 - q0) * C2 * n_type;
-        for (int64_t item = gwarp; item < n_items; item += nwarp) {
-            const int64_t qc = item / n_type;  // (query, chain2) pair inside the step
-            const int type = (int)(item - qc * n_type);
+        // ---------------- update_dp of the previous step + B: queries (anchorer.hpp:2352-2416) ----------------
+        if (pq0 != pq1) apply_winners(pq0, pq1, cand_prev, bp_prev);
+        auto post = [&](uint32_t m, uint32_t qc, uint32_t slot, float cand, uint32_t bp) {  // one lane
+            const uint32_t order = qc * slots + slot;
+            bp_cur[order] = bp;
+            atomicMax(&cand_cur[m], pack(cand, ~order));
+        };
+        const uint32_t n_items = (uint32_t)(q1 - q0) * (uint32_t)C2 * n_kind;
+        for (uint32_t item = gwarp; item < n_items; item += nwarp) {
+            const uint32_t qc = item / n_kind, type = item - qc * n_kind;  // (query, chain2) pair inside the step
+            const bool early = kEarly && item == gwarp;
             const uint4* rp = reinterpret_cast<const uint4*>(&A.qrec[q0 * C2 + qc]);
-            const uint4 r0 = ld_const4<SM>(rp);  // match, weight, offset, q
+            const uint4 r0 = early ? qe.r0 : ld_const4<SM>(rp);  // match, weight, offset, q
             const uint32_t offset = r0.z;
             if (offset == 0) continue;  // nothing on this path reaches the match: every range [0, 0) is empty
-            const uint32_t m = r0.x;
+            const uint4 rs = early ? qe.rs : ld_const4<SM>(rp + qry_second(type));  // tree base, size, S, decision bits of the walk
+            const uint32_t m = r0.x, base = rs.x, n = rs.y, S0 = rs.z, bits = rs.w;
             const float w = __uint_as_float(r0.y);
             const int q = (int)r0.w;
-            __syncwarp();
+            if (n == 0 || S0 == kChainNone) continue;
+            ++n_tree_queries;
+            const bool prefix = type == 0 || ((type - 1) & 1u);
+            const WalkStep wl = walk_step(n, prefix, S0, bits, 0, lane), wr = walk_step(n, prefix, S0, bits, 1, lane);
+            // this lane's blocks: S (lane 0), its node and hanging subtree on either walk
+            uint32_t best_hi = 0, best_lo = 0, best_sel = 0;  // (ord, ~key) and what identifies the match
+            auto consider = [&](uint32_t ord, uint32_t key, uint32_t sel) {
+                if (ord > kOrdLowest && (ord > best_hi || (ord == best_hi && ~key > best_lo))) {
+                    best_hi = ord;
+                    best_lo = ~key;
+                    best_sel = sel;
+                }
+            };
             if (type == 0) {
                 // same diagonal (anchorer.hpp:2379-2389): MaxSearchTree::range_max((0, min), (offset, min))
-                const uint4 r1 = ld_const4<SM>(rp + 1);  // gf_base, gf_n, gf_S, gf_bits
-                if (r1.y == 0 || r1.z == kChainNone) continue;
-                ++n_tree_queries;
-                const uint32_t base = r1.x;
-                const int nb = walk_blocks(r1.y, true, r1.z, r1.w, blk, lane);
-                __syncwarp();
-                unsigned long long lbest = 0;  // pack(ord, ~block index)
-                uint32_t lsel = 0;             // kind << 31 | node, resolved to a match for the winner only
-                for (int b = lane; b < nb && b < kMaxBlocks; b += 32) {
-                    const WalkEntry we = blk[b];
-                    uint32_t ord, sel;
-                    if (we.kind == 0) {
-                        ord = ld_live<SM>(&A.gf_ord[base + we.node]);
-                        sel = we.node;
-                    } else {
-                        const unsigned long long pk = ld_live<SM>(&A.gf_best[base + we.node]);
-                        ord = (uint32_t)(pk >> 32);
-                        sel = 0x80000000u | (~(uint32_t)pk & 0x7fffffffu);  // the insertion sequence number (< 2^31)
-                    }
-                    if (ord > kOrdLowest && ord > (uint32_t)(lbest >> 32)) {
-                        lbest = ((unsigned long long)ord << 32) | (~(uint32_t)b);
-                        lsel = sel;
-                    }
-                }
-                unsigned long long r = lbest;
-#pragma unroll
-                for (int d = 16; d; d >>= 1) {
-                    const unsigned long long o = __shfl_xor_sync(kFull, r, d);
-                    r = o > r ? o : r;
-                }
-                if (!r) continue;
-                const unsigned src = __ffs(__ballot_sync(kFull, lbest == r)) - 1;
-                const uint32_t sel = __shfl_sync(kFull, lsel, src);
-                if (lane == 0) {
-                    const uint32_t bm = (sel & 0x80000000u) ? ld_const<SM>(&A.ins[sel & 0x7fffffffu].match) : ld_const<SM>(&A.gf_match[base + sel]);
-                    post(m, qc, 0, __fadd_rn(funord((uint32_t)(r >> 32)), w), bm);
+                const uint32_t vS = lane == 0 ? ld_live<SM>(&A.gf_ord[base + S0]) : 0u;
+                const uint32_t vl = wl.node_ok ? ld_live<SM>(&A.gf_ord[base + wl.node]) : 0u;
+                const uint32_t vr = wr.node_ok ? ld_live<SM>(&A.gf_ord[base + wr.node]) : 0u;
+                const unsigned long long sl = wl.sub_ok ? ld_live<SM>(&A.gf_best[base + wl.sub]) : 0ull;
+                const unsigned long long sr = wr.sub_ok ? ld_live<SM>(&A.gf_best[base + wr.sub]) : 0ull;
+                consider(vS, 0, S0);
+                consider(vl, walk_key(0, lane, 0), wl.node);
+                consider((uint32_t)(sl >> 32), walk_key(0, lane, 1), 0x80000000u | (~(uint32_t)sl & 0x7fffffffu));  // the insertion sequence number (< 2^31)
+                consider(vr, walk_key(1, lane, 0), wr.node);
+                consider((uint32_t)(sr >> 32), walk_key(1, lane, 1), 0x80000000u | (~(uint32_t)sr & 0x7fffffffu));
+                uint32_t top;
+                const int src = warp_argmax(best_hi, best_lo, top);
+                if (src < 0) continue;
+                if (lane == src) {
+                    const uint32_t bm = (best_sel & 0x80000000u) ? ld_const<SM>(&A.ins[best_sel & 0x7fffffffu].match) : ld_const<SM>(&A.gf_match[base + best_sel]);
+                    post(m, qc, 0, __fadd_rn(funord(top), w), bm);
                 }
                 continue;
             }
-            // orthogonal trees of one parity (anchorer.hpp:2390-2413): par 0 = even pieces (shift > q), par 1 = odd (shift < q)
-            const int par = type - 1;
-            const uint4 r2 = ld_const4<SM>(rp + 2);  // or_base, or_n, ev_S, ev_bits
-            const uint32_t ob = r2.x, n = r2.y;
-            uint32_t S = r2.z, bits = r2.w;
-            if (par) {
-                const uint4 r3 = ld_const4<SM>(rp + 3);  // od_S, od_bits
-                S = r3.x;
-                bits = r3.y;
+            // one orthogonal value set (anchorer.hpp:2390-2413): piece k; parity 0 = even (shift > q), 1 = odd (shift < q)
+            const int t = (int)type - 1, k = t >> 1, par = t & 1;
+            const uint32_t* ord_t = A.or_ord + (int64_t)t * A.n_entry + base;
+            const unsigned long long* bit_t = A.bit + (int64_t)t * A.n_inner;
+            const unsigned lm = __ballot_sync(kFull, wl.sub_ok), rm = __ballot_sync(kFull, wr.sub_ok);
+            const unsigned below = (1u << lane) - 1u;
+            // nodes on the walks: the node's own element counts if its offset lies below the query's
+            {
+                const uint32_t oS = lane == 0 ? ld_const<SM>(&A.or_off[base + S0]) : 0xffffffffu;
+                const uint32_t ol = wl.node_ok ? ld_const<SM>(&A.or_off[base + wl.node]) : 0xffffffffu;
+                const uint32_t orr = wr.node_ok ? ld_const<SM>(&A.or_off[base + wr.node]) : 0xffffffffu;
+                const uint32_t vS = lane == 0 ? ld_live<SM>(&ord_t[S0]) : 0u;
+                const uint32_t vl = wl.node_ok ? ld_live<SM>(&ord_t[wl.node]) : 0u;
+                const uint32_t vr = wr.node_ok ? ld_live<SM>(&ord_t[wr.node]) : 0u;
+                if (oS < offset) consider(vS, 0, S0);
+                if (ol < offset) consider(vl, walk_key(0, lane, 0), wl.node);
+                if (orr < offset) consider(vr, walk_key(1, lane, 0), wr.node);
             }
-            if (n == 0 || S == kChainNone) continue;
-            n_tree_queries += P;
-            const int nb = walk_blocks(n, par == 1, S, bits, blk, lane);
-            __syncwarp();
-            const uint32_t* ranks = A.rank_pool ? A.rank_pool + ((q0 * C2 + qc) * 2 + par) * A.rank_stride : nullptr;
-            unsigned long long lbest[3] = {0, 0, 0};  // per piece: pack(ord, ~block index) of this lane's best block
-            uint32_t lnode[3] = {0, 0, 0};
-            int seen = 0;  // subtree blocks before the current group of 32
-            for (int b0 = 0; b0 < nb && b0 < kMaxBlocks; b0 += 32) {
-                const int b = b0 + lane;
-                const bool mine = b < nb && b < kMaxBlocks;
-                const WalkEntry we = mine ? blk[b] : WalkEntry{0, 0};
-                const unsigned subm = __ballot_sync(kFull, mine && we.kind == 1);
-                const int j = seen + __popc(subm & ((1u << lane) - 1));
-                seen += __popc(subm);
-                if (!mine) continue;
-                if (we.kind == 0) {
-                    const uint32_t off = ld_const<SM>(&A.or_off[ob + we.node]);
-                    uint32_t v[3];
-                    for (int k = 0; k < P; ++k) v[k] = ld_live<SM>(&A.or_ord[(int64_t)(2 * k + par) * A.n_entry + ob + we.node]);
-                    if (off < offset) {
-                        for (int k = 0; k < P; ++k)
-                            if (v[k] > kOrdLowest && v[k] > (uint32_t)(lbest[k] >> 32)) {
-                                lbest[k] = ((unsigned long long)v[k] << 32) | (~(uint32_t)b);
-                                lnode[k] = we.node;
-                            }
-                    }
-                } else {
-                    const uint32_t ib = ld_const<SM>(&A.in_base[ob + we.node]);
-                    const uint32_t cnt = (ranks && j < A.rank_stride) ? ld_const<SM>(&ranks[j])
-                                                                     : count_less<SM>(A.in_off + ib, ld_const<SM>(&A.in_n[ob + we.node]), offset);
-                    if (cnt) {  // Fenwick prefix maximum over the first cnt entries
-                        unsigned long long r[3] = {0, 0, 0};
-                        uint32_t c = cnt;
-                        while (c) {  // the probe addresses only depend on cnt: issue six levels of probes before using any
-                            uint32_t at[6];
+            // hanging subtrees: Fenwick prefix maximum over the elements with offset below the query's
+            const uint32_t* ranks = A.rank_pool ? A.rank_pool + (((q0 * C2 + qc) * 2 + par) * A.rank_stride) : nullptr;
+            uint32_t ib2[2] = {0, 0}, cnt2[2] = {0, 0};
 #pragma unroll
-                            for (int jj = 0; jj < 6; ++jj) {
-                                at[jj] = c ? c - 1 : kChainNone;
-                                c &= c - 1;  // 0 stays 0
-                            }
-                            unsigned long long x[6][3];
-#pragma unroll
-                            for (int jj = 0; jj < 6; ++jj)
-#pragma unroll
-                                for (int k = 0; k < 3; ++k)
-                                    x[jj][k] = (k < P && at[jj] != kChainNone) ? ld_live<SM>(&A.bit[(int64_t)(2 * k + par) * A.n_inner + ib + at[jj]]) : 0ull;
-#pragma unroll
-                            for (int jj = 0; jj < 6; ++jj)
-#pragma unroll
-                                for (int k = 0; k < 3; ++k) r[k] = x[jj][k] > r[k] ? x[jj][k] : r[k];
-                        }
-                        for (int k = 0; k < P; ++k)
-                            if (r[k] && (r[k] >> 32) > (lbest[k] >> 32)) {
-                                lbest[k] = (r[k] & 0xffffffff00000000ull) | (~(uint32_t)b);
-                                lnode[k] = (uint32_t)r[k];
-                            }
-                    }
+            for (int side = 0; side < 2; ++side) {
+                const WalkStep& ws = side ? wr : wl;
+                if (ws.sub_ok) {
+                    const int j = side ? __popc(lm) + __popc(rm & below) : __popc(lm & below);
+                    ib2[side] = ld_const<SM>(&A.in_base[base + ws.sub]);
+                    cnt2[side] = (ranks && j < A.rank_stride) ? ld_const<SM>(&ranks[j])
+                                                               : count_less<SM>(A.in_off + ib2[side], ld_const<SM>(&A.in_n[base + ws.sub]), offset);
                 }
             }
-            for (int k = 0; k < P; ++k) {  // first block, in walk order, that attains the maximum value
-                unsigned long long r = lbest[k];
 #pragma unroll
-                for (int d = 16; d; d >>= 1) {
-                    const unsigned long long o = __shfl_xor_sync(kFull, r, d);
-                    r = o > r ? o : r;
+            for (int side = 0; side < 2; ++side) {
+                uint32_t c = cnt2[side];
+                unsigned long long r = 0;
+                while (c) {  // the probe addresses only depend on the count: eight probes in flight
+                    unsigned long long x[8];
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) {
+                        x[jj] = c ? ld_live<SM>(&bit_t[ib2[side] + c - 1]) : 0ull;
+                        c &= c - 1;  // 0 stays 0
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) r = x[jj] > r ? x[jj] : r;
                 }
-                if (!r) continue;
-                const unsigned src = __ffs(__ballot_sync(kFull, lbest[k] == r)) - 1;
-                const uint32_t node = __shfl_sync(kFull, lnode[k], src);
-                if (lane == 0) {
-                    const int t = 2 * k + par;
-                    const double eq = __dmul_rn(A.gap_extend[k], (double)q);
-                    const double pen = __dmul_rn(A.scale, par ? __dadd_rn(A.gap_open[k], eq) : __dsub_rn(A.gap_open[k], eq));
-                    const float cand = __double2float_rn(__dsub_rn((double)__fadd_rn(funord((uint32_t)(r >> 32)), w), pen));
-                    post(m, qc, (uint32_t)(1 + t), cand, ld_const<SM>(&A.or_match[ob + node]));
-                }
+                if (r) consider((uint32_t)(r >> 32), walk_key(side, lane, 1), (uint32_t)r);
+            }
+            uint32_t top;
+            const int src = warp_argmax(best_hi, best_lo, top);  // first block, in walk order, that attains the maximum value
+            if (src < 0) continue;
+            if (lane == src) {
+                const double eq = __dmul_rn(A.gap_extend[k], (double)q);
+                const double pen = __dmul_rn(A.scale, par ? __dadd_rn(A.gap_open[k], eq) : __dsub_rn(A.gap_open[k], eq));
+                const float cand = __double2float_rn(__dsub_rn((double)__fadd_rn(funord(top), w), pen));
+                post(m, qc, (uint32_t)(1 + t), cand, ld_const<SM>(&A.or_match[base + best_sel]));
             }
         }
-        barrier();
+        if (q0 != q1 || pq0 != pq1) barrier();
+        pq0 = q0; pq1 = q1;
+        i0 = i1; i1 = i2; q0 = q1; q1 = q2;
+        ie = ie_next; qe = qe_next;
     }
-    if (pq0 != pq1) apply_winners(pq0, pq1, A.cand_best + ((A.n_step + 1) & 1) * A.n_match);  // the last step's winners
+    if (pq0 != pq1)  // the last step's winners
+        apply_winners(pq0, pq1, A.cand_best + ((S + 1) & 1) * A.n_match, A.cand_bp + ((S + 1) & 1) * A.cand_bp_stride);
     if (lane == 0 && n_tree_queries) atomicAdd(A.counters, n_tree_queries);
 }
 
-__global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainArgs A) {
-    __shared__ WarpScratch scratch[kWarps];
-    chain_steps<false>(A, scratch);
+__global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constant__ ChainArgs A) {
+    chain_steps<false>(A);
 }
 
 // Small problems: one CTA copies the whole arena into shared memory, rebases the pointers, prepares the queries,
 // runs the same step loop on shared memory and copies the DP values and back-pointers out again.
-__device__ __forceinline__ void chain_small_body(const ChainArgs& G, WarpScratch* scratch, uint4* arena_smem) {
+__device__ __forceinline__ void chain_small_body(const ChainArgs& G, uint4* arena_smem) {
     const char* gbase = G.arena_base;
     const int64_t ncopy = (G.copy_bytes + 15) / 16, nall = (G.arena_bytes + 15) / 16;
     for (int64_t i = threadIdx.x; i < ncopy; i += kThreads)
@@ -565,9 +599,9 @@ __device__ __forceinline__ void chain_small_body(const ChainArgs& G, WarpScratch
     if (G.rank_pool) CLB_REBASE(rank_pool);
 #undef CLB_REBASE
     __syncthreads();
-    prepare_queries<true>(A, scratch[threadIdx.x >> 5].blk, threadIdx.x & 31, threadIdx.x >> 5, kWarps);
+    prepare_queries<true>(A, threadIdx.x & 31, threadIdx.x >> 5, kWarps);
     __syncthreads();
-    chain_steps<true>(A, scratch);
+    chain_steps<true>(A);
     __syncthreads();
     float* const odp = G.out_dp ? G.out_dp : G.dp;
     uint32_t* const obp = G.out_backptr ? G.out_backptr : G.backptr;
@@ -580,19 +614,17 @@ __device__ __forceinline__ void chain_small_body(const ChainArgs& G, WarpScratch
 // Small problems: one CTA copies the whole arena into shared memory, rebases the pointers, prepares the queries,
 // runs the same step loop on shared memory and copies the DP values and back-pointers out again.
 __global__ void __launch_bounds__(kThreads, 1) chain_small_kernel(const ChainArgs G) {
-    __shared__ WarpScratch scratch[kWarps];
     extern __shared__ uint4 arena_smem[];
-    chain_small_body(G, scratch, arena_smem);
+    chain_small_body(G, arena_smem);
 }
 
 // The same for a batch of independent problems: CTA b solves problem b (clb_chain_dp_batch).
 __global__ void __launch_bounds__(kThreads, 1) chain_small_batch_kernel(const ChainArgs* __restrict__ problems) {
-    __shared__ WarpScratch scratch[kWarps];
     extern __shared__ uint4 arena_smem[];
     __shared__ ChainArgs G;
     if (threadIdx.x == 0) G = problems[blockIdx.x];
     __syncthreads();
-    chain_small_body(G, scratch, arena_smem);
+    chain_small_body(G, arena_smem);
 }
 
 cudaError_t launch_chain_small_batch(const ChainArgs* d_args, int n, int smem_bytes, cudaStream_t stream) {
@@ -606,8 +638,10 @@ cudaError_t launch_chain_small_batch(const ChainArgs* d_args, int n, int smem_by
     return cudaGetLastError();
 }
 
-cudaError_t launch_chain(const ChainArgs& args, int grid, int prepare_grid, cudaStream_t stream, cudaEvent_t after_prepare) {
-    if (grid == 0) {  // the whole problem fits into shared memory
+// grid == 0: the whole problem fits into shared memory (one CTA).  Otherwise one CTA, or `cluster` > 1 CTAs of ONE
+// thread-block cluster (hardware barrier between the phases of a step), or a cooperative grid of `grid` > 1 CTAs.
+cudaError_t launch_chain(ChainArgs args, int grid, int cluster, int prepare_grid, cudaStream_t stream, cudaEvent_t after_prepare) {
+    if (grid == 0) {
         static bool attr_set = false;
         if (!attr_set) {
             cudaError_t e0 = cudaFuncSetAttribute(chain_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmallArena);
@@ -622,9 +656,37 @@ cudaError_t launch_chain(const ChainArgs& args, int grid, int prepare_grid, cuda
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (after_prepare) cudaEventRecord(after_prepare, stream);
-    void* params[] = {(void*)&args};
-    if (grid > 1)
+    if (cluster > 1) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);  // clusters of 16; refusal shows at launch
+            cudaGetLastError();
+            attr_set = true;
+        }
+        args.sync_mode = 1;
+        for (; cluster > 1; cluster /= 2) {  // a cluster size the device cannot place falls back to the next smaller one
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(cluster);
+            cfg.blockDim = dim3(kThreads);
+            cfg.stream = stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = cluster;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            e = cudaLaunchKernelEx(&cfg, chain_kernel, args);
+            if (e == cudaSuccess) return e;
+            cudaGetLastError();
+        }
+    }
+    if (grid > 1) {
+        args.sync_mode = 2;
+        void* params[] = {(void*)&args};
         return cudaLaunchCooperativeKernel((const void*)chain_kernel, dim3(grid), dim3(kThreads), params, 0, stream);
+    }
+    args.sync_mode = 0;
     chain_kernel<<<1, kThreads, 0, stream>>>(args);
     return cudaGetLastError();
 }
