@@ -249,7 +249,7 @@ static int chain_dp_impl(int device, const clb_chain_problem* p, float* dp_out, 
                     const std::string full = kind + "." + name;
                     const uint32_t len = (uint32_t)full.size();
                     fwrite(&len, 4, 1, f); fwrite(full.data(), 1, len, f); fwrite(&code, 4, 1, f); fwrite(&n, 8, 1, f);
-                    if (n) fwrite(data, elem, n, f);
+                    if (n && data) fwrite(data, elem, n, f);
                 };
                 const int64_t M_ = p->n_match, S_ = p->n_step, E_ = p->ins_off[M_], NE = p->end_off[S_], NQ = p->qry_off[S_];
                 const double prm[11] = {(double)p->num_pw, p->gap_open[0], p->gap_open[1], p->gap_open[2], p->gap_extend[0], p->gap_extend[1],
