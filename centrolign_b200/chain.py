@@ -72,6 +72,13 @@ def _bind(lib):
     lib.clb_chain_dp.restype = ctypes.c_int
     lib.clb_chain_dp.argtypes = [ctypes.c_int, ctypes.POINTER(_CProblem), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                  ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ChainStats)]
+    lib.clb_chain_job_create.restype = ctypes.c_int
+    lib.clb_chain_job_create.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_void_p, ctypes.c_void_p]
+    lib.clb_chain_jobs_run.restype = ctypes.c_int
+    lib.clb_chain_jobs_run.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_void_p]
+    lib.clb_chain_job_destroy.restype = None
+    lib.clb_chain_job_destroy.argtypes = [ctypes.c_void_p]
     lib.clb_chain_dp_batch.restype = ctypes.c_int
     lib.clb_chain_dp_batch.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ChainStats)]
@@ -112,6 +119,41 @@ def chain_dp_batch(problems, device: int = 0, stats: Optional[ChainStats] = None
                                   VP(*[a.ctypes.data for a in chains]), lens.ctypes.data, opts.ctypes.data,
                                   ctypes.byref(stats) if stats is not None else None))
     return [(chains[k][: int(lens[k])].copy(), dps[k][: ms[k]], bps[k][: ms[k]], float(opts[k])) for k in range(n)]
+
+
+def chain_dp_jobs(problems, device: int = 0, threads: int = 4):
+    """The batched call in two halves (``clb_chain_job_create`` on ``threads`` host threads, then ONE ``clb_chain_jobs_run``):
+    what the drop-in Anchorer's fill-in pool does.  Returns the same list as chain_dp_batch."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    lib = load_library()
+    _bind(lib)
+    n = len(problems)
+    cps = [_c_problem(p) for p in problems]
+    ms = [p.n_match for p in problems]
+    dps = [np.zeros(max(1, m), np.float32) for m in ms]
+    bps = [np.full(max(1, m), -1, np.int64) for m in ms]
+    chains = [np.zeros(m + 1, np.int64) for m in ms]
+    lens = [ctypes.c_int64(0) for _ in range(n)]
+    opts = [ctypes.c_float(0) for _ in range(n)]
+    jobs = [ctypes.c_void_p(None) for _ in range(n)]
+
+    def create(k):  # ctypes releases the GIL: the layouts really run side by side
+        return lib.clb_chain_job_create(device, ctypes.byref(cps[k][0]), dps[k].ctypes.data, bps[k].ctypes.data, chains[k].ctypes.data,
+                                        ctypes.byref(lens[k]), ctypes.byref(opts[k]), ctypes.byref(jobs[k]))
+
+    try:
+        with ThreadPoolExecutor(max(1, threads)) as pool:
+            for rc in pool.map(create, range(n)):
+                _check(rc)
+        live = [j for j in jobs if j.value]
+        arr = (ctypes.c_void_p * max(1, len(live)))(*[j.value for j in live])
+        _check(lib.clb_chain_jobs_run(device, len(live), arr))
+    finally:
+        for j in jobs:
+            if j.value:
+                lib.clb_chain_job_destroy(j)
+    return [(chains[k][: int(lens[k].value)].copy(), dps[k][: ms[k]], bps[k][: ms[k]], float(opts[k].value)) for k in range(n)]
 
 
 def chain_dp(problem: ChainProblem, device: int = 0, stats: Optional[ChainStats] = None):

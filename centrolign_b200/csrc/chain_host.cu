@@ -32,7 +32,7 @@
 
 namespace clb {
 cudaError_t launch_chain(ChainArgs args, int grid, int cluster, int prepare_grid, cudaStream_t stream, cudaEvent_t after_prepare);
-cudaError_t launch_chain_small_batch(const ChainArgs* d_args, int n, int smem_bytes, cudaStream_t stream);
+cudaError_t launch_chain_small_batch(const ChainArgs* d_args, int n, int smem_bytes, bool any_global, cudaStream_t stream);
 int chain_max_grid(int device);
 int host_fail(int code, const std::string& msg);
 }  // namespace clb
@@ -73,6 +73,7 @@ struct DeviceArena {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp = nullptr;
 };
 constexpr size_t kArenaKeep = size_t(1) << 30;
+constexpr size_t kChainBatchArena = size_t(4) << 20;  // a problem up to this arena size joins a batched launch (one CTA per problem)
 constexpr int kChainClusterMax = 16;  // CTAs of the cluster a mid-sized problem runs in (non-portable size; launch_chain halves it if refused)
 std::mutex g_arena_mu;
 std::map<int, DeviceArena> g_arenas;
@@ -126,10 +127,12 @@ void parallel_sort(std::vector<SortKey>& keys) {
 // A batch of small problems being collected by clb_chain_dp_batch: every problem whose arena fits shared memory is
 // laid out as usual, its copy segments are appended to ONE staging buffer, and its kernel arguments are recorded with
 // arena-relative pointers; flush() then needs one H2D copy, one launch (a CTA per problem) and one D2H copy for all.
+std::atomic<int64_t> g_batch_flushes(0), g_batch_problems(0);  // CLB_COUNT_CALLS: launches of the batched kernel / problems in them
 struct DeferredProblem {
     clb::ChainArgs args;        // pointers relative to the problem's arena (offset from 0)
     size_t arena_off = 0;       // of the problem's copy region in the combined buffer
     size_t res_off = 0;         // of its results (match-count floats / words) in the compact result buffers
+    size_t zero_bytes = 0;      // size of the region behind the copy region that starts as zero
     int64_t n_match = 0;
     const clb_chain_problem* p = nullptr;
     float* dp_out = nullptr;
@@ -225,10 +228,11 @@ static int chain_dp_impl(int device, const clb_chain_problem* p, float* dp_out, 
         static std::once_flag once;
         std::call_once(once, [] {
             atexit([] {
-                fprintf(stderr, "[clb] chain calls %lld matches %lld seconds %.3f (layout %.3f, staging %.3f, gpu %.3f, traceback %.3f)\n",
+                fprintf(stderr, "[clb] chain calls %lld matches %lld seconds %.3f (layout %.3f, staging %.3f, gpu %.3f, traceback %.3f); "
+                                "%lld of them in %lld batched launches\n",
                         (long long)calls.load(), (long long)matches.load(), CallTimer::us().load() * 1e-6,
                         CallTimer::phase()[0].load() * 1e-6, CallTimer::phase()[1].load() * 1e-6, CallTimer::phase()[2].load() * 1e-6,
-                        CallTimer::phase()[3].load() * 1e-6);
+                        CallTimer::phase()[3].load() * 1e-6, (long long)g_batch_problems.load(), (long long)g_batch_flushes.load());
             });
         });
         calls += 1;
@@ -539,7 +543,7 @@ static int chain_dp_impl(int device, const clb_chain_problem* p, float* dp_out, 
             else rank_stride = 0;
         }
         const size_t total = plan.copy_bytes + plan.zero_bytes;
-        if (ctx && total <= (size_t)clb::kChainSmallArena && !getenv("CLB_CHAIN_NO_SMALL")) {
+        if (ctx && total <= kChainBatchArena && !getenv("CLB_CHAIN_NO_SMALL")) {
             // batched small problem: stage the copy region, record arena-relative arguments, finish in flush()
             DeferredProblem d;
             d.arena_off = ctx->staging.size();
@@ -580,7 +584,8 @@ static int chain_dp_impl(int device, const clb_chain_problem* p, float* dp_out, 
             b.copy_bytes = (int64_t)plan.copy_bytes;
             d.res_off = ctx->res_total;
             ctx->res_total += (size_t)M;
-            ctx->max_smem = std::max(ctx->max_smem, (int)((total + 15) / 16 * 16));
+            if (total <= (size_t)clb::kChainSmallArena) ctx->max_smem = std::max(ctx->max_smem, (int)((total + 15) / 16 * 16));
+            d.zero_bytes = plan.zero_bytes;
             d.n_match = M; d.p = p; d.dp_out = dp_out; d.backptr_out = backptr_out; d.chain_out = chain_out; d.chain_len = chain_len;
             d.opt_score = opt_score;
             ctx->items.push_back(d);
@@ -716,6 +721,166 @@ cleanup:
 #undef CHAIN_TRY
 }
 
+// Device and pinned buffers of the batched path, per device, grown on demand and kept (g_batch_mu serialises the flushes of
+// a process: a flush is one copy in, one launch, one copy out).
+namespace {
+struct BatchArena {
+    char* d_arena = nullptr; size_t arena_cap = 0;
+    clb::ChainArgs* d_args = nullptr; size_t args_cap = 0;
+    float* d_dp = nullptr; uint32_t* d_bp = nullptr; size_t res_cap = 0;
+    char* d_zero = nullptr; size_t zero_cap = 0;     // zero regions of the problems that run from global memory
+    char* h_stage = nullptr; size_t stage_cap = 0;   // pinned: copy regions, then the kernel arguments
+    char* h_res = nullptr; size_t hres_cap = 0;      // pinned: dp values, then back-pointers
+    cudaStream_t stream = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+};
+std::mutex g_batch_mu;
+std::map<int, BatchArena> g_batch_arenas;
+
+template <class T>
+cudaError_t grow_device(T*& ptr, size_t& cap, size_t want) {
+    if (want <= cap) return cudaSuccess;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+    const size_t bytes = std::max<size_t>(want + want / 2, 1 << 20);
+    cudaError_t e = cudaMalloc((void**)&ptr, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+}
+cudaError_t grow_pinned(char*& ptr, size_t& cap, size_t want) {
+    if (want <= cap) return cudaSuccess;
+    if (ptr) cudaFreeHost(ptr);
+    ptr = nullptr;
+    cap = 0;
+    const size_t bytes = std::max<size_t>(want + want / 2, 1 << 20);
+    cudaError_t e = cudaHostAlloc((void**)&ptr, bytes, cudaHostAllocDefault);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+}
+
+// One H2D copy, ONE launch (a CTA per problem), one D2H copy and the tracebacks for every deferred problem of `ctxs`.
+int flush_contexts(int device, BatchCtx* const* ctxs, int64_t n_ctx, clb_chain_stats* stats) {
+    size_t stage_bytes = 0, res_total = 0;
+    int64_t nb = 0;
+    int max_smem = 0;
+    for (int64_t c = 0; c < n_ctx; ++c) {
+        stage_bytes += ArenaPlan::align(ctxs[c]->staging.size());
+        res_total += ctxs[c]->res_total;
+        nb += (int64_t)ctxs[c]->items.size();
+        max_smem = std::max(max_smem, ctxs[c]->max_smem);
+    }
+    if (nb == 0) return CLB_OK;
+    int rc = CLB_OK;
+    std::lock_guard<std::mutex> lk(g_batch_mu);
+    BatchArena& ba = g_batch_arenas[device];
+#define BATCH_TRY(expr)                                                                                                \
+    do {                                                                                                               \
+        cudaError_t _e = (expr);                                                                                       \
+        if (_e != cudaSuccess)                                                                                         \
+            return host_fail(_e == cudaErrorMemoryAllocation ? CLB_ENOMEM : CLB_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+    const double t_start = now_ms();
+    BATCH_TRY(cudaSetDevice(device));
+    if (!ba.stream) {
+        BATCH_TRY(cudaStreamCreateWithFlags(&ba.stream, cudaStreamNonBlocking));
+        BATCH_TRY(cudaEventCreate(&ba.e0));
+        BATCH_TRY(cudaEventCreate(&ba.e1));
+    }
+    const size_t args_bytes = (size_t)nb * sizeof(clb::ChainArgs);
+    BATCH_TRY(grow_device(ba.d_arena, ba.arena_cap, stage_bytes));
+    BATCH_TRY(grow_device(ba.d_args, ba.args_cap, args_bytes));
+    if (res_total * 4 > ba.res_cap) {
+        size_t cap_dp = ba.res_cap, cap_bp = ba.res_cap;
+        BATCH_TRY(grow_device(ba.d_dp, cap_dp, res_total * 4));
+        BATCH_TRY(grow_device(ba.d_bp, cap_bp, res_total * 4));
+        ba.res_cap = std::min(cap_dp, cap_bp);
+    }
+    BATCH_TRY(grow_pinned(ba.h_stage, ba.stage_cap, stage_bytes + args_bytes));
+    BATCH_TRY(grow_pinned(ba.h_res, ba.hres_cap, res_total * 8));
+    clb::ChainArgs* h_args = reinterpret_cast<clb::ChainArgs*>(ba.h_stage + stage_bytes);
+    float* h_dp = reinterpret_cast<float*>(ba.h_res);
+    uint32_t* h_bp = reinterpret_cast<uint32_t*>(ba.h_res + res_total * 4);
+    size_t zero_total = 0;  // problems too large for shared memory keep their zero-initialised region in global memory
+    for (int64_t c = 0; c < n_ctx; ++c)
+        for (const DeferredProblem& d : ctxs[c]->items)
+            if (d.args.arena_bytes > (int64_t)clb::kChainSmallArena) zero_total += ArenaPlan::align(d.zero_bytes);
+    BATCH_TRY(grow_device(ba.d_zero, ba.zero_cap, zero_total));
+    {
+        size_t seg = 0, res_base = 0, zero_off = 0;
+        int64_t k = 0;
+        for (int64_t c = 0; c < n_ctx; ++c) {
+            const BatchCtx& ctx = *ctxs[c];
+            if (!ctx.staging.empty()) memcpy(ba.h_stage + seg, ctx.staging.data(), ctx.staging.size());
+            for (const DeferredProblem& d : ctx.items) {
+                clb::ChainArgs a = d.args;
+                const bool in_smem = a.arena_bytes <= (int64_t)clb::kChainSmallArena;
+                // fields of the copy region move to the staged copy; fields of the zero region follow it (shared memory: the
+                // kernel lays both out behind each other) or move to this problem's part of the cleared buffer
+                const ptrdiff_t shift = (ba.d_arena + seg + d.arena_off) - (char*)nullptr;
+                const ptrdiff_t zshift = in_smem ? shift : (ba.d_zero + zero_off) - ((char*)nullptr + a.copy_bytes);
+#define CLB_SHIFT_BY(f, by) a.f = reinterpret_cast<decltype(a.f)>(reinterpret_cast<char*>(const_cast<void*>(static_cast<const void*>(a.f))) + (by))
+#define CLB_SHIFT(f) CLB_SHIFT_BY(f, shift)
+#define CLB_ZSHIFT(f) CLB_SHIFT_BY(f, zshift)
+                CLB_SHIFT(dp); CLB_SHIFT(backptr); CLB_SHIFT(sins_off); CLB_SHIFT(ins); CLB_SHIFT(qry_off); CLB_SHIFT(qry_match);
+                CLB_SHIFT(weight); CLB_SHIFT(qry_chain1); CLB_SHIFT(qa1); CLB_SHIFT(qa2); CLB_SHIFT(qoff);
+                CLB_SHIFT(pair_grp_off); CLB_SHIFT(grp_shift); CLB_SHIFT(grp_base); CLB_SHIFT(grp_n); CLB_SHIFT(pair_base);
+                CLB_SHIFT(gf_key); CLB_SHIFT(gf_match); CLB_SHIFT(or_shift); CLB_SHIFT(or_off);
+                CLB_SHIFT(or_match); CLB_SHIFT(in_base); CLB_SHIFT(in_n); CLB_SHIFT(in_off);
+                CLB_SHIFT(ent_rank); CLB_SHIFT(arena_base);
+                CLB_ZSHIFT(qrec); CLB_ZSHIFT(gf_ord); CLB_ZSHIFT(gf_best); CLB_ZSHIFT(or_ord); CLB_ZSHIFT(bit);
+                CLB_ZSHIFT(cand_best); CLB_ZSHIFT(cand_bp); CLB_ZSHIFT(counters);
+                if (a.rank_pool) CLB_ZSHIFT(rank_pool);
+#undef CLB_ZSHIFT
+#undef CLB_SHIFT
+#undef CLB_SHIFT_BY
+                if (!in_smem) zero_off += ArenaPlan::align(d.zero_bytes);
+                a.out_dp = ba.d_dp + res_base + d.res_off;
+                a.out_backptr = ba.d_bp + res_base + d.res_off;
+                h_args[k++] = a;
+            }
+            seg += ArenaPlan::align(ctx.staging.size());
+            res_base += ctx.res_total;
+        }
+    }
+    const double t_staged = now_ms();
+    BATCH_TRY(cudaMemcpyAsync(ba.d_arena, ba.h_stage, stage_bytes, cudaMemcpyHostToDevice, ba.stream));
+    BATCH_TRY(cudaMemcpyAsync(ba.d_args, h_args, args_bytes, cudaMemcpyHostToDevice, ba.stream));
+    if (zero_total) BATCH_TRY(cudaMemsetAsync(ba.d_zero, 0, zero_total, ba.stream));
+    BATCH_TRY(cudaEventRecord(ba.e0, ba.stream));
+    BATCH_TRY(clb::launch_chain_small_batch(ba.d_args, (int)nb, max_smem, zero_total > 0, ba.stream));
+    BATCH_TRY(cudaEventRecord(ba.e1, ba.stream));
+    BATCH_TRY(cudaMemcpyAsync(h_dp, ba.d_dp, res_total * 4, cudaMemcpyDeviceToHost, ba.stream));
+    BATCH_TRY(cudaMemcpyAsync(h_bp, ba.d_bp, res_total * 4, cudaMemcpyDeviceToHost, ba.stream));
+    BATCH_TRY(cudaStreamSynchronize(ba.stream));
+    float ms = 0.f;
+    BATCH_TRY(cudaEventElapsedTime(&ms, ba.e0, ba.e1));
+#undef BATCH_TRY
+    if (stats) {
+        stats->kernel_ms += ms;
+        stats->kernel_launches += 1;
+    }
+    const double t_done = now_ms();
+    {
+        size_t res_base = 0;
+        for (int64_t c = 0; c < n_ctx && rc == CLB_OK; ++c) {
+            for (const DeferredProblem& d : ctxs[c]->items) {
+                rc = chain_traceback(d.p, h_dp + res_base + d.res_off, h_bp + res_base + d.res_off, d.dp_out, d.backptr_out, d.chain_out, d.chain_len,
+                                     d.opt_score);
+                if (rc != CLB_OK) break;
+            }
+            res_base += ctxs[c]->res_total;
+        }
+    }
+    if (getenv("CLB_TIMING"))
+        fprintf(stderr, "[clb] chain batch: %lld problems in one launch, %.2f MB staged in %.2f ms, kernel %.2f ms, copies+sync %.2f ms, tracebacks %.2f ms\n",
+                (long long)nb, stage_bytes / 1e6, t_staged - t_start, ms, t_done - t_staged - ms, now_ms() - t_done);
+    g_batch_flushes += 1;
+    g_batch_problems += nb;
+    return rc;
+}
+}  // namespace
+
 // Many independent chaining problems in one call.  The Anchorer's fill-in pass (anchorer.hpp:619-699) chains the
 // matches inside every gap of the main chain separately -- thousands of problems of a few dozen matches each; one at a
 // time each pays a layout, a staging copy, a launch on ONE SM and a read-back.  Here every problem that fits shared
@@ -740,88 +905,63 @@ extern "C" int clb_chain_dp_batch(int device, int64_t n_problems, const clb_chai
             stats->d2h_bytes += one.d2h_bytes; stats->kernel_launches += one.kernel_launches;
         }
     }
-    const int64_t nb = (int64_t)ctx.items.size();
-    if (nb > 0) {
-        int rc = CLB_OK;
-        char* d_arena = nullptr;
-        clb::ChainArgs* d_args = nullptr;
-        float* d_dp = nullptr;
-        uint32_t* d_bp = nullptr;
-        cudaStream_t stream = nullptr;
-        cudaEvent_t e0 = nullptr, e1 = nullptr;
-        std::vector<clb::ChainArgs> h_args((size_t)nb);
-        std::vector<float> h_dp(ctx.res_total);
-        std::vector<uint32_t> h_bp(ctx.res_total);
-#define BATCH_TRY(expr)                                                                                                \
-    do {                                                                                                               \
-        cudaError_t _e = (expr);                                                                                       \
-        if (_e != cudaSuccess) {                                                                                       \
-            rc = host_fail(_e == cudaErrorMemoryAllocation ? CLB_ENOMEM : CLB_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
-            goto batch_cleanup;                                                                                        \
-        }                                                                                                              \
-    } while (0)
-        BATCH_TRY(cudaSetDevice(device));
-        BATCH_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-        BATCH_TRY(cudaEventCreate(&e0));
-        BATCH_TRY(cudaEventCreate(&e1));
-        BATCH_TRY(cudaMalloc((void**)&d_arena, std::max<size_t>(ctx.staging.size(), 256)));
-        BATCH_TRY(cudaMalloc((void**)&d_args, (size_t)nb * sizeof(clb::ChainArgs)));
-        BATCH_TRY(cudaMalloc((void**)&d_dp, std::max<size_t>(ctx.res_total, 1) * 4));
-        BATCH_TRY(cudaMalloc((void**)&d_bp, std::max<size_t>(ctx.res_total, 1) * 4));
-        for (int64_t k = 0; k < nb; ++k) {
-            clb::ChainArgs a = ctx.items[k].args;
-            const ptrdiff_t shift = (d_arena + ctx.items[k].arena_off) - (char*)nullptr;
-#define CLB_SHIFT(f) a.f = reinterpret_cast<decltype(a.f)>(reinterpret_cast<char*>(const_cast<void*>(static_cast<const void*>(a.f))) + shift)
-            CLB_SHIFT(dp); CLB_SHIFT(backptr); CLB_SHIFT(sins_off); CLB_SHIFT(ins); CLB_SHIFT(qry_off); CLB_SHIFT(qry_match);
-            CLB_SHIFT(qrec); CLB_SHIFT(weight); CLB_SHIFT(qry_chain1); CLB_SHIFT(qa1); CLB_SHIFT(qa2); CLB_SHIFT(qoff);
-            CLB_SHIFT(pair_grp_off); CLB_SHIFT(grp_shift); CLB_SHIFT(grp_base); CLB_SHIFT(grp_n); CLB_SHIFT(pair_base);
-            CLB_SHIFT(gf_key); CLB_SHIFT(gf_match); CLB_SHIFT(gf_ord); CLB_SHIFT(gf_best); CLB_SHIFT(or_shift); CLB_SHIFT(or_off);
-            CLB_SHIFT(or_match); CLB_SHIFT(or_ord); CLB_SHIFT(in_base); CLB_SHIFT(in_n); CLB_SHIFT(in_off); CLB_SHIFT(bit);
-            CLB_SHIFT(ent_rank); CLB_SHIFT(cand_best); CLB_SHIFT(cand_bp); CLB_SHIFT(counters); CLB_SHIFT(arena_base);
-            if (a.rank_pool) CLB_SHIFT(rank_pool);
-#undef CLB_SHIFT
-            a.out_dp = d_dp + ctx.items[k].res_off;
-            a.out_backptr = d_bp + ctx.items[k].res_off;
-            h_args[(size_t)k] = a;
-        }
-        {
-            const double t_staged = now_ms();
-            BATCH_TRY(cudaMemcpyAsync(d_arena, ctx.staging.data(), ctx.staging.size(), cudaMemcpyHostToDevice, stream));
-            BATCH_TRY(cudaMemcpyAsync(d_args, h_args.data(), (size_t)nb * sizeof(clb::ChainArgs), cudaMemcpyHostToDevice, stream));
-            BATCH_TRY(cudaEventRecord(e0, stream));
-            BATCH_TRY(clb::launch_chain_small_batch(d_args, (int)nb, ctx.max_smem, stream));
-            BATCH_TRY(cudaEventRecord(e1, stream));
-            BATCH_TRY(cudaMemcpyAsync(h_dp.data(), d_dp, ctx.res_total * 4, cudaMemcpyDeviceToHost, stream));
-            BATCH_TRY(cudaMemcpyAsync(h_bp.data(), d_bp, ctx.res_total * 4, cudaMemcpyDeviceToHost, stream));
-            BATCH_TRY(cudaStreamSynchronize(stream));
-            float ms = 0.f;
-            BATCH_TRY(cudaEventElapsedTime(&ms, e0, e1));
-            if (stats) {
-                stats->kernel_ms += ms;
-                stats->kernel_launches += 1;
-            }
-            if (getenv("CLB_TIMING"))
-                fprintf(stderr, "[clb] chain batch: %lld of %lld problems in one launch, %.1f MB staged, kernel %.2f ms, copies+sync %.2f ms\n",
-                        (long long)nb, (long long)n_problems, ctx.staging.size() / 1e6, ms, now_ms() - t_staged - ms);
-        }
-        for (int64_t k = 0; k < nb && rc == CLB_OK; ++k) {
-            const DeferredProblem& d = ctx.items[k];
-            rc = chain_traceback(d.p, h_dp.data() + d.res_off, h_bp.data() + d.res_off, d.dp_out, d.backptr_out, d.chain_out, d.chain_len, d.opt_score);
-        }
-    batch_cleanup:
-        if (d_arena) cudaFree(d_arena);
-        if (d_args) cudaFree(d_args);
-        if (d_dp) cudaFree(d_dp);
-        if (d_bp) cudaFree(d_bp);
-        if (e0) cudaEventDestroy(e0);
-        if (e1) cudaEventDestroy(e1);
-        if (stream) cudaStreamDestroy(stream);
-#undef BATCH_TRY
-        if (rc != CLB_OK) return rc;
-    }
+    BatchCtx* const one_ctx[1] = {&ctx};
+    const int rc = flush_contexts(device, one_ctx, 1, stats);
+    if (rc != CLB_OK) return rc;
     if (stats) stats->total_ms = now_ms() - t_start;
     return CLB_OK;
 }
+
+// The same in two halves, for callers that prepare problems on several host threads (the drop-in Anchorer runs the
+// fill-in subproblems of anchorer.hpp:657-693 on a thread pool): clb_chain_job_create lays one problem out in the CALLING
+// thread -- no device work, thread-safe -- and clb_chain_jobs_run solves the jobs of any number of threads in one launch.
+struct clb_chain_job {
+    BatchCtx ctx;
+    int device = 0;
+};
+
+extern "C" int clb_chain_job_create(int device, const clb_chain_problem* problem, float* dp_out, int64_t* backptr_out, int64_t* chain_out,
+                                    int64_t* chain_len, float* opt_score, clb_chain_job** job) {
+    if (!job) return host_fail(CLB_EINVAL, "clb_chain_job_create: null job pointer");
+    *job = nullptr;
+    if (!problem || !chain_out || !chain_len) return host_fail(CLB_EINVAL, "clb_chain_job_create: null arguments");
+    clb_chain_job* j = new (std::nothrow) clb_chain_job();
+    if (!j) return host_fail(CLB_ENOMEM, "clb_chain_job_create: out of host memory");
+    j->device = device;
+    // a problem too large for one SM's shared memory is solved here and now (ctx stays empty)
+    const int rc = chain_dp_impl(device, problem, dp_out, backptr_out, chain_out, chain_len, opt_score, nullptr, &j->ctx);
+    if (rc != CLB_OK) {
+        delete j;
+        return rc;
+    }
+    if (j->ctx.items.empty()) {  // solved already (or nothing to solve): no job
+        delete j;
+        return CLB_OK;
+    }
+    *job = j;
+    return CLB_OK;
+}
+
+extern "C" int clb_chain_jobs_run(int device, int64_t n_jobs, clb_chain_job* const* jobs) {
+    if (n_jobs < 0 || (n_jobs > 0 && !jobs)) return host_fail(CLB_EINVAL, "clb_chain_jobs_run: null arguments");
+    std::vector<BatchCtx*> ctxs;
+    ctxs.reserve((size_t)n_jobs);
+    for (int64_t k = 0; k < n_jobs; ++k) {
+        if (!jobs[k]) return host_fail(CLB_EINVAL, "clb_chain_jobs_run: null job");
+        if (jobs[k]->device != device) return host_fail(CLB_EINVAL, "clb_chain_jobs_run: job was created for another device");
+        if (!jobs[k]->ctx.items.empty()) ctxs.push_back(&jobs[k]->ctx);
+    }
+    const int rc = flush_contexts(device, ctxs.data(), (int64_t)ctxs.size(), nullptr);
+    if (rc == CLB_OK)
+        for (BatchCtx* c : ctxs) {  // a job runs once
+            c->items.clear();
+            c->staging.clear();
+            c->res_total = 0;
+        }
+    return rc;
+}
+
+extern "C" void clb_chain_job_destroy(clb_chain_job* job) { delete job; }
 
 namespace clb {
 void chain_release_cache() {
@@ -836,5 +976,21 @@ void chain_release_cache() {
         if (kv.second.stream) cudaStreamDestroy(kv.second.stream);
     }
     g_arenas.clear();
+    std::lock_guard<std::mutex> lb(g_batch_mu);
+    for (auto& kv : g_batch_arenas) {
+        cudaSetDevice(kv.first);
+        BatchArena& b = kv.second;
+        if (b.d_arena) cudaFree(b.d_arena);
+        if (b.d_args) cudaFree(b.d_args);
+        if (b.d_dp) cudaFree(b.d_dp);
+        if (b.d_bp) cudaFree(b.d_bp);
+        if (b.d_zero) cudaFree(b.d_zero);
+        if (b.h_stage) cudaFreeHost(b.h_stage);
+        if (b.h_res) cudaFreeHost(b.h_res);
+        if (b.e0) cudaEventDestroy(b.e0);
+        if (b.e1) cudaEventDestroy(b.e1);
+        if (b.stream) cudaStreamDestroy(b.stream);
+    }
+    g_batch_arenas.clear();
 }
 }  // namespace clb

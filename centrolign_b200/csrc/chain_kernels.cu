@@ -304,7 +304,7 @@ __device__ __forceinline__ void chain_steps(const ChainArgs& A) {
     const uint32_t nctas = mode == 0 ? 1u : gridDim.x, cta = mode == 0 ? 0u : blockIdx.x;
     const uint32_t gwarp = (uint32_t)wib * nctas + cta, nwarp = nctas * kWarps;
     const uint32_t gthread = cta * kThreads + threadIdx.x, nthread = nctas * kThreads;
-    const int C2 = A.n_chain2, P = A.num_pw, T = 2 * A.num_pw;
+    const int C2 = A.n_chain2, T = 2 * A.num_pw;
     // work items: an insertion has one item for the gap-free tree of its diagonal and one per orthogonal value set; a
     // (query, chain2) pair has one item for the gap-free tree and one per (piece, parity), in the reference's candidate order
     const uint32_t n_kind = (uint32_t)(T + 1);
@@ -618,22 +618,42 @@ __global__ void __launch_bounds__(kThreads, 1) chain_small_kernel(const ChainArg
     chain_small_body(G, arena_smem);
 }
 
-// The same for a batch of independent problems: CTA b solves problem b (clb_chain_dp_batch).
+// The same for a batch of independent problems: CTA b solves problem b (clb_chain_dp_batch, clb_chain_jobs_run).  A problem
+// whose arena fits shared memory runs there; a larger one runs on its arena in global memory (copy region as staged, zero
+// region cleared by the host's memset), its queries prepared by chain_batch_prepare_kernel beforehand.
+__global__ void __launch_bounds__(256) chain_batch_prepare_kernel(const ChainArgs* __restrict__ problems) {
+    __shared__ ChainArgs G;
+    if (threadIdx.x == 0) G = problems[blockIdx.x];
+    __syncthreads();
+    if (G.arena_bytes <= (int64_t)kChainSmallArena || G.n_qry == 0) return;
+    prepare_queries<false>(G, threadIdx.x & 31, threadIdx.x >> 5, blockDim.x >> 5);
+}
+
 __global__ void __launch_bounds__(kThreads, 1) chain_small_batch_kernel(const ChainArgs* __restrict__ problems) {
     extern __shared__ uint4 arena_smem[];
     __shared__ ChainArgs G;
     if (threadIdx.x == 0) G = problems[blockIdx.x];
     __syncthreads();
-    chain_small_body(G, arena_smem);
+    if (G.arena_bytes <= (int64_t)kChainSmallArena) {
+        chain_small_body(G, arena_smem);
+        return;
+    }
+    chain_steps<false>(G);
+    __syncthreads();
+    for (int64_t m = threadIdx.x; m < G.n_match; m += kThreads) {
+        G.out_dp[m] = G.dp[m];
+        G.out_backptr[m] = G.backptr[m];
+    }
 }
 
-cudaError_t launch_chain_small_batch(const ChainArgs* d_args, int n, int smem_bytes, cudaStream_t stream) {
+cudaError_t launch_chain_small_batch(const ChainArgs* d_args, int n, int smem_bytes, bool any_global, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e0 = cudaFuncSetAttribute(chain_small_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmallArena);
         if (e0 != cudaSuccess) return e0;
         attr_set = true;
     }
+    if (any_global) chain_batch_prepare_kernel<<<n, 256, 0, stream>>>(d_args);
     chain_small_batch_kernel<<<n, kThreads, (size_t)smem_bytes, stream>>>(d_args);
     return cudaGetLastError();
 }

@@ -34,6 +34,7 @@
 #include <vector>
 
 #include "centrolign_b200.h"
+#include "chain_batcher.hpp"
 
 namespace centrolign_b200 {
 
@@ -93,6 +94,22 @@ struct ChainProblem {
         int64_t len = 0;
         if (dp_out) dp_out->assign(weight.size(), 0.0f);
         if (backptr_out) backptr_out->assign(weight.size(), -1);
+        if (ChainBatcher* batcher = stats ? nullptr : ChainBatcher::current()) {
+            // a worker of a fill-in pool: lay the problem out here, share the launch with the other workers (chain_batcher.hpp)
+            clb_chain_job* job = nullptr;
+            const int rc = clb_chain_job_create(device, &p, dp_out ? dp_out->data() : nullptr, backptr_out ? backptr_out->data() : nullptr,
+                                                chain.data(), &len, opt_score, &job);
+            if (rc != CLB_OK) throw std::runtime_error(std::string("centrolign_b200: ") + clb_last_error());
+            if (job) {
+                struct Guard {
+                    clb_chain_job* j;
+                    ~Guard() { clb_chain_job_destroy(j); }
+                } guard{job};
+                batcher->solve(job);
+            }
+            chain.resize((size_t)len);
+            return chain;
+        }
         const int rc = clb_chain_dp(device, &p, dp_out ? dp_out->data() : nullptr, backptr_out ? backptr_out->data() : nullptr,
                                     chain.data(), &len, opt_score, stats);
         if (rc != CLB_OK) throw std::runtime_error(std::string("centrolign_b200: ") + clb_last_error());

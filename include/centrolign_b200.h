@@ -261,6 +261,23 @@ int clb_chain_dp_batch(int device, int64_t n_problems, const clb_chain_problem* 
                        int64_t* const* backptr_out, int64_t* const* chain_out, int64_t* chain_len, float* opt_score,
                        clb_chain_stats* stats /* may be NULL */);
 
+/*
+ * The batched call in two halves, for a caller that prepares problems on several host threads (the drop-in Anchorer runs
+ * the fill-in subproblems of include/centrolign/anchorer.hpp:657-693 on a thread pool, hostcpp/chain_batcher.hpp):
+ *   clb_chain_job_create  lays ONE problem out for the device in the calling thread.  Thread-safe, no device work for a
+ *                         problem that fits one SM's shared memory; a larger problem is solved by clb_chain_dp before the call
+ *                         returns (its outputs are then final and *job is NULL).  The problem arrays and the output
+ *                         pointers (meaning as in clb_chain_dp) must stay valid until the job has run.
+ *   clb_chain_jobs_run    solves the jobs of any number of threads: one staging copy, ONE launch (a CTA per problem), one
+ *                         read-back, then the tracebacks into every job's outputs.  A job runs once.
+ *   clb_chain_job_destroy frees a job (NULL is allowed).
+ */
+typedef struct clb_chain_job clb_chain_job;
+int clb_chain_job_create(int device, const clb_chain_problem* problem, float* dp_out, int64_t* backptr_out, int64_t* chain_out,
+                         int64_t* chain_len, float* opt_score, clb_chain_job** job);
+int clb_chain_jobs_run(int device, int64_t n_jobs, clb_chain_job* const* jobs);
+void clb_chain_job_destroy(clb_chain_job* job);
+
 /* Measured INT32 issue-rate probe (a dependent-free add/max loop on every SM):
  * returns achieved 10^12 INT32 lane-ops per second on `device`, <0 on error. */
 double clb_int32_peak_tops(int device, int use_dpx);

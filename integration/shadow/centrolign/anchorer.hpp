@@ -133,7 +133,7 @@ inline std::vector<anchor_t> anchors_of(const std::vector<int64_t>& chain, const
                                                                       sinks1, sinks2, weight_of);                                  \
         const double t2 = now_s();                                                                                                 \
         float opt_value = 0.0f;                                                                                                    \
-        auto traceback = anchors_of(P.solve(0, &opt_value), P, match_sets);                                                        \
+        auto traceback = anchors_of(P.solve(centrolign_b200::chain_device(), &opt_value), P, match_sets);                                                        \
         if (getenv("CLB_TIMING") && P.n_match() > 10000)                                                                           \
             fprintf(stderr, "[clb] affine chaining of %zu matches (" #MBANK "): reference-side tables %.3f s, flat problem %.3f s, " \
                             "clb_chain_dp %.3f s\n", P.n_match(), t1 - t0, t2 - t1, now_s() - t2);                                 \
@@ -178,7 +178,7 @@ CLB_AFFINE_CHAIN_SPECIALIZATION(b200_chain::PackedShiftMatchVector, b200_chain::
         auto P = centrolign_b200::build_gapfree_chain_problem(match_bank, forward_edges, graph1, order1, chain_merge1,             \
                                                               chain_merge2, match_sets, num_match_sets, sources1, sources2,        \
                                                               sinks1, sinks2, weight_of);                                          \
-        auto traceback = anchors_of(P.solve(0), P, match_sets);                                                                    \
+        auto traceback = anchors_of(P.solve(centrolign_b200::chain_device()), P, match_sets);                                                                    \
         annotate_scores(traceback); /* :2536 */                                                                                    \
         (void)suppress_verbose_logging;                                                                                            \
         return traceback;                                                                                                          \
@@ -186,6 +186,54 @@ CLB_AFFINE_CHAIN_SPECIALIZATION(b200_chain::PackedShiftMatchVector, b200_chain::
 CLB_GAPFREE_CHAIN_SPECIALIZATION(b200_chain::XMerge)
 CLB_GAPFREE_CHAIN_SPECIALIZATION(ChainMerge)
 #undef CLB_GAPFREE_CHAIN_SPECIALIZATION
+
+// ---- fill_in_anchor_chain (anchorer.hpp:619-699) for the production types: the subproblems between the anchors of the
+// main chain are independent -- each has its own subgraphs, matches, budget and result slot -- so they run on a pool of
+// host threads whose chaining calls share kernel launches (centrolign_b200/hostcpp/chain_batcher.hpp).  Extraction, the
+// division of matches and budgets, and the merge of the results are the reference's own functions, called in its order.
+#define CLB_FILL_IN_SPECIALIZATION(XM)                                                                                                      \
+template <>                                                                                                                                 \
+inline void Anchorer::fill_in_anchor_chain<BaseGraph, XM>(                                                                                  \
+    std::vector<anchor_t>& anchors, std::vector<match_set_t>& matches, const BaseGraph& graph1, const BaseGraph& graph2,                    \
+    const SentinelTableau& tableau1, const SentinelTableau& tableau2, const XM& xmerge1, const XM& xmerge2,                                 \
+    bool restrain_memory, ChainAlgorithm local_chaining_algorithm, double anchor_scale,                                                     \
+    const std::unordered_set<std::tuple<size_t, size_t, size_t>>* masked_matches) const {                                                   \
+    if (anchors.empty()) {                                                                                                                  \
+        logging::log(logging::Debug, "Skipping fill-in anchoring on an empty chain");                                                       \
+        return;                                                                                                                             \
+    }                                                                                                                                       \
+    auto gaps = extract_graphs_between(anchors, graph1, graph2, tableau1, tableau2, xmerge1, xmerge2);                                      \
+    project_paths(graph1, graph2, gaps);                                                                                                    \
+    std::vector<std::vector<std::pair<size_t, std::pair<std::vector<size_t>, std::vector<size_t>>>>> origin;                                \
+    auto gap_matches = divvy_matches(matches, graph1, graph2, gaps, origin);                                                                \
+    const auto budgets = assign_reanchor_budget(gaps);                                                                                      \
+    std::vector<std::vector<anchor_t>> gap_chains(gaps.size());                                                                             \
+    centrolign_b200::batched_parallel_for(gaps.size(), centrolign_b200::chain_device(), [&](size_t g) {                                     \
+        auto& sub1 = gaps[g].first;                                                                                                         \
+        auto& sub2 = gaps[g].second;                                                                                                        \
+        XM gap_merge1(sub1.subgraph), gap_merge2(sub2.subgraph);                                                                            \
+        /* masked (set, walk1, walk2) triples in the numbering of this gap's match sets (:662-679) */                                       \
+        std::unordered_set<std::tuple<size_t, size_t, size_t>> masked_here;                                                                 \
+        if (masked_matches && !masked_matches->empty()) {                                                                                   \
+            for (size_t set = 0; set < origin[g].size(); ++set) {                                                                           \
+                const size_t parent_set = origin[g][set].first;                                                                             \
+                const std::vector<size_t>& from1 = origin[g][set].second.first;                                                             \
+                const std::vector<size_t>& from2 = origin[g][set].second.second;                                                            \
+                for (size_t a = 0; a < from1.size(); ++a)                                                                                   \
+                    for (size_t b = 0; b < from2.size(); ++b)                                                                               \
+                        if (masked_matches->count(std::make_tuple(parent_set, from1[a], from2[b]))) masked_here.emplace(set, a, b);         \
+            }                                                                                                                               \
+        }                                                                                                                                   \
+        gap_chains[g] = anchor_chain(gap_matches[g], sub1.subgraph, sub2.subgraph, gap_merge1, gap_merge2, restrain_memory, &sub1.sources,  \
+                                     &sub2.sources, &sub1.sinks, &sub2.sinks, budgets[g], true, local_chaining_algorithm, anchor_scale,     \
+                                     &masked_here);                                                                                         \
+    });                                                                                                                                     \
+    merge_fill_in_chains(anchors, gap_chains, gaps, origin);                                                                                \
+    logging::log(logging::Debug, "Filled-in anchor chain consists of " + std::to_string(anchors.size()) + " anchors");                      \
+}
+CLB_FILL_IN_SPECIALIZATION(b200_chain::XMerge)  // alignment subproblems (core.hpp:336-338)
+CLB_FILL_IN_SPECIALIZATION(ChainMerge)          // per-sequence scale calibration (src/core.cpp:150-157, :222)
+#undef CLB_FILL_IN_SPECIALIZATION
 
 }  // namespace centrolign
 

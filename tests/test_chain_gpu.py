@@ -124,3 +124,25 @@ def test_batched_call_equals_one_by_one():
         n_small += 1
     assert st.kernel_launches >= 1
     assert chain_dp_batch([]) == []
+
+
+def test_jobs_created_on_threads_and_run_in_one_launch():
+    """clb_chain_job_create on several host threads + ONE clb_chain_jobs_run (what the drop-in Anchorer's fill-in pool does,
+    hostcpp/chain_batcher.hpp) returns per problem exactly what clb_chain_dp returns; problems that fit shared memory, problems
+    that run from global memory inside the batch, and problems solved at creation are all in the mix."""
+    from centrolign_b200.chain import chain_dp_jobs
+
+    probs = []
+    for case in sorted(GOLD):
+        for kind in sorted(GOLD[case]):
+            probs.append(GOLD[case][kind])
+    for num_pw in (0, 1, 3):
+        probs += [_handmade(num_pw), _handmade(num_pw, with_query=False), _handmade(num_pw, n=1)]
+    probs = probs * 2
+    for threads in (1, 8):
+        got = chain_dp_jobs(probs, threads=threads)
+        for prob, (chain, dp, bp, opt) in zip(probs, got):
+            rchain, rdp, rbp, ropt = chain_dp(prob)
+            assert np.array_equal(chain, rchain) and opt == ropt
+            assert np.array_equal(dp.view(np.uint32), rdp.view(np.uint32)) and np.array_equal(bp, rbp)
+    assert chain_dp_jobs([]) == []
