@@ -692,8 +692,10 @@ static int chain_dp_impl(int device, const clb_chain_problem* p, float* dp_out, 
         if (getenv("CLB_TIMING")) {
             float pms = 0.f;
             cudaEventElapsedTime(&pms, ar.ev0, ar.evp);
-            fprintf(stderr, "[clb] chain: build %.1f ms, prepare kernel %.2f ms, DP kernel %.2f ms (grid %d, cluster %d, %lld steps, %.0f warp items per step, rank pool %s)\n",
-                    t_built - t_start, pms, ms - pms, grid, cluster, (long long)S, warps_per_step, rank_stride ? "on" : "off");
+            fprintf(stderr, "[clb] chain: build %.1f ms, alloc+stage %.1f ms (%.0f MB arena, %.0f MB copied), prepare kernel %.2f ms, DP kernel %.2f ms, "
+                            "enqueue..sync %.1f ms (grid %d, cluster %d, %lld steps, %.0f warp items per step, rank pool %s)\n",
+                    t_built - t_start, t_staged - t_built, total / 1e6, plan.copy_bytes / 1e6, pms, ms - pms, now_ms() - t_staged, grid, cluster,
+                    (long long)S, warps_per_step, rank_stride ? "on" : "off");
         }
         if (stats) {
             stats->build_ms = t_built - t_start;

@@ -979,6 +979,42 @@ int clb_topological_ranks(uint32_t n_nodes, const uint32_t* pred_off, const uint
     return CLB_OK;
 }
 
+// Context creation off the critical path: a process that knows it will use `device` calls this first thing; the CUDA
+// runtime serialises initialisation itself, so later calls of the library simply find the context there (or wait for it).
+namespace {
+std::mutex g_warm_mu;
+std::thread* g_warm_thread = nullptr;
+void join_warm_up() {
+    std::thread* t = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_warm_mu);
+        t = g_warm_thread;
+        g_warm_thread = nullptr;
+    }
+    if (t) {
+        t->join();
+        delete t;
+    }
+}
+}  // namespace
+
+void clb_warm_up(int device) {
+    std::lock_guard<std::mutex> lk(g_warm_mu);
+    static bool started = false;
+    if (started) return;
+    started = true;
+    g_warm_thread = new (std::nothrow) std::thread([device] {
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) {
+            cudaGetLastError();
+            return;  // no device: the first real call reports it
+        }
+        if (cudaSetDevice(device) == cudaSuccess) cudaFree(nullptr);
+        cudaGetLastError();
+    });
+    if (g_warm_thread) atexit(join_warm_up);
+}
+
 void clb_release_cached_memory(void) {
     g_cache.trim();
     clb::chain_release_cache();

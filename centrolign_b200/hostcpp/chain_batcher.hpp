@@ -103,12 +103,12 @@ private:
 };
 
 // body(i) for every i in [0, n), on a pool of workers whose ChainProblem::solve calls share launches.
-// CLB_FILL_IN_THREADS sets the pool size (default 8 per hardware thread, 32..256); 1 = the serial loop, no batching.
+// CLB_FILL_IN_THREADS sets the pool size (default 4 per hardware thread, 16..128); 1 = the serial loop, no batching.
 template <class Body>
 void batched_parallel_for(size_t n, int device, Body&& body) {
     static const int configured = getenv("CLB_FILL_IN_THREADS") ? atoi(getenv("CLB_FILL_IN_THREADS")) : 0;
     const unsigned hw = std::thread::hardware_concurrency();
-    size_t threads = configured > 0 ? (size_t)configured : std::min<size_t>(256, std::max<size_t>(32, 8 * (size_t)(hw ? hw : 4)));
+    size_t threads = configured > 0 ? (size_t)configured : std::min<size_t>(128, std::max<size_t>(16, 4 * (size_t)(hw ? hw : 4)));
     threads = std::min(threads, n);
     if (threads <= 1 || ChainBatcher::current()) {  // nothing to share, or already inside a pool
         for (size_t i = 0; i < n; ++i) body(i);

@@ -22,7 +22,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "li
 EXPORTS = ["clb_popoa_batch", "clb_batch_create", "clb_batch_upload", "clb_batch_run", "clb_batch_download",
            "clb_batch_destroy", "clb_batch_get_stats", "clb_int32_peak_tops", "clb_last_error", "clb_device_count",
            "clb_release_cached_memory", "clb_pwfa_batch", "clb_chain_dp", "clb_topological_ranks", "clb_popoa_batch_multi",
-           "clb_balanced_partition", "clb_chain_dp_batch", "clb_chain_job_create", "clb_chain_jobs_run", "clb_chain_job_destroy"]
+           "clb_balanced_partition", "clb_chain_dp_batch", "clb_chain_job_create", "clb_chain_jobs_run", "clb_chain_job_destroy", "clb_warm_up"]
 ERROR_NAMES = {0: "CLB_OK", 1: "CLB_EINVAL", 2: "CLB_ECYCLE", 3: "CLB_ECUDA", 4: "CLB_ENOMEM", 5: "CLB_ESTATE"}
 
 

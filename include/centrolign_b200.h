@@ -278,6 +278,12 @@ int clb_chain_job_create(int device, const clb_chain_problem* problem, float* dp
 int clb_chain_jobs_run(int device, int64_t n_jobs, clb_chain_job* const* jobs);
 void clb_chain_job_destroy(clb_chain_job* job);
 
+/* Optional: starts creating the CUDA context of `device` on a background thread and returns at once, so that a process
+ * which knows it will use the library overlaps the ~1 s of context creation with its own start-up work (the drop-in CLI
+ * calls it from a static initializer; measured 8-10 s -> 7-9 s on the 2 x 100 kbp run).  Only the first call in a
+ * process does anything; failures are silent here and surface in the first real call. */
+void clb_warm_up(int device);
+
 /* Measured INT32 issue-rate probe (a dependent-free add/max loop on every SM):
  * returns achieved 10^12 INT32 lane-ops per second on `device`, <0 on error. */
 double clb_int32_peak_tops(int device, int use_dpx);

@@ -115,6 +115,10 @@ public:
 }  // namespace centrolign
 
 #ifdef CLB_SHADOW_STITCHER_TU
+// once per program (this one translation unit): start creating the CUDA context while the CLI reads its input
+namespace {
+const int clb_context_started_at_load = (clb_warm_up(centrolign_b200::chain_device()), 0);
+}
 // the rest of this translation unit is src/stitcher.cpp: its member definitions belong to the reference class
 #define Stitcher StitcherReference
 #define translate translate_b200
