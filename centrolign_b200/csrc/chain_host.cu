@@ -660,6 +660,7 @@ static int chain_dp_impl(int device, const clb_chain_problem* p, float* dp_out, 
         // cluster barrier, the items of a step spread over its SMs), more in a cooperative grid (grid.sync).
         const double warps_per_step = S ? ((double)ins.size() + (double)n_qry * C2) * (T + 1) / (double)S : 0.0;
         const int max_grid = clb::chain_max_grid(device);
+        const int warps_per_cta = P == 0 ? 28 : 16;  // chain_kernels.cu: the gap-free kernel runs with 896 threads
         int cluster = 1;
         if (getenv("CLB_CHAIN_GRID")) {
             grid = std::max(1, std::min(max_grid, atoi(getenv("CLB_CHAIN_GRID"))));
@@ -667,8 +668,8 @@ static int chain_dp_impl(int device, const clb_chain_problem* p, float* dp_out, 
             cluster = std::max(1, std::min(16, atoi(getenv("CLB_CHAIN_CLUSTER"))));
         } else if (warps_per_step > 512.0) {
             grid = std::min<int>(max_grid, (int)(warps_per_step / 12.0) + 1);
-        } else if (warps_per_step > 24.0) {
-            while (cluster < kChainClusterMax && cluster * 16 < warps_per_step) cluster *= 2;
+        } else if (warps_per_step > 1.5 * warps_per_cta) {
+            while (cluster < kChainClusterMax && cluster * warps_per_cta < warps_per_step) cluster *= 2;
         }
         a.arena_base = ar.d;
         a.arena_bytes = (int64_t)total;

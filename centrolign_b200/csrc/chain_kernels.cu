@@ -294,7 +294,9 @@ __device__ __forceinline__ int warp_argmax(uint32_t hi, uint32_t lo, uint32_t& h
     return __ffs(__ballot_sync(kFull, hi == mh && lo == ml)) - 1;
 }
 
-template <bool SM>
+// NK: work items per insertion / per (query, chain2) pair known at compile time (1 = gap-free chaining, 7 = three gap
+// pieces), 0 = 2 * num_pw + 1 read from the arguments.
+template <bool SM, int NK>
 __device__ __forceinline__ void chain_steps(const ChainArgs& A) {
     cg::grid_group grid = cg::this_grid();
     const int mode = SM ? 0 : A.sync_mode;
@@ -302,12 +304,12 @@ __device__ __forceinline__ void chain_steps(const ChainArgs& A) {
     // the shared-memory flavour is one CTA per problem whatever the grid is (a batch launch has one CTA per problem);
     // with several CTAs, consecutive work items of a step go to different CTAs (a step has a few dozen items)
     const uint32_t nctas = mode == 0 ? 1u : gridDim.x, cta = mode == 0 ? 0u : blockIdx.x;
-    const uint32_t gwarp = (uint32_t)wib * nctas + cta, nwarp = nctas * kWarps;
-    const uint32_t gthread = cta * kThreads + threadIdx.x, nthread = nctas * kThreads;
+    const uint32_t gwarp = (uint32_t)wib * nctas + cta, nwarp = nctas * (blockDim.x >> 5);
+    const uint32_t gthread = cta * blockDim.x + threadIdx.x, nthread = nctas * blockDim.x;
     const int C2 = A.n_chain2, T = 2 * A.num_pw;
     // work items: an insertion has one item for the gap-free tree of its diagonal and one per orthogonal value set; a
     // (query, chain2) pair has one item for the gap-free tree and one per (piece, parity), in the reference's candidate order
-    const uint32_t n_kind = (uint32_t)(T + 1);
+    const uint32_t n_kind = NK ? (uint32_t)NK : (uint32_t)(T + 1);
     const uint32_t slots = n_kind;
     unsigned long long n_tree_queries = 0;
     constexpr bool kEarly = !SM;  // records of the next step are fetched one phase ahead (global memory only)
@@ -438,7 +440,7 @@ __device__ __forceinline__ void chain_steps(const ChainArgs& A) {
                 if (lane == 0) A.gf_ord[gf_base + gf_node] = ford(dpv);
                 const uint32_t anc = (gf_node + 1) >> lane;
                 if (anc) atomicMax(&A.gf_best[gf_base + anc - 1], pack(dpv, ~(uint32_t)i));
-            } else {
+            } else if constexpr (NK != 1) {
                 // anchorer.hpp:2328-2335: odd pieces add, even pieces subtract local_scale * gap_extend * shift
                 const int t = (int)u - 1;
                 const double gap = __dmul_rn(A.scale_ext[t >> 1], (double)shift);
@@ -487,7 +489,7 @@ __device__ __forceinline__ void chain_steps(const ChainArgs& A) {
                     best_sel = sel;
                 }
             };
-            if (type == 0) {
+            if (NK == 1 || type == 0) {
                 // same diagonal (anchorer.hpp:2379-2389): MaxSearchTree::range_max((0, min), (offset, min))
                 const uint32_t vS = lane == 0 ? ld_live<SM>(&A.gf_ord[base + S0]) : 0u;
                 const uint32_t vl = wl.node_ok ? ld_live<SM>(&A.gf_ord[base + wl.node]) : 0u;
@@ -508,6 +510,7 @@ __device__ __forceinline__ void chain_steps(const ChainArgs& A) {
                 }
                 continue;
             }
+            if constexpr (NK != 1) {
             // one orthogonal value set (anchorer.hpp:2390-2413): piece k; parity 0 = even (shift > q), 1 = odd (shift < q)
             const int t = (int)type - 1, k = t >> 1, par = t & 1;
             const uint32_t* ord_t = A.or_ord + (int64_t)t * A.n_entry + base;
@@ -564,6 +567,7 @@ __device__ __forceinline__ void chain_steps(const ChainArgs& A) {
                 const float cand = __double2float_rn(__dsub_rn((double)__fadd_rn(funord(top), w), pen));
                 post(m, qc, (uint32_t)(1 + t), cand, ld_const<SM>(&A.or_match[base + best_sel]));
             }
+            }  // NK != 1
         }
         if (q0 != q1 || pq0 != pq1) barrier();
         pq0 = q0; pq1 = q1;
@@ -575,8 +579,15 @@ __device__ __forceinline__ void chain_steps(const ChainArgs& A) {
     if (lane == 0 && n_tree_queries) atomicAdd(A.counters, n_tree_queries);
 }
 
-__global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constant__ ChainArgs A) {
-    chain_steps<false>(A);
+// The gap-free kernel needs fewer registers and runs with 28 warps: a step of a pairwise problem has about twenty work items.
+constexpr int kThreadsGapFree = 896;
+template <int NK>
+__global__ void __launch_bounds__(NK == 1 ? kThreadsGapFree : kThreads, 1) chain_kernel(const __grid_constant__ ChainArgs A) {
+    chain_steps<false, NK>(A);
+}
+typedef void (*ChainKernel)(const ChainArgs);
+static ChainKernel chain_kernel_for(int num_pw) {
+    return num_pw == 0 ? (ChainKernel)chain_kernel<1> : num_pw == 3 ? (ChainKernel)chain_kernel<7> : (ChainKernel)chain_kernel<0>;
 }
 
 // Small problems: one CTA copies the whole arena into shared memory, rebases the pointers, prepares the queries,
@@ -601,7 +612,7 @@ __device__ __forceinline__ void chain_small_body(const ChainArgs& G, uint4* aren
     __syncthreads();
     prepare_queries<true>(A, threadIdx.x & 31, threadIdx.x >> 5, kWarps);
     __syncthreads();
-    chain_steps<true>(A);
+    chain_steps<true, 0>(A);
     __syncthreads();
     float* const odp = G.out_dp ? G.out_dp : G.dp;
     uint32_t* const obp = G.out_backptr ? G.out_backptr : G.backptr;
@@ -638,7 +649,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_small_batch_kernel(const Ch
         chain_small_body(G, arena_smem);
         return;
     }
-    chain_steps<false>(G);
+    chain_steps<false, 0>(G);
     __syncthreads();
     for (int64_t m = threadIdx.x; m < G.n_match; m += kThreads) {
         G.out_dp[m] = G.dp[m];
@@ -676,10 +687,14 @@ cudaError_t launch_chain(ChainArgs args, int grid, int cluster, int prepare_grid
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (after_prepare) cudaEventRecord(after_prepare, stream);
+    const ChainKernel kern = chain_kernel_for(args.num_pw);
+    const int threads = args.num_pw == 0 ? kThreadsGapFree : kThreads;
     if (cluster > 1) {
         static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);  // clusters of 16; refusal shows at launch
+        if (!attr_set) {  // clusters of 16; a refusal shows at launch
+            cudaFuncSetAttribute(chain_kernel<0>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            cudaFuncSetAttribute(chain_kernel<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            cudaFuncSetAttribute(chain_kernel<7>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
             cudaGetLastError();
             attr_set = true;
         }
@@ -687,7 +702,7 @@ cudaError_t launch_chain(ChainArgs args, int grid, int cluster, int prepare_grid
         for (; cluster > 1; cluster /= 2) {  // a cluster size the device cannot place falls back to the next smaller one
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(cluster);
-            cfg.blockDim = dim3(kThreads);
+            cfg.blockDim = dim3(threads);
             cfg.stream = stream;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension;
@@ -696,7 +711,7 @@ cudaError_t launch_chain(ChainArgs args, int grid, int cluster, int prepare_grid
             at[0].val.clusterDim.z = 1;
             cfg.attrs = at;
             cfg.numAttrs = 1;
-            e = cudaLaunchKernelEx(&cfg, chain_kernel, args);
+            e = cudaLaunchKernelEx(&cfg, kern, args);
             if (e == cudaSuccess) return e;
             cudaGetLastError();
         }
@@ -704,16 +719,16 @@ cudaError_t launch_chain(ChainArgs args, int grid, int cluster, int prepare_grid
     if (grid > 1) {
         args.sync_mode = 2;
         void* params[] = {(void*)&args};
-        return cudaLaunchCooperativeKernel((const void*)chain_kernel, dim3(grid), dim3(kThreads), params, 0, stream);
+        return cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(threads), params, 0, stream);
     }
     args.sync_mode = 0;
-    chain_kernel<<<1, kThreads, 0, stream>>>(args);
+    kern<<<1, threads, 0, stream>>>(args);
     return cudaGetLastError();
 }
 
 int chain_max_grid(int device) {
     int per_sm = 0, sms = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chain_kernel, kThreads, 0) != cudaSuccess) return 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chain_kernel<0>, kThreads, 0) != cudaSuccess) return 1;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 1;
     return per_sm > 0 ? sms : 1;
 }

@@ -1,7 +1,7 @@
 import subprocess, sys, time, os, hashlib
 fa = "/tmp/x.fa"
 subprocess.run([sys.executable, "integration/make_hor_fasta.py", fa, "2", "100000", "1", "0"], check=True)
-for threads in ("1", "64", "1", "64", "1", "64"):
+for threads in ("64", "64", "64"):
     env = dict(os.environ, CLB_FILL_IN_THREADS=threads, CLB_COUNT_CALLS="1")
     t0 = time.perf_counter()
     r = subprocess.run(["oracle/_ref/centrolign_b200", "-v", "0", fa], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
