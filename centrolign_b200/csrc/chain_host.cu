@@ -656,8 +656,8 @@ static int chain_dp_impl(int device, const clb_chain_problem* p, float* dp_out, 
         a.rank_stride = rank_stride;
         a.cand_best = (unsigned long long*)(zr + z_cbest); a.cand_bp = (uint32_t*)(zr + z_cbp); a.counters = (unsigned long long*)(zr + z_cnt);
         // How the phases of a step are separated.  A step has `warps_per_step` independent warp-sized work items on average:
-        // a handful run in one CTA (__syncthreads), a few dozen to a few hundred in ONE thread-block cluster (hardware
-        // cluster barrier, the items of a step spread over its SMs), more in a cooperative grid (grid.sync).
+        // a handful run in one CTA (__syncthreads), up to as many as the largest cluster has warps in ONE thread-block cluster
+        // (hardware cluster barrier, the items of a step spread over its SMs), more in a cooperative grid over all SMs (grid.sync).
         const double warps_per_step = S ? ((double)ins.size() + (double)n_qry * C2) * (T + 1) / (double)S : 0.0;
         const int max_grid = clb::chain_max_grid(device);
         const int warps_per_cta = P == 0 ? 28 : 16;  // chain_kernels.cu: the gap-free kernel runs with 896 threads
@@ -666,8 +666,8 @@ static int chain_dp_impl(int device, const clb_chain_problem* p, float* dp_out, 
             grid = std::max(1, std::min(max_grid, atoi(getenv("CLB_CHAIN_GRID"))));
         } else if (getenv("CLB_CHAIN_CLUSTER")) {
             cluster = std::max(1, std::min(16, atoi(getenv("CLB_CHAIN_CLUSTER"))));
-        } else if (warps_per_step > 512.0) {
-            grid = std::min<int>(max_grid, (int)(warps_per_step / 12.0) + 1);
+        } else if (warps_per_step > (double)kChainClusterMax * warps_per_cta) {
+            grid = max_grid;  // more items than the largest cluster has warps: measured 335 ms (cluster of 16) -> 232 ms (148 CTAs) at 441 items
         } else if (warps_per_step > 1.5 * warps_per_cta) {
             while (cluster < kChainClusterMax && cluster * warps_per_cta < warps_per_step) cluster *= 2;
         }

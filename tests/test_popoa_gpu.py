@@ -239,6 +239,18 @@ def test_size_independent_properties_large_windows():
         assert_valid_and_rescore(batch, w, PROD, int(scores[w]), alns[w])
 
 
+def test_30k_by_30k_window(monkeypatch):
+    """One window of 30 000 x 30 000 nodes (9e8 cells, the largest single fill the workspace layout is meant for, VERDICT
+    round 1 item 7): it runs, its alignment is a valid walk pair that re-scores to the reported optimum, and the generic
+    fill step (a different code path through the same matrix) reports the same score and alignment."""
+    batch = synth_windows(1, first_index=77, seed=5, len_min=30000, len_max=30000)
+    scores, alns = po_poa_batch(batch, PROD)
+    assert_valid_and_rescore(batch, 0, PROD, int(scores[0]), alns[0])
+    monkeypatch.setenv("CLB_DEBUG_FLAGS", "2")
+    scores2, alns2 = po_poa_batch(batch, PROD)
+    assert int(scores2[0]) == int(scores[0]) and np.array_equal(alns2[0], alns[0])
+
+
 def assert_valid_and_rescore(batch, w, p, score, aln):
     lab1, po1, pr1, src1, snk1 = batch.g1.window(w)
     lab2, po2, pr2, src2, snk2 = batch.g2.window(w)
