@@ -286,11 +286,21 @@ def other_paths(device):
             ones = [chain_dp(p, device=device) for p in many[: 4 * len(small)]]
             t_one = (time.perf_counter() - t0) / (4 * len(small)) * len(many)
             assert all(np.array_equal(a[0], b[0]) for a, b in zip(got, ones)), "batched chaining differs from the single calls"
+            from centrolign_b200.chain import chain_dp_jobs
+
+            n_threads = min(16, os.cpu_count() or 1)
+            chain_dp_jobs(many[: len(small)], device=device, threads=n_threads)
+            t0 = time.perf_counter()
+            got_jobs = chain_dp_jobs(many, device=device, threads=n_threads)
+            t_jobs = time.perf_counter() - t0
+            assert all(np.array_equal(a[0], b[0]) for a, b in zip(got_jobs, got)), "threaded job creation changes the chains"
             chain_out["batched_fill_in"] = {"problems": len(many), "matches_total": int(sum(p.n_match for p in many)),
                                             "batch_call_ms": t_batch * 1e3, "kernel_ms": bst.kernel_ms, "gpu_launches": int(bst.kernel_launches),
-                                            "one_by_one_ms_extrapolated": t_one * 1e3, "speedup": t_one / t_batch,
+                                            "jobs_call_ms": t_jobs * 1e3, "jobs_threads": n_threads,
+                                            "one_by_one_ms_extrapolated": t_one * 1e3, "speedup": t_one / t_batch, "speedup_jobs": t_one / t_jobs,
                                             "what": "clb_chain_dp_batch: host layout per problem, ONE staging copy, ONE launch (a CTA per problem), "
-                                                    "ONE read-back; one_by_one = clb_chain_dp per problem (timed on a fifth of them)"}
+                                                    "ONE read-back; jobs = clb_chain_job_create on host threads (what the drop-in Anchorer's fill-in pool "
+                                                    "does) + ONE clb_chain_jobs_run; one_by_one = clb_chain_dp per problem (timed on a fifth of them)"}
     except Exception as exc:
         chain_out["batched_fill_in"] = {"error": str(exc)[:200]}
     out["chain_dp"] = chain_out
