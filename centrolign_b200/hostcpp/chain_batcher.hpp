@@ -37,7 +37,10 @@ inline int chain_device() {
 
 class ChainBatcher {
 public:
-    ChainBatcher(int device, int workers, size_t max_batch) : device_(device), active_(workers), max_batch_(max_batch) {}
+    // `run` takes a batch of jobs to the device (clb_chain_jobs_run; the unit test passes a stand-in that needs no GPU)
+    typedef int (*RunJobs)(int device, int64_t n_jobs, clb_chain_job* const* jobs);
+    ChainBatcher(int device, int workers, size_t max_batch, RunJobs run = clb_chain_jobs_run)
+        : device_(device), active_(workers), max_batch_(max_batch), run_(run) {}
 
     // the batcher of the pool the calling thread works for, or nullptr: ChainProblem::solve asks
     static ChainBatcher*& current() {
@@ -60,7 +63,7 @@ public:
                 lk.unlock();
                 std::vector<clb_chain_job*> jobs(batch.size());
                 for (size_t k = 0; k < batch.size(); ++k) jobs[k] = batch[k]->job;
-                const int rc = clb_chain_jobs_run(device_, (int64_t)jobs.size(), jobs.data());
+                const int rc = run_(device_, (int64_t)jobs.size(), jobs.data());
                 const std::string err = rc == CLB_OK ? std::string() : std::string(clb_last_error());
                 lk.lock();
                 for (Waiting* w : batch) {
@@ -95,6 +98,7 @@ private:
     const int device_;
     int active_;
     const size_t max_batch_;
+    const RunJobs run_;
     std::mutex mu_;
     std::condition_variable cv_;
     std::vector<Waiting*> waiting_;
@@ -105,16 +109,17 @@ private:
 // body(i) for every i in [0, n), on a pool of workers whose ChainProblem::solve calls share launches.
 // CLB_FILL_IN_THREADS sets the pool size (default 4 per hardware thread, 16..128); 1 = the serial loop, no batching.
 template <class Body>
-void batched_parallel_for(size_t n, int device, Body&& body) {
+void batched_parallel_for(size_t n, int device, Body&& body, ChainBatcher::RunJobs run = clb_chain_jobs_run, int pool_size = 0) {
     static const int configured = getenv("CLB_FILL_IN_THREADS") ? atoi(getenv("CLB_FILL_IN_THREADS")) : 0;
     const unsigned hw = std::thread::hardware_concurrency();
-    size_t threads = configured > 0 ? (size_t)configured : std::min<size_t>(128, std::max<size_t>(16, 4 * (size_t)(hw ? hw : 4)));
+    size_t threads = pool_size > 0 ? (size_t)pool_size
+                     : configured > 0 ? (size_t)configured : std::min<size_t>(128, std::max<size_t>(16, 4 * (size_t)(hw ? hw : 4)));
     threads = std::min(threads, n);
     if (threads <= 1 || ChainBatcher::current()) {  // nothing to share, or already inside a pool
         for (size_t i = 0; i < n; ++i) body(i);
         return;
     }
-    ChainBatcher batcher(device, (int)threads, 4 * 148);
+    ChainBatcher batcher(device, (int)threads, 4 * 148, run);
     std::atomic<size_t> next(0);
     std::mutex err_mu;
     std::exception_ptr first_error;

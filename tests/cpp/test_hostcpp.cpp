@@ -2,11 +2,18 @@
 // reference's Graph concept, on the golden cases of the reference's own unit test
 // (src/test/test_alignment.cpp:684-773).  Needs a GPU to run; `--link-only` just proves that it
 // builds and links against libcentrolign_b200.so.
+#include <algorithm>
+#include <chrono>
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
+#include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
+#include "chain_batcher.hpp"
 #include "po_poa_b200.hpp"
 
 struct MiniGraph {  // node_size / label / previous, like centrolign::BaseGraph (graph.hpp:94-149)
@@ -35,7 +42,74 @@ static int check(const centrolign_b200::Alignment& got, const std::vector<centro
     return 1;
 }
 
+// ---- ChainBatcher without a device: jobs are integers in disguise, the stand-in runner squares them ----
+namespace batcher_test {
+std::mutex mu;
+std::vector<size_t> batch_sizes;
+std::vector<int> runs_of;   // how often job k was run
+std::vector<long> result;   // k * k once job k has run
+int fail_on = -1;           // job whose batch reports an error
+int fake_run(int, int64_t n, clb_chain_job* const* jobs) {
+    std::lock_guard<std::mutex> lk(mu);
+    batch_sizes.push_back((size_t)n);
+    bool fail = false;
+    for (int64_t i = 0; i < n; ++i) {
+        const long k = (long)(reinterpret_cast<uintptr_t>(jobs[i]) - 1);
+        runs_of[(size_t)k] += 1;
+        result[(size_t)k] = k * k;
+        fail |= k == fail_on;
+    }
+    return fail ? CLB_ECUDA : CLB_OK;
+}
+int run(int n_items, int pool, bool with_failure) {
+    batch_sizes.clear();
+    runs_of.assign((size_t)n_items, 0);
+    result.assign((size_t)n_items, -1);
+    fail_on = with_failure ? n_items / 2 : -1;
+    std::vector<long> seen((size_t)n_items, -2);
+    bool threw = false;
+    try {
+        centrolign_b200::batched_parallel_for((size_t)n_items, 0, [&](size_t k) {
+            if (k % 7 == 3) return;  // a gap without matches: no chaining call at all
+            if (k % 5 == 0) std::this_thread::sleep_for(std::chrono::microseconds(200 + 37 * (k % 11)));
+            clb_chain_job* job = reinterpret_cast<clb_chain_job*>(uintptr_t(k + 1));
+            if (centrolign_b200::ChainBatcher* b = centrolign_b200::ChainBatcher::current()) b->solve(job);
+            else if (fake_run(0, 1, &job) != CLB_OK) throw std::runtime_error("serial call failed");  // the serial loop: one call per gap
+            seen[k] = result[k];  // the job has run when solve returns
+        }, fake_run, pool);
+    } catch (const std::runtime_error&) {
+        threw = true;
+    }
+    int bad = 0;
+    if (threw != with_failure) { std::fprintf(stderr, "FAILED batcher: exception %d, expected %d\n", (int)threw, (int)with_failure); ++bad; }
+    size_t total = 0, largest = 0;
+    for (size_t b : batch_sizes) { total += b; largest = std::max(largest, b); }
+    for (int k = 0; k < n_items && !with_failure; ++k) {
+        const bool skipped = k % 7 == 3;
+        if (runs_of[(size_t)k] != (skipped ? 0 : 1) || seen[(size_t)k] != (skipped ? -2 : (long)k * k)) {
+            std::fprintf(stderr, "FAILED batcher: job %d ran %d times, worker saw %ld\n", k, runs_of[(size_t)k], seen[(size_t)k]);
+            ++bad;
+            break;
+        }
+    }
+    if (!with_failure && pool > 1 && largest < 2) { std::fprintf(stderr, "FAILED batcher: no launch was shared (%zu launches)\n", batch_sizes.size()); ++bad; }
+    if (largest > (size_t)pool) { std::fprintf(stderr, "FAILED batcher: a batch of %zu from a pool of %d\n", largest, pool); ++bad; }
+    std::printf("batcher: %d items, pool %d%s: %zu launches, largest %zu, %zu jobs\n", n_items, pool, with_failure ? ", failing job" : "", batch_sizes.size(),
+                largest, total);
+    return bad;
+}
+}  // namespace batcher_test
+
 int main(int argc, char** argv) {
+    if (argc > 1 && !std::strcmp(argv[1], "--batcher")) {  // host-only: the rendezvous of the fill-in pool (chain_batcher.hpp)
+        int bad = 0;
+        bad += batcher_test::run(2000, 32, false);
+        bad += batcher_test::run(50, 64, false);   // more workers than items
+        bad += batcher_test::run(300, 1, false);   // serial loop: no batcher at all
+        bad += batcher_test::run(400, 16, true);   // an error in one launch reaches the caller as an exception
+        std::printf(bad ? "FAILED\n" : "batcher passed all tests!\n");
+        return bad ? 1 : 0;
+    }
     if (argc > 1 && !std::strcmp(argv[1], "--link-only")) {
         std::printf("linked, %d CUDA device(s)\n", clb_device_count());
         return 0;

@@ -20,7 +20,7 @@ def _build():
         pytest.skip("libcentrolign_b200.so not built")
     src = os.path.join(ROOT, "tests", "cpp", "test_hostcpp.cpp")
     if not os.path.exists(BIN) or os.path.getmtime(BIN) < max(os.path.getmtime(src), os.path.getmtime(lib)):
-        subprocess.run(["g++", "-std=c++11", "-O1", "-I" + os.path.join(ROOT, "include"),
+        subprocess.run(["g++", "-std=c++11", "-O1", "-pthread", "-I" + os.path.join(ROOT, "include"),
                         "-I" + os.path.join(ROOT, "centrolign_b200", "hostcpp"), src,
                         "-L" + os.path.dirname(lib), "-lcentrolign_b200", "-Wl,-rpath," + os.path.dirname(lib), "-o", BIN],
                        check=True)
@@ -30,6 +30,15 @@ def test_wrapper_compiles_and_links():
     _build()
     out = subprocess.run([BIN, "--link-only"], stdout=subprocess.PIPE, text=True, check=True).stdout
     assert "linked" in out
+
+
+def test_fill_in_pool_rendezvous():
+    """hostcpp/chain_batcher.hpp without a device: every job of a pool of worker threads runs exactly once, its worker
+    continues only after it ran, launches are shared, a pool of one is the serial loop, and an error in one launch comes
+    back as an exception."""
+    _build()
+    res = subprocess.run([BIN, "--batcher"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert res.returncode == 0 and "batcher passed all tests!" in res.stdout, res.stdout
 
 
 @pytest.mark.gpu
