@@ -56,6 +56,25 @@ def test_multi_cta_gives_the_same_values(grid, monkeypatch):
     assert np.array_equal(dp.view(np.uint32), ref_dp.view(np.uint32)) and opt == ref_opt
 
 
+@pytest.mark.parametrize("mode", ["CLB_CHAIN_CLUSTER=1", "CLB_CHAIN_CLUSTER=2", "CLB_CHAIN_CLUSTER=8", "CLB_CHAIN_CLUSTER=16", "CLB_CHAIN_GRID=8",
+                                  "CLB_CHAIN_GRID=148"])
+@pytest.mark.parametrize("num_pw", [0, 1, 2, 3])
+def test_every_way_to_separate_the_phases_and_every_piece_count(mode, num_pw, monkeypatch):
+    """One CTA, a thread-block cluster of 2 / 8 / 16 CTAs and a cooperative grid must give every DP value and back-pointer
+    of the oracle, for the gap-free instance of the step loop (1 item kind), the three-piece instance (7) and the generic one
+    (1 or 2 gap pieces: the same matches chained with truncated gap parameters)."""
+    src = GOLD["msa4_3k"]["gapfree" if num_pw == 0 else "affine"]
+    k = max(1, num_pw)
+    prob = ChainProblem(num_pw, tuple(src.gap_open[:k]), tuple(src.gap_extend[:k]), src.scale, src.n_chain1, src.n_chain2, src.min_score, src.arrays)
+    name, value = mode.split("=")
+    monkeypatch.setenv(name, value)
+    monkeypatch.setenv("CLB_CHAIN_NO_SMALL", "1")  # not the shared-memory kernel: that one is a single CTA by construction
+    chain, dp, bp, opt = chain_dp(prob)
+    ochain, odp, obp, oopt = chain_oracle(prob)
+    assert np.array_equal(chain, ochain) and opt == oopt
+    assert np.array_equal(dp.view(np.uint32), odp.view(np.uint32)) and np.array_equal(bp, obp)
+
+
 @pytest.mark.parametrize("case,kind", CASES)
 def test_every_dp_value_and_backpointer_equals_the_oracle(case, kind):
     """Stronger than chain identity: all DP values bit for bit and all back-pointers, against the literal C
