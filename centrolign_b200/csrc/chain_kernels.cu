@@ -6,17 +6,20 @@
 //
 // A preparation kernel first computes, for all (query, path of graph 2) pairs at once, everything that does not
 // depend on DP values: the gap-free tree of the query's diagonal and the shape of its three tree walks.
-// Then one persistent cooperative kernel walks the graph-1 nodes ("steps") in topological order.  Per step:
+// Then one persistent kernel walks the graph-1 nodes ("steps") in topological order.  Per step:
 //   A  every match ending here enters its DP value into the gap-free tree of its diagonal and into the
-//      2*NumPW orthogonal value sets, for every path pair of its end point -- all entries of the step in
-//      parallel, one warp per entry, lanes over the ancestors of the entry's node (atomicMax on packed words);
-//   B  every (match starting behind a forward edge, path of graph 2) pair is one warp: it answers the
-//      gap-free query and the 2*NumPW orthogonal queries by the reference's own tree walks, lanes over the
-//      blocks of a walk, keeps the first strictly greater candidate in the reference's order (gap-free, then
-//      pieces 0..2P-1) and posts it with atomicMax keyed by (value, earlier query first);
-//   C  the winning candidate of each match is applied if it beats the match's current value (update_dp,
-//      match_bank.hpp:171-184).
-// Phases are separated by a grid-wide barrier (cooperative groups), or __syncthreads() when one CTA runs.
+//      2*NumPW orthogonal value sets, for every path pair of its end point.  A work item is (entry, gap-free tree) or
+//      (entry, one orthogonal value set): one warp, lanes over the ancestors of the entry's node (atomicMax on packed
+//      words, Fenwick updates);
+//   B  a work item is (match starting behind a forward edge, path of graph 2, gap-free tree) or (..., piece, parity):
+//      one warp answers the query by the reference's own tree walk -- lane j owns the j-th node of either walk and the
+//      subtree hanging off it (closed form, walk_step) -- keeps the first strictly greater candidate in the
+//      reference's order (gap-free, then pieces 0..2P-1) and posts it with atomicMax keyed by (value, earlier first);
+//      beside the queries, other threads apply the winners of the PREVIOUS step if they beat the match's current value
+//      (update_dp, match_bank.hpp:171-184): queries never read DP values, insertions take max(stored, pending winner).
+// The phases are separated by __syncthreads() (one CTA), by the hardware barrier of ONE thread-block cluster of up to 16
+// CTAs (barrier.cluster.arrive.release / wait.acquire), or by a cooperative grid.sync(); the host picks by the number of
+// work items per step (chain_host.cu).  Records that do not depend on DP values are loaded one phase ahead.
 // Scores are float, gap terms double, every operation with an explicit rounding intrinsic so that no FMA
 // contraction can change a bit relative to the reference's scalar code.
 #include <cooperative_groups.h>
