@@ -13,7 +13,7 @@
 // straddle a strip boundary (128 columns) or start a panel (256 rows) -- the generator below keeps them away.  Scores are
 // checked against a plain CPU DP over the two graphs.
 // build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -o scan_fill_snp scan_fill_snp.cu
-// run:   ./scan_fill_snp [n nodes per graph, multiple of 256 (default 4096)] [windows (592)] [warps per CTA 8|12|16 (8)] [SNP rate per 1000 (50)]
+// run:   ./scan_fill_snp [n nodes per graph, multiple of 256 (default 4096)] [windows (592)] [warps per CTA 8|12|16 (8)] [SNP rate per 1000 (50)] [columns per lane 4|8 (4)]
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdint>
@@ -33,27 +33,27 @@ struct Params {
     int oe[3], e[3];
 };
 
-template <int W>
+template <int W, int C>  // C columns per lane: a strip is 32 * C columns wide
 __global__ void __launch_bounds__(W * 32, 1)
 snp_kernel(const unsigned char* __restrict__ seq_a, const unsigned char* __restrict__ typ_a, const unsigned char* __restrict__ seq_b,
            const unsigned char* __restrict__ typ_b, const int* __restrict__ pos_b, const int* __restrict__ row0, const int* __restrict__ col0, int n1, int n2,
            const Params prm, int* __restrict__ park_all, int* __restrict__ score_out) {
     extern __shared__ int4 smem4[];
     int4* ring = smem4;                                                         // [W][kRing] boundary column of a tile: {M, P'_1, P'_2, P'_3}
-    int4* rows = ring + W * kRing;                                              // [W][2][4][32] state of the last two rows of the tile in work
-    volatile int* prod = reinterpret_cast<volatile int*>(rows + W * 2 * 4 * 32);  // [W] rows published by warp w, counted over all its tiles
+    int4* rows = ring + W * kRing;                                              // [W][2][C][32] state of the last two rows of the tile in work
+    volatile int* prod = reinterpret_cast<volatile int*>(rows + W * 2 * C * 32);  // [W] rows published by warp w, counted over all its tiles
     volatile int* cons = prod + W;                                              // [W] rows of warp w's output its right neighbour has read
     unsigned char* sa = reinterpret_cast<unsigned char*>(const_cast<int*>(cons + W));  // [n1 + 1] labels of the rows
     unsigned char* ta = sa + n1 + 1;                                            // [n1 + 1] shapes of the rows
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const size_t wa = (size_t)blockIdx.x * (n1 + 1), wb = (size_t)blockIdx.x * (n2 + 1);
-    const int nstrips = n2 / 128;
+    const int nstrips = n2 / (32 * C);
     const int cntw = w < nstrips ? (nstrips - w + W - 1) / W : 0;  // tiles per panel of this warp
-    int* park = park_all + (size_t)blockIdx.x * nstrips * 17 * 32;
+    int* park = park_all + (size_t)blockIdx.x * nstrips * (4 * C + 1) * 32;
     for (int i = threadIdx.x; i <= n1; i += W * 32) { sa[i] = seq_a[wa + i]; ta[i] = typ_a[wa + i]; }
     if (threadIdx.x < W) { prod[threadIdx.x] = 0; cons[threadIdx.x] = 0; }
     __syncthreads();
-    int4* myrows = rows + w * (2 * 4 * 32) + lane;  // slot r: myrows[(r * 4 + c) * 32]
+    int4* myrows = rows + w * (2 * C * 32) + lane;  // slot r: myrows[(r * C + c) * 32]
     const int eo[3] = {prm.e[0] - prm.oe[0], prm.e[1] - prm.oe[1], prm.e[2] - prm.oe[2]};
 
     for (int p0 = 0; p0 < n1; p0 += kRing) {  // panel: rows p0+1 .. p0+kRing
@@ -65,13 +65,13 @@ snp_kernel(const unsigned char* __restrict__ seq_a, const unsigned char* __restr
             const int base_out = (pidx * cntw + s / W) * kRing;
             const int sprev = s >= W ? s - W : (pidx > 0 ? w + (cntw - 1) * W : -1);
             const bool wait_reader = sprev >= 0 && sprev + 1 < nstrips;
-            const int j0 = s * 128 + lane * 4;  // this lane's columns are j0+1 .. j0+4
-            unsigned char bc[4];
-            bool isB[4], isJ[4];
-            int pe[4][3], hq[4][3], Mp[4], G[4][3], lp1, lp2 = kMinInf;  // pos(c) * e_k and (e_k - oe_k) - pos(c) * e_k
-            int* pk = park + (size_t)s * 17 * 32 + lane;
+            const int j0 = (s * 32 + lane) * C;  // this lane's columns are j0+1 .. j0+C
+            unsigned char bc[C];
+            bool isB[C], isJ[C];
+            int pe[C][3], hq[C][3], Mp[C], G[C][3], lp1, lp2 = kMinInf;  // pos(c) * e_k and (e_k - oe_k) - pos(c) * e_k
+            int* pk = park + (size_t)s * (4 * C + 1) * 32 + lane;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < C; ++c) {
                 bc[c] = seq_b[wb + j0 + c + 1];
                 const unsigned char t = typ_b[wb + j0 + c + 1];
                 isB[c] = t == TB;
@@ -88,9 +88,9 @@ snp_kernel(const unsigned char* __restrict__ seq_a, const unsigned char* __restr
 #pragma unroll
                     for (int k = 0; k < 3; ++k) G[c][k] = pk[(c * 4 + 1 + k) * 32];
                 }
-                myrows[((p0 & 1) * 4 + c) * 32] = make_int4(Mp[c], G[c][0], G[c][1], G[c][2]);  // state of row p0
+                myrows[((p0 & 1) * C + c) * 32] = make_int4(Mp[c], G[c][0], G[c][1], G[c][2]);  // state of row p0
             }
-            lp1 = s == 0 ? col0[wa + p0] : (p0 == 0 ? row0[wb + s * 128] : pk[16 * 32]);  // M(p0, column left of the strip)
+            lp1 = s == 0 ? col0[wa + p0] : (p0 == 0 ? row0[wb + s * 32 * C] : pk[4 * C * 32]);  // M(p0, column left of the strip)
             for (int r0 = 0; r0 < prow; r0 += 32) {
                 const int r1 = min(r0 + 32, prow);
                 if (s > 0) while (prod[slot_in] < base_in + r1) __nanosleep(100);
@@ -107,14 +107,14 @@ snp_kernel(const unsigned char* __restrict__ seq_a, const unsigned char* __restr
                     }
                     const int ai = sa[i];
                     const int rt = ta[i];  // warp-uniform
-                    int Mn[4], Gn[4][3], Pk[3];
+                    int Mn[C], Gn[C][3], Pk[3];
                     // one row, given the effective "row above" (EM, EG) and the effective M left of the strip in that row
-                    auto body = [&](const int (&EM)[4], const int (&EG)[4][3], const int lpe) {
-                        int em1 = __shfl_up_sync(kFull, EM[3], 1), em2 = __shfl_up_sync(kFull, EM[2], 1);
+                    auto body = [&](const int (&EM)[C], const int (&EG)[C][3], const int lpe) {
+                        int em1 = __shfl_up_sync(kFull, EM[C - 1], 1), em2 = __shfl_up_sync(kFull, EM[C - 2], 1);
                         if (lane == 0) { em1 = lpe; em2 = kMinInf; }
-                        int Mq[4], T[3] = {kMinInf, kMinInf, kMinInf}, Tw[3], tq[4][3];
+                        int Mq[C], T[3] = {kMinInf, kMinInf, kMinInf}, Tw[3], tq[C][3];
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
+                        for (int c = 0; c < C; ++c) {
                             const int d1 = c == 0 ? em1 : EM[c - 1];
                             const int d2 = c == 0 ? em2 : (c == 1 ? em1 : EM[c - 2]);
                             int d = isB[c] ? d2 : d1;
@@ -124,7 +124,7 @@ snp_kernel(const unsigned char* __restrict__ seq_a, const unsigned char* __restr
 #pragma unroll
                             for (int k = 0; k < 3; ++k) {
                                 tq[c][k] = Mq[c] + pe[c][k];
-                                if (c == 3) Tw[k] = T[k];
+                                if (c == C - 1) Tw[k] = T[k];
                                 T[k] = max(T[k], tq[c][k]);
                             }
                         }
@@ -144,7 +144,7 @@ snp_kernel(const unsigned char* __restrict__ seq_a, const unsigned char* __restr
                             Pp[k] = yp;
                         }
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
+                        for (int c = 0; c < C; ++c) {
                             int h[3];
 #pragma unroll
                             for (int k = 0; k < 3; ++k) {
@@ -163,10 +163,10 @@ snp_kernel(const unsigned char* __restrict__ seq_a, const unsigned char* __restr
                     if (rt == TR) {
                         body(Mp, G, lp1);
                     } else {
-                        int EM[4], EG[4][3];
+                        int EM[C], EG[C][3];
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const int4 v = myrows[((i & 1) * 4 + c) * 32];  // state of row i-2
+                        for (int c = 0; c < C; ++c) {
+                            const int4 v = myrows[((i & 1) * C + c) * 32];  // state of row i-2
                             if (rt == TB) {
                                 EM[c] = v.x; EG[c][0] = v.y; EG[c][1] = v.z; EG[c][2] = v.w;
                             } else {
@@ -177,15 +177,15 @@ snp_kernel(const unsigned char* __restrict__ seq_a, const unsigned char* __restr
                     }
                     const bool needed_later = r + 2 < prow && ta[i + 2] != TR;  // warp-uniform: row i+2 takes this row as a "row above"
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
+                    for (int c = 0; c < C; ++c) {
                         Mp[c] = Mn[c];
 #pragma unroll
                         for (int k = 0; k < 3; ++k) G[c][k] = Gn[c][k];
-                        if (needed_later) myrows[((i & 1) * 4 + c) * 32] = make_int4(Mn[c], Gn[c][0], Gn[c][1], Gn[c][2]);
+                        if (needed_later) myrows[((i & 1) * C + c) * 32] = make_int4(Mn[c], Gn[c][0], Gn[c][1], Gn[c][2]);
                     }
                     lp2 = lp1;
                     lp1 = L.x;
-                    if (lane == 31 && s + 1 < nstrips) ring[slot_out * kRing + r] = make_int4(Mn[3], Pk[0], Pk[1], Pk[2]);
+                    if (lane == 31 && s + 1 < nstrips) ring[slot_out * kRing + r] = make_int4(Mn[C - 1], Pk[0], Pk[1], Pk[2]);
                 }
                 __syncwarp();
                 if (lane == 0) {
@@ -196,14 +196,14 @@ snp_kernel(const unsigned char* __restrict__ seq_a, const unsigned char* __restr
             }
             if (p0 + kRing < n1) {  // park the state for this strip's tile of the next panel (its first row is a plain row)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < C; ++c) {
                     pk[(c * 4) * 32] = Mp[c];
 #pragma unroll
                     for (int k = 0; k < 3; ++k) pk[(c * 4 + 1 + k) * 32] = G[c][k];
                 }
-                pk[16 * 32] = lp1;
+                pk[4 * C * 32] = lp1;
             } else if (s == nstrips - 1 && lane == 31) {
-                score_out[blockIdx.x] = Mp[3];
+                score_out[blockIdx.x] = Mp[C - 1];
             }
         }
     }
@@ -255,17 +255,17 @@ int cpu_score(const Graph& a, const Graph& b, int n1, int n2, const Params& p) {
     return M[n1][n2];
 }
 
-template <int W>
+template <int W, int C>
 float run(const unsigned char* da, const unsigned char* dta, const unsigned char* db, const unsigned char* dtb, const int* dpos, const int* drow0,
           const int* dcol0, int n, int windows, const Params& prm, int* dpark, int* dscore, int reps) {
-    const size_t smem = (size_t)W * kRing * 16 + (size_t)W * 2 * 4 * 32 * 16 + 2 * W * 4 + 2 * (n + 1) + 16;
-    cudaFuncSetAttribute(snp_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = (size_t)W * kRing * 16 + (size_t)W * 2 * C * 32 * 16 + 2 * W * 4 + 2 * (n + 1) + 16;
+    cudaFuncSetAttribute(snp_kernel<W, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    snp_kernel<W><<<windows, W * 32, smem>>>(da, dta, db, dtb, dpos, drow0, dcol0, n, n, prm, dpark, dscore);  // warm-up
+    snp_kernel<W, C><<<windows, W * 32, smem>>>(da, dta, db, dtb, dpos, drow0, dcol0, n, n, prm, dpark, dscore);  // warm-up
     cudaEventRecord(e0);
-    for (int r = 0; r < reps; ++r) snp_kernel<W><<<windows, W * 32, smem>>>(da, dta, db, dtb, dpos, drow0, dcol0, n, n, prm, dpark, dscore);
+    for (int r = 0; r < reps; ++r) snp_kernel<W, C><<<windows, W * 32, smem>>>(da, dta, db, dtb, dpos, drow0, dcol0, n, n, prm, dpark, dscore);
     cudaEventRecord(e1);
     cudaEventSynchronize(e1);
     float ms = 0.f;
@@ -281,6 +281,7 @@ int main(int argc, char** argv) {
     const int windows = argc > 2 ? atoi(argv[2]) : 592;
     const int W = argc > 3 ? atoi(argv[3]) : 8;
     const unsigned snp = argc > 4 ? (unsigned)atoi(argv[4]) : 50;
+    const int C = argc > 5 ? atoi(argv[5]) : 4;
     if (n % 256 || n < 256) { printf("n must be a multiple of 256\n"); return 1; }
     const Params prm = {20, 80, {60 + 30, 800 + 5, 2500 + 1}, {30, 5, 1}};
     unsigned long long x = 88172645463325252ull;
@@ -320,7 +321,7 @@ int main(int argc, char** argv) {
             other.push_back(r < 35 ? (unsigned char)((base[j] + 1 + rnd() % 3) & 3) : base[j]);
             if (r >= 35 && r < 40) other.push_back((unsigned char)(rnd() & 3));
         }
-        Graph ga = make_graph(base, 256), gb = make_graph(other, 128);
+        Graph ga = make_graph(base, 256), gb = make_graph(other, 32 * C);
         for (int i = 0; i <= n; ++i) {
             la[wdw * stride + i] = ga.lab[i]; ta[wdw * stride + i] = ga.typ[i];
             lb[wdw * stride + i] = gb.lab[i]; tb[wdw * stride + i] = gb.typ[i];
@@ -335,16 +336,16 @@ int main(int argc, char** argv) {
     cudaMalloc(&da, la.size()); cudaMalloc(&dta, ta.size()); cudaMalloc(&db, lb.size()); cudaMalloc(&dtb, tb.size());
     cudaMalloc(&dpos, posb.size() * 4); cudaMalloc(&drow0, row0.size() * 4); cudaMalloc(&dcol0, col0.size() * 4);
     cudaMalloc(&dscore, windows * sizeof(int));
-    cudaMalloc(&dpark, (size_t)windows * (n / 128) * 17 * 32 * sizeof(int));
+    cudaMalloc(&dpark, (size_t)windows * (n / (32 * C)) * (4 * C + 1) * 32 * sizeof(int));
     cudaMemcpy(da, la.data(), la.size(), cudaMemcpyHostToDevice); cudaMemcpy(dta, ta.data(), ta.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(db, lb.data(), lb.size(), cudaMemcpyHostToDevice); cudaMemcpy(dtb, tb.data(), tb.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(dpos, posb.data(), posb.size() * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(drow0, row0.data(), row0.size() * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(dcol0, col0.data(), col0.size() * 4, cudaMemcpyHostToDevice);
     const int reps = 3;
-    const float ms = W == 12 ? run<12>(da, dta, db, dtb, dpos, drow0, dcol0, n, windows, prm, dpark, dscore, reps)
-                     : W == 16 ? run<16>(da, dta, db, dtb, dpos, drow0, dcol0, n, windows, prm, dpark, dscore, reps)
-                               : run<8>(da, dta, db, dtb, dpos, drow0, dcol0, n, windows, prm, dpark, dscore, reps);
+#define RUN(WW, CC) run<WW, CC>(da, dta, db, dtb, dpos, drow0, dcol0, n, windows, prm, dpark, dscore, reps)
+    const float ms = C == 8 ? (W == 12 ? RUN(12, 8) : W == 16 ? RUN(16, 8) : RUN(8, 8)) : (W == 12 ? RUN(12, 4) : W == 16 ? RUN(16, 4) : RUN(8, 4));
+#undef RUN
     std::vector<int> score(windows);
     cudaMemcpy(score.data(), dscore, windows * sizeof(int), cudaMemcpyDeviceToHost);
     int checked = 0, bad = 0;
@@ -356,7 +357,7 @@ int main(int argc, char** argv) {
     size_t nb = 0;
     for (unsigned char t : tb) nb += t == TB;
     const double cells = (double)windows * (n + 1.0) * (n + 1.0);
-    printf("scan_fill_snp: %d windows of %d x %d nodes, %.1f %% of the nodes in SNP bubbles, %d warps per CTA: %.3f ms, %.1f GCUPS; %d windows checked "
-           "against the CPU DP, %d differ\n", windows, n, n, 300.0 * nb / tb.size(), W, ms, cells / (ms * 1e-3) * 1e-9, checked, bad);
+    printf("scan_fill_snp: %d windows of %d x %d nodes, %.1f %% of the nodes in SNP bubbles, %d warps per CTA, %d columns per lane: %.3f ms, %.1f GCUPS; %d windows "
+           "checked against the CPU DP, %d differ\n", windows, n, n, 300.0 * nb / tb.size(), W, C, ms, cells / (ms * 1e-3) * 1e-9, checked, bad);
     return bad ? 2 : 0;
 }
