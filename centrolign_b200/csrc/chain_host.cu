@@ -73,6 +73,7 @@ struct DeviceArena {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp = nullptr;
 };
 constexpr size_t kArenaKeep = size_t(1) << 30;
+constexpr size_t kDirectCopyBytes = size_t(32) << 20;  // copy regions above this size go to the device without a pinned staging twin
 constexpr size_t kChainBatchArena = size_t(4) << 20;  // a problem up to this arena size joins a batched launch (one CTA per problem)
 constexpr int kChainClusterMax = 16;  // CTAs of the cluster a mid-sized problem runs in (non-portable size; launch_chain halves it if refused)
 std::mutex g_arena_mu;
@@ -616,18 +617,28 @@ static int chain_dp_impl(int device, const clb_chain_problem* p, float* dp_out, 
             CHAIN_TRY(cudaMalloc((void**)&ar.d, want));
             ar.cap = want;
         }
-        if (ar.hcap < plan.copy_bytes) {
+        // A large problem is copied segment by segment straight from the caller's arrays: pinning a staging twin of tens to
+        // hundreds of MB costs more (≈ 1 ms per MB) than the driver's own staging of a pageable copy, and a problem of that size
+        // comes a few times per alignment.  Small problems -- thousands per alignment -- share one pinned twin that stays.
+        const bool direct = plan.copy_bytes > kDirectCopyBytes && ar.hcap < plan.copy_bytes;
+        if (!direct && ar.hcap < plan.copy_bytes) {
             if (ar.h) cudaFreeHost(ar.h);
             ar.h = nullptr;
             ar.hcap = 0;
-            const size_t want = keep ? std::max(plan.copy_bytes, std::min(kArenaKeep, 2 * plan.copy_bytes)) : plan.copy_bytes;
+            const size_t want = std::max(plan.copy_bytes, std::min(kDirectCopyBytes, 2 * plan.copy_bytes));
             CHAIN_TRY(cudaHostAlloc((void**)&ar.h, want, cudaHostAllocDefault));
             ar.hcap = want;
         }
-        for (const auto& sg : plan.segs)
-            if (sg.bytes) memcpy(ar.h + sg.off, sg.src, sg.bytes);
+        if (!direct)
+            for (const auto& sg : plan.segs)
+                if (sg.bytes) memcpy(ar.h + sg.off, sg.src, sg.bytes);
         const double t_staged = now_ms();
-        CHAIN_TRY(cudaMemcpyAsync(ar.d, ar.h, plan.copy_bytes, cudaMemcpyHostToDevice, ar.stream));
+        if (direct) {
+            for (const auto& sg : plan.segs)
+                if (sg.bytes) CHAIN_TRY(cudaMemcpyAsync(ar.d + sg.off, sg.src, sg.bytes, cudaMemcpyHostToDevice, ar.stream));
+        } else {
+            CHAIN_TRY(cudaMemcpyAsync(ar.d, ar.h, plan.copy_bytes, cudaMemcpyHostToDevice, ar.stream));
+        }
         char* zr = ar.d + plan.copy_bytes;
         CHAIN_TRY(cudaMemsetAsync(zr, 0, plan.zero_bytes, ar.stream));
         a.num_pw = P; a.n_chain1 = C1; a.n_chain2 = C2; a.scale = p->scale;
