@@ -47,6 +47,36 @@ def test_argument_validation_and_no_cpu_fallback():
     assert ei.value.code == 1
 
 
+def test_chain_job_entry_points_without_a_device():
+    """The two-halves form of the batched chaining call: argument errors and the no-device case come back as codes (no crash,
+    no job object left behind); running zero jobs and destroying NULL are allowed; the context warm-up is silent."""
+    from centrolign_b200 import chain
+
+    lib = _lib_or_skip()
+    chain._bind(lib)
+    job = ctypes.c_void_p(None)
+    assert lib.clb_chain_job_create(0, None, None, None, None, None, None, ctypes.byref(job)) == 1 and not job.value  # CLB_EINVAL
+    assert lib.clb_chain_job_create(0, None, None, None, None, None, None, None) == 1
+    assert lib.clb_chain_jobs_run(0, 0, None) == 0
+    assert lib.clb_chain_jobs_run(0, 1, None) == 1
+    lib.clb_chain_job_destroy(None)
+    lib.clb_warm_up.restype = None
+    lib.clb_warm_up.argtypes = [ctypes.c_int]
+    lib.clb_warm_up(0)
+    lib.clb_warm_up(0)  # only the first call does anything
+    if lib.clb_device_count() == 0:
+        import sys
+
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import test_chain_gpu as t
+
+        cp, keep = chain._c_problem(t._handmade(3))
+        n = ctypes.c_int64(0)
+        out = (ctypes.c_int64 * 4)()
+        rc = lib.clb_chain_job_create(0, ctypes.byref(cp), None, None, out, ctypes.byref(n), None, ctypes.byref(job))
+        assert rc == 3 and not job.value  # CLB_ECUDA: no device, no CPU fallback
+
+
 def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(popoa, "_lib", None)
     monkeypatch.setattr(popoa, "_LIB_PATH", "/nonexistent/libcentrolign_b200.so")
