@@ -513,8 +513,20 @@ static int chain_dp_impl(int device, const clb_chain_problem* p, float* dp_out, 
         ArenaPlan plan;
         std::vector<uint32_t> bp0(M, clb::kChainNone);
         const size_t o_dp = plan.copy(p->dp_init, M * sizeof(float)), o_bp = plan.copy(bp0);
-        const size_t o_sins = plan.copy(sins_off), o_ins = plan.copy(ins);
-        const size_t o_qoff = plan.copy(p->qry_off, (S + 1) * sizeof(int64_t)), o_qm = plan.copy(p->qry_match, n_qry * sizeof(uint32_t));
+        // the device walks only the steps in which something happens (a caller may list every node of graph 1 as a step; the
+        // builders of hostcpp/chain_b200.hpp list the nodes with events): the offsets are cumulative, so dropping an empty step
+        // drops one equal entry of either list
+        std::vector<int64_t> sins_live, qry_live;
+        sins_live.reserve(S + 1); qry_live.reserve(S + 1);
+        sins_live.push_back(sins_off[0]); qry_live.push_back(p->qry_off[0]);
+        for (int64_t s = 0; s < S; ++s)
+            if (sins_off[s + 1] != sins_off[s] || p->qry_off[s + 1] != p->qry_off[s]) {
+                sins_live.push_back(sins_off[s + 1]);
+                qry_live.push_back(p->qry_off[s + 1]);
+            }
+        const int64_t S_live = (int64_t)sins_live.size() - 1;
+        const size_t o_sins = plan.copy(sins_live), o_ins = plan.copy(ins);
+        const size_t o_qoff = plan.copy(qry_live), o_qm = plan.copy(p->qry_match, n_qry * sizeof(uint32_t));
         const size_t o_w = plan.copy(p->weight, M * sizeof(float)), o_qc1 = plan.copy(p->qry_chain1, n_qry * sizeof(uint32_t));
         const size_t o_qa1 = plan.copy(p->qa1, (size_t)M * C1 * sizeof(int32_t)), o_qa2 = plan.copy(p->qa2, (size_t)M * C2 * sizeof(int32_t));
         const size_t o_qo = plan.copy(p->qoff, (size_t)M * C2 * sizeof(uint32_t));
@@ -561,7 +573,7 @@ static int chain_dp_impl(int device, const clb_chain_problem* p, float* dp_out, 
                 b.gap_extend[k] = p->gap_extend[k];
                 b.scale_ext[k] = p->scale * p->gap_extend[k];
             }
-            b.n_match = M; b.n_step = S; b.n_entry = E; b.n_inner = n_inner; b.n_qry = n_qry; b.n_ins = (int64_t)ins.size();
+            b.n_match = M; b.n_step = S_live; b.n_entry = E; b.n_inner = n_inner; b.n_qry = n_qry; b.n_ins = (int64_t)ins.size();
             b.cand_bp_stride = max_q * C2 * (T + 1); b.sync_mode = 0;
             b.dp = (float*)(base + o_dp); b.backptr = (uint32_t*)(base + o_bp);
             b.sins_off = (const int64_t*)(base + o_sins); b.ins = (const clb::InsRec*)(base + o_ins);
@@ -647,7 +659,7 @@ static int chain_dp_impl(int device, const clb_chain_problem* p, float* dp_out, 
             a.gap_extend[k] = p->gap_extend[k];
             a.scale_ext[k] = p->scale * p->gap_extend[k];  // anchorer.hpp:2330: local_scale * gap_extend[pw / 2] (* shift on the device)
         }
-        a.n_match = M; a.n_step = S; a.n_entry = E; a.n_inner = n_inner; a.n_qry = n_qry; a.n_ins = (int64_t)ins.size();
+        a.n_match = M; a.n_step = S_live; a.n_entry = E; a.n_inner = n_inner; a.n_qry = n_qry; a.n_ins = (int64_t)ins.size();
         a.cand_bp_stride = max_q * C2 * (T + 1);
         a.dp = (float*)(ar.d + o_dp); a.backptr = (uint32_t*)(ar.d + o_bp);
         a.sins_off = (const int64_t*)(ar.d + o_sins); a.ins = (const clb::InsRec*)(ar.d + o_ins);
@@ -669,7 +681,7 @@ static int chain_dp_impl(int device, const clb_chain_problem* p, float* dp_out, 
         // How the phases of a step are separated.  A step has `warps_per_step` independent warp-sized work items on average:
         // a handful run in one CTA (__syncthreads), up to as many as the largest cluster has warps in ONE thread-block cluster
         // (hardware cluster barrier, the items of a step spread over its SMs), more in a cooperative grid over all SMs (grid.sync).
-        const double warps_per_step = S ? ((double)ins.size() + (double)n_qry * C2) * (T + 1) / (double)S : 0.0;
+        const double warps_per_step = S_live ? ((double)ins.size() + (double)n_qry * C2) * (T + 1) / (double)S_live : 0.0;
         const int max_grid = clb::chain_max_grid(device);
         const int warps_per_cta = P == 0 ? 28 : 16;  // chain_kernels.cu: the gap-free kernel runs with 896 threads
         int cluster = 1;
@@ -705,9 +717,9 @@ static int chain_dp_impl(int device, const clb_chain_problem* p, float* dp_out, 
             float pms = 0.f;
             cudaEventElapsedTime(&pms, ar.ev0, ar.evp);
             fprintf(stderr, "[clb] chain: build %.1f ms, alloc+stage %.1f ms (%.0f MB arena, %.0f MB copied), prepare kernel %.2f ms, DP kernel %.2f ms, "
-                            "enqueue..sync %.1f ms (grid %d, cluster %d, %lld steps, %.0f warp items per step, rank pool %s)\n",
+                            "enqueue..sync %.1f ms (grid %d, cluster %d, %lld of %lld steps with events, %.0f warp items per step, rank pool %s)\n",
                     t_built - t_start, t_staged - t_built, total / 1e6, plan.copy_bytes / 1e6, pms, ms - pms, now_ms() - t_staged, grid, cluster,
-                    (long long)S, warps_per_step, rank_stride ? "on" : "off");
+                    (long long)S_live, (long long)S, warps_per_step, rank_stride ? "on" : "off");
         }
         if (stats) {
             stats->build_ms = t_built - t_start;
